@@ -1,0 +1,15 @@
+"""cgb_b200 — B200-native PSWM scanning and regulation posteriors (the hot path of
+ErillLab/cgb): ``pssm_model.PSSMModel`` / ``binding_model.TFBindingModel`` call
+surface over hand-written sm_100a kernels behind a C ABI (include/cgbk.h).
+
+Importing the package does not need a GPU; any scoring call does (no CPU fallback).
+"""
+from .binding_model import TFBindingModel
+from .gene_regions import GeneTable, python_slice_bounds
+from .genome_buffer import PackedGenome
+from .pssm_model import PSSMModel
+from .site_collection import SiteCollection
+from .site_search import Site, calculate_regulation_probabilities, identify_sites
+
+__all__ = ["TFBindingModel", "PSSMModel", "SiteCollection", "PackedGenome", "GeneTable",
+           "Site", "identify_sites", "calculate_regulation_probabilities", "python_slice_bounds"]

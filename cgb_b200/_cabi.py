@@ -1,0 +1,99 @@
+"""ctypes binding of libcgbk.so (include/cgbk.h).
+
+There is no CPU fallback: if the CUDA library has not been built, importing a
+compute entry point raises.  Status codes are mapped to the exception types the
+reference raises for the same condition.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libcgbk.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
+MAX_MOTIF = 32
+SEQ_ALIGN = 512
+MAX_HIST_BINS = 4096
+CTR_CANDIDATES, CTR_HITS, CTR_DIRTY_TILES, CTR_COUNT = 0, 1, 2, 8
+BG_N, BG_SUM, BG_SUMSQ, BG_MEAN, BG_STD, BG_COUNT = 0, 1, 2, 3, 4, 8
+RC_MATRIX_ORDER, RC_REVSEQ_ORDER, SINGLE_WINDOW_F64 = 0, 1, 2
+
+
+class Genome(C.Structure):
+    _fields_ = [("d_bases2", C.c_void_p), ("d_amb", C.c_void_p), ("d_lower", C.c_void_p),
+                ("cap_bases", C.c_int64)]
+
+
+class CgbkError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/cgbk.h declares
+SYMBOLS = {
+    "cgbk_version": (C.c_int, []),
+    "cgbk_last_error": (C.c_char_p, []),
+    "cgbk_patser_threshold": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 4),
+    "cgbk_bases2_words": (C.c_int64, [C.c_int64]),
+    "cgbk_pack_ascii": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int64, C.c_void_p]),
+    "cgbk_model_create": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "cgbk_model_destroy": (None, [C.c_void_p]),
+    "cgbk_seqset_create": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int, C.c_int,
+                                      C.POINTER(C.c_void_p)]),
+    "cgbk_seqset_destroy": (None, [C.c_void_p]),
+    "cgbk_seqset_total_windows": (C.c_int64, [C.c_void_p, C.c_int]),
+    "cgbk_score_windows": (C.c_int, [C.c_void_p, C.POINTER(Genome), C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
+                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
+    "cgbk_posteriors": (C.c_int, [C.c_void_p, C.POINTER(Genome), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "cgbk_scan_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int64]),
+    "cgbk_scan_hits": (C.c_int, [C.c_void_p, C.POINTER(Genome), C.c_void_p, C.c_double, C.c_int, C.c_void_p,
+                                  C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "cgbk_background_stats": (C.c_int, [C.c_void_p, C.POINTER(Genome), C.c_void_p, C.c_double, C.c_double,
+                                         C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
+                                         C.c_void_p]),
+    "cgbk_background_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cgbk_last_launch_info": (C.c_int, [C.POINTER(C.c_int64)]),
+}
+
+
+def lib():
+    """The loaded library; raises if it was never built (no fallback path)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CgbkError(
+                "libcgbk.so is missing (%s): build it with `python -m cgb_b200.build`; "
+                "cgb_b200 has no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.cgbk_version() != 100:
+            raise CgbkError("libcgbk.so version %d does not match the Python layer" % L.cgbk_version())
+        _lib = L
+    return _lib
+
+
+def check(status):
+    """Map a cgbk status code to the reference's exception types."""
+    if status == OK:
+        return
+    msg = lib().cgbk_last_error().decode("utf-8", "replace")
+    if status == ERR_INVALID:
+        raise ValueError(msg)
+    if status == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise CgbkError(msg)
+
+
+def last_launch_info():
+    out = (C.c_int64 * 3)()
+    check(lib().cgbk_last_launch_info(out))
+    return {"launches": out[0], "tiles": out[1], "lane_bases": out[2]}

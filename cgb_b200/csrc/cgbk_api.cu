@@ -1,0 +1,564 @@
+// C ABI of libcgbk.so: handles, host float64 motif math, table construction and
+// the launch sequences of the kernels in cgbk_exact.cu / cgbk_fast.cu.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "cgbk_internal.cuh"
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static thread_local long long g_launch_info[3] = {0, 0, 0};
+
+int cgbk_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cgbk_check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return CGBK_OK;
+    return cgbk_set_error(CGBK_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CUDA_TRY(expr)                                         \
+    do {                                                       \
+        int _rc = cgbk_check_cuda((expr), #expr);              \
+        if (_rc != CGBK_OK) return _rc;                        \
+    } while (0)
+
+extern "C" int cgbk_version(void) { return CGBK_VERSION; }
+extern "C" const char* cgbk_last_error(void) { return g_err; }
+
+extern "C" int cgbk_last_launch_info(int64_t* out3) {
+    if (!out3) return cgbk_set_error(CGBK_ERR_INVALID, "out3 is NULL");
+    for (int i = 0; i < 3; ++i) out3[i] = g_launch_info[i];
+    return CGBK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host float64 motif math
+//   Biopython 1.76 PositionSpecificScoringMatrix.mean/min/max and
+//   thresholds.ScoreDistribution (pssm= branch) + threshold_patser, reached from
+//   cgb/pssm_model.py:57-70.  Uniform background, as PSSMModel passes none.
+// ---------------------------------------------------------------------------
+static double py_floordiv(double vx, double wx) {   // CPython float_floor_div
+    double mod = fmod(vx, wx);
+    double div = (vx - mod) / wx;
+    if (mod != 0.0) {
+        if ((wx < 0) != (mod < 0)) { mod += wx; div -= 1.0; }
+    }
+    double floordiv;
+    if (div != 0.0) {
+        floordiv = floor(div);
+        if (div - floordiv > 0.5) floordiv += 1.0;
+    } else {
+        floordiv = copysign(0.0, vx / wx);
+    }
+    return floordiv;
+}
+
+static void pssm_stats(const double* lo, int m, double* ic, double* mn, double* mx) {
+    double sx = 0.0, smin = 0.0, smax = 0.0;
+    for (int i = 0; i < m; ++i) {
+        double cmin = lo[i * 4], cmax = lo[i * 4];
+        for (int k = 0; k < 4; ++k) {
+            const double v = lo[i * 4 + k];
+            if (v < cmin) cmin = v;
+            if (v > cmax) cmax = v;
+            if (isnan(v)) continue;
+            if (isinf(v) && v < 0) continue;
+            const double p = 0.25 * pow(2.0, v);
+            sx += p * v;
+        }
+        smin += cmin; smax += cmax;
+    }
+    *ic = sx; *mn = smin; *mx = smax;
+}
+
+extern "C" int cgbk_patser_threshold(const double* lo, int m, int precision, double* threshold,
+                                     double* ic_out, double* min_out, double* max_out) {
+    if (!lo || m <= 0 || precision <= 0) return cgbk_set_error(CGBK_ERR_INVALID, "bad motif or precision");
+    for (int i = 0; i < 4 * m; ++i)
+        if (!isfinite(lo[i]))
+            return cgbk_set_error(CGBK_ERR_INVALID, "non-finite log-odds at position %d", i / 4);
+    double ic, pmin, pmax;
+    pssm_stats(lo, m, &ic, &pmin, &pmax);
+    if (ic_out) *ic_out = ic;
+    if (min_out) *min_out = pmin;
+    if (max_out) *max_out = pmax;
+    if (!threshold) return CGBK_OK;
+    const double min_score = pmin < 0.0 ? pmin : 0.0;
+    const double interval = (pmax > 0.0 ? pmax : 0.0) - min_score;
+    const long long n_points = (long long)precision * m;
+    if (n_points < 2) return cgbk_set_error(CGBK_ERR_INVALID, "precision*m must be >= 2");
+    const double step = interval / (double)(n_points - 1);
+    auto index_diff = [&](double x) -> long long { return (long long)py_floordiv(x + 0.5 * step, step); };
+    std::vector<double> dens(n_points, 0.0), next(n_points, 0.0);
+    long long start = -index_diff(min_score);
+    if (start < 0) start += n_points;            // Python negative index
+    if (start < 0 || start >= n_points) return cgbk_set_error(CGBK_ERR_INVALID, "degenerate score range");
+    dens[start] = 1.0;
+    for (int pos = 0; pos < m; ++pos) {
+        std::fill(next.begin(), next.end(), 0.0);
+        for (int k = 0; k < 4; ++k) {             // letters in alphabet order
+            const long long d = index_diff(lo[pos * 4 + k]);
+            for (long long i = 0; i < n_points; ++i) {
+                long long j = i + d;
+                if (j < 0) j = 0;
+                if (j > n_points - 1) j = n_points - 1;
+                next[j] += dens[i] * 0.25;
+            }
+        }
+        dens.swap(next);
+    }
+    const double fpr = pow(2.0, -ic);
+    long long i = n_points;
+    double prob = 0.0;
+    while (prob < fpr) {
+        i -= 1;
+        if (i < 0) return cgbk_set_error(CGBK_ERR_INVALID, "threshold search ran off the distribution");
+        prob += dens[i];
+    }
+    *threshold = min_score + (double)i * step;
+    return CGBK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// packing
+// ---------------------------------------------------------------------------
+extern "C" int64_t cgbk_bases2_words(int64_t cap_bases) { return cap_bases / 16; }
+
+extern "C" int cgbk_pack_ascii(const uint8_t* d_ascii, int64_t n, int64_t dst_off, uint32_t* d_bases2,
+                               uint32_t* d_amb, uint32_t* d_lower, int64_t cap_bases, void* stream) {
+    if (n < 0 || dst_off < 0 || dst_off % CGBK_SEQ_ALIGN != 0)
+        return cgbk_set_error(CGBK_ERR_INVALID, "dst_off must be a non-negative multiple of %d", CGBK_SEQ_ALIGN);
+    const int64_t padded = ((n + CGBK_SEQ_ALIGN - 1) / CGBK_SEQ_ALIGN) * CGBK_SEQ_ALIGN;
+    if (dst_off + padded > cap_bases)
+        return cgbk_set_error(CGBK_ERR_INVALID, "sequence of %lld bases at offset %lld exceeds capacity %lld",
+                              (long long)n, (long long)dst_off, (long long)cap_bases);
+    if (n > 0 && (!d_ascii || !d_bases2 || !d_amb || !d_lower))
+        return cgbk_set_error(CGBK_ERR_INVALID, "NULL device pointer");
+    CUDA_TRY(launch_pack(d_ascii, n, dst_off, d_bases2, d_amb, d_lower, (cudaStream_t)stream));
+    return CGBK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------
+static void group_partial(const double* tab, int m, int g, int e, double* out) {
+    double s = 0.0;
+    for (int k = 0; k < 4; ++k) {
+        const int j = 4 * g + k;
+        if (j < m) s += tab[j * 4 + ((e >> (2 * k)) & 3)];
+    }
+    *out = s;
+}
+
+extern "C" int cgbk_model_create(const double* lo, int m, int device, cgbk_model** out) {
+    if (!lo || !out) return cgbk_set_error(CGBK_ERR_INVALID, "NULL argument");
+    if (m < 1) return cgbk_set_error(CGBK_ERR_INVALID, "motif length must be >= 1");
+    if (m > CGBK_MAX_MOTIF)
+        return cgbk_set_error(CGBK_ERR_UNSUPPORTED, "motif length %d exceeds CGBK_MAX_MOTIF=%d", m, CGBK_MAX_MOTIF);
+    for (int i = 0; i < 4 * m; ++i)
+        if (!isfinite(lo[i]))
+            return cgbk_set_error(CGBK_ERR_INVALID, "non-finite log-odds at position %d (zero probability "
+                                  "without pseudocounts is not supported)", i / 4);
+    CUDA_TRY(cudaSetDevice(device));
+    cgbk_model* M = (cgbk_model*)calloc(1, sizeof(cgbk_model));
+    M->m = m; M->G = (m + 3) / 4; M->device = device;
+    double ic;
+    pssm_stats(lo, m, &ic, &M->min_score, &M->max_score);
+    double R = 0.0;
+    for (int j = 0; j < m; ++j) {
+        double colmax = 0.0;
+        for (int k = 0; k < 4; ++k) {
+            M->fwd[j * 4 + k] = lo[j * 4 + k];
+            M->rc[j * 4 + k] = lo[(m - 1 - j) * 4 + (3 - k)];
+            colmax = fmax(colmax, fabs(lo[j * 4 + k]));
+        }
+        R += colmax;
+    }
+    for (int j = 0; j < m; ++j) {
+        // sum(pssm[l][pos] for l in 'ACGT') / 4, Python's left-to-right sum from int 0
+        M->mean_f[j] = (((0 + M->fwd[j * 4]) + M->fwd[j * 4 + 1]) + M->fwd[j * 4 + 2] + M->fwd[j * 4 + 3]) / 4;
+        M->mean_r[j] = (((0 + M->rc[j * 4]) + M->rc[j * 4 + 1]) + M->rc[j * 4 + 2] + M->rc[j * 4 + 3]) / 4;
+    }
+    // exact tables
+    std::vector<double> ex(CGBK_EXACT_DOUBLES, 0.0);
+    memcpy(ex.data(), M->fwd, sizeof(M->fwd));
+    memcpy(ex.data() + CGBK_MAXM * 4, M->rc, sizeof(M->rc));
+    memcpy(ex.data() + CGBK_MAXM * 8, M->mean_f, sizeof(M->mean_f));
+    memcpy(ex.data() + CGBK_MAXM * 8 + CGBK_MAXM, M->mean_r, sizeof(M->mean_r));
+    // int32 fixed-point tables: scale 2^kexp with |any window sum| < 2^30
+    int kexp = 24;
+    if (R > 0) {
+        const int k2 = (int)floor(log2(1073741824.0 / R));
+        if (k2 < kexp) kexp = k2;
+    }
+    M->kexp = kexp;
+    const double scale = ldexp(1.0, kexp);
+    std::vector<long long> qf(4 * m), qr(4 * m);
+    for (int i = 0; i < 4 * m; ++i) { qf[i] = llrint(M->fwd[i] * scale); qr[i] = llrint(M->rc[i] * scale); }
+    const int G = M->G;
+    std::vector<uint32_t> precise((size_t)256 * 2 * G);
+    for (int e = 0; e < 256; ++e)
+        for (int g = 0; g < G; ++g) {
+            long long sf = 0, sr = 0;
+            for (int k = 0; k < 4; ++k) {
+                const int j = 4 * g + k;
+                if (j < m) { sf += qf[j * 4 + ((e >> (2 * k)) & 3)]; sr += qr[j * 4 + ((e >> (2 * k)) & 3)]; }
+            }
+            precise[(size_t)e * 2 * G + 2 * g] = (uint32_t)(int32_t)sf;
+            precise[(size_t)e * 2 * G + 2 * g + 1] = (uint32_t)(int32_t)sr;
+        }
+    cudaError_t e1 = cudaMalloc(&M->d_exact, sizeof(double) * CGBK_EXACT_DOUBLES);
+    cudaError_t e2 = cudaMalloc(&M->d_precise, sizeof(uint32_t) * 256 * 2 * G);
+    cudaError_t e3 = cudaMalloc(&M->d_coarse, sizeof(uint32_t) * 256 * G);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        cgbk_model_destroy(M);
+        return cgbk_set_error(CGBK_ERR_CUDA, "cudaMalloc of model tables failed");
+    }
+    cudaError_t c1 = cudaMemcpy(M->d_exact, ex.data(), sizeof(double) * CGBK_EXACT_DOUBLES, cudaMemcpyHostToDevice);
+    cudaError_t c2 = cudaMemcpy(M->d_precise, precise.data(), sizeof(uint32_t) * precise.size(), cudaMemcpyHostToDevice);
+    if (c1 != cudaSuccess || c2 != cudaSuccess) {
+        cgbk_model_destroy(M);
+        return cgbk_set_error(CGBK_ERR_CUDA, "upload of model tables failed");
+    }
+    M->coarse_valid = 0;
+    *out = M;
+    return CGBK_OK;
+}
+
+extern "C" void cgbk_model_destroy(cgbk_model* M) {
+    if (!M) return;
+    if (M->d_exact) cudaFree(M->d_exact);
+    if (M->d_precise) cudaFree(M->d_precise);
+    if (M->d_coarse) cudaFree(M->d_coarse);
+    free(M);
+}
+
+// 16-bit filter tables for one threshold (see cgbk_fast.cu header).
+//   per strand: deficit d_g[e] = max_g - x_g[e]; a window can reach thr' = thr - margin
+//   only if sum_g d_g <= Dd = M - thr'.  Quantised deficits floor(d*S), saturated at
+//   Dq + 1, are stored as surpluses u = Qcap - dq, with a constant K folded into group 0
+//   so that "sum >= 0x8000" <=> "sum of quantised deficits <= Dq".  No false negatives.
+static const double kFilterMargin = 1e-4;   // covers the float32 rounding of the exact score
+
+static void build_coarse_strand(const double* tab, int m, int G, double thr, uint32_t* halves /*[256][G]*/) {
+    std::vector<double> x((size_t)256 * G), gmax(G, -INFINITY);
+    for (int g = 0; g < G; ++g)
+        for (int e = 0; e < 256; ++e) {
+            group_partial(tab, m, g, e, &x[(size_t)e * G + g]);
+            gmax[g] = fmax(gmax[g], x[(size_t)e * G + g]);
+        }
+    double Mx = 0.0;
+    for (int g = 0; g < G; ++g) Mx += gmax[g];
+    double Dd = Mx - (thr - kFilterMargin);
+    if (!(Dd >= 0.0)) {   // threshold above the maximum score (or NaN): this strand can never hit
+        for (size_t i = 0; i < (size_t)256 * G; ++i) halves[i] = 0;
+        return;
+    }
+    if (Dd < 1e-9) Dd = 1e-9;
+    long long target = (G > 1) ? (32768 - G) / (G - 1) : 32767;
+    if (target > 32767) target = 32767;
+    double S = (double)target / Dd;
+    long long Dq = (long long)floor(Dd * S);
+    while (Dq > target) { S = nextafter(S, 0.0); Dq = (long long)floor(Dd * S); }
+    const long long Qcap = Dq + 1;
+    const long long U = (long long)G * Qcap - Dq;
+    const long long K = 0x8000 - U;     // >= 0 by the choice of target
+    for (int e = 0; e < 256; ++e)
+        for (int g = 0; g < G; ++g) {
+            const double d = gmax[g] - x[(size_t)e * G + g];
+            long long dq = (long long)floor(d * S);
+            if (dq > Qcap || !(d * S < 4e9)) dq = Qcap;
+            long long u = Qcap - dq + (g == 0 ? K : 0);
+            halves[(size_t)e * G + g] = (uint32_t)u;
+        }
+}
+
+static int ensure_coarse(cgbk_model* M, double thr, cudaStream_t st) {
+    if (M->coarse_valid && M->coarse_thr == thr) return CGBK_OK;
+    const int G = M->G;
+    std::vector<uint32_t> hf((size_t)256 * G), hr((size_t)256 * G), packed((size_t)256 * G);
+    build_coarse_strand(M->fwd, M->m, G, thr, hf.data());
+    build_coarse_strand(M->rc, M->m, G, thr, hr.data());
+    for (size_t i = 0; i < packed.size(); ++i) packed[i] = (hf[i] << 16) | (hr[i] & 0xffffu);
+    // the previous scan on this stream may still be reading the table
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemcpy(M->d_coarse, packed.data(), sizeof(uint32_t) * packed.size(), cudaMemcpyHostToDevice));
+    M->coarse_valid = 1;
+    M->coarse_thr = thr;
+    return CGBK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// sequence sets and tiling
+// ---------------------------------------------------------------------------
+extern "C" int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len, int n_seq, int device,
+                                  cgbk_seqset** out) {
+    if (!seq_off || !seq_len || !out || n_seq < 1) return cgbk_set_error(CGBK_ERR_INVALID, "bad sequence table");
+    for (int i = 0; i < n_seq; ++i) {
+        if (seq_off[i] < 0 || seq_off[i] % CGBK_SEQ_ALIGN != 0 || seq_len[i] < 0)
+            return cgbk_set_error(CGBK_ERR_INVALID, "sequence %d: offset must be a multiple of %d", i, CGBK_SEQ_ALIGN);
+        if (i > 0 && seq_off[i] < seq_off[i - 1] + seq_len[i - 1])
+            return cgbk_set_error(CGBK_ERR_INVALID, "sequence %d overlaps its predecessor", i);
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    cgbk_seqset* S = (cgbk_seqset*)calloc(1, sizeof(cgbk_seqset));
+    S->n_seq = n_seq; S->device = device;
+    S->h_off = (int64_t*)malloc(sizeof(int64_t) * n_seq);
+    S->h_len = (int64_t*)malloc(sizeof(int64_t) * n_seq);
+    memcpy(S->h_off, seq_off, sizeof(int64_t) * n_seq);
+    memcpy(S->h_len, seq_len, sizeof(int64_t) * n_seq);
+    cudaError_t e1 = cudaMalloc(&S->d_off, sizeof(int64_t) * n_seq);
+    cudaError_t e2 = cudaMalloc(&S->d_len, sizeof(int64_t) * n_seq);
+    cudaError_t e3 = cudaMalloc(&S->d_tile_prefix, sizeof(int64_t) * (n_seq + 1));
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        cgbk_seqset_destroy(S);
+        return cgbk_set_error(CGBK_ERR_CUDA, "cudaMalloc of sequence table failed");
+    }
+    cudaMemcpy(S->d_off, seq_off, sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice);
+    cudaMemcpy(S->d_len, seq_len, sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice);
+    S->cached_m = -1; S->cached_L = -1;
+    *out = S;
+    return CGBK_OK;
+}
+
+extern "C" void cgbk_seqset_destroy(cgbk_seqset* S) {
+    if (!S) return;
+    if (S->d_off) cudaFree(S->d_off);
+    if (S->d_len) cudaFree(S->d_len);
+    if (S->d_tile_prefix) cudaFree(S->d_tile_prefix);
+    free(S->h_off); free(S->h_len);
+    free(S);
+}
+
+extern "C" int64_t cgbk_seqset_total_windows(const cgbk_seqset* S, int m) {
+    int64_t t = 0;
+    for (int i = 0; i < S->n_seq; ++i)
+        if (S->h_len[i] - m + 1 > 0) t += S->h_len[i] - m + 1;
+    return t;
+}
+
+static int64_t count_tiles(const cgbk_seqset* S, int m, int L) {
+    const int64_t stride = 32ll * L - 32;
+    int64_t t = 0;
+    for (int i = 0; i < S->n_seq; ++i) {
+        const int64_t nwin = S->h_len[i] - m + 1;
+        if (nwin > 0) t += (nwin + stride - 1) / stride;
+    }
+    return t;
+}
+
+static int ensure_tiles(cgbk_seqset* S, int m, int L, cudaStream_t st) {
+    if (S->cached_m == m && S->cached_L == L) return CGBK_OK;
+    const int64_t stride = 32ll * L - 32;
+    std::vector<int64_t> prefix(S->n_seq + 1);
+    prefix[0] = 0;
+    for (int i = 0; i < S->n_seq; ++i) {
+        const int64_t nwin = S->h_len[i] - m + 1;
+        prefix[i + 1] = prefix[i] + (nwin > 0 ? (nwin + stride - 1) / stride : 0);
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemcpy(S->d_tile_prefix, prefix.data(), sizeof(int64_t) * prefix.size(), cudaMemcpyHostToDevice));
+    S->n_tiles = prefix[S->n_seq];
+    S->cached_m = m; S->cached_L = L;
+    return CGBK_OK;
+}
+
+static int device_sms(int device) {
+    static int cached_dev = -1, cached = 0;
+    if (cached_dev != device) {
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, device);
+        cached_dev = device;
+    }
+    return cached > 0 ? cached : 148;
+}
+
+// lane segment length: the longest of 128/64/32 bases that still leaves >= 2 tiles per warp
+static int choose_L(const cgbk_seqset* S, int m, int warps_total) {
+    for (int L = 128; L > 32; L >>= 1)
+        if (count_tiles(S, m, L) >= 2ll * warps_total) return L;
+    return 32;
+}
+
+#define PARTIAL_CAP 1024
+#define WORK_HEADER (64 + 3 * 8 * PARTIAL_CAP)
+
+extern "C" int64_t cgbk_scan_workspace_bytes(const cgbk_seqset* S, int m, int64_t cand_cap) {
+    if (!S) return 0;
+    int64_t b = WORK_HEADER + 4 * count_tiles(S, m, 32) + 64 + 8 * (cand_cap > 0 ? cand_cap : 0);
+    return (b + 255) / 256 * 256;
+}
+
+static int carve(const cgbk_seqset* S, int m, void* d_work, int64_t work_bytes, int64_t cand_cap, FastWork* w) {
+    const int64_t need = cgbk_scan_workspace_bytes(S, m, cand_cap);
+    if (!d_work || work_bytes < need)
+        return cgbk_set_error(CGBK_ERR_INVALID, "workspace of %lld bytes is smaller than the %lld required",
+                              (long long)work_bytes, (long long)need);
+    unsigned char* p = (unsigned char*)d_work;
+    w->counters = (long long*)p;
+    w->partials = (double*)(p + 64);
+    w->partial_cap = PARTIAL_CAP;
+    const int64_t dirty_bytes = (4 * count_tiles(S, m, 32) + 63) / 64 * 64;
+    w->dirty_tiles = (unsigned int*)(p + WORK_HEADER);
+    w->cands = (unsigned long long*)(p + WORK_HEADER + dirty_bytes);
+    w->cand_cap = cand_cap;
+    return CGBK_OK;
+}
+
+static GenomeView view_of(const cgbk_genome* g) {
+    GenomeView v;
+    v.bases2 = g->d_bases2; v.amb = g->d_amb; v.lower = g->d_lower; v.cap_bases = g->cap_bases;
+    return v;
+}
+
+static int check_genome(const cgbk_genome* g) {
+    if (!g || !g->d_bases2 || !g->d_amb || !g->d_lower || g->cap_bases <= 0 || g->cap_bases % CGBK_SEQ_ALIGN)
+        return cgbk_set_error(CGBK_ERR_INVALID, "bad cgbk_genome (NULL plane or capacity not a multiple of %d)",
+                              CGBK_SEQ_ALIGN);
+    return CGBK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// exact entry points
+// ---------------------------------------------------------------------------
+extern "C" int cgbk_score_windows(const cgbk_model* M, const cgbk_genome* genome, const int64_t* d_start,
+                                  const int64_t* d_out_off, int n_regions, int64_t total, int flags,
+                                  float* d_f32, float* d_r32, double* d_both, double* d_f64, double* d_r64,
+                                  void* stream) {
+    if (!M) return cgbk_set_error(CGBK_ERR_INVALID, "NULL model");
+    int rc = check_genome(genome);
+    if (rc) return rc;
+    if (n_regions < 0 || total < 0 || (total > 0 && (!d_start || !d_out_off)))
+        return cgbk_set_error(CGBK_ERR_INVALID, "bad region table");
+    CUDA_TRY(launch_score_windows(M, view_of(genome), (const long long*)d_start, (const long long*)d_out_off,
+                                  n_regions, total, flags, d_f32, d_r32, d_both, d_f64, d_r64,
+                                  (cudaStream_t)stream));
+    return CGBK_OK;
+}
+
+extern "C" int cgbk_posteriors(const cgbk_model* M, const cgbk_genome* genome, const int64_t* d_start,
+                               const int32_t* d_nwin, int n_regions, const double* d_ms_m,
+                               const double* d_ms_bg, double p_motif, double alpha, double* d_post,
+                               void* stream) {
+    if (!M) return cgbk_set_error(CGBK_ERR_INVALID, "NULL model");
+    int rc = check_genome(genome);
+    if (rc) return rc;
+    if (n_regions < 0 || (n_regions > 0 && (!d_start || !d_nwin || !d_post || !d_ms_m || !d_ms_bg)))
+        return cgbk_set_error(CGBK_ERR_INVALID, "bad promoter table");
+    CUDA_TRY(launch_posteriors(M, view_of(genome), (const long long*)d_start, d_nwin, n_regions, d_ms_m,
+                               d_ms_bg, p_motif, alpha, d_post, (cudaStream_t)stream));
+    return CGBK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// tiled scans
+// ---------------------------------------------------------------------------
+static SeqTable table_of(const cgbk_seqset* S) {
+    SeqTable t;
+    t.off = (const long long*)S->d_off; t.len = (const long long*)S->d_len;
+    t.tile_prefix = (const long long*)S->d_tile_prefix; t.n_seq = S->n_seq; t.n_tiles = S->n_tiles;
+    return t;
+}
+
+extern "C" int cgbk_scan_hits(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqset* set,
+                              double threshold, int flags, cgbk_hit* d_hits, int64_t hit_cap,
+                              int64_t* d_counters, void* d_work, int64_t work_bytes, int64_t cand_cap,
+                              void* stream) {
+    if (!M || !set || !d_counters) return cgbk_set_error(CGBK_ERR_INVALID, "NULL argument");
+    if (isnan(threshold)) return cgbk_set_error(CGBK_ERR_INVALID, "threshold is NaN");
+    int rc = check_genome(genome);
+    if (rc) return rc;
+    if (hit_cap < 0 || cand_cap < 1 || (hit_cap > 0 && !d_hits))
+        return cgbk_set_error(CGBK_ERR_INVALID, "bad output capacity");
+    cudaStream_t st = (cudaStream_t)stream;
+    cgbk_seqset* S = const_cast<cgbk_seqset*>(set);
+    FastWork w;
+    rc = carve(S, M->m, d_work, work_bytes, cand_cap, &w);
+    if (rc) return rc;
+    const int threads = fast_threads(M->G, 0);
+    const int sms = device_sms(M->device);
+    const int L = choose_L(S, M->m, sms * (threads / 32));
+    rc = ensure_tiles(S, M->m, L, st);
+    if (rc) return rc;
+    rc = ensure_coarse(M, threshold, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(w.counters, 0, 64, st));
+    int launches = 0;
+    if (S->n_tiles > 0) {
+        const int wpb = threads / 32;
+        long long grid = (S->n_tiles + wpb - 1) / wpb;
+        if (grid > sms) grid = sms;
+        CUDA_TRY(launch_fast_filter(M, view_of(genome), table_of(S), w, L, (int)grid, st));
+        CUDA_TRY(launch_rescore(M, view_of(genome), table_of(S), w, threshold, flags, d_hits, hit_cap, L, st));
+        launches = 3;
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_counters, w.counters, 64, cudaMemcpyDeviceToDevice, st));
+    g_launch_info[0] = launches; g_launch_info[1] = S->n_tiles; g_launch_info[2] = L;
+    return CGBK_OK;
+}
+
+extern "C" int cgbk_background_stats(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqset* set,
+                                     double hist_lo, double hist_hi, int n_bins, unsigned long long* d_hist,
+                                     double* d_stats, int accumulate, void* d_work, int64_t work_bytes,
+                                     void* stream) {
+    if (!M || !set || !d_stats) return cgbk_set_error(CGBK_ERR_INVALID, "NULL argument");
+    int rc = check_genome(genome);
+    if (rc) return rc;
+    if (d_hist) {
+        if (n_bins < 1 || n_bins > CGBK_MAX_HIST_BINS || !(hist_hi > hist_lo))
+            return cgbk_set_error(CGBK_ERR_INVALID, "histogram needs 1..%d bins and hi > lo", CGBK_MAX_HIST_BINS);
+    } else {
+        n_bins = 1; hist_lo = 0.0; hist_hi = 1.0;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cgbk_seqset* S = const_cast<cgbk_seqset*>(set);
+    FastWork w;
+    rc = carve(S, M->m, d_work, work_bytes, 0, &w);
+    if (rc) return rc;
+    const int threads = fast_threads(M->G, 1);
+    const int sms = device_sms(M->device);
+    const int L = choose_L(S, M->m, sms * (threads / 32));
+    rc = ensure_tiles(S, M->m, L, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(w.counters, 0, 64, st));
+    if (!accumulate) {
+        if (d_hist) CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * n_bins, st));
+        CUDA_TRY(cudaMemsetAsync(d_stats, 0, sizeof(double) * CGBK_BG_COUNT, st));
+    }
+    const double inv_binw = (double)n_bins / (hist_hi - hist_lo);
+    const int wpb = threads / 32;
+    long long grid = (S->n_tiles + wpb - 1) / wpb;
+    if (grid > sms) grid = sms;
+    if (grid < 1) grid = 1;
+    int launches = 1;
+    if (S->n_tiles > 0) {
+        CUDA_TRY(launch_fast_stats(M, view_of(genome), table_of(S), w, L, (int)grid, hist_lo, inv_binw, n_bins,
+                                   d_hist, st));
+        CUDA_TRY(launch_dirty_stats(M, view_of(genome), table_of(S), w, L, hist_lo, inv_binw, n_bins, d_hist,
+                                    (int)grid, st));
+        CUDA_TRY(launch_bg_finalize(w.partials, (int)grid + 148, d_stats, 1, st));
+        launches = 3;
+    } else {
+        CUDA_TRY(launch_bg_finalize(w.partials, 0, d_stats, 1, st));
+    }
+    g_launch_info[0] = launches; g_launch_info[1] = S->n_tiles; g_launch_info[2] = L;
+    return CGBK_OK;
+}
+
+extern "C" int cgbk_background_finalize(double* d_stats, void* stream) {
+    if (!d_stats) return cgbk_set_error(CGBK_ERR_INVALID, "NULL stats");
+    CUDA_TRY(launch_bg_finalize(nullptr, 0, d_stats, 1, (cudaStream_t)stream));
+    return CGBK_OK;
+}

@@ -1,0 +1,350 @@
+// Exact kernels: packing, per-window float64 scoring in the reference's order,
+// candidate re-scoring, ambiguous ("dirty") tiles, posteriors, moment finalisation.
+//
+// These kernels carry the bit-exact semantics of the reference
+// (cgb/pssm_model.py:88-133, cgb/binding_model.py:94-113, cgb/genome.py:433-445);
+// the throughput kernels live in cgbk_fast.cu and hand their candidates here.
+#include "cgbk_device.cuh"
+
+// ---------------------------------------------------------------------------
+// pack: ASCII -> 2-bit bases + ambiguity / lower-case bit planes
+//   replaces "str(record.seq)" (cgb/chromid.py:57-60) as the sequence store.
+//   One thread packs 32 bases: 32 B in, 8 B + 4 B + 4 B out (all coalesced).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pack4(uint32_t w, uint32_t& codes8, uint32_t& amb4, uint32_t& low4) {
+    const uint32_t t = ((w >> 1) ^ (w >> 2)) & 0x03030303u;        // A0 C1 G2 T3 per byte
+    codes8 = (t | (t >> 6) | (t >> 12) | (t >> 18)) & 0xffu;
+    const uint32_t u = w & 0xdfdfdfdfu;                             // fold case
+    const uint32_t valid = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) |
+                           __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
+    const uint32_t gather = (1u << 24) | (1u << 17) | (1u << 10) | (1u << 3);
+    amb4 = (((~valid) & 0x01010101u) * gather >> 24) & 0xfu;
+    low4 = ((((w >> 5) & valid) & 0x01010101u) * gather >> 24) & 0xfu;
+    // ambiguous bytes pack as base 0 so the planes are deterministic
+    uint32_t keep = (valid & 0x01010101u) * gather >> 24;           // 1 bit per byte
+    uint32_t keep2 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) keep2 |= ((keep >> k) & 1u) * (3u << (2 * k));
+    codes8 &= keep2;
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ ascii, long long n,
+                                                   long long dst_off, uint32_t* __restrict__ b2,
+                                                   uint32_t* __restrict__ amb,
+                                                   uint32_t* __restrict__ lower, long long n_chunks) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(ascii) & 15) == 0;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n_chunks;
+         c += (long long)gridDim.x * blockDim.x) {
+        const long long base = c * 32;
+        uint32_t w[8];
+        if (aligned && base + 32 <= n) {
+            const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(ascii + base));
+            const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(ascii + base) + 1);
+            w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w;
+            w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const long long i = base + k * 4 + b;
+                    // past the end: pad with 'A' (packs to 0, not ambiguous)
+                    const uint32_t ch = (i < n) ? (uint32_t)ascii[i] : 0x41u;
+                    v |= ch << (8 * b);
+                }
+                w[k] = v;
+            }
+        }
+        uint32_t lo = 0, hi = 0, am = 0, lw = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t c8, a4, l4;
+            pack4(w[k], c8, a4, l4);
+            if (k < 4) lo |= c8 << (8 * k); else hi |= c8 << (8 * (k - 4));
+            am |= a4 << (4 * k);
+            lw |= l4 << (4 * k);
+        }
+        const long long chunk = (dst_off >> 5) + c;
+        reinterpret_cast<uint2*>(b2)[chunk] = make_uint2(lo, hi);
+        amb[chunk] = am;
+        lower[chunk] = lw;
+    }
+}
+
+cudaError_t launch_pack(const uint8_t* d_ascii, long long n, long long dst_off, uint32_t* b2,
+                        uint32_t* amb, uint32_t* lower, cudaStream_t st) {
+    const long long padded = ((n + CGBK_SEQ_ALIGN - 1) / CGBK_SEQ_ALIGN) * CGBK_SEQ_ALIGN;
+    const long long n_chunks = padded / 32;
+    if (n_chunks == 0) return cudaSuccess;
+    long long blocks = (n_chunks + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    pack_kernel<<<(int)blocks, 256, 0, st>>>(d_ascii, n, dst_off, b2, amb, lower, n_chunks);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// score_windows: PSSMModel.score_seq (cgb/pssm_model.py:103-133), one thread per window
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) score_windows_kernel(
+    const double* __restrict__ d_exact, int m, GenomeView g, const long long* __restrict__ d_start,
+    const long long* __restrict__ d_out_off, int n_regions, long long total, int flags,
+    float* __restrict__ f32, float* __restrict__ r32, double* __restrict__ both,
+    double* __restrict__ f64, double* __restrict__ r64) {
+    __shared__ ExactTables tab;
+    stage_exact(&tab, d_exact);
+    __syncthreads();
+    const bool revseq = (flags & CGBK_RC_REVSEQ_ORDER) != 0;
+    const bool single64 = (flags & CGBK_SINGLE_WINDOW_F64) != 0;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n_regions;     // d_out_off[lo] <= t < d_out_off[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(d_out_off + mid) <= t) lo = mid; else hi = mid;
+        }
+        const long long first = __ldg(d_out_off + lo);
+        const long long nwin = __ldg(d_out_off + lo + 1) - first;
+        const long long p = __ldg(d_start + lo) + (t - first);
+        double f, r;
+        const bool repaired = exact_window(g, &tab, m, p, revseq, f, r);
+        const float ff = (float)f, rf = (float)r;      // Biopython stores float32
+        double fs = (double)ff, rs = (double)rf;
+        if (single64 && nwin == 1) {
+            // len(seq)==m: scalars wrapped in Python lists, a repaired score stays float64
+            if (repaired) { fs = f; rs = r; }
+            if (f64) f64[lo] = fs;
+            if (r64) r64[lo] = rs;
+        }
+        if (f32) f32[t] = ff;
+        if (r32) r32[t] = rf;
+        if (both) both[t] = softmax2_f64(fs, rs);
+    }
+}
+
+cudaError_t launch_score_windows(const cgbk_model* mdl, GenomeView g, const long long* d_start,
+                                 const long long* d_out_off, int n_regions, long long total,
+                                 int flags, float* f32, float* r32, double* both, double* f64,
+                                 double* r64, cudaStream_t st) {
+    if (total <= 0) return cudaSuccess;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    score_windows_kernel<<<(int)blocks, 256, 0, st>>>(mdl->d_exact, mdl->m, g, d_start, d_out_off,
+                                                     n_regions, total, flags, f32, r32, both, f64,
+                                                     r64);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// posteriors: TFBindingModel.binding_probability (cgb/binding_model.py:94-113)
+// one warp per promoter region, warp-level sum over window positions
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) posterior_kernel(
+    const double* __restrict__ d_exact, int m, GenomeView g, const long long* __restrict__ d_start,
+    const int* __restrict__ d_nwin, int n_regions, const double* __restrict__ ms_m,
+    const double* __restrict__ ms_bg, double p_motif, double alpha, double* __restrict__ post) {
+    __shared__ ExactTables tab;
+    stage_exact(&tab, d_exact);
+    __syncthreads();
+    const double mu_m = ms_m[0], std_m = ms_m[1], mu_bg = ms_bg[0], std_bg = ms_bg[1];
+    const double norm_c = sqrt(2.0 * 3.141592653589793);     // scipy _norm_pdf_C
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int reg = blockIdx.x * warps_per_block + (threadIdx.x >> 5); reg < n_regions;
+         reg += gridDim.x * warps_per_block) {
+        const long long start = __ldg(d_start + reg);
+        const int nwin = __ldg(d_nwin + reg);
+        double acc = 0.0;
+        for (int w = lane; w < nwin; w += 32) {
+            double f, r;
+            exact_window(g, &tab, m, start + w, false, f, r);
+            const double s = softmax2_f64((double)(float)f, (double)(float)r);
+            const double ym = (s - mu_m) / std_m, yb = (s - mu_bg) / std_bg;
+            const double pdf_m = exp(-(ym * ym) / 2.0) / norm_c / std_m;
+            const double pdf_bg = exp(-(yb * yb) / 2.0) / norm_c / std_bg;
+            const double lh_m = alpha * pdf_m + (1 - alpha) * pdf_bg;
+            acc += log(pdf_bg) - log(lh_m);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            double res;
+            if (nwin <= 0) {
+                res = nan("");      // the reference raises inside Biopython for len(seq) < m
+            } else {
+                const double lh_ratio = exp(acc);
+                res = 1 / (1 + lh_ratio * (1 - p_motif) / p_motif);
+            }
+            post[reg] = res;
+        }
+    }
+}
+
+cudaError_t launch_posteriors(const cgbk_model* mdl, GenomeView g, const long long* d_start,
+                              const int* d_nwin, int n_regions, const double* d_ms_m,
+                              const double* d_ms_bg, double p_motif, double alpha, double* d_post,
+                              cudaStream_t st) {
+    if (n_regions <= 0) return cudaSuccess;
+    int blocks = (n_regions + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    posterior_kernel<<<blocks, 256, 0, st>>>(mdl->d_exact, mdl->m, g, d_start, d_nwin, n_regions,
+                                            d_ms_m, d_ms_bg, p_motif, alpha, d_post);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// hits: exact re-scoring of filter candidates + exact scan of dirty tiles
+//   genome.py:436,443: float32 score compared with the float64 threshold
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void emit_hit(cgbk_hit* hits, long long cap, long long* counters,
+                                         long long gpos, int strand, float score) {
+    const unsigned long long k =
+        atomicAdd(reinterpret_cast<unsigned long long*>(counters + CGBK_CTR_HITS), 1ull);
+    if ((long long)k < cap) {
+        cgbk_hit h;
+        h.gpos = gpos; h.strand = strand; h.score = score;
+        hits[k] = h;
+    }
+}
+
+__global__ void __launch_bounds__(128) rescore_kernel(const double* __restrict__ d_exact, int m,
+                                                      GenomeView g, FastWork w, double thr,
+                                                      int flags, cgbk_hit* hits, long long hit_cap) {
+    __shared__ ExactTables tab;
+    stage_exact(&tab, d_exact);
+    __syncthreads();
+    const bool revseq = (flags & CGBK_RC_REVSEQ_ORDER) != 0;
+    long long n = w.counters[CGBK_CTR_CANDIDATES];
+    if (n > w.cand_cap) n = w.cand_cap;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long rec = w.cands[i];
+        const long long gpos = (long long)(rec & 0x3fffffffffffffffull);
+        double f, r;
+        exact_window(g, &tab, m, gpos, revseq, f, r);
+        const float ff = (float)f, rf = (float)r;
+        if ((rec >> 63) && (double)ff >= thr) emit_hit(hits, hit_cap, w.counters, gpos, 1, ff);
+        if (((rec >> 62) & 1ull) && (double)rf >= thr) emit_hit(hits, hit_cap, w.counters, gpos, -1, rf);
+    }
+}
+
+// tile geometry shared with cgbk_fast.cu: a warp tile covers 32*L lookup positions and
+// owns the windows [A, A + 32*L - 32) of its sequence.
+__device__ __forceinline__ void tile_range(const SeqTable& seqs, unsigned int tile, int L, int m,
+                                           long long& gbase, long long& w_lo, long long& w_hi) {
+    const int s = find_seq(seqs, tile);
+    const long long local = (long long)tile - __ldg(seqs.tile_prefix + s);
+    const long long stride = 32ll * L - 32;
+    const long long nwin = __ldg(seqs.len + s) - m + 1;
+    gbase = __ldg(seqs.off + s);
+    w_lo = local * stride;
+    w_hi = w_lo + stride < nwin ? w_lo + stride : nwin;
+}
+
+__global__ void __launch_bounds__(128) dirty_hits_kernel(const double* __restrict__ d_exact, int m,
+                                                         GenomeView g, SeqTable seqs, FastWork w,
+                                                         int L, double thr, int flags,
+                                                         cgbk_hit* hits, long long hit_cap) {
+    __shared__ ExactTables tab;
+    stage_exact(&tab, d_exact);
+    __syncthreads();
+    const bool revseq = (flags & CGBK_RC_REVSEQ_ORDER) != 0;
+    const long long nd = w.counters[CGBK_CTR_DIRTY_TILES];
+    for (long long d = blockIdx.x; d < nd; d += gridDim.x) {
+        long long gbase, lo, hi;
+        tile_range(seqs, w.dirty_tiles[d], L, m, gbase, lo, hi);
+        for (long long x = lo + threadIdx.x; x < hi; x += blockDim.x) {
+            double f, r;
+            exact_window(g, &tab, m, gbase + x, revseq, f, r);
+            const float ff = (float)f, rf = (float)r;
+            if ((double)ff >= thr) emit_hit(hits, hit_cap, w.counters, gbase + x, 1, ff);
+            if ((double)rf >= thr) emit_hit(hits, hit_cap, w.counters, gbase + x, -1, rf);
+        }
+    }
+}
+
+cudaError_t launch_rescore(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
+                           double thr, int flags, cgbk_hit* hits, long long hit_cap, int L,
+                           cudaStream_t st) {
+    rescore_kernel<<<148 * 2, 128, 0, st>>>(mdl->d_exact, mdl->m, g, w, thr, flags, hits, hit_cap);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dirty_hits_kernel<<<148 * 2, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, w, L, thr, flags, hits,
+                                              hit_cap);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// background statistics: dirty tiles (exact, ambiguity aware) and the final reduce
+// ---------------------------------------------------------------------------
+#define DIRTY_STATS_BLOCKS 148
+
+__global__ void __launch_bounds__(128) dirty_stats_kernel(const double* __restrict__ d_exact, int m,
+                                                          GenomeView g, SeqTable seqs, FastWork w,
+                                                          int L, double hist_lo, double inv_binw,
+                                                          int n_bins, unsigned long long* d_hist,
+                                                          int partial_base) {
+    __shared__ ExactTables tab;
+    __shared__ double scratch[96];
+    stage_exact(&tab, d_exact);
+    __syncthreads();
+    double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+    const long long nd = w.counters[CGBK_CTR_DIRTY_TILES];
+    for (long long d = blockIdx.x; d < nd; d += gridDim.x) {
+        long long gbase, lo, hi;
+        tile_range(seqs, w.dirty_tiles[d], L, m, gbase, lo, hi);
+        for (long long x = lo + threadIdx.x; x < hi; x += blockDim.x) {
+            double f, r;
+            exact_window(g, &tab, m, gbase + x, false, f, r);
+            const double s = softmax2_f64((double)(float)f, (double)(float)r);
+            s1 += s; s2 += s * s; cnt += 1.0;
+            if (d_hist) {
+                int bin = (int)floor((s - hist_lo) * inv_binw);
+                bin = bin < 0 ? 0 : (bin >= n_bins ? n_bins - 1 : bin);
+                atomicAdd(d_hist + bin, 1ull);
+            }
+        }
+    }
+    block_reduce3(s1, s2, cnt, scratch);
+    if (threadIdx.x == 0) {
+        double* p = w.partials + 3ll * (partial_base + blockIdx.x);
+        p[0] = s1; p[1] = s2; p[2] = cnt;
+    }
+}
+
+cudaError_t launch_dirty_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
+                               int L, double hist_lo, double inv_binw, int n_bins,
+                               unsigned long long* d_hist, int partial_base, cudaStream_t st) {
+    dirty_stats_kernel<<<DIRTY_STATS_BLOCKS, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, w, L,
+                                                          hist_lo, inv_binw, n_bins, d_hist,
+                                                          partial_base);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) bg_finalize_kernel(const double* __restrict__ partials,
+                                                          int n_partials, double* stats,
+                                                          int accumulate) {
+    __shared__ double scratch[96];
+    double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) {
+        s1 += partials[3 * i]; s2 += partials[3 * i + 1]; cnt += partials[3 * i + 2];
+    }
+    block_reduce3(s1, s2, cnt, scratch);
+    if (threadIdx.x == 0) {
+        if (accumulate) {
+            cnt += stats[CGBK_BG_N]; s1 += stats[CGBK_BG_SUM]; s2 += stats[CGBK_BG_SUMSQ];
+        }
+        stats[CGBK_BG_N] = cnt; stats[CGBK_BG_SUM] = s1; stats[CGBK_BG_SUMSQ] = s2;
+        const double mean = cnt > 0 ? s1 / cnt : nan("");
+        double var = cnt > 0 ? s2 / cnt - mean * mean : nan("");
+        if (var < 0) var = 0;
+        stats[CGBK_BG_MEAN] = mean;
+        stats[CGBK_BG_STD] = sqrt(var);
+    }
+}
+
+cudaError_t launch_bg_finalize(const double* partials, int n_partials, double* d_stats,
+                               int accumulate, cudaStream_t st) {
+    bg_finalize_kernel<<<1, 256, 0, st>>>(partials, n_partials, d_stats, accumulate);
+    return cudaGetLastError();
+}

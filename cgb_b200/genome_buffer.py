@@ -1,0 +1,136 @@
+"""PackedGenome: chromosome / plasmid sequences as 2-bit planes in HBM.
+
+Replaces the reference's sequence store and slicing on the hot path:
+``Chromid.sequence`` / ``subsequence`` / ``length`` (cgb/chromid.py:57-60,87-97)
+and the per-call ``Seq(seq, alphabet)`` of cgb/pssm_model.py:113.  A genome is a
+list of replicons; each is packed on the GPU from its ASCII bytes into
+
+  bases2  2 bits/base (A0 C1 G2 T3), 16 bases per uint32, read as coalesced uint2/uint4
+  amb     1 bit/base: byte outside ACGTacgt (what Biopython's _pwm.c turns into NaN)
+  lower   1 bit/base: lower-case acgt (only PSSMModel._calculate cares, pssm_model.py:96-100)
+
+at 512-base aligned offsets of one concatenated buffer.  PyTorch only provides
+the device memory and the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def _as_bytes(seq):
+    if isinstance(seq, (bytes, bytearray, memoryview)):
+        return bytes(seq)
+    if isinstance(seq, np.ndarray):
+        return seq.astype(np.uint8, copy=False).tobytes()
+    return str(seq).encode("ascii")
+
+
+class PackedGenome:
+    def __init__(self, seq_lens, device=None):
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _cabi.CgbkError("PackedGenome needs a CUDA device (there is no CPU path)")
+        self.seq_len = np.asarray(seq_lens, dtype=np.int64)
+        if self.seq_len.ndim != 1 or len(self.seq_len) == 0:
+            raise ValueError("at least one sequence is required")
+        A = _cabi.SEQ_ALIGN
+        padded = (self.seq_len + A - 1) // A * A
+        # one extra aligned block between sequences keeps a window of <= 32 bases that
+        # starts near the end of one sequence from reading into the next one's bits
+        padded = padded + A
+        self.seq_off = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64)
+        self.cap_bases = int(self.seq_off[-1] + padded[-1])
+        with torch.cuda.device(self.device):
+            self.bases2 = torch.zeros(self.cap_bases // 16, dtype=torch.int32, device=self.device)
+            self.amb = torch.zeros(self.cap_bases // 32, dtype=torch.int32, device=self.device)
+            self.lower = torch.zeros(self.cap_bases // 32, dtype=torch.int32, device=self.device)
+        self._struct = _cabi.Genome(self.bases2.data_ptr(), self.amb.data_ptr(), self.lower.data_ptr(),
+                                    self.cap_bases)
+        self._seqset = C.c_void_p()
+        off = (C.c_int64 * len(self.seq_off))(*self.seq_off.tolist())
+        ln = (C.c_int64 * len(self.seq_len))(*self.seq_len.tolist())
+        _cabi.check(_cabi.lib().cgbk_seqset_create(off, ln, len(self.seq_len), self.device.index or 0,
+                                                   C.byref(self._seqset)))
+        self._work = {}
+
+    # ------------------------------------------------------------------ build
+    @classmethod
+    def from_sequences(cls, seqs, device=None, pinned=None):
+        """Pack ASCII sequences (str / bytes / uint8 arrays).  ``pinned``: optional
+        list of pinned uint8 host tensors already holding the bytes (skips the
+        staging copy; used by the end-to-end benchmark)."""
+        if pinned is None:
+            raw = [_as_bytes(s) for s in seqs]
+            lens = [len(r) for r in raw]
+        else:
+            raw = None
+            lens = [int(p.numel()) for p in pinned]
+        g = cls(lens, device)
+        stream = torch.cuda.current_stream(g.device)
+        for k in range(len(lens)):
+            if lens[k] == 0:
+                continue
+            if pinned is not None:
+                host = pinned[k]
+            else:
+                host = torch.frombuffer(bytearray(raw[k]), dtype=torch.uint8)
+            dev = host.to(g.device, non_blocking=True)
+            g.pack_into(k, dev, stream)
+        return g
+
+    def pack_into(self, k, dev_ascii, stream=None):
+        """Pack device-resident ASCII bytes as sequence ``k``."""
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        n = int(dev_ascii.numel())
+        if n != int(self.seq_len[k]):
+            raise ValueError("sequence %d holds %d bytes, expected %d" % (k, n, int(self.seq_len[k])))
+        _cabi.check(_cabi.lib().cgbk_pack_ascii(
+            dev_ascii.data_ptr(), n, int(self.seq_off[k]), self.bases2.data_ptr(), self.amb.data_ptr(),
+            self.lower.data_ptr(), self.cap_bases, stream.cuda_stream))
+        # keep the source alive until the stream has consumed it
+        dev_ascii.record_stream(stream) if dev_ascii.is_cuda else None
+
+    # ------------------------------------------------------------- accessors
+    @property
+    def n_seq(self):
+        return len(self.seq_len)
+
+    def length(self, k=0):
+        """Chromid.length (cgb/chromid.py:87-90)."""
+        return int(self.seq_len[k])
+
+    def total_windows(self, m):
+        return int(_cabi.lib().cgbk_seqset_total_windows(self._seqset, int(m)))
+
+    def struct_ref(self):
+        return C.byref(self._struct)
+
+    @property
+    def seqset(self):
+        return self._seqset
+
+    def workspace(self, m, cand_cap):
+        """Device scratch for the tiled scans, cached per (m, cand_cap)."""
+        key = (int(m), int(cand_cap))
+        w = self._work.get(key)
+        if w is None:
+            nbytes = int(_cabi.lib().cgbk_scan_workspace_bytes(self._seqset, int(m), int(cand_cap)))
+            w = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._work = {key: w}
+        return w
+
+    def __del__(self):
+        try:
+            if getattr(self, "_seqset", None) is not None and self._seqset.value:
+                _cabi.lib().cgbk_seqset_destroy(self._seqset)
+                self._seqset = C.c_void_p()
+        except Exception:
+            pass

@@ -1,0 +1,356 @@
+"""PSSMModel: weighted-mixture PSWM model scored on the GPU.
+
+Drop-in for the reference's ``cgb/pssm_model.py:14-169`` (same constructor,
+properties and methods, same return shapes and exceptions), plus the batched
+entry points a GPU needs so that a genome is scanned in one launch sequence
+instead of one Python call per gene:
+
+  score_seqs            many sequences per launch      (score_seq, :103-133)
+  scan_hits             thresholded both-strand hits   (genome.py:433-445)
+  background_stats      genome-wide soft-max histogram + moments (genome.py:215-226)
+  fit_background        build_bayesian_estimator from those moments (binding_model.py:71-92)
+  binding_probabilities batched promoter posteriors    (binding_model.py:94-113, gene.py:129-146)
+
+All scoring goes through libcgbk (include/cgbk.h); host code here only does
+float64 motif algebra and descriptor bookkeeping.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from functools import cached_property
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .binding_model import TFBindingModel
+from .genome_buffer import PackedGenome
+from .gene_regions import python_slice_bounds
+from .motif_matrix import PositionWeightMatrix, psum
+
+
+def log2(x):
+    """cgb/misc.py:14-16."""
+    return math.log(x, 2)
+
+
+class PSSMModel(TFBindingModel):
+    def __init__(self, collections, weights,
+                 background={'A': 0.25, 'C': 0.25, 'G': 0.25, 'T': 0.25}, alphabet="ACGT",
+                 device=None):
+        """pssm_model.py:31-35.  ``device``: CUDA device of the scoring tables
+        (default: the current device at first use)."""
+        super(PSSMModel, self).__init__(collections, background, alphabet)
+        self._pwm = self._combine_pwms([c.pwm for c in collections], weights, alphabet)
+        self._device = device
+        self._handle = None
+        self._dev_ms_m = None
+        self._dev_ms_bg = None
+        self._bg_stats_dev = None
+
+    @classmethod
+    def from_pwm(cls, pwm_values, sites=(), background=None, alphabet="ACGT", device=None):
+        """Model from a ready PWM (letter -> m probabilities), e.g. a JASPAR
+        matrix; ``sites`` (optional) feed score_self / the estimator."""
+        class _Coll:
+            pass
+        coll = _Coll()
+        coll.pwm = PositionWeightMatrix(alphabet, pwm_values)
+        coll.sites = list(sites)
+        bg = background or {'A': 0.25, 'C': 0.25, 'G': 0.25, 'T': 0.25}
+        return cls([coll], [1.0], bg, alphabet, device)
+
+    # ------------------------------------------------------------ properties
+    @cached_property
+    def pwm(self):
+        """pssm_model.py:37-40."""
+        return self._pwm
+
+    @cached_property
+    def length(self):
+        """pssm_model.py:42-45."""
+        return self.pwm.length
+
+    @cached_property
+    def pssm(self):
+        """pssm_model.py:47-50."""
+        return self._pwm.log_odds(self.background)
+
+    @cached_property
+    def rev_comp_pssm(self):
+        """pssm_model.py:52-55."""
+        return self.pssm.reverse_complement()
+
+    @cached_property
+    def IC(self):
+        """pssm_model.py:57-60."""
+        return self.pssm.mean()
+
+    @cached_property
+    def patser_threshold(self):
+        """pssm_model.py:62-70 (Hertz & Stormo 1999: -log2(FPR) = IC)."""
+        dist = self.pssm.distribution(precision=10**3)
+        return dist.threshold_patser()
+
+    def threshold(self, threshold_type='patser'):
+        """pssm_model.py:72-77."""
+        if threshold_type == 'patser':
+            thr = self.patser_threshold
+        else:
+            raise ValueError
+        return thr
+
+    @cached_property
+    def sites(self):
+        """pssm_model.py:79-82."""
+        return [site for coll in self._collection_set for site in coll.sites]
+
+    @staticmethod
+    def _combine_pwms(pwms, weights, alphabet):
+        """pssm_model.py:159-169."""
+        length = pwms[0].length
+        assert all(length == pwm.length for pwm in pwms)
+        pwm_vals = {let: [psum(pwm[let][i]*w for pwm, w in zip(pwms, weights))
+                          for i in range(length)]
+                    for let in alphabet}
+        return PositionWeightMatrix(alphabet, pwm_vals)
+
+    def _calculate(self, pssm, sequence):
+        """pssm_model.py:88-101: host restatement of the ambiguity rule, kept for
+        API compatibility.  The scoring path applies the same rule on the device."""
+        score = 0.0
+        for pos in range(len(sequence)):
+            try:
+                score += pssm[sequence[pos]][pos]
+            except KeyError:
+                score += psum(pssm[l][pos] for l in 'ACGT') / 4
+        return score
+
+    # ---------------------------------------------------------- device state
+    def _dev(self):
+        if self._device is None:
+            if not torch.cuda.is_available():
+                raise _cabi.CgbkError("no CUDA device: cgb_b200 has no CPU fallback")
+            self._device = torch.device("cuda", torch.cuda.current_device())
+        return torch.device(self._device)
+
+    def _model(self):
+        if self._handle is None:
+            if sorted(self.alphabet) != ["A", "C", "G", "T"]:
+                raise ValueError("PSSM has wrong alphabet: %s - Use only with DNA motifs" % self.alphabet)
+            rows = self.pssm.rows()
+            m = len(rows)
+            flat = (C.c_double * (4 * m))(*[x for row in rows for x in row])
+            h = C.c_void_p()
+            dev = self._dev()
+            _cabi.check(_cabi.lib().cgbk_model_create(flat, m, dev.index or 0, C.byref(h)))
+            self._handle = h
+        return self._handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                _cabi.lib().cgbk_model_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def _stream(self):
+        return torch.cuda.current_stream(self._dev()).cuda_stream
+
+    # ---------------------------------------------------------------- scoring
+    def score_seqs(self, seqs, both=True):
+        """``[score_seq(s, both) for s in seqs]`` with one pack + one kernel launch."""
+        m = self.length
+        seqs = [str(s) if not isinstance(s, (bytes, bytearray)) else s for s in seqs]
+        lens = np.array([len(s) for s in seqs], dtype=np.int64)
+        if len(seqs) == 0:
+            return []
+        if (lens < m).any():
+            # Biopython's C scorer fails on the negative window count
+            raise ValueError("negative dimensions are not allowed")
+        model = self._model()
+        dev = self._dev()
+        g = PackedGenome.from_sequences(seqs, dev)
+        nwin = lens - m + 1
+        out_off = np.concatenate([[0], np.cumsum(nwin)]).astype(np.int64)
+        total = int(out_off[-1])
+        d_start = torch.from_numpy(g.seq_off.copy()).to(dev)
+        d_off = torch.from_numpy(out_off).to(dev)
+        f32 = torch.empty(total, dtype=torch.float32, device=dev)
+        r32 = torch.empty(total, dtype=torch.float32, device=dev)
+        b64 = torch.empty(total, dtype=torch.float64, device=dev)
+        f64 = torch.zeros(len(seqs), dtype=torch.float64, device=dev)
+        r64 = torch.zeros(len(seqs), dtype=torch.float64, device=dev)
+        _cabi.check(_cabi.lib().cgbk_score_windows(
+            model, g.struct_ref(), d_start.data_ptr(), d_off.data_ptr(), len(seqs), total,
+            _cabi.RC_MATRIX_ORDER | _cabi.SINGLE_WINDOW_F64,
+            f32.data_ptr(), r32.data_ptr(), b64.data_ptr(), f64.data_ptr(), r64.data_ptr(), self._stream()))
+        if both:
+            host = b64.cpu().numpy()
+            return [host[out_off[k]:out_off[k + 1]].tolist() for k in range(len(seqs))]
+        host = f32.cpu().numpy()
+        single = f64.cpu().numpy()
+        out = []
+        for k in range(len(seqs)):
+            if nwin[k] == 1:
+                # pssm_model.py:117-119: a bare scalar wrapped in a list; a repaired
+                # (ambiguous) score stays a Python float, an ordinary one is float32
+                v = float(single[k])
+                out.append([np.float32(v) if float(np.float32(v)) == v else v])
+            else:
+                out.append(host[out_off[k]:out_off[k + 1]].copy())
+        return out
+
+    def score_seq(self, seq, both=True):
+        """pssm_model.py:103-133: scores of all positions; both strands combined
+        with the soft-max ``log2(2**s + 2**rc)`` unless ``both`` is False."""
+        return self.score_seqs([seq], both)[0]
+
+    def score_self(self):
+        """pssm_model.py:84-86 (one batched launch instead of one call per site)."""
+        return self.score_seqs(self.sites, True)
+
+    # ------------------------------------------------------------ tiled scans
+    def scan_hits(self, genome, threshold=None, revseq_order=True, hit_cap=None):
+        """All windows of every sequence of ``genome`` whose PSSM score on either
+        strand is >= threshold: (seq_index, pos, strand, score) arrays sorted by
+        (seq, pos, +strand first).  ``revseq_order`` selects the accumulation order
+        of the minus strand: True = identify_sites (genome.py:440-445), False =
+        rev_comp_pssm (pssm_model.py:115)."""
+        if threshold is None:
+            threshold = self.threshold()
+        threshold = float(threshold)
+        model = self._model()
+        m = self.length
+        dev = self._dev()
+        nwin = genome.total_windows(m)
+        if hit_cap is None:
+            # expected hits at the Patser operating point, with head-room
+            hit_cap = int(2 * nwin * 2.0 ** (-max(self.IC, 0.0)) * 4) + 4096
+        flags = _cabi.RC_REVSEQ_ORDER if revseq_order else _cabi.RC_MATRIX_ORDER
+        counters = torch.zeros(_cabi.CTR_COUNT, dtype=torch.int64, device=dev)
+        while True:
+            cand_cap = 4 * hit_cap
+            work = genome.workspace(m, cand_cap)
+            hits = torch.empty(hit_cap * 2, dtype=torch.int64, device=dev)   # 16-byte records
+            _cabi.check(_cabi.lib().cgbk_scan_hits(
+                model, genome.struct_ref(), genome.seqset, threshold, flags, hits.data_ptr(), hit_cap,
+                counters.data_ptr(), work.data_ptr(), work.numel(), cand_cap, self._stream()))
+            c = counters.cpu().numpy()
+            n_cand, n_hits = int(c[_cabi.CTR_CANDIDATES]), int(c[_cabi.CTR_HITS])
+            if n_cand <= cand_cap and n_hits <= hit_cap:
+                break
+            hit_cap = max(n_hits, (n_cand + 3) // 4) + 1024
+        self.last_scan_counters = {"candidates": n_cand, "hits": n_hits,
+                                   "dirty_tiles": int(c[_cabi.CTR_DIRTY_TILES])}
+        rec = hits[:2 * n_hits].cpu().numpy().view(np.dtype([("gpos", "<i8"), ("strand", "<i4"), ("score", "<f4")]))
+        gpos, strand, score = rec["gpos"].copy(), rec["strand"].copy(), rec["score"].copy()
+        seq = np.searchsorted(genome.seq_off, gpos, side="right") - 1
+        pos = gpos - genome.seq_off[seq]
+        order = np.lexsort((-strand, pos, seq))
+        return seq[order], pos[order], strand[order], score[order]
+
+    def background_stats(self, genome, n_bins=1024, hist_lo=None, hist_hi=None, accumulate_into=None):
+        """Soft-max score distribution over ALL windows of ``genome`` (both strands
+        combined as in score_seq): returns a dict with device tensors ``stats``
+        (float64[8]: n, sum, sumsq, mean, std) and ``hist`` (int64[n_bins]) plus the
+        bin range.  No host synchronisation happens here."""
+        model = self._model()
+        m = self.length
+        dev = self._dev()
+        if hist_lo is None:
+            hist_lo = math.floor(self.pssm.min)
+        if hist_hi is None:
+            hist_hi = math.ceil(self.pssm.max) + 1.0       # soft-max <= max + 1
+        if accumulate_into is None:
+            stats = torch.zeros(_cabi.BG_COUNT, dtype=torch.float64, device=dev)
+            hist = torch.zeros(n_bins, dtype=torch.int64, device=dev)
+            acc = 0
+        else:
+            stats, hist = accumulate_into["stats"], accumulate_into["hist"]
+            acc = 1
+        work = genome.workspace(m, 0)
+        _cabi.check(_cabi.lib().cgbk_background_stats(
+            model, genome.struct_ref(), genome.seqset, float(hist_lo), float(hist_hi), int(n_bins),
+            hist.data_ptr(), stats.data_ptr(), acc, work.data_ptr(), work.numel(), self._stream()))
+        return {"stats": stats, "hist": hist, "hist_lo": float(hist_lo), "hist_hi": float(hist_hi),
+                "n_bins": int(n_bins)}
+
+    def fit_background(self, genome=None, bg=None, sync=True):
+        """build_bayesian_estimator (binding_model.py:71-92) with the background
+        moments taken from the genome-wide scan (or from a finished
+        ``background_stats`` result, e.g. after a cross-rank all-reduce)."""
+        if bg is None:
+            bg = self.background_stats(genome)
+        self._bg_stats_dev = bg["stats"]
+        self._dev_ms_bg = bg["stats"][_cabi.BG_MEAN:_cabi.BG_STD + 1]
+        if getattr(self, "_mu_m", None) is None or self._dev_ms_m is None:
+            pssm_scores = self.score_self()
+            self._mu_m, self._std_m = np.mean(pssm_scores), np.std(pssm_scores)
+            self._dev_ms_m = torch.tensor([float(self._mu_m), float(self._std_m)], dtype=torch.float64,
+                                          device=self._dev())
+        if sync:
+            host = bg["stats"].cpu().numpy()
+            self._mu_bg, self._std_bg = float(host[_cabi.BG_MEAN]), float(host[_cabi.BG_STD])
+        return bg
+
+    def _estimator_changed(self):
+        dev = self._dev()
+        self._dev_ms_m = torch.tensor([float(self._mu_m), float(self._std_m)], dtype=torch.float64, device=dev)
+        self._dev_ms_bg = torch.tensor([float(self._mu_bg), float(self._std_bg)], dtype=torch.float64, device=dev)
+
+    def _require_estimator(self):
+        if self._dev_ms_m is None or self._dev_ms_bg is None:
+            # the reference fails with AttributeError on the unset _mu_m
+            raise AttributeError("'PSSMModel' object has no attribute '_mu_m' "
+                                 "(call build_bayesian_estimator or fit_background first)")
+
+    def binding_probabilities(self, genome, starts, ends, p_motif, alpha=1/350.0, seq_index=0,
+                              out=None, region_tensors=None):
+        """Posterior of regulation for promoter regions ``sequence[start:end]``
+        (Python slice semantics, gene.py:127) of one replicon: device float64
+        tensor, one value per region (binding_model.py:94-113 for each)."""
+        self._require_estimator()
+        model = self._model()
+        m = self.length
+        dev = self._dev()
+        if region_tensors is None:
+            region_tensors = self.promoter_descriptors(genome, starts, ends, seq_index)
+        d_start, d_nwin = region_tensors
+        n = int(d_start.numel())
+        if out is None:
+            out = torch.empty(n, dtype=torch.float64, device=dev)
+        _cabi.check(_cabi.lib().cgbk_posteriors(
+            model, genome.struct_ref(), d_start.data_ptr(), d_nwin.data_ptr(), n,
+            self._dev_ms_m.data_ptr(), self._dev_ms_bg.data_ptr(), float(p_motif), float(alpha),
+            out.data_ptr(), self._stream()))
+        return out
+
+    def promoter_descriptors(self, genome, starts, ends, seq_index=0):
+        """(start offset, window count) device tensors for cgbk_posteriors."""
+        m = self.length
+        L = genome.length(seq_index)
+        s, e = python_slice_bounds(starts, ends, L)
+        nwin = e - s - m + 1
+        if (nwin < 1).any():
+            raise ValueError("negative dimensions are not allowed")   # Biopython, len(seq) < m
+        dev = self._dev()
+        d_start = torch.from_numpy((s + int(genome.seq_off[seq_index])).astype(np.int64)).to(dev)
+        d_nwin = torch.from_numpy(nwin.astype(np.int32)).to(dev)
+        return d_start, d_nwin
+
+    def _posterior_of_sequences(self, seqs, p_motif, alpha):
+        self._require_estimator()
+        m = self.length
+        seqs = [str(s) if not isinstance(s, (bytes, bytearray)) else s for s in seqs]
+        lens = np.array([len(s) for s in seqs], dtype=np.int64)
+        if (lens < m).any():
+            raise ValueError("negative dimensions are not allowed")
+        dev = self._dev()
+        g = PackedGenome.from_sequences(seqs, dev)
+        d_start = torch.from_numpy(g.seq_off.copy()).to(dev)
+        d_nwin = torch.from_numpy((lens - m + 1).astype(np.int32)).to(dev)
+        out = self.binding_probabilities(g, None, None, p_motif, alpha, region_tensors=(d_start, d_nwin))
+        return out.cpu().numpy()

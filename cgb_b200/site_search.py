@@ -1,0 +1,78 @@
+"""Thresholded binding-site search and the per-gene posterior loop.
+
+Replaces the two per-gene Python loops of the reference with one tiled scan and
+one batched posterior launch per genome:
+
+  identify_sites                      cgb/genome.py:394-455   (HOT LOOP C)
+  calculate_regulation_probabilities  cgb/genome.py:330-333, cgb/gene.py:129-146 (HOT LOOP B)
+
+The reference scores each gene's upstream region separately (twice: the region
+and its reverse complement); here every replicon is scanned once on the GPU and
+the genome-wide hit list is joined with the gene regions on the host.  A window
+belongs to a region iff it lies fully inside it, exactly the windows
+``score_seq(region)`` enumerates; a site under two overlapping regions is reported
+once per gene, as in the reference.
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+
+import numpy as np
+
+from .gene_regions import python_slice_bounds
+
+# cgb/genome.py:22 — chromid is the replicon index in the PackedGenome, gene the
+# row of the GeneTable
+Site = namedtuple('Site', 'chromid start end strand score gene')
+
+
+def identify_sites(model, genome, gene_tables, promoter_up_distance=300, promoter_dw_distance=50,
+                   use_up_dist_site_scan=False, threshold=None):
+    """genome.py:394-448: sites with score >= threshold in the upstream region of
+    every gene, both strands, sorted by score (stable, descending).
+
+    ``gene_tables``: one GeneTable per replicon that has genes.  Returns the list
+    of :class:`Site` in the reference's order."""
+    if threshold is None:
+        threshold = model.threshold()
+    m = model.length
+    seq, pos, strand, score = model.scan_hits(genome, threshold, revseq_order=True)
+    sites = []
+    for gt in gene_tables:
+        k = gt.seq_index
+        L = genome.length(k)
+        if use_up_dist_site_scan:
+            start, end = gt.upstream_noncoding_region_location(promoter_up_distance, promoter_dw_distance)
+        else:
+            start, end = gt.upstream_noncoding_region_location(None, promoter_dw_distance)
+        s, e = python_slice_bounds(start, end, L)
+        sel = seq == k
+        hp, hs, hv = pos[sel], strand[sel], score[sel]
+        order = np.argsort(hp, kind="stable")
+        hp, hs, hv = hp[order], hs[order], hv[order]
+        # windows fully inside [s, e): s <= p <= e - m
+        lo = np.searchsorted(hp, s, side="left")
+        hi = np.searchsorted(hp, e - m, side="right")
+        for gi in range(len(gt)):
+            if e[gi] - s[gi] < m or hi[gi] <= lo[gi]:
+                continue
+            p = hp[lo[gi]:hi[gi]]
+            st = hs[lo[gi]:hi[gi]]
+            sc = hv[lo[gi]:hi[gi]]
+            # reported coordinate: enumerate(scores, start=start) uses the UNclamped
+            # region start (genome.py:435,442)
+            label = p - s[gi] + start[gi]
+            for strand_value in (1, -1):              # + strand hits first, then - strand
+                idx = np.nonzero(st == strand_value)[0]
+                for j in idx:
+                    sites.append(Site(k, int(label[j]), int(label[j]) + m, strand_value, sc[j], gi))
+    sites.sort(key=lambda site: site.score, reverse=True)
+    return sites
+
+
+def calculate_regulation_probabilities(model, genome, gene_table, prior, alpha,
+                                       promoter_up_distance=300, promoter_dw_distance=50):
+    """genome.py:330-333 + gene.py:129-146: posterior probability of regulation
+    for every gene of one replicon (device float64 tensor, gene order)."""
+    start, end = gene_table.promoter_region_location(promoter_up_distance, promoter_dw_distance)
+    return model.binding_probabilities(genome, start, end, prior, alpha, seq_index=gene_table.seq_index)

@@ -1,0 +1,177 @@
+/* cgbk.h — C ABI of the B200-native cgb hot path (libcgbk.so).
+ *
+ * Scope: PSWM log-odds scanning of both DNA strands, the genome-wide background
+ * score histogram/moments, thresholded hit lists and the per-promoter Bayesian
+ * posterior of ErillLab/cgb.  Plain pointers and sizes only: no
+ * torch types.  All d_* pointers are DEVICE pointers owned by the caller (e.g.
+ * torch.Tensor.data_ptr()); `stream` is a cudaStream_t (NULL = default stream).
+ * Every call is asynchronous on `stream` unless stated otherwise and returns a
+ * status code; cgbk_last_error() returns the message of the calling thread's last
+ * failure.  The library never frees caller memory and keeps no global state
+ * besides per-thread error text.
+ *
+ * Each entry point names the reference interface (file:line under
+ * /root/reference) it replaces.
+ */
+#ifndef CGBK_H
+#define CGBK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGBK_VERSION 100
+
+/* status codes; the Python layer maps them to the reference's exception types */
+#define CGBK_OK 0
+#define CGBK_ERR_INVALID 1      /* bad argument            -> ValueError   */
+#define CGBK_ERR_CUDA 2         /* CUDA runtime failure    -> RuntimeError */
+#define CGBK_ERR_UNSUPPORTED 3  /* e.g. motif longer than CGBK_MAX_MOTIF   */
+
+#define CGBK_MAX_MOTIF 32       /* longest PSWM the kernels accept (bases) */
+#define CGBK_SEQ_ALIGN 512      /* sequence starts are multiples of this (bases) */
+#define CGBK_MAX_HIST_BINS 4096
+
+typedef struct cgbk_model cgbk_model;    /* opaque: one PSSM (log-odds) on one device */
+typedef struct cgbk_seqset cgbk_seqset;  /* opaque: sequence table of a packed buffer */
+
+/* Packed genome buffer ("Chromid.sequence", cgb/chromid.py:57-60, as HBM planes).
+ * Coordinates are base offsets into one concatenated, padded buffer; sequence k
+ * occupies [seq_off[k], seq_off[k]+seq_len[k]) with seq_off[k] % CGBK_SEQ_ALIGN == 0. */
+typedef struct {
+    const uint32_t* d_bases2;  /* 2 bits/base, 16 bases/word, base p at bits 2*(p%16); A0 C1 G2 T3 */
+    const uint32_t* d_amb;     /* 1 bit/base, 32 bases/word: byte outside ACGTacgt (Biopython _pwm.c default:) */
+    const uint32_t* d_lower;   /* 1 bit/base: lower-case acgt (matters only to pssm_model.py:96-100) */
+    int64_t cap_bases;         /* capacity of the three planes in bases (multiple of CGBK_SEQ_ALIGN) */
+} cgbk_genome;
+
+/* One thresholded site: cgb/genome.py:22 `Site` minus the Python objects. */
+typedef struct {
+    int64_t gpos;    /* window start, offset into the packed buffer */
+    int32_t strand;  /* +1 / -1 (genome.py:438,445) */
+    float score;     /* float32 PSSM score of that strand, as Biopython's calculate() stores it */
+} cgbk_hit;
+
+/* Counters written by cgbk_scan_hits (device int64[8]). */
+#define CGBK_CTR_CANDIDATES 0   /* windows passed by the 16-bit filter */
+#define CGBK_CTR_HITS 1         /* hits found (may exceed hit_cap: re-run with a larger buffer) */
+#define CGBK_CTR_DIRTY_TILES 2  /* tiles holding non-ACGT bytes, scored by the exact kernel */
+#define CGBK_CTR_COUNT 8
+
+/* Layout of the device double[] written by cgbk_background_stats. */
+#define CGBK_BG_N 0        /* number of windows */
+#define CGBK_BG_SUM 1      /* sum of soft-max scores */
+#define CGBK_BG_SUMSQ 2    /* sum of squares */
+#define CGBK_BG_MEAN 3     /* np.mean(bg_scores)          (binding_model.py:87) */
+#define CGBK_BG_STD 4      /* np.std(bg_scores), ddof = 0 (binding_model.py:87) */
+#define CGBK_BG_COUNT 8
+
+/* flags */
+#define CGBK_RC_MATRIX_ORDER 0  /* minus strand = rev_comp_pssm.calculate(seq)   (pssm_model.py:115) */
+#define CGBK_RC_REVSEQ_ORDER 1  /* minus strand = pssm.calculate(revcomp(seq))   (genome.py:440-445) */
+#define CGBK_SINGLE_WINDOW_F64 2 /* len(seq)==m quirk: repaired scores stay float64 (pssm_model.py:117-127) */
+
+int cgbk_version(void);
+const char* cgbk_last_error(void);
+
+/* ---- host float64 motif math (no GPU) ------------------------------------- */
+
+/* PSSMModel.patser_threshold (cgb/pssm_model.py:62-70): Biopython
+ * pssm.distribution(precision).threshold_patser() on a [m][4] (A,C,G,T) log-odds
+ * table with the uniform background; also returns pssm.mean() (IC, :57-60),
+ * pssm.min and pssm.max.  Any output pointer may be NULL. */
+int cgbk_patser_threshold(const double* logodds, int m, int precision,
+                          double* threshold, double* ic, double* min_score, double* max_score);
+
+/* ---- packing ("str(record.seq)" -> HBM planes) ----------------------------- */
+
+/* Words (uint32) the bases2 plane needs for cap_bases bases; amb/lower need half. */
+int64_t cgbk_bases2_words(int64_t cap_bases);
+
+/* ASCII bytes d_ascii[0..n) -> planes at base offset dst_off (multiple of
+ * CGBK_SEQ_ALIGN); the tail up to the next multiple of CGBK_SEQ_ALIGN is zeroed.
+ * Replaces Chromid.sequence / subsequence (cgb/chromid.py:57-60,92-97) and the
+ * per-call Seq(...) of pssm_model.py:113. */
+int cgbk_pack_ascii(const uint8_t* d_ascii, int64_t n, int64_t dst_off,
+                    uint32_t* d_bases2, uint32_t* d_amb, uint32_t* d_lower,
+                    int64_t cap_bases, void* stream);
+
+/* ---- handles ---------------------------------------------------------------- */
+
+/* logodds: host [m][4] float64, columns A,C,G,T (PSSMModel.pssm, pssm_model.py:47-50).
+ * The reverse-complement table (pssm_model.py:52-55) is derived inside.  Synchronous. */
+int cgbk_model_create(const double* logodds, int m, int device, cgbk_model** out);
+void cgbk_model_destroy(cgbk_model* model);
+
+/* Sequence table of a packed buffer (host int64 arrays).  Synchronous. */
+int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len, int n_seq, int device,
+                       cgbk_seqset** out);
+void cgbk_seqset_destroy(cgbk_seqset* set);
+int64_t cgbk_seqset_total_windows(const cgbk_seqset* set, int m);
+
+/* ---- exact kernels (float64 accumulate in the reference's order) ------------- */
+
+/* PSSMModel.score_seq (cgb/pssm_model.py:103-133) for n_regions windows-ranges.
+ * Region k covers windows gpos = d_start[k] + i, i in [0, d_out_off[k+1]-d_out_off[k]);
+ * d_out_off is the exclusive prefix sum of window counts (n_regions+1 entries).
+ * Outputs (each may be NULL): float32 forward / minus-strand scores after the
+ * ambiguity repair (what both=False returns) and the float64 soft-max
+ * log2(2**f + 2**r) (both=True).  flags: CGBK_RC_*, CGBK_SINGLE_WINDOW_F64 (then
+ * d_f64 / d_r64 receive the un-rounded pair of each 1-window region). */
+int cgbk_score_windows(const cgbk_model* model, const cgbk_genome* genome,
+                       const int64_t* d_start, const int64_t* d_out_off, int n_regions,
+                       int64_t total_windows, int flags,
+                       float* d_fwd32, float* d_rc32, double* d_both64,
+                       double* d_f64, double* d_r64, void* stream);
+
+/* TFBindingModel.binding_probability (cgb/binding_model.py:94-113) for a batch of
+ * promoter regions (Gene.promoter_region, cgb/gene.py:111-127): region k scores
+ * windows [d_start[k], d_start[k]+d_nwin[k]).  d_mu_std_m / d_mu_std_bg are
+ * DEVICE double[2] {mean, std} (so the background pair can come straight from
+ * cgbk_background_stats without a host round trip).  d_post[k] = posterior. */
+int cgbk_posteriors(const cgbk_model* model, const cgbk_genome* genome,
+                    const int64_t* d_start, const int32_t* d_nwin, int n_regions,
+                    const double* d_mu_std_m, const double* d_mu_std_bg,
+                    double p_motif, double alpha, double* d_post, void* stream);
+
+/* ---- tiled scan kernels (sm_100a hot path) ---------------------------------- */
+
+/* Bytes of device workspace cgbk_scan_hits / cgbk_background_stats need. */
+int64_t cgbk_scan_workspace_bytes(const cgbk_seqset* set, int m, int64_t cand_cap);
+
+/* Genome.identify_sites hit loop (cgb/genome.py:433-445) over every window of every
+ * sequence of the set: writes all windows with float32 score >= threshold (compared
+ * in float64) on either strand, unordered, to d_hits[0..hit_cap); d_counters is a
+ * device int64[CGBK_CTR_COUNT] (zeroed inside).  flags: CGBK_RC_*.  Filter kernel on
+ * 16-bit k-mer tables, then exact float64 re-scoring of every candidate, so the
+ * result is bit-exact with the reference. */
+int cgbk_scan_hits(cgbk_model* model, const cgbk_genome* genome, const cgbk_seqset* set,
+                   double threshold, int flags,
+                   cgbk_hit* d_hits, int64_t hit_cap, int64_t* d_counters,
+                   void* d_work, int64_t work_bytes, int64_t cand_cap, void* stream);
+
+/* Background distribution of Genome.build_PSSM_model (cgb/genome.py:215-226) taken
+ * over ALL windows of the set instead of a 10 000-window sample: soft-max score of
+ * every window -> histogram (uint64 d_hist[n_bins] over [hist_lo, hist_hi), clamped)
+ * and moments (device double[CGBK_BG_COUNT], layout above).  With accumulate != 0
+ * the raw n/sum/sumsq/hist are added to what the buffers hold (mean/std are
+ * recomputed), for multi-call or multi-rank accumulation. */
+int cgbk_background_stats(cgbk_model* model, const cgbk_genome* genome, const cgbk_seqset* set,
+                          double hist_lo, double hist_hi, int n_bins,
+                          unsigned long long* d_hist, double* d_stats, int accumulate,
+                          void* d_work, int64_t work_bytes, void* stream);
+
+/* Recompute CGBK_BG_MEAN / CGBK_BG_STD from n/sum/sumsq in d_stats (after an
+ * all-reduce of the raw sums across ranks). */
+int cgbk_background_finalize(double* d_stats, void* stream);
+
+/* Launch statistics of the calling thread's last tiled-scan call (for bench.py):
+ * out[0] = kernels launched, out[1] = tiles, out[2] = bases per lane segment. */
+int cgbk_last_launch_info(int64_t* out3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGBK_H */

@@ -1,0 +1,133 @@
+"""CPU-side checks of the product: host float64 motif algebra against the golden
+vectors, the reference-facing API surface, coordinate rules, and that libcgbk.so
+loads and exports every symbol include/cgbk.h declares (no GPU compute here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cgb_b200 import GeneTable, PSSMModel, SiteCollection, TFBindingModel, _cabi, python_slice_bounds
+from oracle import np_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _collections(lexa):
+    return [SiteCollection(mo["sites"], None, mo["name"]) for mo in lexa["motifs"]]
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "cgbk.h")).read()
+    declared = set(re.findall(r"\b(cgbk_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
+    lib = C.CDLL(_cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _cabi.lib().cgbk_version() == 100
+
+
+def test_site_collection_pwm(golden, lexa):
+    for c, g in zip(_collections(lexa), golden["collections"]):
+        assert c.site_count == g["n_sites"] and c.length == 22
+        for l in "ACGT":
+            assert list(c.pwm[l]) == g["pwm"][l]
+        # the golden IC / threshold are those of PSSMModel([c], [1.0]) (re-normalised mix)
+        M = PSSMModel([c], [1.0])
+        assert M.IC == g["IC"] and M.threshold() == g["patser_threshold"]
+        assert abs(c.IC - g["IC"]) < 1e-12
+        assert c.sites[0] == g["first_site"]
+
+
+@pytest.mark.parametrize("wname", ["equal", "site_count"])
+def test_pssm_model_host_math(golden, lexa, lexa_weights, wname):
+    rec = golden["models"][wname]
+    M = PSSMModel(_collections(lexa), lexa_weights[wname])
+    assert isinstance(M, TFBindingModel)
+    assert M.length == 22 and M.alphabet == "ACGT" and M.background["A"] == 0.25
+    for l in "ACGT":
+        assert list(M.pwm[l]) == rec["pwm"][l]
+        assert list(M.pssm[l]) == rec["pssm"][l]
+        assert list(M.rev_comp_pssm[l]) == rec["rev_comp_pssm"][l]
+    assert M.IC == rec["IC"]
+    assert M.threshold() == rec["patser_threshold"] == M.patser_threshold
+    with pytest.raises(ValueError):
+        M.threshold("other")
+    assert len(M.sites) == 164 and M.site_collections[0].name == "LexA_Mtu"
+    with pytest.raises(AttributeError):
+        M.bayesian_estimator                       # never assigned in the reference either
+    # host restatement of the ambiguity rule (pssm_model.py:88-101)
+    om = O.OracleModel([mo["sites"] for mo in lexa["motifs"]], lexa_weights[wname])
+    site = "gaatcaaacNTGTGTTCGACAG"
+    assert M._calculate(M.pssm, site) == O._calculate_ambiguous(om.fwd, site.encode())
+    assert M._calculate(M.rev_comp_pssm, site) == O._calculate_ambiguous(om.rc, site.encode())
+
+
+def test_patser_threshold_cabi_matches_oracle(lexa):
+    rng = np.random.default_rng(5)
+    for m in (8, 13, 30):
+        pwm = rng.dirichlet([0.5] * 4, size=m) * 0.9 + 0.025
+        lo = np.log2(pwm / 0.25)
+        om = O.OracleModel.from_logodds(lo)
+        flat = (C.c_double * (4 * m))(*lo.ravel().tolist())
+        thr, ic, mn, mx = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        _cabi.check(_cabi.lib().cgbk_patser_threshold(flat, m, 1000, C.byref(thr), C.byref(ic),
+                                                      C.byref(mn), C.byref(mx)))
+        assert ic.value == O.pssm_mean(om.pssm)
+        assert mn.value == O.pssm_min(om.pssm) and mx.value == O.pssm_max(om.pssm)
+        assert abs(thr.value - O.patser_threshold(om.pssm)) < 1e-9
+
+
+def test_errors_map_to_reference_exception_types():
+    lo = (C.c_double * 8)(*([0.1] * 8))
+    with pytest.raises(ValueError):
+        _cabi.check(_cabi.lib().cgbk_patser_threshold(lo, 0, 1000, None, None, None, None))
+    bad = (C.c_double * 4)(0.0, float("-inf"), 0.0, 0.0)
+    with pytest.raises(ValueError):
+        _cabi.check(_cabi.lib().cgbk_patser_threshold(bad, 1, 1000, None, None, None, None))
+    a = SiteCollection(["ACGT", "ACGA"])
+    b = SiteCollection(["ACGTT"])
+    with pytest.raises(AssertionError):
+        PSSMModel([a, b], [0.5, 0.5])               # pssm_model.py:164
+    with pytest.raises(KeyError):
+        SiteCollection(["ACGN"])                     # Biopython counts only alphabet letters
+
+
+def test_gene_table_matches_oracle_rules():
+    rng = np.random.default_rng(7)
+    L = 50000
+    starts = np.sort(rng.choice(np.arange(10, L - 2000), size=40, replace=False))
+    ends = np.minimum(starts + rng.integers(60, 1500, size=40), L)
+    strand = rng.choice([1, -1], size=40)
+    # edge cases: gene at the very start / end of the replicon
+    starts[0], ends[0], strand[0] = 5, 300, -1
+    ends[-1], strand[-1] = L - 3, -1
+    gt = GeneTable(starts, ends, strand, L)
+    genes = [O.OGene(int(s), int(e), int(t)) for s, e, t in zip(starts, ends, strand)]
+    for up, down in ((None, 50), (300, 50), (0, 50), (1000, 0), (250, 100)):
+        s, e = gt.upstream_noncoding_region_location(up, down)
+        for i in range(len(genes)):
+            assert (int(s[i]), int(e[i])) == O.upstream_noncoding_region_location(genes, i, L, up, down)
+    for up, down in ((300, 50), (0, 0), (1000, 1000)):
+        s, e = gt.promoter_region_location(up, down)
+        for i in range(len(genes)):
+            assert (int(s[i]), int(e[i])) == O.promoter_region_location(genes[i], L, up, down)
+
+
+def test_python_slice_bounds():
+    seq = "ACGT" * 25
+    L = len(seq)
+    cases = [(0, 10), (-10, 5), (-10, 200), (90, 300), (-300, 20), (50, 40), (120, 130), (-5, -1)]
+    s, e = python_slice_bounds([c[0] for c in cases], [c[1] for c in cases], L)
+    for (a, b), si, ei in zip(cases, s, e):
+        assert seq[a:b] == seq[si:ei], (a, b)
+
+
+def test_scoring_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    M = PSSMModel([SiteCollection(["ACGTAC", "ACGTAA"])], [1.0])
+    with pytest.raises(RuntimeError):
+        M.score_seq("ACGTACGTAC")
