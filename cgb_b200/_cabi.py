@@ -59,6 +59,8 @@ SYMBOLS = {
                                          C.c_void_p]),
     "cgbk_background_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cgbk_last_launch_info": (C.c_int, [C.POINTER(C.c_int64)]),
+    "cgbk_profile_enable": (C.c_int, [C.c_int]),
+    "cgbk_profile_last_ms": (C.c_int, [C.POINTER(C.c_float)]),
 }
 
 
@@ -91,6 +93,16 @@ def check(status):
     if status == ERR_UNSUPPORTED:
         raise NotImplementedError(msg)
     raise CgbkError(msg)
+
+
+def profile_enable(on=True):
+    check(lib().cgbk_profile_enable(1 if on else 0))
+
+
+def profile_last_ms():
+    ms = C.c_float()
+    check(lib().cgbk_profile_last_ms(C.byref(ms)))
+    return ms.value
 
 
 def last_launch_info():

@@ -35,6 +35,32 @@ int cgbk_check_cuda(cudaError_t e, const char* what) {
         if (_rc != CGBK_OK) return _rc;                        \
     } while (0)
 
+// optional event timing of the tiled kernel (bench.py roofline)
+static thread_local int g_prof_on = 0;
+static thread_local cudaEvent_t g_prof_ev[2] = {nullptr, nullptr};
+static thread_local int g_prof_valid = 0;
+
+extern "C" int cgbk_profile_enable(int on) {
+    if (on && !g_prof_ev[0]) {
+        CUDA_TRY(cudaEventCreate(&g_prof_ev[0]));
+        CUDA_TRY(cudaEventCreate(&g_prof_ev[1]));
+    }
+    g_prof_on = on ? 1 : 0;
+    g_prof_valid = 0;
+    return CGBK_OK;
+}
+
+extern "C" int cgbk_profile_last_ms(float* ms) {
+    if (!ms) return cgbk_set_error(CGBK_ERR_INVALID, "ms is NULL");
+    if (!g_prof_valid) return cgbk_set_error(CGBK_ERR_INVALID, "no profiled scan recorded");
+    CUDA_TRY(cudaEventSynchronize(g_prof_ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(ms, g_prof_ev[0], g_prof_ev[1]));
+    return CGBK_OK;
+}
+
+#define PROF_START(st) do { if (g_prof_on) CUDA_TRY(cudaEventRecord(g_prof_ev[0], (st))); } while (0)
+#define PROF_STOP(st) do { if (g_prof_on) { CUDA_TRY(cudaEventRecord(g_prof_ev[1], (st))); g_prof_valid = 1; } } while (0)
+
 extern "C" int cgbk_version(void) { return CGBK_VERSION; }
 extern "C" const char* cgbk_last_error(void) { return g_err; }
 
@@ -500,7 +526,9 @@ extern "C" int cgbk_scan_hits(cgbk_model* M, const cgbk_genome* genome, const cg
         const int wpb = threads / 32;
         long long grid = (S->n_tiles + wpb - 1) / wpb;
         if (grid > sms) grid = sms;
+        PROF_START(st);
         CUDA_TRY(launch_fast_filter(M, view_of(genome), table_of(S), w, L, (int)grid, st));
+        PROF_STOP(st);
         CUDA_TRY(launch_rescore(M, view_of(genome), table_of(S), w, threshold, flags, d_hits, hit_cap, L, st));
         launches = 3;
     }
@@ -544,8 +572,10 @@ extern "C" int cgbk_background_stats(cgbk_model* M, const cgbk_genome* genome, c
     if (grid < 1) grid = 1;
     int launches = 1;
     if (S->n_tiles > 0) {
+        PROF_START(st);
         CUDA_TRY(launch_fast_stats(M, view_of(genome), table_of(S), w, L, (int)grid, hist_lo, inv_binw, n_bins,
                                    d_hist, st));
+        PROF_STOP(st);
         CUDA_TRY(launch_dirty_stats(M, view_of(genome), table_of(S), w, L, hist_lo, inv_binw, n_bins, d_hist,
                                     (int)grid, st));
         CUDA_TRY(launch_bg_finalize(w.partials, (int)grid + 148, d_stats, 1, st));

@@ -252,11 +252,14 @@ class PSSMModel(TFBindingModel):
         order = np.lexsort((-strand, pos, seq))
         return seq[order], pos[order], strand[order], score[order]
 
-    def background_stats(self, genome, n_bins=1024, hist_lo=None, hist_hi=None, accumulate_into=None):
+    def background_stats(self, genome, n_bins=1024, hist_lo=None, hist_hi=None, accumulate_into=None,
+                         out=None):
         """Soft-max score distribution over ALL windows of ``genome`` (both strands
         combined as in score_seq): returns a dict with device tensors ``stats``
         (float64[8]: n, sum, sumsq, mean, std) and ``hist`` (int64[n_bins]) plus the
-        bin range.  No host synchronisation happens here."""
+        bin range.  ``accumulate_into``: a previous result to add this genome to;
+        ``out``: a previous result whose buffers are overwritten (no allocation).
+        No host synchronisation happens here."""
         model = self._model()
         m = self.length
         dev = self._dev()
@@ -264,7 +267,10 @@ class PSSMModel(TFBindingModel):
             hist_lo = math.floor(self.pssm.min)
         if hist_hi is None:
             hist_hi = math.ceil(self.pssm.max) + 1.0       # soft-max <= max + 1
-        if accumulate_into is None:
+        if out is not None:
+            stats, hist, acc = out["stats"], out["hist"], 0
+            n_bins = int(hist.numel())
+        elif accumulate_into is None:
             stats = torch.zeros(_cabi.BG_COUNT, dtype=torch.float64, device=dev)
             hist = torch.zeros(n_bins, dtype=torch.int64, device=dev)
             acc = 0

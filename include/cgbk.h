@@ -171,6 +171,13 @@ int cgbk_background_finalize(double* d_stats, void* stream);
  * out[0] = kernels launched, out[1] = tiles, out[2] = bases per lane segment. */
 int cgbk_last_launch_info(int64_t* out3);
 
+/* Optional device timing of the dominant (tiled scan) kernel for bench.py: when
+ * enabled, cgbk_scan_hits / cgbk_background_stats record CUDA events on `stream`
+ * right before and after that kernel; cgbk_profile_last_ms synchronises on the stop
+ * event and returns the elapsed milliseconds of the calling thread's last scan. */
+int cgbk_profile_enable(int on);
+int cgbk_profile_last_ms(float* ms);
+
 #ifdef __cplusplus
 }
 #endif
