@@ -49,14 +49,16 @@ SYMBOLS = {
     "cgbk_score_windows": (C.c_int, [C.c_void_p, C.POINTER(Genome), C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                       C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p]),
-    "cgbk_posteriors": (C.c_int, [C.c_void_p, C.POINTER(Genome), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
-                                   C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "cgbk_posteriors": (C.c_int, [C.c_void_p, C.POINTER(Genome), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                                   C.c_void_p]),
+    "cgbk_score_plane_ints": (C.c_int64, [C.c_void_p, C.c_int]),
     "cgbk_scan_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int64]),
     "cgbk_scan_hits": (C.c_int, [C.c_void_p, C.POINTER(Genome), C.c_void_p, C.c_double, C.c_int, C.c_void_p,
                                   C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "cgbk_background_stats": (C.c_int, [C.c_void_p, C.POINTER(Genome), C.c_void_p, C.c_double, C.c_double,
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
-                                         C.c_void_p]),
+                                         C.c_void_p, C.c_int64, C.c_void_p]),
     "cgbk_background_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cgbk_last_launch_info": (C.c_int, [C.POINTER(C.c_int64)]),
     "cgbk_profile_enable": (C.c_int, [C.c_int]),

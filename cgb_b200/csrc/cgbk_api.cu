@@ -180,6 +180,19 @@ extern "C" int cgbk_pack_ascii(const uint8_t* d_ascii, int64_t n, int64_t dst_of
 // ---------------------------------------------------------------------------
 // model
 // ---------------------------------------------------------------------------
+// Row-major [256][NW] table -> the chunk-major layout fill_tables() (cgbk_fast.cu) reads with
+// vector loads: all 16-byte chunks [c][e][4], then the 8-byte chunk [e][2], then the 4-byte chunk [e].
+static void chunked_layout(const uint32_t* rows, int NW, uint32_t* out) {
+    const int n16 = NW / 4, has8 = (NW % 4) >= 2 ? 1 : 0, has4 = NW % 2;
+    for (int e = 0; e < 256; ++e) {
+        for (int c = 0; c < n16; ++c)
+            for (int k = 0; k < 4; ++k) out[(c * 256 + e) * 4 + k] = rows[e * NW + 4 * c + k];
+        if (has8)
+            for (int k = 0; k < 2; ++k) out[n16 * 1024 + e * 2 + k] = rows[e * NW + 4 * n16 + k];
+        if (has4) out[n16 * 1024 + has8 * 512 + e] = rows[e * NW + NW - 1];
+    }
+}
+
 static void group_partial(const double* tab, int m, int g, int e, double* out) {
     double s = 0.0;
     for (int k = 0; k < 4; ++k) {
@@ -254,7 +267,9 @@ extern "C" int cgbk_model_create(const double* lo, int m, int device, cgbk_model
         return cgbk_set_error(CGBK_ERR_CUDA, "cudaMalloc of model tables failed");
     }
     cudaError_t c1 = cudaMemcpy(M->d_exact, ex.data(), sizeof(double) * CGBK_EXACT_DOUBLES, cudaMemcpyHostToDevice);
-    cudaError_t c2 = cudaMemcpy(M->d_precise, precise.data(), sizeof(uint32_t) * precise.size(), cudaMemcpyHostToDevice);
+    std::vector<uint32_t> precise_ch(precise.size());
+    chunked_layout(precise.data(), 2 * G, precise_ch.data());
+    cudaError_t c2 = cudaMemcpy(M->d_precise, precise_ch.data(), sizeof(uint32_t) * precise_ch.size(), cudaMemcpyHostToDevice);
     if (c1 != cudaSuccess || c2 != cudaSuccess) {
         cgbk_model_destroy(M);
         return cgbk_set_error(CGBK_ERR_CUDA, "upload of model tables failed");
@@ -319,9 +334,12 @@ static int ensure_coarse(cgbk_model* M, double thr, cudaStream_t st) {
     build_coarse_strand(M->fwd, M->m, G, thr, hf.data());
     build_coarse_strand(M->rc, M->m, G, thr, hr.data());
     for (size_t i = 0; i < packed.size(); ++i) packed[i] = (hf[i] << 16) | (hr[i] & 0xffffu);
-    // the previous scan on this stream may still be reading the table
-    CUDA_TRY(cudaStreamSynchronize(st));
-    CUDA_TRY(cudaMemcpy(M->d_coarse, packed.data(), sizeof(uint32_t) * packed.size(), cudaMemcpyHostToDevice));
+    std::vector<uint32_t> chunked(packed.size());
+    chunked_layout(packed.data(), G, chunked.data());
+    // stream-ordered: a previous scan on this stream may still be reading the table (pageable
+    // source: the runtime stages the bytes before returning)
+    CUDA_TRY(cudaMemcpyAsync(M->d_coarse, chunked.data(), sizeof(uint32_t) * chunked.size(),
+                             cudaMemcpyHostToDevice, st));
     M->coarse_valid = 1;
     M->coarse_thr = thr;
     return CGBK_OK;
@@ -346,15 +364,21 @@ extern "C" int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len
     S->h_len = (int64_t*)malloc(sizeof(int64_t) * n_seq);
     memcpy(S->h_off, seq_off, sizeof(int64_t) * n_seq);
     memcpy(S->h_len, seq_len, sizeof(int64_t) * n_seq);
-    cudaError_t e1 = cudaMalloc(&S->d_off, sizeof(int64_t) * n_seq);
-    cudaError_t e2 = cudaMalloc(&S->d_len, sizeof(int64_t) * n_seq);
-    cudaError_t e3 = cudaMalloc(&S->d_tile_prefix, sizeof(int64_t) * (n_seq + 1));
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    S->h_tile_prefix = (int64_t*)calloc(n_seq + 1, sizeof(int64_t));
+    // one device block: off[n] | len[n] | tile_prefix[n + 1]
+    int64_t* block = nullptr;
+    if (cudaMalloc(&block, sizeof(int64_t) * (3 * (size_t)n_seq + 1)) != cudaSuccess) {
         cgbk_seqset_destroy(S);
         return cgbk_set_error(CGBK_ERR_CUDA, "cudaMalloc of sequence table failed");
     }
-    cudaMemcpy(S->d_off, seq_off, sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice);
-    cudaMemcpy(S->d_len, seq_len, sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice);
+    S->d_off = block; S->d_len = block + n_seq; S->d_tile_prefix = block + 2 * n_seq;
+    std::vector<int64_t> both(2 * (size_t)n_seq);
+    memcpy(both.data(), seq_off, sizeof(int64_t) * n_seq);
+    memcpy(both.data() + n_seq, seq_len, sizeof(int64_t) * n_seq);
+    if (cudaMemcpy(block, both.data(), sizeof(int64_t) * both.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cgbk_seqset_destroy(S);
+        return cgbk_set_error(CGBK_ERR_CUDA, "upload of sequence table failed");
+    }
     S->cached_m = -1; S->cached_L = -1;
     *out = S;
     return CGBK_OK;
@@ -362,10 +386,8 @@ extern "C" int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len
 
 extern "C" void cgbk_seqset_destroy(cgbk_seqset* S) {
     if (!S) return;
-    if (S->d_off) cudaFree(S->d_off);
-    if (S->d_len) cudaFree(S->d_len);
-    if (S->d_tile_prefix) cudaFree(S->d_tile_prefix);
-    free(S->h_off); free(S->h_len);
+    if (S->d_off) cudaFree(S->d_off);     // d_len / d_tile_prefix live in the same block
+    free(S->h_off); free(S->h_len); free(S->h_tile_prefix);
     free(S);
 }
 
@@ -389,14 +411,15 @@ static int64_t count_tiles(const cgbk_seqset* S, int m, int L) {
 static int ensure_tiles(cgbk_seqset* S, int m, int L, cudaStream_t st) {
     if (S->cached_m == m && S->cached_L == L) return CGBK_OK;
     const int64_t stride = 32ll * L - 32;
-    std::vector<int64_t> prefix(S->n_seq + 1);
+    int64_t* prefix = S->h_tile_prefix;
     prefix[0] = 0;
     for (int i = 0; i < S->n_seq; ++i) {
         const int64_t nwin = S->h_len[i] - m + 1;
         prefix[i + 1] = prefix[i] + (nwin > 0 ? (nwin + stride - 1) / stride : 0);
     }
-    CUDA_TRY(cudaStreamSynchronize(st));
-    CUDA_TRY(cudaMemcpy(S->d_tile_prefix, prefix.data(), sizeof(int64_t) * prefix.size(), cudaMemcpyHostToDevice));
+    // stream-ordered after any earlier scan of this set on the same stream
+    CUDA_TRY(cudaMemcpyAsync(S->d_tile_prefix, prefix, sizeof(int64_t) * (S->n_seq + 1),
+                             cudaMemcpyHostToDevice, st));
     S->n_tiles = prefix[S->n_seq];
     S->cached_m = m; S->cached_L = L;
     return CGBK_OK;
@@ -474,17 +497,31 @@ extern "C" int cgbk_score_windows(const cgbk_model* M, const cgbk_genome* genome
     return CGBK_OK;
 }
 
-extern "C" int cgbk_posteriors(const cgbk_model* M, const cgbk_genome* genome, const int64_t* d_start,
-                               const int32_t* d_nwin, int n_regions, const double* d_ms_m,
-                               const double* d_ms_bg, double p_motif, double alpha, double* d_post,
-                               void* stream) {
+static SeqTable table_of(const cgbk_seqset* S);
+
+extern "C" int cgbk_posteriors(const cgbk_model* M, const cgbk_genome* genome, const cgbk_seqset* set,
+                               const int32_t* d_plane, const int64_t* d_start, const int32_t* d_nwin,
+                               int n_regions, const double* d_ms_m, const double* d_ms_bg, double p_motif,
+                               double alpha, double* d_post, void* stream) {
     if (!M) return cgbk_set_error(CGBK_ERR_INVALID, "NULL model");
     int rc = check_genome(genome);
     if (rc) return rc;
     if (n_regions < 0 || (n_regions > 0 && (!d_start || !d_nwin || !d_post || !d_ms_m || !d_ms_bg)))
         return cgbk_set_error(CGBK_ERR_INVALID, "bad promoter table");
-    CUDA_TRY(launch_posteriors(M, view_of(genome), (const long long*)d_start, d_nwin, n_regions, d_ms_m,
-                               d_ms_bg, p_motif, alpha, d_post, (cudaStream_t)stream));
+    PlaneView pv;
+    pv.plane = nullptr; pv.L = 32; pv.D = 4 * (M->G - 1); pv.inv_scale = ldexp(1.0, -M->kexp);
+    SeqTable seqs = {};
+    if (d_plane) {
+        if (!set) return cgbk_set_error(CGBK_ERR_INVALID, "a score plane needs the sequence set it was written for");
+        if (set->cached_m != M->m)
+            return cgbk_set_error(CGBK_ERR_INVALID, "the score plane was not written for this motif length "
+                                  "(run cgbk_background_stats with d_plane first)");
+        pv.plane = d_plane; pv.L = set->cached_L;
+        seqs = table_of(set);
+    }
+    CUDA_TRY(launch_posteriors(M, view_of(genome), seqs, pv, (const long long*)d_start, d_nwin, n_regions,
+                               d_ms_m, d_ms_bg, p_motif, alpha, d_post, (cudaStream_t)stream));
+    g_launch_info[0] = 1;
     return CGBK_OK;
 }
 
@@ -495,6 +532,12 @@ static SeqTable table_of(const cgbk_seqset* S) {
     SeqTable t;
     t.off = (const long long*)S->d_off; t.len = (const long long*)S->d_len;
     t.tile_prefix = (const long long*)S->d_tile_prefix; t.n_seq = S->n_seq; t.n_tiles = S->n_tiles;
+    for (int i = 0; i < CGBK_INLINE_SEQS; ++i) {
+        const bool have = i < S->n_seq && S->n_seq <= CGBK_INLINE_SEQS;
+        t.off_v[i] = have ? S->h_off[i] : 0;
+        t.len_v[i] = have ? S->h_len[i] : 0;
+        t.prefix_v[i] = have ? S->h_tile_prefix[i] : 0;
+    }
     return t;
 }
 
@@ -515,7 +558,9 @@ extern "C" int cgbk_scan_hits(cgbk_model* M, const cgbk_genome* genome, const cg
     if (rc) return rc;
     const int threads = fast_threads(M->G, 0);
     const int sms = device_sms(M->device);
-    const int L = choose_L(S, M->m, sms * (threads / 32));
+    // the tiling depends only on (set, m), not on the kernel variant: a score plane written by
+    // the stats scan stays addressable after a hit scan of the same set
+    const int L = choose_L(S, M->m, sms * 16);
     rc = ensure_tiles(S, M->m, L, st);
     if (rc) return rc;
     rc = ensure_coarse(M, threshold, st);
@@ -537,18 +582,32 @@ extern "C" int cgbk_scan_hits(cgbk_model* M, const cgbk_genome* genome, const cg
     return CGBK_OK;
 }
 
+// ints the score plane needs for any tiling of this set (the L = 32 tiling is the largest)
+extern "C" int64_t cgbk_score_plane_ints(const cgbk_seqset* S, int m) {
+    if (!S) return 0;
+    int64_t best = 0;
+    for (int L = 32; L <= 128; L <<= 1) {
+        const int64_t need = count_tiles(S, m, L) * (int64_t)((L / 32 + 1) * 1024);
+        if (need > best) best = need;
+    }
+    return best;
+}
+
 extern "C" int cgbk_background_stats(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqset* set,
                                      double hist_lo, double hist_hi, int n_bins, unsigned long long* d_hist,
-                                     double* d_stats, int accumulate, void* d_work, int64_t work_bytes,
-                                     void* stream) {
+                                     double* d_stats, int accumulate, int32_t* d_plane, int64_t plane_ints,
+                                     void* d_work, int64_t work_bytes, void* stream) {
     if (!M || !set || !d_stats) return cgbk_set_error(CGBK_ERR_INVALID, "NULL argument");
     int rc = check_genome(genome);
     if (rc) return rc;
     if (d_hist) {
         if (n_bins < 1 || n_bins > CGBK_MAX_HIST_BINS || !(hist_hi > hist_lo))
             return cgbk_set_error(CGBK_ERR_INVALID, "histogram needs 1..%d bins and hi > lo", CGBK_MAX_HIST_BINS);
+        if ((hist_hi - hist_lo) * ldexp(1.0, M->kexp) >= 4294967296.0 ||
+            fabs(hist_lo) * ldexp(1.0, M->kexp) >= 2147483648.0)
+            return cgbk_set_error(CGBK_ERR_INVALID, "histogram range too wide for the fixed-point scores");
     } else {
-        n_bins = 1; hist_lo = 0.0; hist_hi = 1.0;
+        n_bins = 1; hist_lo = M->min_score - 1.0; hist_hi = M->max_score + 2.0;
     }
     cudaStream_t st = (cudaStream_t)stream;
     cgbk_seqset* S = const_cast<cgbk_seqset*>(set);
@@ -557,9 +616,14 @@ extern "C" int cgbk_background_stats(cgbk_model* M, const cgbk_genome* genome, c
     if (rc) return rc;
     const int threads = fast_threads(M->G, 1);
     const int sms = device_sms(M->device);
-    const int L = choose_L(S, M->m, sms * (threads / 32));
+    // the tiling depends only on (set, m), not on the kernel variant: a score plane written by
+    // the stats scan stays addressable after a hit scan of the same set
+    const int L = choose_L(S, M->m, sms * 16);
     rc = ensure_tiles(S, M->m, L, st);
     if (rc) return rc;
+    if (d_plane && plane_ints < S->n_tiles * (int64_t)((L / 32 + 1) * 1024))
+        return cgbk_set_error(CGBK_ERR_INVALID, "score plane of %lld ints is smaller than the %lld required",
+                              (long long)plane_ints, (long long)cgbk_score_plane_ints(S, M->m));
     CUDA_TRY(cudaMemsetAsync(w.counters, 0, 64, st));
     if (!accumulate) {
         if (d_hist) CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * n_bins, st));
@@ -572,14 +636,14 @@ extern "C" int cgbk_background_stats(cgbk_model* M, const cgbk_genome* genome, c
     if (grid < 1) grid = 1;
     int launches = 1;
     if (S->n_tiles > 0) {
+        const StatsParams sp = make_stats_params(M, hist_lo, hist_hi, n_bins, d_hist, d_plane);
         PROF_START(st);
-        CUDA_TRY(launch_fast_stats(M, view_of(genome), table_of(S), w, L, (int)grid, hist_lo, inv_binw, n_bins,
-                                   d_hist, st));
+        CUDA_TRY(launch_fast_stats(M, view_of(genome), table_of(S), w, L, (int)grid, sp, st));
         PROF_STOP(st);
-        CUDA_TRY(launch_dirty_stats(M, view_of(genome), table_of(S), w, L, hist_lo, inv_binw, n_bins, d_hist,
-                                    (int)grid, st));
-        CUDA_TRY(launch_bg_finalize(w.partials, (int)grid + 148, d_stats, 1, st));
-        launches = 3;
+        // exact pass over tiles with non-ACGT bytes; its last block reduces all partial moments
+        CUDA_TRY(launch_dirty_stats(M, view_of(genome), table_of(S), w, L, hist_lo, inv_binw, sp, (int)grid,
+                                    (int)grid + CGBK_DIRTY_STATS_BLOCKS, d_stats, st));
+        launches = 2;
     } else {
         CUDA_TRY(launch_bg_finalize(w.partials, 0, d_stats, 1, st));
     }

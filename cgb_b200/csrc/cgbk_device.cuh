@@ -13,10 +13,10 @@ __device__ __forceinline__ uint64_t load_bases32(const GenomeView& g, long long 
     const long long wi = p >> 4;
     const int sh = (int)(p & 15) * 2;
     const uint32_t w0 = ldw(g.bases2, wi, nw), w1 = ldw(g.bases2, wi + 1, nw);
-    uint64_t lo = (uint64_t)w0 | ((uint64_t)w1 << 32);
-    if (sh == 0) return lo;
     const uint32_t w2 = ldw(g.bases2, wi + 2, nw);
-    return (lo >> sh) | ((uint64_t)w2 << (64 - sh));
+    // funnel shifts: sh in [0, 30]
+    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+    return (uint64_t)lo | ((uint64_t)hi << 32);
 }
 
 // 32 consecutive mask bits starting at base offset p
@@ -28,17 +28,19 @@ __device__ __forceinline__ uint32_t load_bits32(const uint32_t* __restrict__ pla
     return __funnelshift_r(a0, a1, (uint32_t)(p & 31));
 }
 
-// Exact tables staged in shared memory: fwd[m][4], rc[m][4], mean_f[m], mean_r[m]
+// Exact tables staged in shared memory, the two strands interleaved so that one 16-byte
+// load serves both: fr[j][b] = (pssm[b][j], rev_comp_pssm[b][j]); mean[j] likewise.
 struct ExactTables {
-    double fwd[CGBK_MAXM * 4];
-    double rc[CGBK_MAXM * 4];
-    double mean_f[CGBK_MAXM];
-    double mean_r[CGBK_MAXM];
+    double2 fr[CGBK_MAXM * 4];
+    double2 mean[CGBK_MAXM];
 };
 
+// d_exact layout (global): fwd[128] rc[128] mean_f[32] mean_r[32]
 __device__ __forceinline__ void stage_exact(ExactTables* s, const double* __restrict__ d_exact) {
-    double* dst = reinterpret_cast<double*>(s);
-    for (int i = threadIdx.x; i < CGBK_EXACT_DOUBLES; i += blockDim.x) dst[i] = d_exact[i];
+    for (int i = threadIdx.x; i < CGBK_MAXM * 4; i += blockDim.x)
+        s->fr[i] = make_double2(d_exact[i], d_exact[CGBK_MAXM * 4 + i]);
+    for (int i = threadIdx.x; i < CGBK_MAXM; i += blockDim.x)
+        s->mean[i] = make_double2(d_exact[CGBK_MAXM * 8 + i], d_exact[CGBK_MAXM * 9 + i]);
 }
 
 // The reference's arithmetic for one window starting at base offset p.
@@ -52,26 +54,29 @@ __device__ __forceinline__ void stage_exact(ExactTables* s, const double* __rest
 __device__ __forceinline__ bool exact_window(const GenomeView& g, const ExactTables* t, int m,
                                              long long p, bool revseq, double& f, double& r) {
     const uint64_t x = load_bases32(g, p);
+    const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
     const uint32_t maskm = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);
     const uint32_t amb = load_bits32(g.amb, g.cap_bases, p) & maskm;
     double fs = 0.0, rs = 0.0;
+    const int m_lo = m < 16 ? m : 16;
     if (amb == 0) {
-#pragma unroll 4
-        for (int j = 0; j < m; ++j) {
-            const int b = (int)((x >> (2 * j)) & 3);
-            fs += t->fwd[j * 4 + b];
-        }
         if (!revseq) {
 #pragma unroll 4
-            for (int j = 0; j < m; ++j) {
-                const int b = (int)((x >> (2 * j)) & 3);
-                rs += t->rc[j * 4 + b];
+            for (int j = 0; j < m_lo; ++j) {
+                const double2 v = t->fr[j * 4 + ((xl >> (2 * j)) & 3)];
+                fs += v.x; rs += v.y;
+            }
+#pragma unroll 4
+            for (int j = 16; j < m; ++j) {
+                const double2 v = t->fr[j * 4 + ((xh >> (2 * (j - 16))) & 3)];
+                fs += v.x; rs += v.y;
             }
         } else {
-#pragma unroll 4
             for (int j = 0; j < m; ++j) {
-                const int b = (int)((x >> (2 * (m - 1 - j))) & 3);
-                rs += t->fwd[j * 4 + (3 - b)];
+                const int b = (int)((x >> (2 * j)) & 3);
+                const int bq = (int)((x >> (2 * (m - 1 - j))) & 3);
+                fs += t->fr[j * 4 + b].x;
+                rs += t->fr[j * 4 + (3 - bq)].x;
             }
         }
         f = fs; r = rs;
@@ -80,18 +85,14 @@ __device__ __forceinline__ bool exact_window(const GenomeView& g, const ExactTab
     const uint32_t unk = amb | (load_bits32(g.lower, g.cap_bases, p) & maskm);
     for (int j = 0; j < m; ++j) {
         const int b = (int)((x >> (2 * j)) & 3);
-        fs += ((unk >> j) & 1u) ? t->mean_f[j] : t->fwd[j * 4 + b];
-    }
-    if (!revseq) {
-        for (int j = 0; j < m; ++j) {
-            const int b = (int)((x >> (2 * j)) & 3);
-            rs += ((unk >> j) & 1u) ? t->mean_r[j] : t->rc[j * 4 + b];
-        }
-    } else {
-        for (int j = 0; j < m; ++j) {
+        const bool u = (unk >> j) & 1u;
+        fs += u ? t->mean[j].x : t->fr[j * 4 + b].x;
+        if (!revseq) {
+            rs += u ? t->mean[j].y : t->fr[j * 4 + b].y;
+        } else {
             const int q = m - 1 - j;
-            const int b = (int)((x >> (2 * q)) & 3);
-            rs += ((unk >> q) & 1u) ? t->mean_f[j] : t->fwd[j * 4 + (3 - b)];
+            const int bq = (int)((x >> (2 * q)) & 3);
+            rs += ((unk >> q) & 1u) ? t->mean[j].x : t->fr[j * 4 + (3 - bq)].x;
         }
     }
     f = fs; r = rs;
@@ -103,12 +104,29 @@ __device__ __forceinline__ double softmax2_f64(double s, double r) {
     return log(exp2(s) + exp2(r)) / 0.6931471805599453094;
 }
 
-// sequence of tile -> (sequence index, local tile)
+// the same soft-max for float32 strand scores with a float32 tail:
+// max + log2(1 + 2^-(max - min)); |error| ~ 1e-7 (used where 1e-7 is ample: posteriors)
+__device__ __forceinline__ double softmax2_f32tail(float ff, float rf) {
+    const float mx = fmaxf(ff, rf), mn = fminf(ff, rf);
+    return (double)mx + (double)log2f(1.0f + exp2f(mn - mx));
+}
+
+// sequence of a tile: tile_prefix[k] <= tile < tile_prefix[k + 1]
 __device__ __forceinline__ int find_seq(const SeqTable& s, long long tile) {
-    int lo = 0, hi = s.n_seq;   // tile_prefix[lo] <= tile < tile_prefix[hi]
+    int lo = 0, hi = s.n_seq;
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (__ldg(s.tile_prefix + mid) <= tile) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// sequence holding packed offset gpos: off[k] <= gpos < off[k + 1]
+__device__ __forceinline__ int find_seq_by_offset(const SeqTable& s, long long gpos) {
+    int lo = 0, hi = s.n_seq;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(s.off + mid) <= gpos) lo = mid; else hi = mid;
     }
     return lo;
 }
@@ -135,4 +153,5 @@ __device__ __forceinline__ void block_reduce3(double& a, double& b, double& c, d
             c += __shfl_down_sync(0xffffffffu, c, o);
         }
     }
+    __syncthreads();
 }

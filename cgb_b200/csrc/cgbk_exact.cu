@@ -138,32 +138,78 @@ cudaError_t launch_score_windows(const cgbk_model* mdl, GenomeView g, const long
 // ---------------------------------------------------------------------------
 // posteriors: TFBindingModel.binding_probability (cgb/binding_model.py:94-113)
 // one warp per promoter region, warp-level sum over window positions
+//
+//   log(lh_bg) - log(lh_m) = -log(1 - alpha) - log1p(x),
+//   x = alpha/(1-alpha) * pdf_m/pdf_bg = c * exp((yb^2 - ym^2)/2),  c = alpha/(1-alpha) * std_bg/std_m
+// The ratio form needs one exp + one log1p per window instead of the two pdfs and two logs
+// of binding_model.py:106-112; it differs from the literal form only where a pdf underflows
+// to 0 (|z| > 38).  Windows whose x is below 1e-4 -- all but the rare high-scoring ones --
+// take a float32 path (|error| < 1e-9 per window).  With a score plane (PLANE) the window's
+// soft-max score comes from the stats scan (fixed point, |error| ~ 1e-6, harmless at
+// x < 1e-4: d term = x * 1.4 * d s); windows with x >= 1e-4 are re-scored exactly.
 // ---------------------------------------------------------------------------
+template <bool PLANE>
 __global__ void __launch_bounds__(256) posterior_kernel(
-    const double* __restrict__ d_exact, int m, GenomeView g, const long long* __restrict__ d_start,
-    const int* __restrict__ d_nwin, int n_regions, const double* __restrict__ ms_m,
-    const double* __restrict__ ms_bg, double p_motif, double alpha, double* __restrict__ post) {
+    const double* __restrict__ d_exact, int m, GenomeView g, SeqTable seqs, PlaneView pv,
+    const long long* __restrict__ d_start, const int* __restrict__ d_nwin, int n_regions,
+    const double* __restrict__ ms_m, const double* __restrict__ ms_bg, double p_motif, double alpha,
+    double* __restrict__ post) {
     __shared__ ExactTables tab;
     stage_exact(&tab, d_exact);
     __syncthreads();
     const double mu_m = ms_m[0], std_m = ms_m[1], mu_bg = ms_bg[0], std_bg = ms_bg[1];
-    const double norm_c = sqrt(2.0 * 3.141592653589793);     // scipy _norm_pdf_C
+    const double inv_std_m = 1.0 / std_m, inv_std_bg = 1.0 / std_bg;
+    const double c = alpha / (1 - alpha) * (std_bg / std_m);
+    const float cf = (float)c;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
+    const int stride = 32 * pv.L - 32;
     for (int reg = blockIdx.x * warps_per_block + (threadIdx.x >> 5); reg < n_regions;
          reg += gridDim.x * warps_per_block) {
         const long long start = __ldg(d_start + reg);
         const int nwin = __ldg(d_nwin + reg);
-        double acc = 0.0;
+        long long tile_r = 0;
+        int wt0 = 0;
+        if (PLANE) {
+            const int sq = find_seq_by_offset(seqs, start);
+            const long long x0 = start - __ldg(seqs.off + sq);
+            tile_r = x0 / stride;
+            wt0 = (int)(x0 - tile_r * stride);
+            tile_r += __ldg(seqs.tile_prefix + sq);
+        }
+        double acc = 0.0;       // sum of log1p(x_i)
         for (int w = lane; w < nwin; w += 32) {
-            double f, r;
-            exact_window(g, &tab, m, start + w, false, f, r);
-            const double s = softmax2_f64((double)(float)f, (double)(float)r);
-            const double ym = (s - mu_m) / std_m, yb = (s - mu_bg) / std_bg;
-            const double pdf_m = exp(-(ym * ym) / 2.0) / norm_c / std_m;
-            const double pdf_bg = exp(-(yb * yb) / 2.0) / norm_c / std_bg;
-            const double lh_m = alpha * pdf_m + (1 - alpha) * pdf_bg;
-            acc += log(pdf_bg) - log(lh_m);
+            double s;
+            if (PLANE) {
+                int wt = wt0 + w;
+                long long tile = tile_r;
+                while (wt >= stride) { wt -= stride; ++tile; }
+                s = (double)__ldg(pv.plane + plane_index(tile, wt, pv.L, pv.D)) * pv.inv_scale;
+            } else {
+                double f, r;
+                exact_window(g, &tab, m, start + w, false, f, r);
+                s = softmax2_f32tail((float)f, (float)r);      // Biopython's float32 strand scores
+            }
+            double ym = (s - mu_m) * inv_std_m, yb = (s - mu_bg) * inv_std_bg;
+            double e = 0.5 * (yb * yb - ym * ym);
+            const float ef = (float)e;
+            double term = 0.0;                                  // ef < -60: x < 1e-26
+            if (!(ef < -60.0f)) {
+                const float xf = cf * expf(ef);
+                if (xf < 1e-4f) {
+                    term = (double)log1pf(xf);
+                } else {
+                    if (PLANE) {
+                        double f, r;
+                        exact_window(g, &tab, m, start + w, false, f, r);
+                        s = softmax2_f32tail((float)f, (float)r);
+                        ym = (s - mu_m) * inv_std_m; yb = (s - mu_bg) * inv_std_bg;
+                        e = 0.5 * (yb * yb - ym * ym);
+                    }
+                    term = log1p(c * exp(e));
+                }
+            }
+            acc += term;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -172,7 +218,7 @@ __global__ void __launch_bounds__(256) posterior_kernel(
             if (nwin <= 0) {
                 res = nan("");      // the reference raises inside Biopython for len(seq) < m
             } else {
-                const double lh_ratio = exp(acc);
+                const double lh_ratio = exp(-(double)nwin * log1p(-alpha) - acc);
                 res = 1 / (1 + lh_ratio * (1 - p_motif) / p_motif);
             }
             post[reg] = res;
@@ -180,15 +226,19 @@ __global__ void __launch_bounds__(256) posterior_kernel(
     }
 }
 
-cudaError_t launch_posteriors(const cgbk_model* mdl, GenomeView g, const long long* d_start,
-                              const int* d_nwin, int n_regions, const double* d_ms_m,
-                              const double* d_ms_bg, double p_motif, double alpha, double* d_post,
-                              cudaStream_t st) {
+cudaError_t launch_posteriors(const cgbk_model* mdl, GenomeView g, SeqTable seqs, PlaneView pv,
+                              const long long* d_start, const int* d_nwin, int n_regions,
+                              const double* d_ms_m, const double* d_ms_bg, double p_motif,
+                              double alpha, double* d_post, cudaStream_t st) {
     if (n_regions <= 0) return cudaSuccess;
     int blocks = (n_regions + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    posterior_kernel<<<blocks, 256, 0, st>>>(mdl->d_exact, mdl->m, g, d_start, d_nwin, n_regions,
-                                            d_ms_m, d_ms_bg, p_motif, alpha, d_post);
+    if (pv.plane)
+        posterior_kernel<true><<<blocks, 256, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, pv, d_start, d_nwin,
+                                                      n_regions, d_ms_m, d_ms_bg, p_motif, alpha, d_post);
+    else
+        posterior_kernel<false><<<blocks, 256, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, pv, d_start, d_nwin,
+                                                       n_regions, d_ms_m, d_ms_bg, p_motif, alpha, d_post);
     return cudaGetLastError();
 }
 
@@ -275,56 +325,11 @@ cudaError_t launch_rescore(const cgbk_model* mdl, GenomeView g, SeqTable seqs, F
 }
 
 // ---------------------------------------------------------------------------
-// background statistics: dirty tiles (exact, ambiguity aware) and the final reduce
+// background statistics: dirty tiles (exact, ambiguity aware), then -- in the block that
+// finishes last -- the deterministic reduction of every per-block partial into d_stats
 // ---------------------------------------------------------------------------
-#define DIRTY_STATS_BLOCKS 148
-
-__global__ void __launch_bounds__(128) dirty_stats_kernel(const double* __restrict__ d_exact, int m,
-                                                          GenomeView g, SeqTable seqs, FastWork w,
-                                                          int L, double hist_lo, double inv_binw,
-                                                          int n_bins, unsigned long long* d_hist,
-                                                          int partial_base) {
-    __shared__ ExactTables tab;
-    __shared__ double scratch[96];
-    stage_exact(&tab, d_exact);
-    __syncthreads();
-    double s1 = 0.0, s2 = 0.0, cnt = 0.0;
-    const long long nd = w.counters[CGBK_CTR_DIRTY_TILES];
-    for (long long d = blockIdx.x; d < nd; d += gridDim.x) {
-        long long gbase, lo, hi;
-        tile_range(seqs, w.dirty_tiles[d], L, m, gbase, lo, hi);
-        for (long long x = lo + threadIdx.x; x < hi; x += blockDim.x) {
-            double f, r;
-            exact_window(g, &tab, m, gbase + x, false, f, r);
-            const double s = softmax2_f64((double)(float)f, (double)(float)r);
-            s1 += s; s2 += s * s; cnt += 1.0;
-            if (d_hist) {
-                int bin = (int)floor((s - hist_lo) * inv_binw);
-                bin = bin < 0 ? 0 : (bin >= n_bins ? n_bins - 1 : bin);
-                atomicAdd(d_hist + bin, 1ull);
-            }
-        }
-    }
-    block_reduce3(s1, s2, cnt, scratch);
-    if (threadIdx.x == 0) {
-        double* p = w.partials + 3ll * (partial_base + blockIdx.x);
-        p[0] = s1; p[1] = s2; p[2] = cnt;
-    }
-}
-
-cudaError_t launch_dirty_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
-                               int L, double hist_lo, double inv_binw, int n_bins,
-                               unsigned long long* d_hist, int partial_base, cudaStream_t st) {
-    dirty_stats_kernel<<<DIRTY_STATS_BLOCKS, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, w, L,
-                                                          hist_lo, inv_binw, n_bins, d_hist,
-                                                          partial_base);
-    return cudaGetLastError();
-}
-
-__global__ void __launch_bounds__(256) bg_finalize_kernel(const double* __restrict__ partials,
-                                                          int n_partials, double* stats,
-                                                          int accumulate) {
-    __shared__ double scratch[96];
+__device__ __forceinline__ void finalize_stats(const double* __restrict__ partials, int n_partials,
+                                               double* stats, int accumulate, double* scratch) {
     double s1 = 0.0, s2 = 0.0, cnt = 0.0;
     for (int i = threadIdx.x; i < n_partials; i += blockDim.x) {
         s1 += partials[3 * i]; s2 += partials[3 * i + 1]; cnt += partials[3 * i + 2];
@@ -341,6 +346,67 @@ __global__ void __launch_bounds__(256) bg_finalize_kernel(const double* __restri
         stats[CGBK_BG_MEAN] = mean;
         stats[CGBK_BG_STD] = sqrt(var);
     }
+}
+
+__global__ void __launch_bounds__(128) dirty_stats_kernel(const double* __restrict__ d_exact, int m,
+                                                          GenomeView g, SeqTable seqs, FastWork w,
+                                                          int L, int D, double hist_lo, double inv_binw,
+                                                          StatsParams sp, int partial_base,
+                                                          int n_partials, double* d_stats) {
+    __shared__ ExactTables tab;
+    __shared__ double scratch[96];
+    __shared__ int is_last;
+    stage_exact(&tab, d_exact);
+    __syncthreads();
+    double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+    const long long nd = w.counters[CGBK_CTR_DIRTY_TILES];
+    for (long long d = blockIdx.x; d < nd; d += gridDim.x) {
+        long long gbase, lo, hi;
+        const unsigned int tile = w.dirty_tiles[d];
+        tile_range(seqs, tile, L, m, gbase, lo, hi);
+        for (long long x = lo + threadIdx.x; x < hi; x += blockDim.x) {
+            double f, r;
+            exact_window(g, &tab, m, gbase + x, false, f, r);
+            const double s = softmax2_f64((double)(float)f, (double)(float)r);
+            s1 += s; s2 += s * s; cnt += 1.0;
+            if (sp.d_hist) {
+                int bin = (int)floor((s - hist_lo) * inv_binw);
+                bin = bin < 0 ? 0 : (bin >= sp.n_bins ? sp.n_bins - 1 : bin);
+                atomicAdd(sp.d_hist + bin, 1ull);
+            }
+            if (sp.plane) sp.plane[plane_index(tile, (int)(x - lo), L, D)] = (int)llrint(s * (double)sp.scale);
+        }
+    }
+    block_reduce3(s1, s2, cnt, scratch);
+    if (threadIdx.x == 0) {
+        double* p = w.partials + 3ll * (partial_base + blockIdx.x);
+        p[0] = s1; p[1] = s2; p[2] = cnt;
+        __threadfence();
+        const unsigned long long done =
+            atomicAdd(reinterpret_cast<unsigned long long*>(w.counters + CGBK_CTR_INTERNAL_DONE), 1ull);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        finalize_stats(w.partials, n_partials, d_stats, 1, scratch);
+    }
+}
+
+cudaError_t launch_dirty_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
+                               int L, double hist_lo, double inv_binw, const StatsParams& sp,
+                               int partial_base, int n_partials, double* d_stats, cudaStream_t st) {
+    dirty_stats_kernel<<<CGBK_DIRTY_STATS_BLOCKS, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, w, L,
+                                                               4 * (mdl->G - 1), hist_lo, inv_binw, sp,
+                                                               partial_base, n_partials, d_stats);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) bg_finalize_kernel(const double* __restrict__ partials,
+                                                          int n_partials, double* stats,
+                                                          int accumulate) {
+    __shared__ double scratch[96];
+    finalize_stats(partials, n_partials, stats, accumulate, scratch);
 }
 
 cudaError_t launch_bg_finalize(const double* partials, int n_partials, double* d_stats,

@@ -16,20 +16,36 @@
 //    the fully unrolled 32-position body, so the window slides through registers;
 //  * shared-memory tables are replicated per bank group (8 copies of each 16-byte
 //    chunk, 16 of an 8-byte chunk, 32 of a 4-byte one), so the random 4-mer lookups
-//    of a warp never bank-conflict: every chunk costs exactly 128 B/lane-group of
-//    crossbar bandwidth, the LSU floor;
-//  * windows that straddle two lanes are finished with warp shuffles: the first
-//    D = 4(G-1) positions of a lane also accumulate the tail of the previous lane's
-//    windows, and those partial sums are handed back with __shfl_down_sync;
+//    of a warp never bank-conflict: every chunk costs exactly one 128-byte crossbar
+//    pass per 8/16/32 lanes, the LSU floor;
+//  * windows that straddle two lanes: the first D = 4(G-1) positions of a lane also
+//    accumulate the tail of the previous lane's windows; those partial sums are
+//    parked in a per-warp shared-memory strip and picked up by the previous lane
+//    when its own segment is done (lane 31's tail belongs to the next tile, which
+//    starts 32 positions early);
+//  * the unrolled body is branch-free (window validity is a select, not a branch) so
+//    that ptxas can hoist the next position's LDS above the current window's epilogue;
 //  * MODE 0 ("filter"): both strands ride in one 32-bit word as two biased 16-bit
-//    deficits; a window whose score could reach the threshold has bit 15 / bit 31
+//    surpluses; a window whose score could reach the threshold has bit 15 / bit 31
 //    set, so the per-window test is one LOP3.  Candidates go to cgbk_exact.cu for
 //    float64 re-scoring in the reference's order (bit-exact hit lists);
-//  * MODE 1 ("stats"): int32 fixed point per strand, soft-max log2(2^f + 2^r) on the
-//    MUFU unit, per-block shared-memory histogram + float64 moments;
+//  * MODE 1 ("stats"): int32 fixed point (2^-kexp) per strand, soft-max
+//    log2(2^f + 2^r) = max + log2(1 + 2^-|f-r|) on the MUFU unit, per-block
+//    shared-memory histogram, and integer moments (sum d, sum d^2 of the score
+//    re-centred and rounded to 2^-18: order independent, hence deterministic).
+//    Optionally every window's fixed-point soft-max score is written to a "score
+//    plane" laid out [tile][row][lane] so that each position is one coalesced 128-byte
+//    store; cgbk_posteriors reads it back instead of re-scoring the promoters;
 //  * tiles that contain a byte outside ACGTacgt are not scored here: their ids are
 //    appended to a list the exact kernels walk (ambiguity repair, pssm_model.py:88-101).
 #include "cgbk_device.cuh"
+
+#ifndef CGBK_STATS_THREADS
+#define CGBK_STATS_THREADS 512
+#endif
+#ifndef CGBK_FILTER_THREADS
+#define CGBK_FILTER_THREADS 640
+#endif
 
 template <int NW>
 struct TableLayout {
@@ -40,16 +56,27 @@ struct TableLayout {
     static constexpr int BYTES = NCH * 32768;
 };
 
+// Global tables arrive chunk-major (see chunked_layout() in cgbk_api.cu): all 16-byte
+// chunks [c][e][4 words], then the 8-byte chunk [e][2], then the 4-byte chunk [e].
+// Eight consecutive lanes write the eight 16-byte replicas of one chunk entry (one
+// conflict-free 128-byte row); the global read of the entry is a broadcast.
 template <int NW>
-__device__ __forceinline__ void fill_tables(uint32_t* smem_words, const uint32_t* __restrict__ gtab) {
+__device__ __forceinline__ void fill_tables(unsigned char* smem, const uint32_t* __restrict__ gtab) {
     using TL = TableLayout<NW>;
-    for (int w = threadIdx.x; w < TL::NCH * 8192; w += blockDim.x) {
-        const int chunk = w >> 13, rem = w & 8191, e = rem >> 5, slot = rem & 31;
-        int k;
-        if (chunk < TL::N16) k = chunk * 4 + (slot & 3);
-        else if (TL::HAS8 && chunk == TL::N16) k = TL::N16 * 4 + (slot & 1);
-        else k = NW - 1;
-        smem_words[w] = __ldg(gtab + e * NW + k);
+    for (int i = threadIdx.x; i < TL::NCH * 256 * 8; i += blockDim.x) {
+        const int ce = i >> 3, r = i & 7;
+        const int c = ce >> 8, e = ce & 255;
+        uint4 v;
+        if (c < TL::N16) {
+            v = __ldg(reinterpret_cast<const uint4*>(gtab) + c * 256 + e);
+        } else if (TL::HAS8 && c == TL::N16) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(gtab + TL::N16 * 1024) + e);
+            v = make_uint4(q.x, q.y, q.x, q.y);
+        } else {
+            const uint32_t q = __ldg(gtab + TL::N16 * 1024 + TL::HAS8 * 512 + e);
+            v = make_uint4(q, q, q, q);
+        }
+        *reinterpret_cast<uint4*>(smem + ce * 128 + r * 16) = v;
     }
 }
 
@@ -82,13 +109,16 @@ __device__ __forceinline__ uint32_t kmer_addr(int t, uint32_t w0, uint32_t w1, u
     return x & 0x7f80u;
 }
 
-struct StatsParams {
-    float inv_scale_f;     // 2^-kexp
-    double inv_scale_d;
-    float hist_lo, inv_binw;
-    int n_bins;
-    unsigned long long* d_hist;
-};
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ uint2 ld_stream2(const uint32_t* __restrict__ b2, long long wi, long long nw) {
     if (wi + 1 < nw) return __ldg(reinterpret_cast<const uint2*>(b2 + wi));
@@ -97,50 +127,73 @@ __device__ __forceinline__ uint2 ld_stream2(const uint32_t* __restrict__ b2, lon
 
 template <int G, int MODE>
 struct FastCfg {
-    static constexpr int THREADS = MODE == 0 ? 512 : (G <= 6 ? 384 : 256);
+    static constexpr int THREADS = MODE == 0 ? CGBK_FILTER_THREADS : (G <= 6 ? CGBK_STATS_THREADS : 256);
+    static constexpr int NW = MODE == 0 ? G : 2 * G;
+    static constexpr int D = 4 * (G - 1);
+    static constexpr int STASH_BYTES = (THREADS / 32) * D * 33 * (MODE == 0 ? 4 : 8);
 };
 
-template <int G, int MODE>
+template <int G, int MODE, bool ONE>
 __global__ void __launch_bounds__((FastCfg<G, MODE>::THREADS), 1)
 fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs, FastWork work, int m,
                  int B, StatsParams sp) {
-    constexpr int NW = MODE == 0 ? G : 2 * G;
-    constexpr int D = 4 * (G - 1);
-    constexpr int DD = D > 0 ? D : 1;
+    using Cfg = FastCfg<G, MODE>;
+    constexpr int NW = Cfg::NW;
+    constexpr int D = Cfg::D;
     using TL = TableLayout<NW>;
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned int* hist = reinterpret_cast<unsigned int*>(smem + TL::BYTES);
+    unsigned char* stash_base = smem + TL::BYTES;
+    unsigned int* hist = reinterpret_cast<unsigned int*>(smem + TL::BYTES + Cfg::STASH_BYTES);
     __shared__ double red_scratch[96];
 
-    fill_tables<NW>(reinterpret_cast<uint32_t*>(smem), gtab);
+    fill_tables<NW>(smem, gtab);
     if (MODE == 1)
-        for (int i = threadIdx.x; i < sp.n_bins; i += blockDim.x) hist[i] = 0u;
+        for (int i = threadIdx.x; i <= sp.n_bins; i += blockDim.x) hist[i] = 0u;   // [n_bins] = discard bin
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const uint32_t o16 = (lane & 7) << 4, o8 = (lane & 15) << 3, o4 = lane << 2;
+    if (ONE) B = 1;
     const int L = 32 * B;
-    const long long stride = 32ll * L - 32;
+    const int stride = 32 * L - 32;
     const long long nwords = g.cap_bases >> 4;
-    double s1 = 0.0, s2 = 0.0;
-    unsigned int cnt = 0;
+    // per-warp strip for the partial sums handed to the previous lane: [D][33]
+    uint32_t* stash32 = reinterpret_cast<uint32_t*>(stash_base) + warp * (D * 33) + lane;
+    uint2* stash64 = reinterpret_cast<uint2*>(stash_base) + warp * (D * 33) + lane;
+    const int n_bins = sp.n_bins, last_bin = sp.n_bins - 1;
+
+    long long sum_d = 0;          // exact integer sum of re-centred scores (2^-18 units)
+    double sum_d2 = 0.0;          // sum of their squares
+    long long cnt = 0;
 
     for (long long tile = (long long)blockIdx.x * wpb + warp; tile < seqs.n_tiles;
          tile += (long long)gridDim.x * wpb) {
-        const int sq = find_seq(seqs, tile);
-        const long long A = (tile - __ldg(seqs.tile_prefix + sq)) * stride;
-        const long long nwin = __ldg(seqs.len + sq) - m + 1;
-        const long long own_hi = A + stride < nwin ? A + stride : nwin;
-        const long long gbase = __ldg(seqs.off + sq);
-        const long long S = A + (long long)lane * L;           // local start of this lane's segment
+        long long gbase, seq_len, tile0;
+        if (seqs.n_seq <= CGBK_INLINE_SEQS) {
+            int sq = 0;
+#pragma unroll
+            for (int i = 1; i < CGBK_INLINE_SEQS; ++i)
+                if (i < seqs.n_seq && seqs.prefix_v[i] <= tile) sq = i;
+            gbase = seqs.off_v[sq]; seq_len = seqs.len_v[sq]; tile0 = seqs.prefix_v[sq];
+        } else {
+            const int sq = find_seq(seqs, tile);
+            gbase = __ldg(seqs.off + sq); seq_len = __ldg(seqs.len + sq); tile0 = __ldg(seqs.tile_prefix + sq);
+        }
+        const long long A = (tile - tile0) * stride;
+        const long long rem = seq_len - m + 1 - A;            // valid windows from A on
+        const int own_n = rem < stride ? (int)rem : stride;   // this tile owns windows [A, A + own_n)
+        const int S = lane * L;                               // tile-local start of this lane's segment
+        const long long wbase = (gbase + A + S) >> 4;
 
-        // tiles touching a non-ACGT byte go to the exact kernels
+        // issue the independent loads of the tile together: ambiguity words + first stream words
         uint32_t any_amb = 0;
         {
-            const long long aw = (gbase + S) >> 5, naw = g.cap_bases >> 5;
+            const long long aw = (gbase + A + S) >> 5, naw = g.cap_bases >> 5;
             for (int b = 0; b < B; ++b) any_amb |= ldw(g.amb, aw + b, naw);
         }
+        uint2 cur = ld_stream2(g.bases2, wbase, nwords);
         if (__any_sync(0xffffffffu, any_amb != 0)) {
+            // tiles touching a non-ACGT byte go to the exact kernels
             if (lane == 0) {
                 const unsigned long long k = atomicAdd(
                     reinterpret_cast<unsigned long long*>(work.counters + CGBK_CTR_DIRTY_TILES), 1ull);
@@ -149,21 +202,23 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
             continue;
         }
 
-        uint32_t sa[32], sb[32], outa[DD], outb[DD];
+        uint32_t sa[32], sb[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) { sa[i] = 0u; sb[i] = 0u; }
-#pragma unroll
-        for (int i = 0; i < DD; ++i) { outa[i] = 0u; outb[i] = 0u; }
+        int acc_d = 0;                 // per-body integer sum (MODE 1)
+        long long acc_d2 = 0;          // per-tile integer sum of squares (MODE 1)
+        // score plane rows of this tile: [(B + 1) * 32][32] ints, row = body*32 + t (last: the tail)
+        int* prow = sp.plane ? sp.plane + tile * (long long)((B + 1) * 1024) + lane : nullptr;
 
-        // one completed window: accumulators (a, b), local window index wl
-        auto complete = [&](uint32_t a, uint32_t b, long long wl) {
+        // one completed window: accumulators (a, b), tile-local window index wt, plane row
+        auto complete = [&](uint32_t a, uint32_t b, int wt, bool live, int row) {
             if (MODE == 0) {
-                if (a & 0x80008000u) {
-                    if (wl < own_hi) {
+                if (a & 0x80008000u) {        // rare: out-of-line
+                    if (live && wt < own_n) {
                         const unsigned long long k = atomicAdd(
                             reinterpret_cast<unsigned long long*>(work.counters + CGBK_CTR_CANDIDATES), 1ull);
                         if ((long long)k < work.cand_cap)
-                            work.cands[k] = (unsigned long long)(gbase + wl) |
+                            work.cands[k] = (unsigned long long)(gbase + A + wt) |
                                             ((unsigned long long)(a >> 31) << 63) |
                                             ((unsigned long long)((a >> 15) & 1u) << 62);
                     }
@@ -171,29 +226,26 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
             } else {
                 const int fq = (int)a, rq = (int)b;
                 const int mx = max(fq, rq), mn = min(fq, rq);
-                const float dq = (float)(mx - mn);
-                const float u = exp2f(-dq * sp.inv_scale_f);
-                const float lg = __log2f(1.0f + u);
-                const float sF = fmaf((float)mx, sp.inv_scale_f, lg);
-                int bin = __float2int_rd((sF - sp.hist_lo) * sp.inv_binw);
-                bin = min(max(bin, 0), sp.n_bins - 1);
-                const double sD = fma((double)mx, sp.inv_scale_d, (double)lg);
-                if (wl < own_hi) {
-                    atomicAdd(hist + bin, 1u);
-                    s1 += sD;
-                    s2 = fma(sD, sD, s2);
-                    cnt += 1u;
-                }
+                const float u = ex2_approx((float)(mx - mn) * sp.neg_inv_scale);     // 2^-|f-r|
+                const float lg = lg2_approx(1.0f + u);
+                const int sfix = mx + __float2int_rn(lg * sp.scale);                 // soft-max, fixed point
+                const bool valid = live && (wt < own_n);
+                int bin = min((int)__umulhi((unsigned)max(sfix - sp.lo_fix, 0), sp.bin_mul), last_bin);
+                bin = valid ? bin : n_bins;
+                int dq = (sfix - sp.c_fix + sp.half) >> sp.sh;
+                dq = valid ? dq : 0;
+                atomicAdd(hist + bin, 1u);
+                acc_d += dq;
+                acc_d2 += (long long)dq * dq;
+                if (prow) prow[row * 32] = sfix;
             }
         };
 
-        const long long wbase = (gbase + S) >> 4;
-        uint2 cur = ld_stream2(g.bases2, wbase, nwords);
         for (int b = 0; b < B; ++b) {
             const uint2 nxt = ld_stream2(g.bases2, wbase + 2 * (b + 1), nwords);
             const uint32_t w0 = cur.x, w1 = cur.y, w2 = nxt.x;
-            const long long Sb = S + 32ll * b;
-            const bool first = (b == 0);
+            const int Sb = S + 32 * b;
+            const bool first = ONE || (b == 0);
 #pragma unroll
             for (int t = 0; t < 32; ++t) {
                 const uint32_t E = kmer_addr(t, w0, w1, w2);
@@ -211,22 +263,42 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 }
                 const int sc = (t - D) & 31;
                 if (t < D) {
-                    if (first) { outa[t] = sa[sc]; outb[t] = sb[sc]; }
-                    else complete(sa[sc], sb[sc], Sb + t - D);
+                    // first body: partial sums of the PREVIOUS lane's last D windows -> strip;
+                    // later bodies: a window that started in the previous body completes
+                    if (first) {
+                        if (MODE == 0) stash32[t * 33] = sa[sc];
+                        else stash64[t * 33] = make_uint2(sa[sc], sb[sc]);
+                    }
+                    if (!ONE) complete(sa[sc], sb[sc], Sb + t - D, !first, b * 32 + t);
                 } else {
-                    complete(sa[sc], sb[sc], Sb + t - D);
+                    complete(sa[sc], sb[sc], Sb + t - D, true, b * 32 + t);
                 }
             }
             cur = nxt;
+            if (MODE == 1) { sum_d += acc_d; acc_d = 0; }
         }
-        // windows straddling into the next lane: fetch the partial sums it accumulated
+        // windows straddling into the next lane: add the partial sums it parked for us
+        if (D > 0) {
+            __syncwarp();
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            const int si = (32 - D + j) & 31;
-            const uint32_t ia = __shfl_down_sync(0xffffffffu, outa[j], 1);
-            uint32_t ib = 0u;
-            if (MODE == 1) ib = __shfl_down_sync(0xffffffffu, outb[j], 1);
-            complete(sa[si] + ia, sb[si] + ib, S + L - D + j);
+            for (int j = 0; j < D; ++j) {
+                const int si = (32 - D + j) & 31;
+                uint32_t ia, ib = 0u;
+                if (MODE == 0) {
+                    ia = stash32[j * 33 + 1];
+                } else {
+                    const uint2 q = stash64[j * 33 + 1];
+                    ia = q.x; ib = q.y;
+                }
+                complete(sa[si] + ia, sb[si] + ib, S + L - D + j, true, B * 32 + j);
+            }
+            __syncwarp();
+        }
+        if (MODE == 1) {
+            sum_d += acc_d;
+            sum_d2 += (double)acc_d2;
+            const int mine = own_n - S;
+            cnt += mine < 0 ? 0 : (mine > L ? L : mine);
         }
     }
 
@@ -235,52 +307,56 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         if (sp.d_hist)
             for (int i = threadIdx.x; i < sp.n_bins; i += blockDim.x)
                 if (hist[i]) atomicAdd(sp.d_hist + i, (unsigned long long)hist[i]);
-        double c = (double)cnt;
-        block_reduce3(s1, s2, c, red_scratch);
+        // block totals: n, sum d (exact in double up to 2^53), sum d^2
+        double a = (double)sum_d, b2 = sum_d2, c = (double)cnt;
+        block_reduce3(a, b2, c, red_scratch);
         if (threadIdx.x == 0) {
+            // s_i = centre + d_i * q  ->  raw moments
+            const double q = sp.q;
             double* p = work.partials + 3ll * blockIdx.x;
-            p[0] = s1; p[1] = s2; p[2] = c;
+            p[0] = c * sp.c + a * q;
+            p[1] = c * sp.c * sp.c + 2.0 * sp.c * q * a + q * q * b2;
+            p[2] = c;
         }
     }
 }
 
-template <int G, int MODE>
+template <int G, int MODE, bool ONE>
 static cudaError_t launch_one(const uint32_t* gtab, GenomeView g, SeqTable seqs, FastWork w, int m, int L,
                               int grid, StatsParams sp, cudaStream_t st) {
-    constexpr int NW = MODE == 0 ? G : 2 * G;
-    const int threads = FastCfg<G, MODE>::THREADS;
-    const size_t smem = TableLayout<NW>::BYTES + (MODE == 1 ? (size_t)sp.n_bins * 4 : 0);
-    static bool configured[2] = {false, false};   // per template instance
-    auto kern = fast_scan_kernel<G, MODE>;
-    if (!configured[0]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             TableLayout<NW>::BYTES + CGBK_MAX_HIST_BINS * 4);
+    using Cfg = FastCfg<G, MODE>;
+    const size_t fixed = TableLayout<Cfg::NW>::BYTES + Cfg::STASH_BYTES;
+    const size_t smem_max = fixed + (MODE == 1 ? (CGBK_MAX_HIST_BINS + 1) * 4 : 0);
+    const size_t smem = fixed + (MODE == 1 ? ((size_t)sp.n_bins + 1) * 4 : 0);
+    static bool configured = false;   // per template instance
+    auto kern = fast_scan_kernel<G, MODE, ONE>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return e;
-        configured[0] = true;
+        configured = true;
     }
-    kern<<<grid, threads, smem, st>>>(gtab, g, seqs, w, m, L / 32, sp);
+    kern<<<grid, Cfg::THREADS, smem, st>>>(gtab, g, seqs, w, m, L / 32, sp);
     return cudaGetLastError();
 }
 
 template <int MODE>
 static cudaError_t dispatch(int G, const uint32_t* gtab, GenomeView g, SeqTable seqs, FastWork w, int m,
                             int L, int grid, StatsParams sp, cudaStream_t st) {
+#define CGBK_CASE(GG)                                                                               \
+    case GG:                                                                                        \
+        return L == 32 ? launch_one<GG, MODE, true>(gtab, g, seqs, w, m, L, grid, sp, st)           \
+                       : launch_one<GG, MODE, false>(gtab, g, seqs, w, m, L, grid, sp, st);
     switch (G) {
-        case 1: return launch_one<1, MODE>(gtab, g, seqs, w, m, L, grid, sp, st);
-        case 2: return launch_one<2, MODE>(gtab, g, seqs, w, m, L, grid, sp, st);
-        case 3: return launch_one<3, MODE>(gtab, g, seqs, w, m, L, grid, sp, st);
-        case 4: return launch_one<4, MODE>(gtab, g, seqs, w, m, L, grid, sp, st);
-        case 5: return launch_one<5, MODE>(gtab, g, seqs, w, m, L, grid, sp, st);
-        case 6: return launch_one<6, MODE>(gtab, g, seqs, w, m, L, grid, sp, st);
-        case 7: return launch_one<7, MODE>(gtab, g, seqs, w, m, L, grid, sp, st);
-        case 8: return launch_one<8, MODE>(gtab, g, seqs, w, m, L, grid, sp, st);
+        CGBK_CASE(1) CGBK_CASE(2) CGBK_CASE(3) CGBK_CASE(4)
+        CGBK_CASE(5) CGBK_CASE(6) CGBK_CASE(7) CGBK_CASE(8)
         default: return cudaErrorInvalidValue;
     }
+#undef CGBK_CASE
 }
 
 int fast_threads(int G, int mode) {
-    if (mode == 0) return 512;
-    return G <= 6 ? 384 : 256;
+    if (mode == 0) return CGBK_FILTER_THREADS;
+    return G <= 6 ? CGBK_STATS_THREADS : 256;
 }
 
 cudaError_t launch_fast_filter(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, int L,
@@ -289,15 +365,31 @@ cudaError_t launch_fast_filter(const cgbk_model* mdl, GenomeView g, SeqTable seq
     return dispatch<0>(mdl->G, mdl->d_coarse, g, seqs, w, mdl->m, L, grid, sp, st);
 }
 
-cudaError_t launch_fast_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, int L,
-                              int grid, double hist_lo, double inv_binw, int n_bins,
-                              unsigned long long* d_hist, cudaStream_t st) {
+StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist_hi, int n_bins,
+                              unsigned long long* d_hist, int* plane) {
     StatsParams sp;
-    sp.inv_scale_d = ldexp(1.0, -mdl->kexp);
-    sp.inv_scale_f = (float)sp.inv_scale_d;
-    sp.hist_lo = (float)hist_lo;
-    sp.inv_binw = (float)inv_binw;
+    const double scale = ldexp(1.0, mdl->kexp);
+    sp.neg_inv_scale = (float)(-1.0 / scale);
+    sp.scale = (float)scale;
+    sp.inv_scale_d = 1.0 / scale;
+    sp.lo_fix = (int)llrint(hist_lo * scale);
+    const double range_fix = (hist_hi - hist_lo) * scale;
+    double mul = 4294967296.0 * (double)n_bins / range_fix;
+    if (mul > 4294967295.0) mul = 4294967295.0;
+    sp.bin_mul = (unsigned int)mul;
     sp.n_bins = n_bins;
+    const double centre = 0.5 * (mdl->min_score + mdl->max_score);
+    sp.c_fix = (int)llrint(centre * scale);
+    sp.c = (double)sp.c_fix / scale;
+    sp.sh = mdl->kexp > 18 ? mdl->kexp - 18 : 0;
+    sp.half = sp.sh > 0 ? (1 << (sp.sh - 1)) : 0;
+    sp.q = ldexp(1.0, -(mdl->kexp - sp.sh));
     sp.d_hist = d_hist;
+    sp.plane = plane;
+    return sp;
+}
+
+cudaError_t launch_fast_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, int L,
+                              int grid, const StatsParams& sp, cudaStream_t st) {
     return dispatch<1>(mdl->G, mdl->d_precise, g, seqs, w, mdl->m, L, grid, sp, st);
 }

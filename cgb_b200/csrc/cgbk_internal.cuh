@@ -42,6 +42,7 @@ struct cgbk_seqset {
     // tile prefix tables are built per (m, lane segment) on demand and cached
     int cached_m, cached_L;
     int64_t* d_tile_prefix;  // [n_seq + 1]
+    int64_t* h_tile_prefix;  // [n_seq + 1] (staging for the async upload; inline copy source)
     int64_t n_tiles;
 };
 
@@ -54,12 +55,19 @@ struct GenomeView {
     long long cap_bases;
 };
 
+#define CGBK_CTR_INTERNAL_DONE 3   // blocks of the dirty-stats kernel that have finished
+#define CGBK_INLINE_SEQS 4   // sequence tables this small travel by value in the kernel parameters
+
 struct SeqTable {
     const long long* off;
     const long long* len;
     const long long* tile_prefix;
     int n_seq;
     long long n_tiles;
+    // copies for n_seq <= CGBK_INLINE_SEQS (constant-bank reads instead of global loads)
+    long long off_v[CGBK_INLINE_SEQS];
+    long long len_v[CGBK_INLINE_SEQS];
+    long long prefix_v[CGBK_INLINE_SEQS];
 };
 
 // per-thread error text + status helpers (cgbk_api.cu)
@@ -69,6 +77,8 @@ int cgbk_check_cuda(cudaError_t e, const char* what);
 // ---------------------------------------------------------------------------
 // launchers implemented in the kernel translation units
 // ---------------------------------------------------------------------------
+struct StatsParams;
+
 struct FastWork {      // carved out of the caller's workspace
     long long* counters;        // CGBK_CTR_COUNT
     unsigned int* dirty_tiles;  // n_tiles entries
@@ -86,27 +96,67 @@ cudaError_t launch_score_windows(const cgbk_model* mdl, GenomeView g, const long
                                  int flags, float* f32, float* r32, double* both, double* f64,
                                  double* r64, cudaStream_t st);
 
-cudaError_t launch_posteriors(const cgbk_model* mdl, GenomeView g, const long long* d_start,
-                              const int* d_nwin, int n_regions, const double* d_ms_m,
-                              const double* d_ms_bg, double p_motif, double alpha, double* d_post,
-                              cudaStream_t st);
+// score plane as the posterior kernel reads it (plane == nullptr: re-score every window)
+struct PlaneView {
+    const int* plane;
+    int L;              // lane segment of the tiling the plane was written with
+    int D;              // 4 * (G - 1)
+    double inv_scale;   // 2^-kexp
+};
+
+cudaError_t launch_posteriors(const cgbk_model* mdl, GenomeView g, SeqTable seqs, PlaneView pv,
+                              const long long* d_start, const int* d_nwin, int n_regions,
+                              const double* d_ms_m, const double* d_ms_bg, double p_motif,
+                              double alpha, double* d_post, cudaStream_t st);
 
 cudaError_t launch_rescore(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
                            double thr, int flags, cgbk_hit* hits, long long hit_cap, int L,
                            cudaStream_t st);
 
+// exact scoring of the dirty tiles of a stats scan, then (last block done) the reduction of
+// all per-block partial moments [0, n_partials) into d_stats
 cudaError_t launch_dirty_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
-                               int L, double hist_lo, double inv_binw, int n_bins,
-                               unsigned long long* d_hist, int partial_base, cudaStream_t st);
+                               int L, double hist_lo, double inv_binw, const StatsParams& sp,
+                               int partial_base, int n_partials, double* d_stats, cudaStream_t st);
 
 cudaError_t launch_bg_finalize(const double* partials, int n_partials, double* d_stats,
                                int accumulate, cudaStream_t st);
 
+#define CGBK_DIRTY_STATS_BLOCKS 148
+
 cudaError_t launch_fast_filter(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
                                int L, int grid, cudaStream_t st);
 
+// parameters of the soft-max / histogram / moment epilogue of the stats scan
+struct StatsParams {
+    float neg_inv_scale;   // -2^-kexp
+    float scale;           // 2^kexp
+    double inv_scale_d;    // 2^-kexp
+    int lo_fix;            // histogram lower edge, fixed point
+    unsigned int bin_mul;  // floor(2^32 * n_bins / range_fix)
+    int n_bins;
+    int c_fix;             // moment centre, fixed point
+    int sh;                // kexp - 18: moment rounding shift
+    int half;              // 1 << (sh - 1) (0 when sh == 0)
+    double c;              // centre in score units
+    double q;              // moment unit in score units: 2^-(kexp - sh)
+    unsigned long long* d_hist;
+    int* plane;            // optional score plane [tile][(B + 1) * 32 rows][32 lanes]
+};
+
+StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist_hi, int n_bins,
+                              unsigned long long* d_hist, int* plane);
+
 cudaError_t launch_fast_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
-                              int L, int grid, double hist_lo, double inv_binw, int n_bins,
-                              unsigned long long* d_hist, cudaStream_t st);
+                              int L, int grid, const StatsParams& sp, cudaStream_t st);
+
+// score plane addressing shared by the writers (cgbk_fast.cu, dirty tiles) and the reader
+// (posteriors): window wt of a tile with lane segment L = 32 * B and overlap D = 4 * (G - 1)
+__host__ __device__ inline long long plane_index(long long tile, int wt, int L, int D) {
+    const int B = L >> 5;
+    const int lane = wt / L, within = wt - lane * L;
+    const int row = within < L - D ? within + D : B * 32 + (within - (L - D));
+    return tile * (long long)((B + 1) * 1024) + row * 32 + lane;
+}
 
 int fast_threads(int G, int mode);

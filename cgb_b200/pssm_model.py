@@ -253,12 +253,15 @@ class PSSMModel(TFBindingModel):
         return seq[order], pos[order], strand[order], score[order]
 
     def background_stats(self, genome, n_bins=1024, hist_lo=None, hist_hi=None, accumulate_into=None,
-                         out=None):
+                         out=None, keep_scores=False):
         """Soft-max score distribution over ALL windows of ``genome`` (both strands
         combined as in score_seq): returns a dict with device tensors ``stats``
         (float64[8]: n, sum, sumsq, mean, std) and ``hist`` (int64[n_bins]) plus the
         bin range.  ``accumulate_into``: a previous result to add this genome to;
         ``out``: a previous result whose buffers are overwritten (no allocation).
+        ``keep_scores``: also keep every window's soft-max score on the device (the
+        "score plane", ~8 bytes per base) so that ``binding_probabilities`` on the
+        same genome does not re-score the promoters.
         No host synchronisation happens here."""
         model = self._model()
         m = self.length
@@ -267,9 +270,11 @@ class PSSMModel(TFBindingModel):
             hist_lo = math.floor(self.pssm.min)
         if hist_hi is None:
             hist_hi = math.ceil(self.pssm.max) + 1.0       # soft-max <= max + 1
+        plane = None
         if out is not None:
             stats, hist, acc = out["stats"], out["hist"], 0
             n_bins = int(hist.numel())
+            plane = out.get("plane") if out.get("genome") is genome else None
         elif accumulate_into is None:
             stats = torch.zeros(_cabi.BG_COUNT, dtype=torch.float64, device=dev)
             hist = torch.zeros(n_bins, dtype=torch.int64, device=dev)
@@ -277,20 +282,30 @@ class PSSMModel(TFBindingModel):
         else:
             stats, hist = accumulate_into["stats"], accumulate_into["hist"]
             acc = 1
+        if keep_scores and plane is None:
+            n_ints = int(_cabi.lib().cgbk_score_plane_ints(genome.seqset, m))
+            plane = torch.empty(max(n_ints, 1), dtype=torch.int32, device=dev)
+        if not keep_scores:
+            plane = None
         work = genome.workspace(m, 0)
         _cabi.check(_cabi.lib().cgbk_background_stats(
             model, genome.struct_ref(), genome.seqset, float(hist_lo), float(hist_hi), int(n_bins),
-            hist.data_ptr(), stats.data_ptr(), acc, work.data_ptr(), work.numel(), self._stream()))
+            hist.data_ptr(), stats.data_ptr(), acc,
+            plane.data_ptr() if plane is not None else None, int(plane.numel()) if plane is not None else 0,
+            work.data_ptr(), work.numel(), self._stream()))
         return {"stats": stats, "hist": hist, "hist_lo": float(hist_lo), "hist_hi": float(hist_hi),
-                "n_bins": int(n_bins)}
+                "n_bins": int(n_bins), "plane": plane, "genome": genome if plane is not None else None}
 
-    def fit_background(self, genome=None, bg=None, sync=True):
+    def fit_background(self, genome=None, bg=None, sync=True, keep_scores=True):
         """build_bayesian_estimator (binding_model.py:71-92) with the background
         moments taken from the genome-wide scan (or from a finished
-        ``background_stats`` result, e.g. after a cross-rank all-reduce)."""
+        ``background_stats`` result, e.g. after a cross-rank all-reduce).  The score
+        plane of the scan (``keep_scores``) is remembered and reused by
+        ``binding_probabilities`` on the same genome."""
         if bg is None:
-            bg = self.background_stats(genome)
+            bg = self.background_stats(genome, keep_scores=keep_scores)
         self._bg_stats_dev = bg["stats"]
+        self._last_bg = bg
         self._dev_ms_bg = bg["stats"][_cabi.BG_MEAN:_cabi.BG_STD + 1]
         if getattr(self, "_mu_m", None) is None or self._dev_ms_m is None:
             pssm_scores = self.score_self()
@@ -314,10 +329,12 @@ class PSSMModel(TFBindingModel):
                                  "(call build_bayesian_estimator or fit_background first)")
 
     def binding_probabilities(self, genome, starts, ends, p_motif, alpha=1/350.0, seq_index=0,
-                              out=None, region_tensors=None):
+                              out=None, region_tensors=None, use_plane=True):
         """Posterior of regulation for promoter regions ``sequence[start:end]``
         (Python slice semantics, gene.py:127) of one replicon: device float64
-        tensor, one value per region (binding_model.py:94-113 for each)."""
+        tensor, one value per region (binding_model.py:94-113 for each).  When the
+        last ``fit_background`` kept the score plane of this genome (``use_plane``),
+        window scores are read from it; otherwise every window is re-scored."""
         self._require_estimator()
         model = self._model()
         m = self.length
@@ -328,8 +345,14 @@ class PSSMModel(TFBindingModel):
         n = int(d_start.numel())
         if out is None:
             out = torch.empty(n, dtype=torch.float64, device=dev)
+        plane = None
+        if use_plane:
+            bg = getattr(self, "_last_bg", None)
+            if bg is not None and bg.get("genome") is genome and bg.get("plane") is not None:
+                plane = bg["plane"]
         _cabi.check(_cabi.lib().cgbk_posteriors(
-            model, genome.struct_ref(), d_start.data_ptr(), d_nwin.data_ptr(), n,
+            model, genome.struct_ref(), genome.seqset, plane.data_ptr() if plane is not None else None,
+            d_start.data_ptr(), d_nwin.data_ptr(), n,
             self._dev_ms_m.data_ptr(), self._dev_ms_bg.data_ptr(), float(p_motif), float(alpha),
             out.data_ptr(), self._stream()))
         return out

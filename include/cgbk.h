@@ -130,8 +130,13 @@ int cgbk_score_windows(const cgbk_model* model, const cgbk_genome* genome,
  * promoter regions (Gene.promoter_region, cgb/gene.py:111-127): region k scores
  * windows [d_start[k], d_start[k]+d_nwin[k]).  d_mu_std_m / d_mu_std_bg are
  * DEVICE double[2] {mean, std} (so the background pair can come straight from
- * cgbk_background_stats without a host round trip).  d_post[k] = posterior. */
+ * cgbk_background_stats without a host round trip).  d_post[k] = posterior.
+ * d_plane (optional, with `set`): the score plane cgbk_background_stats wrote for this
+ * model and set; windows are then read from it and only the rare high-scoring ones
+ * (mixture ratio x >= 1e-4) are re-scored exactly.  NULL: every window is scored in
+ * float64 in the reference's order. */
 int cgbk_posteriors(const cgbk_model* model, const cgbk_genome* genome,
+                    const cgbk_seqset* set, const int32_t* d_plane,
                     const int64_t* d_start, const int32_t* d_nwin, int n_regions,
                     const double* d_mu_std_m, const double* d_mu_std_bg,
                     double p_motif, double alpha, double* d_post, void* stream);
@@ -157,10 +162,15 @@ int cgbk_scan_hits(cgbk_model* model, const cgbk_genome* genome, const cgbk_seqs
  * every window -> histogram (uint64 d_hist[n_bins] over [hist_lo, hist_hi), clamped)
  * and moments (device double[CGBK_BG_COUNT], layout above).  With accumulate != 0
  * the raw n/sum/sumsq/hist are added to what the buffers hold (mean/std are
- * recomputed), for multi-call or multi-rank accumulation. */
+ * recomputed), for multi-call or multi-rank accumulation.  d_plane (optional,
+ * plane_ints >= cgbk_score_plane_ints): receives every window's fixed-point soft-max
+ * score in the scan's own tile order (one coalesced 128-byte store per position), for
+ * cgbk_posteriors. */
+int64_t cgbk_score_plane_ints(const cgbk_seqset* set, int m);
 int cgbk_background_stats(cgbk_model* model, const cgbk_genome* genome, const cgbk_seqset* set,
                           double hist_lo, double hist_hi, int n_bins,
                           unsigned long long* d_hist, double* d_stats, int accumulate,
+                          int32_t* d_plane, int64_t plane_ints,
                           void* d_work, int64_t work_bytes, void* stream);
 
 /* Recompute CGBK_BG_MEAN / CGBK_BG_STD from n/sum/sumsq in d_stats (after an

@@ -302,4 +302,12 @@ def test_config2_posteriors(models, lexa):
                                                 prior, alpha))
     exp = np.array(exp)
     assert (exp > 0.5).sum() >= 20
-    assert np.max(np.abs(post - exp)) < POST_TOL
+    assert np.max(np.abs(post - exp)) < POST_TOL          # scores read from the scan's score plane
+    assert M._last_bg["plane"] is not None
+    s, e = gt.promoter_region_location(300, 50)
+    rescored = M.binding_probabilities(g, s, e, prior, alpha, use_plane=False).cpu().numpy()
+    assert np.max(np.abs(rescored - exp)) < POST_TOL      # every window re-scored in float64
+    # a hit scan between the two must not disturb the plane's tiling
+    M.scan_hits(g)
+    again = calculate_regulation_probabilities(M, g, gt, prior, alpha, 300, 50).cpu().numpy()
+    assert np.array_equal(again, post)
