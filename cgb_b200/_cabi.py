@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libcgbk.so")
+# CGBK_LIB: alternative build of the library (kernel tuning experiments)
+LIB_PATH = os.environ.get("CGBK_LIB") or os.path.join(_HERE, "_lib", "libcgbk.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
 MAX_MOTIF = 32

@@ -38,15 +38,23 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, defines=(), out=None):
+    """``defines``/``out``: tuning builds (e.g. -DCGBK_STATS_THREADS=384) written next to the
+    default library and selected at run time with the CGBK_LIB environment variable."""
+    global LIB
+    if out is not None:
+        return _build(os.path.join(LIBDIR, out), os.path.join(LIBDIR, "obj_" + out), verbose, list(defines))
     if not force and not _stale():
         return LIB
+    return _build(LIB, os.path.join(LIBDIR, "obj"), verbose, list(defines))
+
+
+def _build(LIB, objdir, verbose, defines):
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     common = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
-              "-I", os.path.join(ROOT, "include"), "-I", CSRC] + ARCH
+              "-I", os.path.join(ROOT, "include"), "-I", CSRC] + ARCH + defines
     if verbose:
         common += ["-Xptxas", "-v"]
 

@@ -164,6 +164,9 @@ __global__ void __launch_bounds__(256) posterior_kernel(
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int stride = 32 * pv.L - 32;
+    const int log2L = 31 - __clz(pv.L);                       // L is 32, 64 or 128
+    const int rows_body = pv.L;                               // (L / 32) bodies * 32 rows
+    const long long plane_tile = (long long)(pv.L / 32 + 1) * 1024;
     for (int reg = blockIdx.x * warps_per_block + (threadIdx.x >> 5); reg < n_regions;
          reg += gridDim.x * warps_per_block) {
         const long long start = __ldg(d_start + reg);
@@ -178,38 +181,62 @@ __global__ void __launch_bounds__(256) posterior_kernel(
             tile_r += __ldg(seqs.tile_prefix + sq);
         }
         double acc = 0.0;       // sum of log1p(x_i)
-        for (int w = lane; w < nwin; w += 32) {
-            double s;
-            if (PLANE) {
+        if (PLANE) {
+            // pass 1: every window from the plane on the float32 path; windows whose mixture
+            // ratio x reaches 1e-2 are only marked (bit k = this lane's k-th window)
+            unsigned long long marked = 0ull;
+            int k = 0;
+            for (int w = lane; w < nwin; w += 32, ++k) {
                 int wt = wt0 + w;
                 long long tile = tile_r;
                 while (wt >= stride) { wt -= stride; ++tile; }
-                s = (double)__ldg(pv.plane + plane_index(tile, wt, pv.L, pv.D)) * pv.inv_scale;
-            } else {
-                double f, r;
-                exact_window(g, &tab, m, start + w, false, f, r);
-                s = softmax2_f32tail((float)f, (float)r);      // Biopython's float32 strand scores
-            }
-            double ym = (s - mu_m) * inv_std_m, yb = (s - mu_bg) * inv_std_bg;
-            double e = 0.5 * (yb * yb - ym * ym);
-            const float ef = (float)e;
-            double term = 0.0;                                  // ef < -60: x < 1e-26
-            if (!(ef < -60.0f)) {
-                const float xf = cf * expf(ef);
-                if (xf < 1e-4f) {
-                    term = (double)log1pf(xf);
+                const int ln = wt >> log2L, within = wt & (pv.L - 1);
+                const int row = within < pv.L - pv.D ? within + pv.D : rows_body + (within - (pv.L - pv.D));
+                const int sfix = __ldg(pv.plane + tile * plane_tile + row * 32 + ln);
+                const double s = (double)sfix * pv.inv_scale;
+                const double ym = (s - mu_m) * inv_std_m, yb = (s - mu_bg) * inv_std_bg;
+                const float ef = (float)(0.5 * (yb * yb - ym * ym));
+                // x = c * exp(e); below e = -60 x < 1e-26 adds nothing
+                const float xf = ef < -60.0f ? 0.0f : cf * __expf(ef);
+                if (xf < 1e-2f) {
+                    // log1p(x) = x - x^2/2 + x^3/3 - ... : |error| < 3e-9 for x < 1e-2
+                    acc += (double)(xf * (1.0f - xf * (0.5f - xf * (1.0f / 3.0f))));
+                } else if (k < 64) {
+                    marked |= 1ull << k;
                 } else {
-                    if (PLANE) {
-                        double f, r;
-                        exact_window(g, &tab, m, start + w, false, f, r);
-                        s = softmax2_f32tail((float)f, (float)r);
-                        ym = (s - mu_m) * inv_std_m; yb = (s - mu_bg) * inv_std_bg;
-                        e = 0.5 * (yb * yb - ym * ym);
-                    }
-                    term = log1p(c * exp(e));
+                    double f, r;                               // regions longer than 2048 windows
+                    exact_window(g, &tab, m, start + w, false, f, r);
+                    const double se = softmax2_f32tail((float)f, (float)r);
+                    const double ym2 = (se - mu_m) * inv_std_m, yb2 = (se - mu_bg) * inv_std_bg;
+                    acc += log1p(c * exp(0.5 * (yb2 * yb2 - ym2 * ym2)));
                 }
             }
-            acc += term;
+            // pass 2: the marked windows, exactly (float64 strand sums in the reference's order)
+            while (marked) {
+                const int kk = __ffsll((long long)marked) - 1;
+                marked &= marked - 1;
+                double f, r;
+                exact_window(g, &tab, m, start + lane + 32 * kk, false, f, r);
+                const double se = softmax2_f32tail((float)f, (float)r);
+                const double ym2 = (se - mu_m) * inv_std_m, yb2 = (se - mu_bg) * inv_std_bg;
+                acc += log1p(c * exp(0.5 * (yb2 * yb2 - ym2 * ym2)));
+            }
+        } else {
+            for (int w = lane; w < nwin; w += 32) {
+                double f, r;
+                exact_window(g, &tab, m, start + w, false, f, r);
+                const double s = softmax2_f32tail((float)f, (float)r);   // Biopython's float32 strand scores
+                const double ym = (s - mu_m) * inv_std_m, yb = (s - mu_bg) * inv_std_bg;
+                const double e = 0.5 * (yb * yb - ym * ym);
+                const float ef = (float)e;
+                double term = 0.0;                              // ef < -60: x < 1e-26
+                if (!(ef < -60.0f)) {
+                    const float xf = cf * expf(ef);
+                    if (xf < 1e-4f) term = (double)log1pf(xf);
+                    else term = log1p(c * exp(e));
+                }
+                acc += term;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -356,10 +383,12 @@ __global__ void __launch_bounds__(128) dirty_stats_kernel(const double* __restri
     __shared__ ExactTables tab;
     __shared__ double scratch[96];
     __shared__ int is_last;
-    stage_exact(&tab, d_exact);
-    __syncthreads();
     double s1 = 0.0, s2 = 0.0, cnt = 0.0;
     const long long nd = w.counters[CGBK_CTR_DIRTY_TILES];
+    if (nd > 0) {                       // usually there is nothing to do here
+        stage_exact(&tab, d_exact);
+        __syncthreads();
+    }
     for (long long d = blockIdx.x; d < nd; d += gridDim.x) {
         long long gbase, lo, hi;
         const unsigned int tile = w.dirty_tiles[d];

@@ -166,8 +166,21 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     double sum_d2 = 0.0;          // sum of their squares
     long long cnt = 0;
 
-    for (long long tile = (long long)blockIdx.x * wpb + warp; tile < seqs.n_tiles;
-         tile += (long long)gridDim.x * wpb) {
+    const unsigned hist_saddr = (unsigned)__cvta_generic_to_shared(hist);
+
+    // Tiles are handed out dynamically (one global atomic per warp tile, fetched one tile
+    // ahead): with only a few tiles per warp a static split leaves most warps idle while the
+    // unlucky ones run their extra tile.  All outputs are order independent.
+    unsigned long long* tile_ctr = reinterpret_cast<unsigned long long*>(work.counters + CGBK_CTR_INTERNAL_TILE);
+    const long long first_dyn = (long long)gridDim.x * wpb;   // every warp's first tile is static
+    long long prefetched = 0;                                 // lane 0: id of the tile after the current one
+    if (lane == 0) prefetched = first_dyn + (long long)atomicAdd(tile_ctr, 1ull);
+    auto advance = [&]() -> long long {
+        const long long t = __shfl_sync(0xffffffffu, prefetched, 0);   // fetched one tile ago
+        if (lane == 0) prefetched = first_dyn + (long long)atomicAdd(tile_ctr, 1ull);
+        return t;
+    };
+    for (long long tile = (long long)blockIdx.x * wpb + warp; tile < seqs.n_tiles; tile = advance()) {
         long long gbase, seq_len, tile0;
         if (seqs.n_seq <= CGBK_INLINE_SEQS) {
             int sq = 0;
@@ -234,7 +247,9 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 bin = valid ? bin : n_bins;
                 int dq = (sfix - sp.c_fix + sp.half) >> sp.sh;
                 dq = valid ? dq : 0;
-                atomicAdd(hist + bin, 1u);
+                // plain shared-memory reduction: atomicAdd(.., 1) makes ptxas wrap the ATOMS in a
+                // warp-collective (match + POPC.INC) region that serialises the unrolled body
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_saddr + 4u * (unsigned)bin), "r"(1u));
                 acc_d += dq;
                 acc_d2 += (long long)dq * dq;
                 if (prow) prow[row * 32] = sfix;

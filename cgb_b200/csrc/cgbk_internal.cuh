@@ -56,6 +56,7 @@ struct GenomeView {
 };
 
 #define CGBK_CTR_INTERNAL_DONE 3   // blocks of the dirty-stats kernel that have finished
+#define CGBK_CTR_INTERNAL_TILE 4   // dynamic tile scheduler of the tiled scan
 #define CGBK_INLINE_SEQS 4   // sequence tables this small travel by value in the kernel parameters
 
 struct SeqTable {
