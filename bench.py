@@ -14,8 +14,10 @@ value      bp*motif/s with the packed genome already resident in HBM (per-step C
            events; L2 flushed between steps, flush outside the timed span)
 e2e        the same through the public API from pinned HOST bytes: H2D of the
            ASCII genome + pack + scan + posteriors + D2H of the posteriors
-roofline   the tiled scan kernel (dominant): algorithmic bytes and lookup-adds per
-           launch over its CUDA-event duration
+roofline   the tiled stats-scan kernel (dominant): algorithmic bytes and lookup-adds
+           per launch over its CUDA-event duration (cgbk_profile_*)
+at_scale   (N = 1) the two tiled kernels on a 1 Gbp synthetic sequence, i.e. at the
+           size where launch ramp and tile quantisation no longer matter
 N > 1      one genome per rank (BASELINE configs[2] style sharding, no collective)
 """
 from __future__ import annotations
@@ -23,9 +25,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -40,6 +40,8 @@ UP, DOWN = 300, 50
 M_LEN = 22
 METRIC = "PSWM scan bp*motif/s (both strands): background fit + promoter posteriors"
 UNIT = "bp*motif/s"
+WORKLOAD = ("config2: LexA 22-bp PSWM, synthetic 5 Mbp genome per GPU, 3000 promoters x 350 bp "
+            "(background histogram+moments, then posteriors)")
 
 
 def lexa():
@@ -71,53 +73,6 @@ def peaks():
             p = json.load(f)
         return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
     return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
-
-
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu_index):
-        self.idx = gpu_index
-        self.proc = None
-        self.path = None
-
-    def start(self):
-        try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
-
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        try:
-            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
-            sm = [float(r[1]) for r in rows]
-            out["samples"] = len(sm)
-            if sm:
-                out["sm_mhz"] = float(np.median(sm))
-                out["sm_max_mhz"] = float(rows[0][2])
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for k, name in enumerate(names):
-                if any(r[5 + k].strip().lower() == "active" for r in rows):
-                    out["reasons"].append(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        return out
 
 
 # ----------------------------------------------------------------------------- CPU arms
@@ -154,12 +109,12 @@ def run_reference(args):
         return
     import multiprocessing as mp
     from oracle import c_oracle
+    from cgb_b200.gene_regions import GeneTable, python_slice_bounds
     c_oracle.build()
     cores = os.cpu_count() or 1
     global _REF_SEQ
     _REF_SEQ = synthetic_genome(GENOME_BP, 2).tobytes()
     gs, ge, gstrand = gene_layout(GENOME_BP, N_GENES)
-    from cgb_b200.gene_regions import GeneTable, python_slice_bounds
     gt = GeneTable(gs, ge, gstrand, GENOME_BP)
     ps, pe = python_slice_bounds(*gt.promoter_region_location(UP, DOWN), GENOME_BP)
     # per step: a 1/10 sample of config 2 (500 kbp of background windows + 300 promoters),
@@ -188,8 +143,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "config2: LexA 22-bp PSWM, synthetic 5 Mbp genome, 3000 promoters x 350 bp "
-                               "(background fit + posteriors)",
+        "config": {"workload": WORKLOAD,
                    "sample": "per step 1/10 of config 2: %d background windows + %d promoters" % (nwin, sample_prom)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "1/10 of config 2 per step, %d processes" % cores},
@@ -200,11 +154,55 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def at_scale(M, dev, bp, reps=3):
+    """The two tiled kernels on one `bp`-base synthetic sequence (kernel CUDA-event time)."""
+    import torch
+
+    from cgb_b200 import PackedGenome, _cabi
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4)
+    g = PackedGenome([bp], dev)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    ascii_all = torch.empty(bp, dtype=torch.uint8, device=dev)
+    chunk = 1 << 28
+    for off in range(0, bp, chunk):
+        n = min(chunk, bp - off)
+        ascii_all[off:off + n] = lut[torch.randint(0, 4, (n,), device=dev, generator=gen)]
+    g.pack_into(0, ascii_all)
+    torch.cuda.synchronize()
+    del ascii_all
+    nwin = g.total_windows(M.length)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    hbm_peak, sm_max, _ = peaks()
+    issue_peak = sms * 128 * sm_max * 1e6
+    out = {"bp": bp, "motif_len": M.length}
+    thr = M.threshold()
+    for mode in ("hit_scan", "stats_scan"):
+        times = []
+        for rep in range(reps + 2):
+            if mode == "hit_scan":
+                M.scan_hits(g, thr)
+            else:
+                M.background_stats(g)
+                torch.cuda.synchronize()
+            if rep >= 2:
+                times.append(_cabi.profile_last_ms())
+        ms = float(np.mean(times))
+        rate = nwin / (ms * 1e-3)
+        out[mode] = {"kernel_ms": ms, "bp_motif_per_s": rate,
+                     "issue_frac": rate * 2 * M.length / issue_peak,
+                     "hbm_frac": nwin * 0.25 / (ms * 1e-3) / 1e9 / hbm_peak}
+        if mode == "hit_scan":
+            out[mode].update(M.last_scan_counters)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from cgb_b200 import GeneTable, PackedGenome, PSSMModel, SiteCollection, _cabi
+    from tools.clock_sampler import ClockSampler
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,11 +241,20 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def e2e_step():
+        gg = PackedGenome.from_sequences(None, dev, pinned=[pinned])
+        b = M.background_stats(gg, n_bins=1024, keep_scores=True)
+        M.fit_background(bg=b, sync=False)
+        p = M.binding_probabilities(gg, ps, pe, prior, alpha, out=post)
+        return p.cpu(), b["stats"].cpu()
+
     for _ in range(args.warmup):
         step()
         flush.zero_()
+    for _ in range(max(3, args.warmup)):
+        e2e_step()
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev)
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -268,19 +275,10 @@ def run_ours(args):
     info = _cabi.last_launch_info()
 
     # ---- end to end through the public API, from pinned host memory
-    def e2e_step():
-        gg = PackedGenome.from_sequences(None, dev, pinned=[pinned])
-        b = M.background_stats(gg, n_bins=1024, keep_scores=True)
-        M.fit_background(bg=b, sync=False)
-        p = M.binding_probabilities(gg, ps, pe, prior, alpha, out=post)
-        return p.cpu(), b["stats"].cpu()
-
-    for _ in range(max(3, args.warmup)):
-        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = e2e_step()
+        e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -301,7 +299,7 @@ def run_ours(args):
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         issue_peak = sms * 128 * sm_max * 1e6
         roofline = {
-            "bound": "hbm", "kernel": "fast_scan_kernel<G=6, stats>",
+            "bound": "hbm", "kernel": "fast_scan_kernel<G=6, stats> on one 5 Mbp genome",
             "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
             "peak_source": peak_src, "kernel_ms": k_ms,
@@ -311,6 +309,7 @@ def run_ours(args):
                               "SMs*128 lanes*f_max; the issue bound binds"},
         }
         cpu_baseline = None
+        scale = None
         if world == 1 and not args.no_cpu:
             from oracle import c_oracle
             c_oracle.build()
@@ -320,13 +319,16 @@ def run_ours(args):
             cpu_baseline = {"value": nwin_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
                             "sample": "the full config-2 step once (%d windows + %d promoters, %.1f s)"
                                       % (nwin_cpu, nprom_cpu, t_cpu)}
+        if world == 1 and not args.no_scale:
+            del flush
+            torch.cuda.empty_cache()
+            scale = at_scale(M, dev, args.scale_bp)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32 fixed point (2^-24) + f64 moments/posterior",
             "data": "synthetic",
-            "config": {"workload": "config2: LexA 22-bp PSWM, synthetic 5 Mbp genome per GPU, 3000 promoters x 350 bp "
-                                   "(background histogram+moments, then posteriors)",
+            "config": {"workload": WORKLOAD,
                        "genome_bp": GENOME_BP, "promoters": N_GENES, "posterior_windows": n_post_windows,
                        "l2": "flushed between steps (512 MiB memset, outside the timed span)",
                        "timing": "per-step CUDA events, max over ranks", "tiles": info["tiles"],
@@ -335,7 +337,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel()) + 2 * N_GENES * 8,
                     "d2h_bytes_per_step": N_GENES * 8 + 64, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches_per_step * args.steps,
-            "clocks": clocks, "wall_s_timed_loop": wall,
+            "clocks": clocks, "wall_s_timed_loop": wall, "at_scale": scale,
         }
         print(json.dumps(line))
     if world > 1:
@@ -346,10 +348,12 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-scale", action="store_true", help="skip the at_scale leg")
+    ap.add_argument("--scale-bp", type=int, default=1_000_000_000)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

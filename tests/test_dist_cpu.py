@@ -1,0 +1,119 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: chunk sharding with halo,
+the single all-reduce of the background record, hit gathering, genome assignment.
+The per-rank "scan" is played by the CPU oracle so the data path needs no GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cgb_b200 import _cabi
+from cgb_b200 import dist as cdist
+from oracle import c_oracle, np_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _lexa_model():
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "lexa_sites.json")) as f:
+        d = json.load(f)
+    sites = [mo["sites"] for mo in d["motifs"]]
+    counts = [len(s) for s in sites]
+    return O.OracleModel(sites, [c / float(sum(counts)) for c in counts])
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        om = _lexa_model()
+        m = om.length
+        seq = O.synthetic_genome(n, 9)
+        starts, ends, counts = cdist.chunk_bounds(n, m, world)
+        chunk = seq[starts[rank]:ends[rank]]
+        # per-rank background record from the oracle's scores of this chunk
+        _, _, b = c_oracle.score_seq(om, chunk)
+        assert len(b) == counts[rank]
+        lo, hi, nb = -44.0, 28.0, 72
+        hist, _ = np.histogram(b, bins=np.linspace(lo, hi, nb + 1))
+        stats = torch.zeros(_cabi.BG_COUNT, dtype=torch.float64)
+        stats[0], stats[1], stats[2] = len(b), b.sum(), (b * b).sum()
+        bg = {"stats": stats, "hist": torch.from_numpy(hist.astype(np.int64))}
+        cdist.allreduce_background(bg)
+        # per-rank hits, gathered in global coordinates
+        thr = om.threshold() - 4.0
+        p, s, v = c_oracle.scan_hits(om, chunk, thr)
+        gp, gs, gv = cdist.gather_hits(p, s, v, starts[rank])
+        if rank == 0:
+            q.put((bg["stats"].numpy().copy(), bg["hist"].numpy().copy(), gp, gs, gv))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_chunk_sharded_background_and_hits_gloo():
+    n, world = 60011, 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    stats, hist, gp, gs, gv = res
+    om = _lexa_model()
+    seq = O.synthetic_genome(n, 9)
+    _, _, b = c_oracle.score_seq(om, seq)
+    assert stats[_cabi.BG_N] == len(b) == n - om.length + 1
+    assert abs(stats[_cabi.BG_MEAN] - b.mean()) < 1e-10 and abs(stats[_cabi.BG_STD] - b.std()) < 1e-9
+    exp_hist, _ = np.histogram(b, bins=np.linspace(-44.0, 28.0, 73))
+    assert np.array_equal(hist, exp_hist)
+    p, s, v = c_oracle.scan_hits(om, seq, om.threshold() - 4.0)
+    assert len(p) > 10
+    assert np.array_equal(gp, p) and np.array_equal(gs, s) and np.array_equal(gv, v)
+
+
+def test_chunk_bounds_cover_every_window_once():
+    for n, m, w in ((1000, 22, 8), (30, 22, 8), (21, 22, 4), (10 ** 10, 22, 8), (997, 8, 3)):
+        starts, ends, counts = cdist.chunk_bounds(n, m, w)
+        nwin = max(0, n - m + 1)
+        assert counts.sum() == nwin
+        assert (ends <= n).all() and (starts >= 0).all()
+        cover = 0
+        for r in range(w):
+            if counts[r]:
+                assert starts[r] == cover and ends[r] - starts[r] == counts[r] + m - 1
+                cover += counts[r]
+        assert cover == nwin
+
+
+def test_assign_genomes_balanced_and_complete():
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(2_000_000, 7_000_000, size=100)
+    parts = cdist.assign_genomes(sizes, 8)
+    assert sorted(i for p in parts for i in p) == list(range(100))
+    loads = [sum(int(sizes[i]) for i in p) for p in parts]
+    assert max(loads) - min(loads) <= sizes.max()
+    assert cdist.assign_genomes([5, 1], 4) == [[0], [1], [], []]
+
+
+def test_finalize_stats_host():
+    x = np.random.default_rng(1).normal(-12, 6, size=1000)
+    st = torch.zeros(_cabi.BG_COUNT, dtype=torch.float64)
+    st[0], st[1], st[2] = len(x), x.sum(), (x * x).sum()
+    cdist.finalize_stats_host(st)
+    assert abs(float(st[_cabi.BG_MEAN]) - x.mean()) < 1e-12 and abs(float(st[_cabi.BG_STD]) - x.std()) < 1e-10
