@@ -43,8 +43,9 @@ SYMBOLS = {
                                    C.c_int64, C.c_void_p]),
     "cgbk_model_create": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "cgbk_model_destroy": (None, [C.c_void_p]),
+    "cgbk_seqset_table_ints": (C.c_int64, [C.c_int]),
     "cgbk_seqset_create": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int, C.c_int,
-                                      C.POINTER(C.c_void_p)]),
+                                      C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "cgbk_seqset_destroy": (None, [C.c_void_p]),
     "cgbk_seqset_total_windows": (C.c_int64, [C.c_void_p, C.c_int]),
     "cgbk_score_windows": (C.c_int, [C.c_void_p, C.POINTER(Genome), C.c_void_p, C.c_void_p, C.c_int, C.c_int64,

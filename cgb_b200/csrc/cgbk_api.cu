@@ -167,11 +167,12 @@ extern "C" int cgbk_pack_ascii(const uint8_t* d_ascii, int64_t n, int64_t dst_of
                                uint32_t* d_amb, uint32_t* d_lower, int64_t cap_bases, void* stream) {
     if (n < 0 || dst_off < 0 || dst_off % CGBK_SEQ_ALIGN != 0)
         return cgbk_set_error(CGBK_ERR_INVALID, "dst_off must be a non-negative multiple of %d", CGBK_SEQ_ALIGN);
-    const int64_t padded = ((n + CGBK_SEQ_ALIGN - 1) / CGBK_SEQ_ALIGN) * CGBK_SEQ_ALIGN;
+    int64_t padded = ((n + CGBK_SEQ_ALIGN - 1) / CGBK_SEQ_ALIGN) * CGBK_SEQ_ALIGN;
+    if (padded == 0) padded = CGBK_SEQ_ALIGN;
     if (dst_off + padded > cap_bases)
         return cgbk_set_error(CGBK_ERR_INVALID, "sequence of %lld bases at offset %lld exceeds capacity %lld",
                               (long long)n, (long long)dst_off, (long long)cap_bases);
-    if (n > 0 && (!d_ascii || !d_bases2 || !d_amb || !d_lower))
+    if ((n > 0 && !d_ascii) || !d_bases2 || !d_amb || !d_lower)
         return cgbk_set_error(CGBK_ERR_INVALID, "NULL device pointer");
     CUDA_TRY(launch_pack(d_ascii, n, dst_off, d_bases2, d_amb, d_lower, (cudaStream_t)stream));
     return CGBK_OK;
@@ -348,9 +349,12 @@ static int ensure_coarse(cgbk_model* M, double thr, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // sequence sets and tiling
 // ---------------------------------------------------------------------------
+extern "C" int64_t cgbk_seqset_table_ints(int n_seq) { return 3 * (int64_t)n_seq + 1; }
+
 extern "C" int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len, int n_seq, int device,
-                                  cgbk_seqset** out) {
+                                  int64_t* d_table, void* stream, cgbk_seqset** out) {
     if (!seq_off || !seq_len || !out || n_seq < 1) return cgbk_set_error(CGBK_ERR_INVALID, "bad sequence table");
+    if (!d_table) return cgbk_set_error(CGBK_ERR_INVALID, "d_table (device int64[3 * n_seq + 1]) is NULL");
     for (int i = 0; i < n_seq; ++i) {
         if (seq_off[i] < 0 || seq_off[i] % CGBK_SEQ_ALIGN != 0 || seq_len[i] < 0)
             return cgbk_set_error(CGBK_ERR_INVALID, "sequence %d: offset must be a multiple of %d", i, CGBK_SEQ_ALIGN);
@@ -365,17 +369,18 @@ extern "C" int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len
     memcpy(S->h_off, seq_off, sizeof(int64_t) * n_seq);
     memcpy(S->h_len, seq_len, sizeof(int64_t) * n_seq);
     S->h_tile_prefix = (int64_t*)calloc(n_seq + 1, sizeof(int64_t));
-    // one device block: off[n] | len[n] | tile_prefix[n + 1]
-    int64_t* block = nullptr;
-    if (cudaMalloc(&block, sizeof(int64_t) * (3 * (size_t)n_seq + 1)) != cudaSuccess) {
-        cgbk_seqset_destroy(S);
-        return cgbk_set_error(CGBK_ERR_CUDA, "cudaMalloc of sequence table failed");
-    }
+    // caller-owned device block: off[n] | len[n] | tile_prefix[n + 1]; no cudaMalloc / cudaFree
+    // (both synchronise the device) on the per-genome path
+    int64_t* block = d_table;
     S->d_off = block; S->d_len = block + n_seq; S->d_tile_prefix = block + 2 * n_seq;
-    std::vector<int64_t> both(2 * (size_t)n_seq);
-    memcpy(both.data(), seq_off, sizeof(int64_t) * n_seq);
-    memcpy(both.data() + n_seq, seq_len, sizeof(int64_t) * n_seq);
-    if (cudaMemcpy(block, both.data(), sizeof(int64_t) * both.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+    if (n_seq > CGBK_INLINE_SEQS) {     // small tables travel in the kernel parameters instead
+        e1 = cudaMemcpyAsync(S->d_off, S->h_off, sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice,
+                             (cudaStream_t)stream);
+        e2 = cudaMemcpyAsync(S->d_len, S->h_len, sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice,
+                             (cudaStream_t)stream);
+    }
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
         cgbk_seqset_destroy(S);
         return cgbk_set_error(CGBK_ERR_CUDA, "upload of sequence table failed");
     }
@@ -386,8 +391,7 @@ extern "C" int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len
 
 extern "C" void cgbk_seqset_destroy(cgbk_seqset* S) {
     if (!S) return;
-    if (S->d_off) cudaFree(S->d_off);     // d_len / d_tile_prefix live in the same block
-    free(S->h_off); free(S->h_len); free(S->h_tile_prefix);
+    free(S->h_off); free(S->h_len); free(S->h_tile_prefix);   // the device table is the caller's
     free(S);
 }
 
@@ -417,9 +421,11 @@ static int ensure_tiles(cgbk_seqset* S, int m, int L, cudaStream_t st) {
         const int64_t nwin = S->h_len[i] - m + 1;
         prefix[i + 1] = prefix[i] + (nwin > 0 ? (nwin + stride - 1) / stride : 0);
     }
-    // stream-ordered after any earlier scan of this set on the same stream
-    CUDA_TRY(cudaMemcpyAsync(S->d_tile_prefix, prefix, sizeof(int64_t) * (S->n_seq + 1),
-                             cudaMemcpyHostToDevice, st));
+    // stream-ordered after any earlier scan of this set on the same stream; small tables
+    // travel in the kernel parameters instead
+    if (S->n_seq > CGBK_INLINE_SEQS)
+        CUDA_TRY(cudaMemcpyAsync(S->d_tile_prefix, prefix, sizeof(int64_t) * (S->n_seq + 1),
+                                 cudaMemcpyHostToDevice, st));
     S->n_tiles = prefix[S->n_seq];
     S->cached_m = m; S->cached_L = L;
     return CGBK_OK;

@@ -111,8 +111,27 @@ __device__ __forceinline__ double softmax2_f32tail(float ff, float rf) {
     return (double)mx + (double)log2f(1.0f + exp2f(mn - mx));
 }
 
+// Sequence table accessors: tables of up to CGBK_INLINE_SEQS sequences travel by value in the
+// kernel parameters (constant bank), larger ones live in device memory.
+__device__ __forceinline__ long long seq_off_of(const SeqTable& s, int k) {
+    return s.n_seq <= CGBK_INLINE_SEQS ? s.off_v[k] : __ldg(s.off + k);
+}
+__device__ __forceinline__ long long seq_len_of(const SeqTable& s, int k) {
+    return s.n_seq <= CGBK_INLINE_SEQS ? s.len_v[k] : __ldg(s.len + k);
+}
+__device__ __forceinline__ long long seq_prefix_of(const SeqTable& s, int k) {
+    return s.n_seq <= CGBK_INLINE_SEQS ? s.prefix_v[k] : __ldg(s.tile_prefix + k);
+}
+
 // sequence of a tile: tile_prefix[k] <= tile < tile_prefix[k + 1]
 __device__ __forceinline__ int find_seq(const SeqTable& s, long long tile) {
+    if (s.n_seq <= CGBK_INLINE_SEQS) {
+        int k = 0;
+#pragma unroll
+        for (int i = 1; i < CGBK_INLINE_SEQS; ++i)
+            if (i < s.n_seq && s.prefix_v[i] <= tile) k = i;
+        return k;
+    }
     int lo = 0, hi = s.n_seq;
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -123,6 +142,13 @@ __device__ __forceinline__ int find_seq(const SeqTable& s, long long tile) {
 
 // sequence holding packed offset gpos: off[k] <= gpos < off[k + 1]
 __device__ __forceinline__ int find_seq_by_offset(const SeqTable& s, long long gpos) {
+    if (s.n_seq <= CGBK_INLINE_SEQS) {
+        int k = 0;
+#pragma unroll
+        for (int i = 1; i < CGBK_INLINE_SEQS; ++i)
+            if (i < s.n_seq && s.off_v[i] <= gpos) k = i;
+        return k;
+    }
     int lo = 0, hi = s.n_seq;
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;

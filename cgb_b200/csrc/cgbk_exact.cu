@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ a
 
 cudaError_t launch_pack(const uint8_t* d_ascii, long long n, long long dst_off, uint32_t* b2,
                         uint32_t* amb, uint32_t* lower, cudaStream_t st) {
-    const long long padded = ((n + CGBK_SEQ_ALIGN - 1) / CGBK_SEQ_ALIGN) * CGBK_SEQ_ALIGN;
+    long long padded = ((n + CGBK_SEQ_ALIGN - 1) / CGBK_SEQ_ALIGN) * CGBK_SEQ_ALIGN;
+    if (padded == 0) padded = CGBK_SEQ_ALIGN;      // an empty sequence still owns (and zeroes) one block
     const long long n_chunks = padded / 32;
-    if (n_chunks == 0) return cudaSuccess;
     long long blocks = (n_chunks + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     pack_kernel<<<(int)blocks, 256, 0, st>>>(d_ascii, n, dst_off, b2, amb, lower, n_chunks);
@@ -175,10 +175,10 @@ __global__ void __launch_bounds__(256) posterior_kernel(
         int wt0 = 0;
         if (PLANE) {
             const int sq = find_seq_by_offset(seqs, start);
-            const long long x0 = start - __ldg(seqs.off + sq);
+            const long long x0 = start - seq_off_of(seqs, sq);
             tile_r = x0 / stride;
             wt0 = (int)(x0 - tile_r * stride);
-            tile_r += __ldg(seqs.tile_prefix + sq);
+            tile_r += seq_prefix_of(seqs, sq);
         }
         double acc = 0.0;       // sum of log1p(x_i)
         if (PLANE) {
@@ -258,13 +258,15 @@ cudaError_t launch_posteriors(const cgbk_model* mdl, GenomeView g, SeqTable seqs
                               const double* d_ms_m, const double* d_ms_bg, double p_motif,
                               double alpha, double* d_post, cudaStream_t st) {
     if (n_regions <= 0) return cudaSuccess;
-    int blocks = (n_regions + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    // one warp per promoter, 4 warps per block: a few thousand promoters are all resident at once
+    // (no partial second wave)
+    int blocks = (n_regions + 3) / 4;
+    if (blocks > 148 * 16) blocks = 148 * 16;
     if (pv.plane)
-        posterior_kernel<true><<<blocks, 256, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, pv, d_start, d_nwin,
+        posterior_kernel<true><<<blocks, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, pv, d_start, d_nwin,
                                                       n_regions, d_ms_m, d_ms_bg, p_motif, alpha, d_post);
     else
-        posterior_kernel<false><<<blocks, 256, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, pv, d_start, d_nwin,
+        posterior_kernel<false><<<blocks, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, pv, d_start, d_nwin,
                                                        n_regions, d_ms_m, d_ms_bg, p_motif, alpha, d_post);
     return cudaGetLastError();
 }
@@ -310,10 +312,10 @@ __global__ void __launch_bounds__(128) rescore_kernel(const double* __restrict__
 __device__ __forceinline__ void tile_range(const SeqTable& seqs, unsigned int tile, int L, int m,
                                            long long& gbase, long long& w_lo, long long& w_hi) {
     const int s = find_seq(seqs, tile);
-    const long long local = (long long)tile - __ldg(seqs.tile_prefix + s);
+    const long long local = (long long)tile - seq_prefix_of(seqs, s);
     const long long stride = 32ll * L - 32;
-    const long long nwin = __ldg(seqs.len + s) - m + 1;
-    gbase = __ldg(seqs.off + s);
+    const long long nwin = seq_len_of(seqs, s) - m + 1;
+    gbase = seq_off_of(seqs, s);
     w_lo = local * stride;
     w_hi = w_lo + stride < nwin ? w_lo + stride : nwin;
 }
@@ -385,11 +387,15 @@ __global__ void __launch_bounds__(128) dirty_stats_kernel(const double* __restri
     __shared__ int is_last;
     double s1 = 0.0, s2 = 0.0, cnt = 0.0;
     const long long nd = w.counters[CGBK_CTR_DIRTY_TILES];
-    if (nd > 0) {                       // usually there is nothing to do here
+    // only as many blocks as there are dirty tiles take part (one when there is none, the
+    // usual case: it just reduces the scan's partial moments)
+    const int n_part = nd < 1 ? 1 : (nd < (long long)gridDim.x ? (int)nd : (int)gridDim.x);
+    if ((int)blockIdx.x >= n_part) return;
+    if (nd > 0) {
         stage_exact(&tab, d_exact);
         __syncthreads();
     }
-    for (long long d = blockIdx.x; d < nd; d += gridDim.x) {
+    for (long long d = blockIdx.x; d < nd; d += n_part) {
         long long gbase, lo, hi;
         const unsigned int tile = w.dirty_tiles[d];
         tile_range(seqs, tile, L, m, gbase, lo, hi);
@@ -413,12 +419,12 @@ __global__ void __launch_bounds__(128) dirty_stats_kernel(const double* __restri
         __threadfence();
         const unsigned long long done =
             atomicAdd(reinterpret_cast<unsigned long long*>(w.counters + CGBK_CTR_INTERNAL_DONE), 1ull);
-        is_last = (done == gridDim.x - 1);
+        is_last = (done == (unsigned long long)(n_part - 1));
     }
     __syncthreads();
     if (is_last) {
         __threadfence();
-        finalize_stats(w.partials, n_partials, d_stats, 1, scratch);
+        finalize_stats(w.partials, partial_base + n_part, d_stats, 1, scratch);
     }
 }
 

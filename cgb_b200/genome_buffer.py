@@ -10,7 +10,8 @@ list of replicons; each is packed on the GPU from its ASCII bytes into
   lower   1 bit/base: lower-case acgt (only PSSMModel._calculate cares, pssm_model.py:96-100)
 
 at 512-base aligned offsets of one concatenated buffer.  PyTorch only provides
-the device memory and the stream.
+the device memory and the stream; building a PackedGenome performs no device
+synchronisation and no cudaMalloc once the caching allocator is warm.
 """
 from __future__ import annotations
 
@@ -42,22 +43,29 @@ class PackedGenome:
             raise ValueError("at least one sequence is required")
         A = _cabi.SEQ_ALIGN
         padded = (self.seq_len + A - 1) // A * A
-        # one extra aligned block between sequences keeps a window of <= 32 bases that
-        # starts near the end of one sequence from reading into the next one's bits
-        padded = padded + A
+        padded = np.maximum(padded, A)                  # an empty sequence still owns one block
         self.seq_off = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64)
         self.cap_bases = int(self.seq_off[-1] + padded[-1])
-        with torch.cuda.device(self.device):
-            self.bases2 = torch.zeros(self.cap_bases // 16, dtype=torch.int32, device=self.device)
-            self.amb = torch.zeros(self.cap_bases // 32, dtype=torch.int32, device=self.device)
-            self.lower = torch.zeros(self.cap_bases // 32, dtype=torch.int32, device=self.device)
+        n = len(self.seq_len)
+        lib = _cabi.lib()
+        # one allocation: bases2 | amb | lower | sequence table.  Every word of the planes is
+        # written by the pack kernel (padding included), so nothing is zeroed here.
+        c16, c32 = self.cap_bases // 16, self.cap_bases // 32
+        n_table = 2 * (3 * n + 1)                       # int64[3n + 1] as int32 pairs
+        self._storage = torch.empty(c16 + 2 * c32 + n_table, dtype=torch.int32, device=self.device)
+        self.bases2 = self._storage[:c16]
+        self.amb = self._storage[c16:c16 + c32]
+        self.lower = self._storage[c16 + c32:c16 + 2 * c32]
+        self._table = self._storage[c16 + 2 * c32:]
         self._struct = _cabi.Genome(self.bases2.data_ptr(), self.amb.data_ptr(), self.lower.data_ptr(),
                                     self.cap_bases)
         self._seqset = C.c_void_p()
-        off = (C.c_int64 * len(self.seq_off))(*self.seq_off.tolist())
-        ln = (C.c_int64 * len(self.seq_len))(*self.seq_len.tolist())
-        _cabi.check(_cabi.lib().cgbk_seqset_create(off, ln, len(self.seq_len), self.device.index or 0,
-                                                   C.byref(self._seqset)))
+        off = (C.c_int64 * n)(*self.seq_off.tolist())
+        ln = (C.c_int64 * n)(*self.seq_len.tolist())
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _cabi.check(lib.cgbk_seqset_create(off, ln, n, self.device.index or 0, self._table.data_ptr(), stream,
+                                           C.byref(self._seqset)))
+        self._packed = np.zeros(n, dtype=bool)
         self._work = {}
 
     # ------------------------------------------------------------------ build
@@ -75,28 +83,30 @@ class PackedGenome:
         g = cls(lens, device)
         stream = torch.cuda.current_stream(g.device)
         for k in range(len(lens)):
-            if lens[k] == 0:
-                continue
             if pinned is not None:
                 host = pinned[k]
             else:
-                host = torch.frombuffer(bytearray(raw[k]), dtype=torch.uint8)
-            dev = host.to(g.device, non_blocking=True)
+                host = torch.frombuffer(bytearray(raw[k]), dtype=torch.uint8) if lens[k] else \
+                    torch.empty(0, dtype=torch.uint8)
+            dev = host.to(g.device, non_blocking=True) if lens[k] else torch.empty(0, dtype=torch.uint8,
+                                                                                   device=g.device)
             g.pack_into(k, dev, stream)
         return g
 
     def pack_into(self, k, dev_ascii, stream=None):
-        """Pack device-resident ASCII bytes as sequence ``k``."""
+        """Pack device-resident ASCII bytes as sequence ``k`` (writes the sequence's
+        whole aligned block, zero padding included)."""
         if stream is None:
             stream = torch.cuda.current_stream(self.device)
         n = int(dev_ascii.numel())
         if n != int(self.seq_len[k]):
             raise ValueError("sequence %d holds %d bytes, expected %d" % (k, n, int(self.seq_len[k])))
         _cabi.check(_cabi.lib().cgbk_pack_ascii(
-            dev_ascii.data_ptr(), n, int(self.seq_off[k]), self.bases2.data_ptr(), self.amb.data_ptr(),
-            self.lower.data_ptr(), self.cap_bases, stream.cuda_stream))
-        # keep the source alive until the stream has consumed it
-        dev_ascii.record_stream(stream) if dev_ascii.is_cuda else None
+            dev_ascii.data_ptr() if n else None, n, int(self.seq_off[k]), self.bases2.data_ptr(),
+            self.amb.data_ptr(), self.lower.data_ptr(), self.cap_bases, stream.cuda_stream))
+        if n:
+            dev_ascii.record_stream(stream)       # keep the source alive until the kernel has read it
+        self._packed[k] = True
 
     # ------------------------------------------------------------- accessors
     @property

@@ -102,6 +102,11 @@ class PSSMModel(TFBindingModel):
         return thr
 
     @cached_property
+    def _score_bounds(self):
+        """Default histogram range: [floor(min score), ceil(max score) + 1) (soft-max <= max + 1)."""
+        return float(math.floor(self.pssm.min)), float(math.ceil(self.pssm.max) + 1.0)
+
+    @cached_property
     def sites(self):
         """pssm_model.py:79-82."""
         return [site for coll in self._collection_set for site in coll.sites]
@@ -267,9 +272,9 @@ class PSSMModel(TFBindingModel):
         m = self.length
         dev = self._dev()
         if hist_lo is None:
-            hist_lo = math.floor(self.pssm.min)
+            hist_lo = self._score_bounds[0]
         if hist_hi is None:
-            hist_hi = math.ceil(self.pssm.max) + 1.0       # soft-max <= max + 1
+            hist_hi = self._score_bounds[1]
         plane = None
         if out is not None:
             stats, hist, acc = out["stats"], out["hist"], 0
@@ -361,14 +366,35 @@ class PSSMModel(TFBindingModel):
         """(start offset, window count) device tensors for cgbk_posteriors."""
         m = self.length
         L = genome.length(seq_index)
-        s, e = python_slice_bounds(starts, ends, L)
-        nwin = e - s - m + 1
-        if (nwin < 1).any():
+        starts = np.asarray(starts, dtype=np.int64)
+        ends = np.asarray(ends, dtype=np.int64)
+        if starts.min(initial=0) >= 0 and ends.min(initial=0) >= 0:
+            s = np.minimum(starts, L)                   # common case: no negative slice index
+            e = np.maximum(np.minimum(ends, L), s)
+        else:
+            s, e = python_slice_bounds(starts, ends, L)
+        nwin = e - s
+        nwin -= m - 1
+        if nwin.min(initial=1) < 1:
             raise ValueError("negative dimensions are not allowed")   # Biopython, len(seq) < m
         dev = self._dev()
-        d_start = torch.from_numpy((s + int(genome.seq_off[seq_index])).astype(np.int64)).to(dev)
-        d_nwin = torch.from_numpy(nwin.astype(np.int32)).to(dev)
-        return d_start, d_nwin
+        # one pinned staging buffer [n x int64 starts | n x int32 counts], one async H2D copy
+        n = len(s)
+        nbytes = 12 * n
+        stage = getattr(self, "_desc_stage", None)
+        if stage is None or stage.numel() < nbytes:
+            stage = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
+            self._desc_stage = stage
+        ev = getattr(self, "_desc_event", None)
+        if ev is not None:
+            ev.synchronize()                       # the previous copy out of the staging buffer is done
+        host = stage.numpy()
+        host[:8 * n].view(np.int64)[:] = s + int(genome.seq_off[seq_index])
+        host[8 * n:12 * n].view(np.int32)[:] = nwin
+        d = stage[:nbytes].to(dev, non_blocking=True)
+        self._desc_event = torch.cuda.Event()
+        self._desc_event.record(torch.cuda.current_stream(dev))
+        return d[:8 * n].view(torch.int64), d[8 * n:12 * n].view(torch.int32)
 
     def _posterior_of_sequences(self, seqs, p_motif, alpha):
         self._require_estimator()

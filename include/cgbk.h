@@ -105,9 +105,12 @@ int cgbk_pack_ascii(const uint8_t* d_ascii, int64_t n, int64_t dst_off,
 int cgbk_model_create(const double* logodds, int m, int device, cgbk_model** out);
 void cgbk_model_destroy(cgbk_model* model);
 
-/* Sequence table of a packed buffer (host int64 arrays).  Synchronous. */
+/* Sequence table of a packed buffer (host int64 arrays).  d_table: caller-owned device
+ * int64[cgbk_seqset_table_ints(n_seq)] that must outlive the set (the library allocates
+ * nothing on the per-genome path); the upload is ordered on `stream`. */
+int64_t cgbk_seqset_table_ints(int n_seq);
 int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len, int n_seq, int device,
-                       cgbk_seqset** out);
+                       int64_t* d_table, void* stream, cgbk_seqset** out);
 void cgbk_seqset_destroy(cgbk_seqset* set);
 int64_t cgbk_seqset_total_windows(const cgbk_seqset* set, int m);
 
