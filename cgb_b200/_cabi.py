@@ -62,6 +62,13 @@ SYMBOLS = {
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_int64, C.c_void_p]),
     "cgbk_background_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cgbk_pipeline_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int, C.c_int]),
+    "cgbk_pipeline_staging_bytes": (C.c_int64, [C.c_int]),
+    "cgbk_regulation_pipeline": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int,
+                                            C.c_double, C.c_double, C.c_double, C.c_double,
+                                            C.c_double, C.c_double, C.c_int,
+                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cgbk_last_launch_info": (C.c_int, [C.POINTER(C.c_int64)]),
     "cgbk_profile_enable": (C.c_int, [C.c_int]),
     "cgbk_profile_last_ms": (C.c_int, [C.POINTER(C.c_float)]),

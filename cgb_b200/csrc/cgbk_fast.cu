@@ -243,7 +243,8 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 const float lg = lg2_approx(1.0f + u);
                 const int sfix = mx + __float2int_rn(lg * sp.scale);                 // soft-max, fixed point
                 const bool valid = live && (wt < own_n);
-                int bin = min((int)__umulhi((unsigned)max(sfix - sp.lo_fix, 0), sp.bin_mul), last_bin);
+                int bin = min((int)(__umulhi((unsigned)max(sfix - sp.lo_fix, 0), sp.bin_mul) >> sp.bin_shift),
+                              last_bin);
                 bin = valid ? bin : n_bins;
                 int dq = (sfix - sp.c_fix + sp.half) >> sp.sh;
                 dq = valid ? dq : 0;
@@ -389,9 +390,14 @@ StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist
     sp.inv_scale_d = 1.0 / scale;
     sp.lo_fix = (int)llrint(hist_lo * scale);
     const double range_fix = (hist_hi - hist_lo) * scale;
+    // bin = (u * n_bins / range_fix) as umulhi(u, M) >> k with M = floor(2^(32+k) n_bins / range_fix)
+    // scaled up to just below 2^32, i.e. bin edges exact to a relative 2^-31
     double mul = 4294967296.0 * (double)n_bins / range_fix;
+    int k = 0;
+    while (k < 24 && mul * 2.0 < 4294967295.0) { mul *= 2.0; ++k; }
     if (mul > 4294967295.0) mul = 4294967295.0;
     sp.bin_mul = (unsigned int)mul;
+    sp.bin_shift = k;
     sp.n_bins = n_bins;
     const double centre = 0.5 * (mdl->min_score + mdl->max_score);
     sp.c_fix = (int)llrint(centre * scale);

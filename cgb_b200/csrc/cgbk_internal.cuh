@@ -134,7 +134,8 @@ struct StatsParams {
     float scale;           // 2^kexp
     double inv_scale_d;    // 2^-kexp
     int lo_fix;            // histogram lower edge, fixed point
-    unsigned int bin_mul;  // floor(2^32 * n_bins / range_fix)
+    unsigned int bin_mul;  // floor(2^(32 + bin_shift) * n_bins / range_fix)
+    int bin_shift;
     int n_bins;
     int c_fix;             // moment centre, fixed point
     int sh;                // kexp - 18: moment rounding shift

@@ -312,9 +312,11 @@ class PSSMModel(TFBindingModel):
         self._bg_stats_dev = bg["stats"]
         self._last_bg = bg
         self._dev_ms_bg = bg["stats"][_cabi.BG_MEAN:_cabi.BG_STD + 1]
-        if getattr(self, "_mu_m", None) is None or self._dev_ms_m is None:
+        if getattr(self, "_mu_m", None) is None:
             pssm_scores = self.score_self()
             self._mu_m, self._std_m = np.mean(pssm_scores), np.std(pssm_scores)
+            self._dev_ms_m = None
+        if self._dev_ms_m is None:
             self._dev_ms_m = torch.tensor([float(self._mu_m), float(self._std_m)], dtype=torch.float64,
                                           device=self._dev())
         if sync:
@@ -328,6 +330,9 @@ class PSSMModel(TFBindingModel):
         self._dev_ms_bg = torch.tensor([float(self._mu_bg), float(self._std_bg)], dtype=torch.float64, device=dev)
 
     def _require_estimator(self):
+        if (self._dev_ms_m is None or self._dev_ms_bg is None) and \
+                getattr(self, "_mu_m", None) is not None and getattr(self, "_mu_bg", None) is not None:
+            self._estimator_changed()
         if self._dev_ms_m is None or self._dev_ms_bg is None:
             # the reference fails with AttributeError on the unset _mu_m
             raise AttributeError("'PSSMModel' object has no attribute '_mu_m' "
@@ -409,3 +414,63 @@ class PSSMModel(TFBindingModel):
         d_nwin = torch.from_numpy((lens - m + 1).astype(np.int32)).to(dev)
         out = self.binding_probabilities(g, None, None, p_motif, alpha, region_tensors=(d_start, d_nwin))
         return out.cpu().numpy()
+
+    # ------------------------------------------------ one call per replicon, host in / host out
+    def regulation_pipeline(self, sequence, starts, ends, p_motif, alpha=1/350.0, n_bins=1024,
+                            hist_lo=None, hist_hi=None):
+        """Background fit over ALL windows of ``sequence`` (genome.py:215-226) followed by the
+        posterior of regulation of every promoter slice ``sequence[start:end]``
+        (genome.py:330-333, gene.py:129-146) in ONE library call with host buffers
+        (``cgbk_regulation_pipeline``).
+
+        ``sequence``: str / bytes / uint8 numpy array / uint8 CPU tensor (a pinned tensor is
+        copied asynchronously).  Returns ``(posteriors, stats, hist)`` as numpy arrays
+        (``stats``: n, sum, sumsq, mean, std of the background) and sets ``_mu_bg`` /
+        ``_std_bg`` like ``build_bayesian_estimator``."""
+        if isinstance(sequence, torch.Tensor):
+            seq_t = sequence
+        elif isinstance(sequence, np.ndarray):
+            seq_t = torch.from_numpy(np.ascontiguousarray(sequence, dtype=np.uint8))
+        else:
+            raw = sequence if isinstance(sequence, (bytes, bytearray)) else str(sequence).encode("ascii")
+            seq_t = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+        n_bases = int(seq_t.numel())
+        model = self._model()
+        dev = self._dev()
+        if getattr(self, "_mu_m", None) is None:
+            pssm_scores = self.score_self()
+            self._mu_m, self._std_m = np.mean(pssm_scores), np.std(pssm_scores)
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        ends = np.ascontiguousarray(ends, dtype=np.int64)
+        n = len(starts)
+        lib = _cabi.lib()
+        if hist_lo is None:
+            hist_lo = self._score_bounds[0]
+        if hist_hi is None:
+            hist_hi = self._score_bounds[1]
+        need = int(lib.cgbk_pipeline_scratch_bytes(n_bases, n, self.length, n_bins))
+        scratch = getattr(self, "_pipe_scratch", None)
+        if scratch is None or scratch.numel() < need or scratch.device != dev:
+            scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+            self._pipe_scratch = scratch
+        host = getattr(self, "_pipe_host", None)
+        stage_bytes = int(lib.cgbk_pipeline_staging_bytes(n))
+        host_need = stage_bytes + 8 * n + 64 + 8 * n_bins
+        if host is None or host.numel() < host_need:
+            host = torch.empty(host_need, dtype=torch.uint8).pin_memory()
+            self._pipe_host = host
+        hp = host.data_ptr()
+        p_post, p_stats, p_hist = hp + stage_bytes, hp + stage_bytes + 8 * n, hp + stage_bytes + 8 * n + 64
+        _cabi.check(lib.cgbk_regulation_pipeline(
+            model, seq_t.data_ptr(), n_bases, starts.ctypes.data, ends.ctypes.data, n,
+            float(self._mu_m), float(self._std_m), float(p_motif), float(alpha),
+            float(hist_lo), float(hist_hi), int(n_bins), scratch.data_ptr(), scratch.numel(),
+            hp, stage_bytes, p_post, p_stats, p_hist if n_bins > 0 else None, self._stream()))
+        arr = host.numpy()
+        post = arr[stage_bytes:stage_bytes + 8 * n].view(np.float64).copy()
+        stats = arr[stage_bytes + 8 * n:stage_bytes + 8 * n + 64].view(np.float64).copy()
+        hist = arr[stage_bytes + 8 * n + 64:stage_bytes + 8 * n + 64 + 8 * n_bins].view(np.uint64).copy()
+        self._mu_bg, self._std_bg = float(stats[_cabi.BG_MEAN]), float(stats[_cabi.BG_STD])
+        self._dev_ms_bg = None                         # re-uploaded lazily by _require_estimator
+        self._last_bg = None
+        return post, stats, hist

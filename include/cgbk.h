@@ -180,6 +180,32 @@ int cgbk_background_stats(cgbk_model* model, const cgbk_genome* genome, const cg
  * all-reduce of the raw sums across ranks). */
 int cgbk_background_finalize(double* d_stats, void* stream);
 
+/* ---- host-buffer entry point -------------------------------------------------- */
+
+/* One replicon, HOST buffers in and out: the hot-path part of the reference's per-genome
+ * loop (cgb/__init__.py:686-695) -- Genome.build_PSSM_model's background fit
+ * (cgb/genome.py:215-226, over all windows) then Genome.calculate_regulation_probabilities
+ * (cgb/genome.py:330-333, cgb/gene.py:129-146, cgb/binding_model.py:94-113).
+ *   h_ascii[n_bases]      the sequence bytes (pinned memory makes the copy asynchronous)
+ *   h_start/h_end[n]      promoter slices sequence[start:end] (Python slice semantics,
+ *                         cgb/gene.py:127, cgb/chromid.py:94); a slice shorter than the motif
+ *                         is CGBK_ERR_INVALID (the reference raises there too)
+ *   mu_m, std_m           motif score distribution (binding_model.py:85)
+ *   d_scratch             device, >= cgbk_pipeline_scratch_bytes(n_bases, n, m, n_bins)
+ *   h_staging             pinned host, >= cgbk_pipeline_staging_bytes(n)
+ *   h_post[n]             posteriors; h_stats[CGBK_BG_COUNT]; h_hist[n_bins] (or NULL)
+ * Enqueues everything on `stream` and returns after one stream synchronisation. */
+int64_t cgbk_pipeline_scratch_bytes(int64_t n_bases, int n_regions, int m, int n_bins);
+int64_t cgbk_pipeline_staging_bytes(int n_regions);
+int cgbk_regulation_pipeline(cgbk_model* model, const uint8_t* h_ascii, int64_t n_bases,
+                             const int64_t* h_start, const int64_t* h_end, int n_regions,
+                             double mu_m, double std_m, double p_motif, double alpha,
+                             double hist_lo, double hist_hi, int n_bins,
+                             void* d_scratch, int64_t scratch_bytes,
+                             void* h_staging, int64_t staging_bytes,
+                             double* h_post, double* h_stats, unsigned long long* h_hist,
+                             void* stream);
+
 /* Launch statistics of the calling thread's last tiled-scan call (for bench.py):
  * out[0] = kernels launched, out[1] = tiles, out[2] = bases per lane segment. */
 int cgbk_last_launch_info(int64_t* out3);

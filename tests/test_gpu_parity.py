@@ -32,6 +32,11 @@ def models(lexa, lexa_weights):
     return out
 
 
+def lexa_weights_site_count(lexa):
+    counts = [len(mo["sites"]) for mo in lexa["motifs"]]
+    return [c / float(sum(counts)) for c in counts]
+
+
 def random_model(m, seed):
     rng = np.random.default_rng(seed)
     pwm = rng.dirichlet([0.5] * 4, size=m) * 0.92 + 0.02
@@ -240,7 +245,7 @@ def test_background_stats(models, m):
     edges = np.linspace(bg["hist_lo"], bg["hist_hi"], 1025)
     exp_hist, _ = np.histogram(b, bins=edges)
     # a score within float32 resolution of a bin edge may land in the neighbouring bin
-    near_edge = np.abs(b[:, None] - edges[np.searchsorted(edges, b)[:, None] + np.array([-1, 0])]).min(axis=1) < 2e-5
+    near_edge = np.abs(b[:, None] - edges[np.searchsorted(edges, b)[:, None] + np.array([-1, 0])]).min(axis=1) < 4e-6
     assert np.abs(np.cumsum(hist) - np.cumsum(exp_hist)).max() <= max(2, near_edge.sum())
     # accumulate a second genome into the same buffers
     g2 = PackedGenome.from_sequences([O.synthetic_genome(50000, 54)])
@@ -311,3 +316,13 @@ def test_config2_posteriors(models, lexa):
     M.scan_hits(g)
     again = calculate_regulation_probabilities(M, g, gt, prior, alpha, 300, 50).cpu().numpy()
     assert np.array_equal(again, post)
+    # the one-call host-buffer entry point (cgbk_regulation_pipeline): same numbers
+    M2 = PSSMModel(M.site_collections, lexa_weights_site_count(lexa))
+    p2, stats2, hist2 = M2.regulation_pipeline(seq, s, e, prior, alpha, n_bins=256)
+    assert np.max(np.abs(p2 - exp)) < POST_TOL
+    assert stats2[_cabi.BG_N] == len(b) and hist2.sum() == len(b)
+    assert abs(M2._mu_bg - om._mu_bg) < 1e-6 and abs(M2._std_bg - om._std_bg) < 1e-6
+    assert abs(M2.binding_probability(seq[1000:1350].decode(), prior, alpha) -
+               M.binding_probability(seq[1000:1350].decode(), prior, alpha)) < 1e-9
+    with pytest.raises(ValueError):
+        M2.regulation_pipeline(seq, [0], [10], prior, alpha)       # slice shorter than the motif
