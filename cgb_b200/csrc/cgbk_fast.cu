@@ -125,6 +125,28 @@ __device__ __forceinline__ uint2 ld_stream2(const uint32_t* __restrict__ b2, lon
     return make_uint2(wi < nw ? __ldg(b2 + wi) : 0u, 0u);
 }
 
+// Rare path of the filter kernel, deliberately NOT inlined (it would otherwise be replicated
+// at each of the 52 completion sites of the unrolled body and push the hot loop out of the
+// instruction cache): examine 4 consecutive windows wt0..wt0+3 of this lane whose flag OR was
+// non-zero and append those that are the tile's own to the candidate list.
+__device__ __noinline__ void emit_candidates4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int wt0,
+                                              int lane_first, int own_n, long long gpos0,
+                                              long long* counters, unsigned long long* cands,
+                                              long long cand_cap) {
+    const uint32_t a[4] = {a0, a1, a2, a3};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int wt = wt0 + k;
+        if ((a[k] & 0x80008000u) && wt >= lane_first && wt < own_n) {
+            const unsigned long long slot =
+                atomicAdd(reinterpret_cast<unsigned long long*>(counters + CGBK_CTR_CANDIDATES), 1ull);
+            if ((long long)slot < cand_cap)
+                cands[slot] = (unsigned long long)(gpos0 + wt) | ((unsigned long long)(a[k] >> 31) << 63) |
+                              ((unsigned long long)((a[k] >> 15) & 1u) << 62);
+        }
+    }
+}
+
 template <int G, int MODE>
 struct FastCfg {
     static constexpr int THREADS = MODE == 0 ? CGBK_FILTER_THREADS : (G <= 6 ? CGBK_STATS_THREADS : 256);
@@ -202,7 +224,11 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         uint32_t any_amb = 0;
         {
             const long long aw = (gbase + A + S) >> 5, naw = g.cap_bases >> 5;
-            for (int b = 0; b < B; ++b) any_amb |= ldw(g.amb, aw + b, naw);
+            const long long left = naw - aw;
+            const int n_ok = left < (long long)B ? (left < 0 ? 0 : (int)left) : B;     // B <= 4
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (b < n_ok) any_amb |= __ldg(g.amb + aw + b);
         }
         uint2 cur = ld_stream2(g.bases2, wbase, nwords);
         if (__any_sync(0xffffffffu, any_amb != 0)) {
@@ -224,17 +250,19 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         int* prow = sp.plane ? sp.plane + tile * (long long)((B + 1) * 1024) + lane : nullptr;
 
         // one completed window: accumulators (a, b), tile-local window index wt, plane row
-        auto complete = [&](uint32_t a, uint32_t b, int wt, bool live, int row) {
+        uint32_t flag_or = 0u, pend[4] = {0u, 0u, 0u, 0u};     // MODE 0: deferred candidate test
+        auto complete = [&](uint32_t a, uint32_t b, int wt, bool live, int row, int q /* window % 4 */) {
             if (MODE == 0) {
-                if (a & 0x80008000u) {        // rare: out-of-line
-                    if (live && wt < own_n) {
-                        const unsigned long long k = atomicAdd(
-                            reinterpret_cast<unsigned long long*>(work.counters + CGBK_CTR_CANDIDATES), 1ull);
-                        if ((long long)k < work.cand_cap)
-                            work.cands[k] = (unsigned long long)(gbase + A + wt) |
-                                            ((unsigned long long)(a >> 31) << 63) |
-                                            ((unsigned long long)((a >> 15) & 1u) << 62);
-                    }
+                // Filter: only OR the two flag bits here (one LOP3).  Every 4th window the OR is
+                // tested and, in the rare case it is set, the four windows are examined out of
+                // line (emit_candidates4).  Partial sums of windows that are not this lane's
+                // (first body, t < D) can never carry a flag bit: they lack group 0's offset.
+                flag_or |= a & 0x80008000u;
+                pend[q] = a;
+                if (q == 3) {
+                    if (flag_or) emit_candidates4(pend[0], pend[1], pend[2], pend[3], wt - 3, S, own_n,
+                                                  gbase + A, work.counters, work.cands, work.cand_cap);
+                    flag_or = 0u;
                 }
             } else {
                 const int fq = (int)a, rq = (int)b;
@@ -285,9 +313,9 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                         if (MODE == 0) stash32[t * 33] = sa[sc];
                         else stash64[t * 33] = make_uint2(sa[sc], sb[sc]);
                     }
-                    if (!ONE) complete(sa[sc], sb[sc], Sb + t - D, !first, b * 32 + t);
+                    if (!ONE) complete(sa[sc], sb[sc], Sb + t - D, !first, b * 32 + t, t & 3);
                 } else {
-                    complete(sa[sc], sb[sc], Sb + t - D, true, b * 32 + t);
+                    complete(sa[sc], sb[sc], Sb + t - D, true, b * 32 + t, t & 3);
                 }
             }
             cur = nxt;
@@ -306,7 +334,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                     const uint2 q = stash64[j * 33 + 1];
                     ia = q.x; ib = q.y;
                 }
-                complete(sa[si] + ia, sb[si] + ib, S + L - D + j, true, B * 32 + j);
+                complete(sa[si] + ia, sb[si] + ib, S + L - D + j, true, B * 32 + j, j & 3);
             }
             __syncwarp();
         }
