@@ -283,9 +283,44 @@ def run_ours(args):
     barrier()
     wall = time.perf_counter() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(np.sum(step_ms))
+    eager_total_ms = float(np.sum(step_ms))
+    total_ms = eager_total_ms
     launches_per_step = 3                           # tiled scan, dirty tiles + moment reduction, posteriors
     info = _cabi.last_launch_info()
+
+    # ---- the same K steps replayed from a CUDA graph (the step is launch-bound: 3 kernels and
+    # 3 memsets of ~50 us in total).  `value` is taken from these replays; the eager loop above
+    # provides the per-kernel CUDA-event time for the roofline.
+    graph_mode = "eager"
+    if not args.no_graph:
+        try:
+            _cabi.profile_enable(False)             # event records are not wanted inside the graph
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                step()
+            for _ in range(3):
+                graph.replay()
+                flush.zero_()
+            barrier()
+            for i in range(args.steps):
+                ev[i][0].record()
+                graph.replay()
+                ev[i][1].record()
+                flush.zero_()
+            barrier()
+            total_ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
+            graph_mode = "cuda_graph"
+        except Exception as exc:                    # keep the eager number
+            graph_mode = "eager (graph capture failed: %s)" % str(exc)[:80]
+            total_ms = eager_total_ms
+        finally:
+            _cabi.profile_enable(True)
 
     # ---- end to end through the public API, from pinned host memory
     barrier()
@@ -355,7 +390,9 @@ def run_ours(args):
             "config": {"workload": WORKLOAD,
                        "genome_bp": GENOME_BP, "promoters": N_GENES, "posterior_windows": n_post_windows,
                        "l2": "flushed between steps (512 MiB memset, outside the timed span)",
-                       "timing": "per-step CUDA events, max over ranks", "tiles": info["tiles"],
+                       "timing": "per-step CUDA events, max over ranks; value: %s; roofline kernel time: eager steps"
+                                 % graph_mode,
+                       "eager_ms_per_step": eager_total_ms / args.steps, "tiles": info["tiles"],
                        "lane_bases": info["lane_bases"], "sharding": "one genome per rank, no collective"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel()) + 12 * N_GENES + 16,
@@ -379,6 +416,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-scale", action="store_true", help="skip the at_scale leg")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--scale-bp", type=int, default=1_000_000_000)
     args = ap.parse_args()
     if args.warmup < 3:

@@ -185,30 +185,43 @@ __global__ void __launch_bounds__(256) posterior_kernel(
             // pass 1: every window from the plane on the float32 path; windows whose mixture
             // ratio x reaches 1e-2 are only marked (bit k = this lane's k-th window)
             unsigned long long marked = 0ull;
-            int k = 0;
-            for (int w = lane; w < nwin; w += 32, ++k) {
-                int wt = wt0 + w;
-                long long tile = tile_r;
-                while (wt >= stride) { wt -= stride; ++tile; }
-                const int ln = wt >> log2L, within = wt & (pv.L - 1);
-                const int row = within < pv.L - pv.D ? within + pv.D : rows_body + (within - (pv.L - pv.D));
-                const int sfix = __ldg(pv.plane + tile * plane_tile + row * 32 + ln);
-                const double s = (double)sfix * pv.inv_scale;
-                const double ym = (s - mu_m) * inv_std_m, yb = (s - mu_bg) * inv_std_bg;
-                const float ef = (float)(0.5 * (yb * yb - ym * ym));
-                // x = c * exp(e); below e = -60 x < 1e-26 adds nothing
-                const float xf = ef < -60.0f ? 0.0f : cf * __expf(ef);
-                if (xf < 1e-2f) {
-                    // log1p(x) = x - x^2/2 + x^3/3 - ... : |error| < 3e-9 for x < 1e-2
-                    acc += (double)(xf * (1.0f - xf * (0.5f - xf * (1.0f / 3.0f))));
-                } else if (k < 64) {
-                    marked |= 1ull << k;
-                } else {
-                    double f, r;                               // regions longer than 2048 windows
-                    exact_window(g, &tab, m, start + w, false, f, r);
-                    const double se = softmax2_f32tail((float)f, (float)r);
-                    const double ym2 = (se - mu_m) * inv_std_m, yb2 = (se - mu_bg) * inv_std_bg;
-                    acc += log1p(c * exp(0.5 * (yb2 * yb2 - ym2 * ym2)));
+#ifndef CGBK_POST_PF
+#define CGBK_POST_PF 1
+#endif
+            constexpr int PF = CGBK_POST_PF;   // plane loads issued ahead per lane (measured: 1, 4, 12 are within 2 us of each other)
+            for (int base = 0, k0 = 0; base < nwin; base += 32 * PF, k0 += PF) {
+                int sfix[PF];
+#pragma unroll
+                for (int j = 0; j < PF; ++j) {              // all loads first: independent L2 round trips
+                    const int w = base + lane + 32 * j;
+                    int wt = wt0 + w;
+                    long long tile = tile_r;
+                    while (wt >= stride) { wt -= stride; ++tile; }
+                    const int ln = wt >> log2L, within = wt & (pv.L - 1);
+                    const int row = within < pv.L - pv.D ? within + pv.D : rows_body + (within - (pv.L - pv.D));
+                    sfix[j] = w < nwin ? __ldg(pv.plane + tile * plane_tile + row * 32 + ln) : 0;
+                }
+#pragma unroll
+                for (int j = 0; j < PF; ++j) {
+                    const int w = base + lane + 32 * j;
+                    const double s = (double)sfix[j] * pv.inv_scale;
+                    const double ym = (s - mu_m) * inv_std_m, yb = (s - mu_bg) * inv_std_bg;
+                    const float ef = (float)(0.5 * (yb * yb - ym * ym));
+                    // x = c * exp(e); below e = -60 x < 1e-26 adds nothing
+                    float xf = ef < -60.0f ? 0.0f : cf * __expf(ef);
+                    if (w >= nwin) xf = 0.0f;
+                    if (xf < 1e-2f) {
+                        // log1p(x) = x - x^2/2 + x^3/3 - ... : |error| < 3e-9 for x < 1e-2
+                        acc += (double)(xf * (1.0f - xf * (0.5f - xf * (1.0f / 3.0f))));
+                    } else if (k0 + j < 64) {
+                        marked |= 1ull << (k0 + j);
+                    } else {
+                        double f, r;                           // regions longer than 2048 windows
+                        exact_window(g, &tab, m, start + w, false, f, r);
+                        const double se = softmax2_f32tail((float)f, (float)r);
+                        const double ym2 = (se - mu_m) * inv_std_m, yb2 = (se - mu_bg) * inv_std_bg;
+                        acc += log1p(c * exp(0.5 * (yb2 * yb2 - ym2 * ym2)));
+                    }
                 }
             }
             // pass 2: the marked windows, exactly (float64 strand sums in the reference's order)

@@ -60,23 +60,36 @@ struct TableLayout {
 // chunks [c][e][4 words], then the 8-byte chunk [e][2], then the 4-byte chunk [e].
 // Eight consecutive lanes write the eight 16-byte replicas of one chunk entry (one
 // conflict-free 128-byte row); the global read of the entry is a broadcast.
-template <int NW>
+template <int NW, int THREADS>
 __device__ __forceinline__ void fill_tables(unsigned char* smem, const uint32_t* __restrict__ gtab) {
     using TL = TableLayout<NW>;
-    for (int i = threadIdx.x; i < TL::NCH * 256 * 8; i += blockDim.x) {
-        const int ce = i >> 3, r = i & 7;
+    constexpr int TOTAL = TL::NCH * 256 * 8;
+    constexpr int ITER = (TOTAL + THREADS - 1) / THREADS;
+    // all global loads first (they are independent), then the stores: one L2 round trip
+    // instead of ITER serialized ones
+    uint4 v[ITER];
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+        const int i = threadIdx.x + k * THREADS;
+        const int ce = i >> 3;
         const int c = ce >> 8, e = ce & 255;
-        uint4 v;
-        if (c < TL::N16) {
-            v = __ldg(reinterpret_cast<const uint4*>(gtab) + c * 256 + e);
-        } else if (TL::HAS8 && c == TL::N16) {
-            const uint2 q = __ldg(reinterpret_cast<const uint2*>(gtab + TL::N16 * 1024) + e);
-            v = make_uint4(q.x, q.y, q.x, q.y);
-        } else {
-            const uint32_t q = __ldg(gtab + TL::N16 * 1024 + TL::HAS8 * 512 + e);
-            v = make_uint4(q, q, q, q);
+        v[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < TOTAL) {
+            if (c < TL::N16) {
+                v[k] = __ldg(reinterpret_cast<const uint4*>(gtab) + c * 256 + e);
+            } else if (TL::HAS8 && c == TL::N16) {
+                const uint2 q = __ldg(reinterpret_cast<const uint2*>(gtab + TL::N16 * 1024) + e);
+                v[k] = make_uint4(q.x, q.y, q.x, q.y);
+            } else {
+                const uint32_t q = __ldg(gtab + TL::N16 * 1024 + TL::HAS8 * 512 + e);
+                v[k] = make_uint4(q, q, q, q);
+            }
         }
-        *reinterpret_cast<uint4*>(smem + ce * 128 + r * 16) = v;
+    }
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+        const int i = threadIdx.x + k * THREADS;
+        if (i < TOTAL) *reinterpret_cast<uint4*>(smem + (i >> 3) * 128 + (i & 7) * 16) = v[k];
     }
 }
 
@@ -168,7 +181,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     unsigned int* hist = reinterpret_cast<unsigned int*>(smem + TL::BYTES + Cfg::STASH_BYTES);
     __shared__ double red_scratch[96];
 
-    fill_tables<NW>(smem, gtab);
+    fill_tables<NW, Cfg::THREADS>(smem, gtab);
     if (MODE == 1)
         for (int i = threadIdx.x; i <= sp.n_bins; i += blockDim.x) hist[i] = 0u;   // [n_bins] = discard bin
     __syncthreads();
