@@ -18,12 +18,15 @@ class GeneTable:
     """Genes of one replicon in annotation order: start, end (0-based, end
     exclusive, as Biopython FeatureLocation) and strand (+1 / -1)."""
 
-    def __init__(self, start, end, strand, chrom_len, seq_index=0):
+    def __init__(self, start, end, strand, chrom_len, seq_index=0, locus_tag=None, protein_id=None,
+                 product=None):
         self.start = np.asarray(start, dtype=np.int64)
         self.end = np.asarray(end, dtype=np.int64)
         self.strand = np.asarray(strand, dtype=np.int64)
         self.chrom_len = int(chrom_len)
         self.seq_index = int(seq_index)
+        # optional annotation columns of the identified_sites report (genome.py:470-493)
+        self.locus_tag, self.protein_id, self.product = locus_tag, protein_id, product
         if not (len(self.start) == len(self.end) == len(self.strand)):
             raise ValueError("start/end/strand must have equal lengths")
 

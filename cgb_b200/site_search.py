@@ -76,3 +76,62 @@ def calculate_regulation_probabilities(model, genome, gene_table, prior, alpha,
     for every gene of one replicon (device float64 tensor, gene order)."""
     start, end = gene_table.promoter_region_location(promoter_up_distance, promoter_dw_distance)
     return model.binding_probabilities(genome, start, end, prior, alpha, seq_index=gene_table.seq_index)
+
+
+# ---------------------------------------------------------------------------
+# identified_sites report (SURVEY.md §8f rank 1)
+# ---------------------------------------------------------------------------
+CSV_HEADER = ['score', 'site', 'chromid', 'start', 'end', 'strand', 'distance', 'category',
+              'gene_strand', 'gene_start', 'gene_end', 'gene_locus_tag', 'protein_id', 'gene_product']
+
+_COMPLEMENT = str.maketrans("ACGTacgtNn", "TGCAtgcaNn")
+
+
+def relative_distance_to_start(gene_start, gene_end, gene_strand, site_start, site_end):
+    """Gene.relative_distance_to_start (cgb/gene.py:290-316): distance of the site's distal end
+    to the gene start; negative = upstream."""
+    if gene_strand == 1:
+        if site_start <= gene_start:
+            return site_start - gene_start
+        return site_end - gene_start
+    if site_end >= gene_end:
+        return gene_end - site_end
+    return gene_end - site_start
+
+
+def identified_sites_rows(sites, sequences, gene_tables, promoter_up_distance, accessions=None):
+    """Rows of the reference's ``identified_sites/<genome>.csv`` (cgb/genome.py:457-494), one per
+    Site, in the order given.  ``sequences[k]``: replicon k as str (for the site sequence,
+    Chromid.subsequence incl. the reverse complement of minus-strand sites, chromid.py:92-97);
+    ``gene_tables``: the GeneTables handed to identify_sites (optional ``locus_tag`` /
+    ``protein_id`` / ``product`` lists on them fill the last columns)."""
+    by_seq = {gt.seq_index: gt for gt in gene_tables}
+    rows = []
+    for site in sites:
+        gt = by_seq[site.chromid]
+        gi = site.gene
+        g_start, g_end, g_strand = int(gt.start[gi]), int(gt.end[gi]), int(gt.strand[gi])
+        dist = relative_distance_to_start(g_start, g_end, g_strand, site.start, site.end)
+        # all downstream sites are "operator"; upstream ones beyond promoter_up are "intergenic"
+        category = 'operator'
+        if dist < 0:
+            if abs(dist) > promoter_up_distance:
+                category = 'intergenic'
+        seq = sequences[site.chromid][site.start:site.end]
+        if site.strand == -1:
+            seq = seq.translate(_COMPLEMENT)[::-1]
+        meta = lambda name: (getattr(gt, name)[gi] if getattr(gt, name, None) is not None else '')
+        rows.append([site.score, seq, accessions[site.chromid] if accessions else site.chromid,
+                     site.start, site.end, site.strand, dist, category, g_strand, g_start, g_end,
+                     meta('locus_tag'), meta('protein_id'), meta('product')])
+    return rows
+
+
+def write_identified_sites_csv(filename, sites, sequences, gene_tables, promoter_up_distance, accessions=None):
+    """Genome._output_identified_sites (cgb/genome.py:457-494)."""
+    import csv
+    with open(filename, 'w', newline='') as csvfile:
+        w = csv.writer(csvfile)
+        w.writerow(CSV_HEADER)
+        for row in identified_sites_rows(sites, sequences, gene_tables, promoter_up_distance, accessions):
+            w.writerow(row)

@@ -546,3 +546,42 @@ def synthetic_genes(n, n_genes):
         e = min(n, s + min(1000, step // 2))
         genes.append(OGene(s, e, 1 if i % 2 == 0 else -1))
     return genes
+
+
+# ---------------------------------------------------------------------------
+# identified_sites report rows (genome.py:457-494, gene.py:290-316)
+# ---------------------------------------------------------------------------
+def relative_distance_to_start(gene, site_start, site_end):
+    """gene.py:290-316."""
+    dist = 0
+    if gene.strand == 1:
+        if site_start <= gene.start:
+            dist = site_start - gene.start
+        else:
+            dist = site_end - gene.start
+    else:
+        if site_end >= gene.end:
+            dist = gene.end - site_end
+        else:
+            dist = gene.end - site_start
+    return dist
+
+
+def identified_sites_rows(sites, sequence, genes, promoter_up, accession="chromid", annotations=None):
+    """genome.py:473-494 for OSite tuples of one chromid; ``annotations[gi]`` =
+    (locus_tag, protein_id, product)."""
+    rows = []
+    for site in sites:
+        gene = genes[site.gene]
+        dist = relative_distance_to_start(gene, site.start, site.end)
+        category = 'operator'
+        if dist < 0:
+            if abs(dist) > promoter_up:
+                category = 'intergenic'
+        site_seq = sequence[site.start:site.end]
+        if site.strand == -1:
+            site_seq = reverse_complement(site_seq)
+        ann = annotations[site.gene] if annotations else ('', '', '')
+        rows.append([site.score, site_seq, accession, site.start, site.end, site.strand, dist, category,
+                     gene.strand, gene.start, gene.end, ann[0], ann[1], ann[2]])
+    return rows

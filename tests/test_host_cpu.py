@@ -131,3 +131,40 @@ def test_scoring_without_gpu_fails_loudly():
     M = PSSMModel([SiteCollection(["ACGTAC", "ACGTAA"])], [1.0])
     with pytest.raises(RuntimeError):
         M.score_seq("ACGTACGTAC")
+
+
+def test_identified_sites_rows_match_reference_format(tmp_path):
+    """the identified_sites CSV rows (genome.py:457-494) from Site tuples."""
+    import csv
+
+    from cgb_b200 import Site
+    from cgb_b200.site_search import (CSV_HEADER, identified_sites_rows, relative_distance_to_start,
+                                      write_identified_sites_csv)
+    rng = np.random.default_rng(11)
+    L = 5000
+    seq = O.synthetic_genome(L, 12).decode()
+    genes = O.synthetic_genes(L, 6)
+    ann = [("tag%d" % i, "WP_%05d.1" % i if i % 2 else "", "product %d" % i) for i in range(len(genes))]
+    gt = GeneTable([g.start for g in genes], [g.end for g in genes], [g.strand for g in genes], L,
+                   locus_tag=[a[0] for a in ann], protein_id=[a[1] for a in ann], product=[a[2] for a in ann])
+    sites, osites = [], []
+    for _ in range(40):
+        gi = int(rng.integers(0, len(genes)))
+        start = int(rng.integers(0, L - 22))
+        strand = int(rng.choice([1, -1]))
+        score = np.float32(rng.uniform(9, 25))
+        sites.append(Site(0, start, start + 22, strand, score, gi))
+        osites.append(O.OSite(start, start + 22, strand, score, gi))
+    for up in (300, 50):
+        got = identified_sites_rows(sites, [seq], [gt], up, accessions=["NC_TEST.1"])
+        exp = O.identified_sites_rows(osites, seq, genes, up, "NC_TEST.1", ann)
+        assert got == exp
+    for g in genes:      # every branch of gene.py:290-316
+        for s, e in ((g.start - 40, g.start - 18), (g.start, g.start + 22), (g.start + 5, g.start + 27),
+                     (g.end - 22, g.end), (g.end, g.end + 22), (g.end - 5, g.end + 17)):
+            assert relative_distance_to_start(g.start, g.end, g.strand, s, e) == O.relative_distance_to_start(g, s, e)
+    path = tmp_path / "sites.csv"
+    write_identified_sites_csv(str(path), sites, [seq], [gt], 300, accessions=["NC_TEST.1"])
+    rows = list(csv.reader(open(path)))
+    assert rows[0] == CSV_HEADER and len(rows) == 41
+    assert rows[1][1] == got[0][1] and rows[1][7] in ("operator", "intergenic")
