@@ -7,9 +7,9 @@ Importing the package does not need a GPU; any scoring call does (no CPU fallbac
 from .binding_model import TFBindingModel
 from .gene_regions import GeneTable, python_slice_bounds
 from .genome_buffer import PackedGenome
-from .pssm_model import PSSMModel
+from .pssm_model import PSSMModel, scan_hits_many
 from .site_collection import SiteCollection
 from .site_search import Site, calculate_regulation_probabilities, identify_sites
 
 __all__ = ["TFBindingModel", "PSSMModel", "SiteCollection", "PackedGenome", "GeneTable",
-           "Site", "identify_sites", "calculate_regulation_probabilities", "python_slice_bounds"]
+           "Site", "identify_sites", "scan_hits_many", "calculate_regulation_probabilities", "python_slice_bounds"]

@@ -224,33 +224,46 @@ class PSSMModel(TFBindingModel):
         (seq, pos, +strand first).  ``revseq_order`` selects the accumulation order
         of the minus strand: True = identify_sites (genome.py:440-445), False =
         rev_comp_pssm (pssm_model.py:115)."""
+        pending = self._launch_scan(genome, threshold, revseq_order, hit_cap)
+        return self._collect_scan(genome, pending)
+
+    def _launch_scan(self, genome, threshold=None, revseq_order=True, hit_cap=None):
+        """Enqueue one hit scan (no host synchronisation); see ``_collect_scan``."""
         if threshold is None:
             threshold = self.threshold()
         threshold = float(threshold)
         model = self._model()
         m = self.length
         dev = self._dev()
-        nwin = genome.total_windows(m)
         if hit_cap is None:
             # expected hits at the Patser operating point, with head-room
+            nwin = genome.total_windows(m)
             hit_cap = int(2 * nwin * 2.0 ** (-max(self.IC, 0.0)) * 4) + 4096
         flags = _cabi.RC_REVSEQ_ORDER if revseq_order else _cabi.RC_MATRIX_ORDER
-        counters = torch.zeros(_cabi.CTR_COUNT, dtype=torch.int64, device=dev)
+        counters = torch.empty(_cabi.CTR_COUNT, dtype=torch.int64, device=dev)
+        cand_cap = 4 * hit_cap
+        work = genome.workspace(m, cand_cap)
+        hits = torch.empty(hit_cap * 2, dtype=torch.int64, device=dev)   # 16-byte records
+        _cabi.check(_cabi.lib().cgbk_scan_hits(
+            model, genome.struct_ref(), genome.seqset, threshold, flags, hits.data_ptr(), hit_cap,
+            counters.data_ptr(), work.data_ptr(), work.numel(), cand_cap, self._stream()))
+        return {"hits": hits, "counters": counters, "hit_cap": hit_cap, "cand_cap": cand_cap,
+                "threshold": threshold, "revseq_order": revseq_order}
+
+    def _collect_scan(self, genome, pending):
+        """Wait for a launched scan, re-run it with larger buffers if a capacity was exceeded
+        (two-phase count -> fill), and return the sorted hit arrays."""
         while True:
-            cand_cap = 4 * hit_cap
-            work = genome.workspace(m, cand_cap)
-            hits = torch.empty(hit_cap * 2, dtype=torch.int64, device=dev)   # 16-byte records
-            _cabi.check(_cabi.lib().cgbk_scan_hits(
-                model, genome.struct_ref(), genome.seqset, threshold, flags, hits.data_ptr(), hit_cap,
-                counters.data_ptr(), work.data_ptr(), work.numel(), cand_cap, self._stream()))
-            c = counters.cpu().numpy()
+            c = pending["counters"].cpu().numpy()
             n_cand, n_hits = int(c[_cabi.CTR_CANDIDATES]), int(c[_cabi.CTR_HITS])
-            if n_cand <= cand_cap and n_hits <= hit_cap:
+            if n_cand <= pending["cand_cap"] and n_hits <= pending["hit_cap"]:
                 break
-            hit_cap = max(n_hits, (n_cand + 3) // 4) + 1024
+            pending = self._launch_scan(genome, pending["threshold"], pending["revseq_order"],
+                                        max(n_hits, (n_cand + 3) // 4) + 1024)
         self.last_scan_counters = {"candidates": n_cand, "hits": n_hits,
                                    "dirty_tiles": int(c[_cabi.CTR_DIRTY_TILES])}
-        rec = hits[:2 * n_hits].cpu().numpy().view(np.dtype([("gpos", "<i8"), ("strand", "<i4"), ("score", "<f4")]))
+        rec = pending["hits"][:2 * n_hits].cpu().numpy().view(
+            np.dtype([("gpos", "<i8"), ("strand", "<i4"), ("score", "<f4")]))
         gpos, strand, score = rec["gpos"].copy(), rec["strand"].copy(), rec["score"].copy()
         seq = np.searchsorted(genome.seq_off, gpos, side="right") - 1
         pos = gpos - genome.seq_off[seq]
@@ -474,3 +487,14 @@ class PSSMModel(TFBindingModel):
         self._dev_ms_bg = None                         # re-uploaded lazily by _require_estimator
         self._last_bg = None
         return post, stats, hist
+
+
+def scan_hits_many(models, genome, thresholds=None, revseq_order=True):
+    """Hit scans of many motifs over one packed genome (BASELINE configs[4]: JASPAR-scale motif
+    sets): all scans are enqueued back to back on the current stream and collected afterwards,
+    so the GPU never waits for the host between motifs.  Returns one
+    ``(seq_index, pos, strand, score)`` tuple per model, as ``PSSMModel.scan_hits``."""
+    if thresholds is None:
+        thresholds = [None] * len(models)
+    pending = [M._launch_scan(genome, thr, revseq_order) for M, thr in zip(models, thresholds)]
+    return [M._collect_scan(genome, p) for M, p in zip(models, pending)]

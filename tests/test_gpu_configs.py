@@ -93,6 +93,7 @@ def test_config5_many_motifs_one_sequence():
     seq = O.synthetic_genome(400000, 5, n_frac=0.0003)
     g = PackedGenome.from_sequences([seq])
     total_hits = 0
+    models, singles = [], []
     for k in range(24):
         m = int(rng.integers(8, 31))
         # JASPAR-like: 20 sites sampled from a Dirichlet(0.5)-column PWM, pseudocount 1
@@ -105,7 +106,13 @@ def test_config5_many_motifs_one_sequence():
         ep, es, ev = c_oracle.scan_hits(om, seq, om.threshold())
         assert np.array_equal(pos, ep) and np.array_equal(strand, es) and np.array_equal(score, ev), (k, m)
         total_hits += len(pos)
+        models.append(M)
+        singles.append((pos, strand, score))
         st = M.background_stats(g)["stats"].cpu().numpy()
         _, _, b = c_oracle.score_seq(om, seq)
         assert abs(st[_cabi.BG_MEAN] - b.mean()) < 1e-6 and abs(st[_cabi.BG_STD] - b.std()) < 1e-6, (k, m)
     assert total_hits > 100
+    # all motifs enqueued back to back, collected afterwards
+    from cgb_b200 import scan_hits_many
+    for (pos, strand, score), res in zip(singles, scan_hits_many(models, g)):
+        assert np.array_equal(res[1], pos) and np.array_equal(res[2], strand) and np.array_equal(res[3], score)
