@@ -288,14 +288,27 @@ cudaError_t launch_posteriors(const cgbk_model* mdl, GenomeView g, SeqTable seqs
 // hits: exact re-scoring of filter candidates + exact scan of dirty tiles
 //   genome.py:436,443: float32 score compared with the float64 threshold
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void emit_hit(cgbk_hit* hits, long long cap, long long* counters,
-                                         long long gpos, int strand, float score) {
-    const unsigned long long k =
-        atomicAdd(reinterpret_cast<unsigned long long*>(counters + CGBK_CTR_HITS), 1ull);
-    if ((long long)k < cap) {
-        cgbk_hit h;
-        h.gpos = gpos; h.strand = strand; h.score = score;
-        hits[k] = h;
+// Warp-convergent append of up to two hits per lane (+ strand, - strand) with ONE global atomic
+// per warp: with low-information motifs millions of hits would otherwise serialise on the counter.
+__device__ __forceinline__ void emit_hits_warp(cgbk_hit* hits, long long cap, long long* counters,
+                                               long long gpos, bool hf, float ff, bool hr, float rf) {
+    const unsigned int mf = __ballot_sync(0xffffffffu, hf), mr = __ballot_sync(0xffffffffu, hr);
+    const int nf = __popc(mf), tot = nf + __popc(mr);
+    if (tot == 0) return;                                   // warp-uniform
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0)
+        base = atomicAdd(reinterpret_cast<unsigned long long*>(counters + CGBK_CTR_HITS),
+                         (unsigned long long)tot);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const unsigned int lt = (1u << lane) - 1u;
+    if (hf) {
+        const long long k = (long long)base + __popc(mf & lt);
+        if (k < cap) { cgbk_hit h; h.gpos = gpos; h.strand = 1; h.score = ff; hits[k] = h; }
+    }
+    if (hr) {
+        const long long k = (long long)base + nf + __popc(mr & lt);
+        if (k < cap) { cgbk_hit h; h.gpos = gpos; h.strand = -1; h.score = rf; hits[k] = h; }
     }
 }
 
@@ -308,15 +321,23 @@ __global__ void __launch_bounds__(128) rescore_kernel(const double* __restrict__
     const bool revseq = (flags & CGBK_RC_REVSEQ_ORDER) != 0;
     long long n = w.counters[CGBK_CTR_CANDIDATES];
     if (n > w.cand_cap) n = w.cand_cap;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long rec = w.cands[i];
-        const long long gpos = (long long)(rec & 0x3fffffffffffffffull);
-        double f, r;
-        exact_window(g, &tab, m, gpos, revseq, f, r);
-        const float ff = (float)f, rf = (float)r;
-        if ((rec >> 63) && (double)ff >= thr) emit_hit(hits, hit_cap, w.counters, gpos, 1, ff);
-        if (((rec >> 62) & 1ull) && (double)rf >= thr) emit_hit(hits, hit_cap, w.counters, gpos, -1, rf);
+    // warp-uniform trip count so that the hits of a warp are appended with one atomic
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < n;
+         i0 += (long long)gridDim.x * blockDim.x) {
+        const long long i = i0 + (threadIdx.x & 31);
+        bool hf = false, hr = false;
+        long long gpos = 0;
+        float ff = 0.f, rf = 0.f;
+        if (i < n) {
+            const unsigned long long rec = w.cands[i];
+            gpos = (long long)(rec & 0x3fffffffffffffffull);
+            double f, r;
+            exact_window(g, &tab, m, gpos, revseq, f, r);
+            ff = (float)f; rf = (float)r;
+            hf = (rec >> 63) && (double)ff >= thr;
+            hr = ((rec >> 62) & 1ull) && (double)rf >= thr;
+        }
+        emit_hits_warp(hits, hit_cap, w.counters, gpos, hf, ff, hr, rf);
     }
 }
 
@@ -345,12 +366,18 @@ __global__ void __launch_bounds__(128) dirty_hits_kernel(const double* __restric
     for (long long d = blockIdx.x; d < nd; d += gridDim.x) {
         long long gbase, lo, hi;
         tile_range(seqs, w.dirty_tiles[d], L, m, gbase, lo, hi);
-        for (long long x = lo + threadIdx.x; x < hi; x += blockDim.x) {
-            double f, r;
-            exact_window(g, &tab, m, gbase + x, revseq, f, r);
-            const float ff = (float)f, rf = (float)r;
-            if ((double)ff >= thr) emit_hit(hits, hit_cap, w.counters, gbase + x, 1, ff);
-            if ((double)rf >= thr) emit_hit(hits, hit_cap, w.counters, gbase + x, -1, rf);
+        for (long long x0 = lo + (threadIdx.x & ~31); x0 < hi; x0 += blockDim.x) {
+            const long long x = x0 + (threadIdx.x & 31);
+            bool hf = false, hr = false;
+            float ff = 0.f, rf = 0.f;
+            if (x < hi) {
+                double f, r;
+                exact_window(g, &tab, m, gbase + x, revseq, f, r);
+                ff = (float)f; rf = (float)r;
+                hf = (double)ff >= thr;
+                hr = (double)rf >= thr;
+            }
+            emit_hits_warp(hits, hit_cap, w.counters, gbase + x, hf, ff, hr, rf);
         }
     }
 }

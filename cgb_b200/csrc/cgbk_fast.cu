@@ -142,8 +142,17 @@ __device__ __forceinline__ uint2 ld_stream2(const uint32_t* __restrict__ b2, lon
 // at each of the 52 completion sites of the unrolled body and push the hot loop out of the
 // instruction cache): examine 4 consecutive windows wt0..wt0+3 of this lane whose flag OR was
 // non-zero and append those that are the tile's own to the candidate list.
+//
+// Candidates are first parked in a small per-warp shared-memory buffer (one shared-memory
+// atomic each) and moved to the global list by flush_candidates() at warp-convergent points
+// with ONE global atomic per flush and coalesced stores: with low-information motifs ~1 % of
+// the windows are candidates and a global atomic per candidate on a single counter would
+// serialise the whole scan.  A full buffer falls back to the direct global append.
+#define CGBK_CAND_STAGE 96      // entries per warp
+
 __device__ __noinline__ void emit_candidates4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int wt0,
                                               int lane_first, int own_n, long long gpos0,
+                                              unsigned long long* stage, unsigned int* stage_cnt,
                                               long long* counters, unsigned long long* cands,
                                               long long cand_cap) {
     const uint32_t a[4] = {a0, a1, a2, a3};
@@ -151,13 +160,39 @@ __device__ __noinline__ void emit_candidates4(uint32_t a0, uint32_t a1, uint32_t
     for (int k = 0; k < 4; ++k) {
         const int wt = wt0 + k;
         if ((a[k] & 0x80008000u) && wt >= lane_first && wt < own_n) {
-            const unsigned long long slot =
-                atomicAdd(reinterpret_cast<unsigned long long*>(counters + CGBK_CTR_CANDIDATES), 1ull);
-            if ((long long)slot < cand_cap)
-                cands[slot] = (unsigned long long)(gpos0 + wt) | ((unsigned long long)(a[k] >> 31) << 63) |
-                              ((unsigned long long)((a[k] >> 15) & 1u) << 62);
+            const unsigned long long rec = (unsigned long long)(gpos0 + wt) |
+                                           ((unsigned long long)(a[k] >> 31) << 63) |
+                                           ((unsigned long long)((a[k] >> 15) & 1u) << 62);
+            const unsigned int idx = atomicAdd(stage_cnt, 1u);
+            if (idx < CGBK_CAND_STAGE) {
+                stage[idx] = rec;
+            } else {
+                const unsigned long long slot =
+                    atomicAdd(reinterpret_cast<unsigned long long*>(counters + CGBK_CTR_CANDIDATES), 1ull);
+                if ((long long)slot < cand_cap) cands[slot] = rec;
+            }
         }
     }
+}
+
+// warp-convergent: move this warp's parked candidates to the global list
+__device__ __noinline__ void flush_candidates(unsigned long long* stage, unsigned int* stage_cnt, int lane,
+                                                 long long* counters, unsigned long long* cands,
+                                                 long long cand_cap) {
+    __syncwarp();
+    unsigned int n = *stage_cnt;
+    if (n == 0) return;                                     // warp-uniform
+    if (n > CGBK_CAND_STAGE) n = CGBK_CAND_STAGE;
+    unsigned long long base = 0;
+    if (lane == 0)
+        base = atomicAdd(reinterpret_cast<unsigned long long*>(counters + CGBK_CTR_CANDIDATES),
+                         (unsigned long long)n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (unsigned int i = lane; i < n; i += 32)
+        if ((long long)(base + i) < cand_cap) cands[base + i] = stage[i];
+    __syncwarp();
+    if (lane == 0) *stage_cnt = 0u;
+    __syncwarp();
 }
 
 template <int G, int MODE>
@@ -165,7 +200,9 @@ struct FastCfg {
     static constexpr int THREADS = MODE == 0 ? CGBK_FILTER_THREADS : (G <= 6 ? CGBK_STATS_THREADS : 256);
     static constexpr int NW = MODE == 0 ? G : 2 * G;
     static constexpr int D = 4 * (G - 1);
-    static constexpr int STASH_BYTES = (THREADS / 32) * D * 33 * (MODE == 0 ? 4 : 8);
+    static constexpr int STASH_BYTES = ((THREADS / 32) * D * 33 * (MODE == 0 ? 4 : 8) + 15) / 16 * 16;
+    // MODE 0: per-warp candidate staging [CGBK_CAND_STAGE] u64 + one counter word (padded to 16 B)
+    static constexpr int CAND_BYTES = MODE == 0 ? (THREADS / 32) * (CGBK_CAND_STAGE * 8 + 16) : 0;
 };
 
 template <int G, int MODE, bool ONE>
@@ -180,10 +217,15 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     unsigned char* stash_base = smem + TL::BYTES;
     unsigned int* hist = reinterpret_cast<unsigned int*>(smem + TL::BYTES + Cfg::STASH_BYTES);
     __shared__ double red_scratch[96];
+    // MODE 0: this warp's candidate staging buffer and its fill count
+    unsigned char* cand_base = smem + TL::BYTES + Cfg::STASH_BYTES + (threadIdx.x >> 5) * (CGBK_CAND_STAGE * 8 + 16);
+    unsigned long long* cand_stage = reinterpret_cast<unsigned long long*>(cand_base);
+    unsigned int* cand_cnt = reinterpret_cast<unsigned int*>(cand_base + CGBK_CAND_STAGE * 8);
 
     fill_tables<NW, Cfg::THREADS>(smem, gtab);
     if (MODE == 1)
         for (int i = threadIdx.x; i <= sp.n_bins; i += blockDim.x) hist[i] = 0u;   // [n_bins] = discard bin
+    if (MODE == 0 && (threadIdx.x & 31) == 0) *cand_cnt = 0u;
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -264,6 +306,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
 
         // one completed window: accumulators (a, b), tile-local window index wt, plane row
         uint32_t flag_or = 0u, pend[4] = {0u, 0u, 0u, 0u};     // MODE 0: deferred candidate test
+        bool staged = false;                                   // MODE 0: this lane parked candidates
         auto complete = [&](uint32_t a, uint32_t b, int wt, bool live, int row, int q /* window % 4 */) {
             if (MODE == 0) {
                 // Filter: only OR the two flag bits here (one LOP3).  Every 4th window the OR is
@@ -273,8 +316,11 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 flag_or |= a & 0x80008000u;
                 pend[q] = a;
                 if (q == 3) {
-                    if (flag_or) emit_candidates4(pend[0], pend[1], pend[2], pend[3], wt - 3, S, own_n,
-                                                  gbase + A, work.counters, work.cands, work.cand_cap);
+                    if (flag_or) {
+                        emit_candidates4(pend[0], pend[1], pend[2], pend[3], wt - 3, S, own_n, gbase + A,
+                                         cand_stage, cand_cnt, work.counters, work.cands, work.cand_cap);
+                        staged = true;      // something may be parked: flush at the next convergent point
+                    }
                     flag_or = 0u;
                 }
             } else {
@@ -333,6 +379,10 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
             }
             cur = nxt;
             if (MODE == 1) { sum_d += acc_d; acc_d = 0; }
+            if (MODE == 0 && __any_sync(0xffffffffu, staged)) {     // a vote, no memory access, when idle
+                flush_candidates(cand_stage, cand_cnt, lane, work.counters, work.cands, work.cand_cap);
+                staged = false;
+            }
         }
         // windows straddling into the next lane: add the partial sums it parked for us
         if (D > 0) {
@@ -350,6 +400,10 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 complete(sa[si] + ia, sb[si] + ib, S + L - D + j, true, B * 32 + j, j & 3);
             }
             __syncwarp();
+            if (MODE == 0 && __any_sync(0xffffffffu, staged)) {
+                flush_candidates(cand_stage, cand_cnt, lane, work.counters, work.cands, work.cand_cap);
+                staged = false;
+            }
         }
         if (MODE == 1) {
             sum_d += acc_d;
@@ -382,7 +436,7 @@ template <int G, int MODE, bool ONE>
 static cudaError_t launch_one(const uint32_t* gtab, GenomeView g, SeqTable seqs, FastWork w, int m, int L,
                               int grid, StatsParams sp, cudaStream_t st) {
     using Cfg = FastCfg<G, MODE>;
-    const size_t fixed = TableLayout<Cfg::NW>::BYTES + Cfg::STASH_BYTES;
+    const size_t fixed = TableLayout<Cfg::NW>::BYTES + Cfg::STASH_BYTES + Cfg::CAND_BYTES;
     const size_t smem_max = fixed + (MODE == 1 ? (CGBK_MAX_HIST_BINS + 1) * 4 : 0);
     const size_t smem = fixed + (MODE == 1 ? ((size_t)sp.n_bins + 1) * 4 : 0);
     static bool configured = false;   // per template instance
