@@ -224,7 +224,8 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
 
     fill_tables<NW, Cfg::THREADS>(smem, gtab);
     if (MODE == 1)
-        for (int i = threadIdx.x; i <= sp.n_bins; i += blockDim.x) hist[i] = 0u;   // [n_bins] = discard bin
+        for (int i = threadIdx.x; i < (sp.n_bins + 1) * sp.hist_words; i += blockDim.x)
+            hist[i] = 0u;                                    // row n_bins = discard bin
     if (MODE == 0 && (threadIdx.x & 31) == 0) *cand_cnt = 0u;
     __syncthreads();
 
@@ -243,7 +244,10 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     double sum_d2 = 0.0;          // sum of their squares
     long long cnt = 0;
 
-    const unsigned hist_saddr = (unsigned)__cvta_generic_to_shared(hist);
+    // histogram row of bin b starts at b * hist_words words; with 32 words per row every lane
+    // counts into its own bank (conflict free), with 1 word per row lanes share the counters
+    const unsigned hist_saddr = (unsigned)__cvta_generic_to_shared(hist) + (sp.hist_words == 32 ? 4u * lane : 0u);
+    const unsigned hist_row_bytes = 4u * (unsigned)sp.hist_words;
 
     // Tiles are handed out dynamically (one global atomic per warp tile, fetched one tile
     // ahead): with only a few tiles per warp a static split leaves most warps idle while the
@@ -337,7 +341,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 dq = valid ? dq : 0;
                 // plain shared-memory reduction: atomicAdd(.., 1) makes ptxas wrap the ATOMS in a
                 // warp-collective (match + POPC.INC) region that serialises the unrolled body
-                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_saddr + 4u * (unsigned)bin), "r"(1u));
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_saddr + hist_row_bytes * (unsigned)bin), "r"(1u));
                 acc_d += dq;
                 acc_d2 += (long long)dq * dq;
                 if (prow) prow[row * 32] = sfix;
@@ -416,8 +420,12 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     if (MODE == 1) {
         __syncthreads();
         if (sp.d_hist)
-            for (int i = threadIdx.x; i < sp.n_bins; i += blockDim.x)
-                if (hist[i]) atomicAdd(sp.d_hist + i, (unsigned long long)hist[i]);
+            for (int i = threadIdx.x; i < sp.n_bins; i += blockDim.x) {
+                unsigned int v = 0;
+                for (int l = 0; l < sp.hist_words; ++l)       // rotate the start: no bank conflict
+                    v += hist[i * sp.hist_words + ((l + i) & (sp.hist_words - 1))];
+                if (v) atomicAdd(sp.d_hist + i, (unsigned long long)v);
+            }
         // block totals: n, sum d (exact in double up to 2^53), sum d^2
         double a = (double)sum_d, b2 = sum_d2, c = (double)cnt;
         block_reduce3(a, b2, c, red_scratch);
@@ -437,8 +445,9 @@ static cudaError_t launch_one(const uint32_t* gtab, GenomeView g, SeqTable seqs,
                               int grid, StatsParams sp, cudaStream_t st) {
     using Cfg = FastCfg<G, MODE>;
     const size_t fixed = TableLayout<Cfg::NW>::BYTES + Cfg::STASH_BYTES + Cfg::CAND_BYTES;
-    const size_t smem_max = fixed + (MODE == 1 ? (CGBK_MAX_HIST_BINS + 1) * 4 : 0);
-    const size_t smem = fixed + (MODE == 1 ? ((size_t)sp.n_bins + 1) * 4 : 0);
+    // histogram: (n_bins + 1) rows of 1 word (<= 4096 bins) or of 32 words (<= 256 bins, conflict free)
+    const size_t smem_max = fixed + (MODE == 1 ? (size_t)(256 + 1) * 128 : 0);
+    const size_t smem = fixed + (MODE == 1 ? ((size_t)sp.n_bins + 1) * 4 * sp.hist_words : 0);
     static bool configured = false;   // per template instance
     auto kern = fast_scan_kernel<G, MODE, ONE>;
     if (!configured) {
@@ -494,6 +503,7 @@ StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist
     sp.bin_mul = (unsigned int)mul;
     sp.bin_shift = k;
     sp.n_bins = n_bins;
+    sp.hist_words = n_bins <= 256 ? 32 : 1;
     const double centre = 0.5 * (mdl->min_score + mdl->max_score);
     sp.c_fix = (int)llrint(centre * scale);
     sp.c = (double)sp.c_fix / scale;

@@ -137,6 +137,7 @@ struct StatsParams {
     unsigned int bin_mul;  // floor(2^(32 + bin_shift) * n_bins / range_fix)
     int bin_shift;
     int n_bins;
+    int hist_words;        // shared-memory words per histogram bin: 32 (one per lane, <= 256 bins) or 1
     int c_fix;             // moment centre, fixed point
     int sh;                // kexp - 18: moment rounding shift
     int half;              // 1 << (sh - 1) (0 when sh == 0)

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--m", type=int, default=22)
     ap.add_argument("--plane", action="store_true", help="also write the score plane in the stats scan")
+    ap.add_argument("--bins", type=int, default=1024, help="histogram bins of the stats scan")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -75,7 +76,7 @@ def main():
                 res = M.scan_hits(g, thr)
                 extra = dict(M.last_scan_counters)
             else:
-                bg = M.background_stats(g, keep_scores=args.plane)
+                bg = M.background_stats(g, n_bins=args.bins, keep_scores=args.plane)
                 torch.cuda.synchronize()
                 st = bg["stats"].cpu().numpy()
                 extra = {"n": float(st[0]), "mean": float(st[3]), "std": float(st[4])}
