@@ -116,3 +116,65 @@ def test_config5_many_motifs_one_sequence():
     from cgb_b200 import scan_hits_many
     for (pos, strand, score), res in zip(singles, scan_hits_many(models, g)):
         assert np.array_equal(res[1], pos) and np.array_equal(res[2], strand) and np.array_equal(res[3], score)
+
+
+def test_config2_full_size(lexa, lexa_weights):
+    """BASELINE configs[1] at its full size: 5 Mbp genome, 3 000 promoters, against the C oracle."""
+    site_lists = [mo["sites"] for mo in lexa["motifs"]]
+    M = PSSMModel(_collections(lexa), lexa_weights["site_count"])
+    om = O.OracleModel(site_lists, lexa_weights["site_count"])
+    L, n_genes = 5_000_000, 3000
+    seq = O.synthetic_genome(L, 2)
+    step = L // n_genes
+    start = np.arange(n_genes, dtype=np.int64) * step + step // 3
+    end = np.minimum(L, start + min(1000, step // 2))
+    strand = np.where(np.arange(n_genes) % 2 == 0, 1, -1)
+    gt = GeneTable(start, end, strand, L)
+    ps, pe = gt.promoter_region_location(300, 50)
+    prior, alpha = lexa["prior_regulation_probability"], lexa["alpha"]
+    post, stats, hist = M.regulation_pipeline(seq, ps, pe, prior, alpha, n_bins=1024)
+    b = c_oracle.score_seq(om, seq)[2]
+    O.build_bayesian_estimator(om, b)
+    assert stats[_cabi.BG_N] == len(b) == L - 21 and hist.sum() == len(b)
+    assert abs(stats[_cabi.BG_MEAN] - om._mu_bg) < 1e-6 and abs(stats[_cabi.BG_STD] - om._std_bg) < 1e-6
+    exp = np.array([c_oracle.binding_probability(om, seq[int(s):int(e)], om._mu_m, om._std_m, om._mu_bg,
+                                                 om._std_bg, prior, alpha) for s, e in zip(ps, pe)])
+    assert np.max(np.abs(post - exp)) < 1e-6
+
+
+def test_large_sequence_tiling_invariance(lexa, lexa_weights):
+    """Size-independent properties at 200 Mbp (no oracle at this size): the hit list and the
+    background record do not depend on how the sequence is cut into chunks / tiles, every window
+    is counted exactly once, and hits are sorted and unique."""
+    M = PSSMModel(_collections(lexa), lexa_weights["site_count"])
+    n, world = 200_000_000, 8
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(44)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
+    ascii_all = lut[torch.randint(0, 4, (n,), device="cuda", generator=gen)]
+    whole = PackedGenome([n])
+    whole.pack_into(0, ascii_all)
+    _, pos, strand, score = M.scan_hits(whole)
+    bg_whole = M.background_stats(whole, n_bins=256)
+    key = pos * 2 + (strand < 0)
+    assert (np.diff(key) > 0).all()                                   # sorted, no duplicates
+    assert (score.astype(np.float64) >= M.threshold()).all()
+    starts, ends, counts = cdist.chunk_bounds(n, M.length, world)
+    bg = None
+    parts = []
+    for r in range(world):
+        g = PackedGenome([int(ends[r] - starts[r])])
+        g.pack_into(0, ascii_all[int(starts[r]):int(ends[r])].clone())
+        bg = M.background_stats(g, n_bins=256, accumulate_into=bg)
+        _, p, s, v = M.scan_hits(g)
+        parts.append((p + starts[r], s, v))
+    assert np.array_equal(np.concatenate([x[0] for x in parts]), pos)
+    assert np.array_equal(np.concatenate([x[1] for x in parts]), strand)
+    assert np.array_equal(np.concatenate([x[2] for x in parts]), score)
+    a, w = bg["stats"].cpu().numpy(), bg_whole["stats"].cpu().numpy()
+    assert a[_cabi.BG_N] == w[_cabi.BG_N] == n - M.length + 1
+    # integer moments inside a scan; the sums of the 8 chunk calls are then added in float64
+    assert abs(a[_cabi.BG_SUM] - w[_cabi.BG_SUM]) <= 1e-14 * abs(w[_cabi.BG_SUM])
+    assert abs(a[_cabi.BG_MEAN] - w[_cabi.BG_MEAN]) < 1e-12 and abs(a[_cabi.BG_STD] - w[_cabi.BG_STD]) < 1e-12
+    assert torch.equal(bg["hist"], bg_whole["hist"])
+    assert int(bg["hist"].sum().item()) == n - M.length + 1
