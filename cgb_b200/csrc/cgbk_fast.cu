@@ -40,8 +40,20 @@
 //    appended to a list the exact kernels walk (ambiguity repair, pssm_model.py:88-101).
 #include "cgbk_device.cuh"
 
+// Threads per CTA (one CTA per SM).  Measured on B200 at 1 Gbp / 5 Mbp, LexA m = 22, stats kernel:
+// 256: 4.47e11 / 26.3 us, 320: 4.76e11 / 24.3, 384: 4.92e11 / 25.5, 448: 4.72e11 / 27.4,
+// 512: 4.76e11 / 26.3 (128 registers, spills), 640: 4.08e11.
 #ifndef CGBK_STATS_THREADS
-#define CGBK_STATS_THREADS 512
+#define CGBK_STATS_THREADS 384
+#endif
+#ifndef CGBK_STATS_EW
+#define CGBK_STATS_EW 4
+#endif
+#ifndef CGBK_STATS_BATCH
+#define CGBK_STATS_BATCH 1
+#endif
+#ifndef CGBK_FILTER_BATCH
+#define CGBK_FILTER_BATCH 1
 #endif
 #ifndef CGBK_FILTER_THREADS
 #define CGBK_FILTER_THREADS 640
@@ -212,6 +224,11 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     using Cfg = FastCfg<G, MODE>;
     constexpr int NW = Cfg::NW;
     constexpr int D = Cfg::D;
+    // completed windows are handled in groups: 4 for the filter's deferred flag test, CGBK_STATS_EW
+    // for the stats epilogue (its dependent chains run side by side)
+    constexpr int EW = MODE == 0 ? 4 : CGBK_STATS_EW;
+    // stream positions whose table look-ups are issued together before their accumulation
+    constexpr int SB = MODE == 0 ? CGBK_FILTER_BATCH : CGBK_STATS_BATCH;
     using TL = TableLayout<NW>;
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char* stash_base = smem + TL::BYTES;
@@ -309,7 +326,9 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         int* prow = sp.plane ? sp.plane + tile * (long long)((B + 1) * 1024) + lane : nullptr;
 
         // one completed window: accumulators (a, b), tile-local window index wt, plane row
-        uint32_t flag_or = 0u, pend[4] = {0u, 0u, 0u, 0u};     // MODE 0: deferred candidate test
+        uint32_t flag_or = 0u, pend[EW], pendb[EW];            // the last (up to) EW completed windows
+#pragma unroll
+        for (int i = 0; i < EW; ++i) { pend[i] = 0u; pendb[i] = 0u; }
         bool staged = false;                                   // MODE 0: this lane parked candidates
         auto complete = [&](uint32_t a, uint32_t b, int wt, bool live, int row, int q /* window % 4 */) {
             if (MODE == 0) {
@@ -328,23 +347,43 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                     flag_or = 0u;
                 }
             } else {
-                const int fq = (int)a, rq = (int)b;
-                const int mx = max(fq, rq), mn = min(fq, rq);
-                const float u = ex2_approx((float)(mx - mn) * sp.neg_inv_scale);     // 2^-|f-r|
-                const float lg = lg2_approx(1.0f + u);
-                const int sfix = mx + __float2int_rn(lg * sp.scale);                 // soft-max, fixed point
-                const bool valid = live && (wt < own_n);
-                int bin = min((int)(__umulhi((unsigned)max(sfix - sp.lo_fix, 0), sp.bin_mul) >> sp.bin_shift),
-                              last_bin);
-                bin = valid ? bin : n_bins;
-                int dq = (sfix - sp.c_fix + sp.half) >> sp.sh;
-                dq = valid ? dq : 0;
-                // plain shared-memory reduction: atomicAdd(.., 1) makes ptxas wrap the ATOMS in a
-                // warp-collective (match + POPC.INC) region that serialises the unrolled body
-                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_saddr + hist_row_bytes * (unsigned)bin), "r"(1u));
-                acc_d += dq;
-                acc_d2 += (long long)dq * dq;
-                if (prow) prow[row * 32] = sfix;
+                // Stats: the soft-max / histogram / moment epilogue is one long dependent chain
+                // (max, I2F, EX2, LG2, F2I, mul-hi, select, RED: ~170 cycles).  Four windows are
+                // therefore collected and their chains run side by side, stage by stage.
+                pend[q] = a;
+                pendb[q] = b;
+                if (q == EW - 1) {
+                    int mx[EW], sfix[EW];
+                    float u[EW];
+#pragma unroll
+                    for (int k = 0; k < EW; ++k) {
+                        const int fq = (int)pend[k], rq = (int)pendb[k];
+                        mx[k] = max(fq, rq);
+                        u[k] = (float)(mx[k] - min(fq, rq)) * sp.neg_inv_scale;
+                    }
+#pragma unroll
+                    for (int k = 0; k < EW; ++k) u[k] = ex2_approx(u[k]);                 // 2^-|f-r|
+#pragma unroll
+                    for (int k = 0; k < EW; ++k) u[k] = lg2_approx(1.0f + u[k]);
+#pragma unroll
+                    for (int k = 0; k < EW; ++k) sfix[k] = mx[k] + __float2int_rn(u[k] * sp.scale);   // fixed point
+#pragma unroll
+                    for (int k = 0; k < EW; ++k) {
+                        const bool valid = live && (wt - (EW - 1) + k < own_n);
+                        int bin = min((int)(__umulhi((unsigned)max(sfix[k] - sp.lo_fix, 0), sp.bin_mul) >> sp.bin_shift),
+                                      last_bin);
+                        bin = valid ? bin : n_bins;
+                        // plain shared-memory reduction (atomicAdd(.., 1) would be wrapped in a
+                        // warp-collective region by ptxas)
+                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_saddr + hist_row_bytes * (unsigned)bin),
+                                     "r"(1u));
+                        int dq = (sfix[k] - sp.c_fix + sp.half) >> sp.sh;
+                        dq = valid ? dq : 0;
+                        acc_d += dq;
+                        acc_d2 += (long long)dq * dq;
+                        if (prow) prow[(row - (EW - 1) + k) * 32] = sfix[k];
+                    }
+                }
             }
         };
 
@@ -354,10 +393,16 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
             const int Sb = S + 32 * b;
             const bool first = ONE || (b == 0);
 #pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                const uint32_t E = kmer_addr(t, w0, w1, w2);
-                uint32_t v[NW];
-                lookup<NW>(smem, E, o16, o8, o4, v);
+            for (int t0 = 0; t0 < 32; t0 += SB) {
+              // look up SB consecutive positions first (independent LDS in flight together) ...
+              uint32_t vv[SB][NW];
+#pragma unroll
+              for (int u = 0; u < SB; ++u) lookup<NW>(smem, kmer_addr(t0 + u, w0, w1, w2), o16, o8, o4, vv[u]);
+              // ... then accumulate and complete them in order
+#pragma unroll
+              for (int u = 0; u < SB; ++u) {
+                const int t = t0 + u;
+                const uint32_t (&v)[NW] = vv[u];
 #pragma unroll
                 for (int gi = 0; gi < G; ++gi) {
                     const int si = (t - 4 * gi) & 31;
@@ -376,10 +421,11 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                         if (MODE == 0) stash32[t * 33] = sa[sc];
                         else stash64[t * 33] = make_uint2(sa[sc], sb[sc]);
                     }
-                    if (!ONE) complete(sa[sc], sb[sc], Sb + t - D, !first, b * 32 + t, t & 3);
+                    if (!ONE) complete(sa[sc], sb[sc], Sb + t - D, !first, b * 32 + t, (t - D) & (EW - 1));
                 } else {
-                    complete(sa[sc], sb[sc], Sb + t - D, true, b * 32 + t, t & 3);
+                    complete(sa[sc], sb[sc], Sb + t - D, true, b * 32 + t, (t - D) & (EW - 1));
                 }
+              }
             }
             cur = nxt;
             if (MODE == 1) { sum_d += acc_d; acc_d = 0; }
@@ -401,7 +447,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                     const uint2 q = stash64[j * 33 + 1];
                     ia = q.x; ib = q.y;
                 }
-                complete(sa[si] + ia, sb[si] + ib, S + L - D + j, true, B * 32 + j, j & 3);
+                complete(sa[si] + ia, sb[si] + ib, S + L - D + j, true, B * 32 + j, (32 - D + j) & (EW - 1));
             }
             __syncwarp();
             if (MODE == 0 && __any_sync(0xffffffffu, staged)) {
