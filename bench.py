@@ -225,7 +225,7 @@ def run_ours(args):
     desc = M.promoter_descriptors(g, ps, pe)
     n_windows = g.total_windows(M.length)
     n_post_windows = int(desc[1].sum().item())
-    bg = M.background_stats(g, n_bins=1024, keep_scores=True)
+    bg = M.background_stats(g, n_bins=256, keep_scores=True)
     M.fit_background(bg=bg, sync=True)            # also scores the model's own sites once (mu_m, std_m)
     post = torch.empty(N_GENES, dtype=torch.float64, device=dev)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -248,12 +248,12 @@ def run_ours(args):
         # the reference-facing host-buffer call (cgbk_regulation_pipeline through
         # PSSMModel.regulation_pipeline): pinned host ASCII + promoter slices in, host
         # posteriors / background moments / histogram out
-        return M.regulation_pipeline(pinned, ps, pe, prior, alpha, n_bins=1024)
+        return M.regulation_pipeline(pinned, ps, pe, prior, alpha, n_bins=256)
 
     def e2e_step_multi_call():
         # the same through the individual batched calls (pack, stats, posteriors)
         gg = PackedGenome.from_sequences(None, dev, pinned=[pinned])
-        b = M.background_stats(gg, n_bins=1024, keep_scores=True)
+        b = M.background_stats(gg, n_bins=256, keep_scores=True)
         M.fit_background(bg=b, sync=False)
         p = M.binding_probabilities(gg, ps, pe, prior, alpha, out=post)
         post_host.copy_(p, non_blocking=True)
@@ -396,7 +396,7 @@ def run_ours(args):
                        "lane_bases": info["lane_bases"], "sharding": "one genome per rank, no collective"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel()) + 12 * N_GENES + 16,
-                    "d2h_bytes_per_step": N_GENES * 8 + 64 + 1024 * 8, "ms_per_step": e2e_ms / args.steps,
+                    "d2h_bytes_per_step": N_GENES * 8 + 64 + 256 * 8, "ms_per_step": e2e_ms / args.steps,
                     "call": "PSSMModel.regulation_pipeline -> cgbk_regulation_pipeline (host buffers)",
                     "multi_call_ms_per_step": 1e3 * e2e_multi_s / args.steps},
             "gpu_launches": launches_per_step * args.steps,

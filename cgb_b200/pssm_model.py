@@ -270,7 +270,7 @@ class PSSMModel(TFBindingModel):
         order = np.lexsort((-strand, pos, seq))
         return seq[order], pos[order], strand[order], score[order]
 
-    def background_stats(self, genome, n_bins=1024, hist_lo=None, hist_hi=None, accumulate_into=None,
+    def background_stats(self, genome, n_bins=256, hist_lo=None, hist_hi=None, accumulate_into=None,
                          out=None, keep_scores=False):
         """Soft-max score distribution over ALL windows of ``genome`` (both strands
         combined as in score_seq): returns a dict with device tensors ``stats``
@@ -429,7 +429,7 @@ class PSSMModel(TFBindingModel):
         return out.cpu().numpy()
 
     # ------------------------------------------------ one call per replicon, host in / host out
-    def regulation_pipeline(self, sequence, starts, ends, p_motif, alpha=1/350.0, n_bins=1024,
+    def regulation_pipeline(self, sequence, starts, ends, p_motif, alpha=1/350.0, n_bins=256,
                             hist_lo=None, hist_hi=None):
         """Background fit over ALL windows of ``sequence`` (genome.py:215-226) followed by the
         posterior of regulation of every promoter slice ``sequence[start:end]``

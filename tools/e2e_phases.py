@@ -41,7 +41,7 @@ def main():
         devb = pinned.to(dev, non_blocking=True); t.append(time.perf_counter())
         gobj.pack_into(0, devb); t.append(time.perf_counter())
         t.append(sync())
-        b = M.background_stats(gobj, n_bins=1024, keep_scores=True); t.append(time.perf_counter())
+        b = M.background_stats(gobj, n_bins=256, keep_scores=True); t.append(time.perf_counter())
         M.fit_background(bg=b, sync=False); t.append(time.perf_counter())
         t.append(sync())
         desc = M.promoter_descriptors(gobj, ps, pe); t.append(time.perf_counter())

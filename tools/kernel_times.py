@@ -28,7 +28,7 @@ def main():
     gt = GeneTable(gs, ge, gstrand, bench.GENOME_BP)
     ps, pe = gt.promoter_region_location(bench.UP, bench.DOWN)
     desc = M.promoter_descriptors(g, ps, pe)
-    bg = M.background_stats(g, n_bins=1024, keep_scores=True)
+    bg = M.background_stats(g, n_bins=256, keep_scores=True)
     M.fit_background(bg=bg)
     post = torch.empty(bench.N_GENES, dtype=torch.float64, device=dev)
     reps = 200

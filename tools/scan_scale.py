@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--m", type=int, default=22)
     ap.add_argument("--plane", action="store_true", help="also write the score plane in the stats scan")
-    ap.add_argument("--bins", type=int, default=1024, help="histogram bins of the stats scan")
+    ap.add_argument("--bins", type=int, default=256, help="histogram bins of the stats scan")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
