@@ -469,6 +469,8 @@ static int carve(const cgbk_seqset* S, int m, void* d_work, int64_t work_bytes, 
     w->dirty_tiles = (unsigned int*)(p + WORK_HEADER);
     w->cands = (unsigned long long*)(p + WORK_HEADER + dirty_bytes);
     w->cand_cap = cand_cap;
+    w->tile_begin = 0; w->tile_end = 0;          // set by the caller once the tiling is known
+    w->ctr_slot = CGBK_CTR_INTERNAL_TILE; w->partial_base = 0;
     return CGBK_OK;
 }
 
@@ -571,6 +573,7 @@ extern "C" int cgbk_scan_hits(cgbk_model* M, const cgbk_genome* genome, const cg
     if (rc) return rc;
     rc = ensure_coarse(M, threshold, st);
     if (rc) return rc;
+    w.tile_end = S->n_tiles;
     CUDA_TRY(cudaMemsetAsync(w.counters, 0, 64, st));
     int launches = 0;
     if (S->n_tiles > 0) {
@@ -599,10 +602,10 @@ extern "C" int64_t cgbk_score_plane_ints(const cgbk_seqset* S, int m) {
     return best;
 }
 
-extern "C" int cgbk_background_stats(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqset* set,
-                                     double hist_lo, double hist_hi, int n_bins, unsigned long long* d_hist,
-                                     double* d_stats, int accumulate, int32_t* d_plane, int64_t plane_ints,
-                                     void* d_work, int64_t work_bytes, void* stream) {
+int cgbk_bg_scan_begin(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqset* set, double hist_lo,
+                       double hist_hi, int n_bins, unsigned long long* d_hist, double* d_stats,
+                       int accumulate, int32_t* d_plane, int64_t plane_ints, void* d_work,
+                       int64_t work_bytes, cudaStream_t st, BgScan* run) {
     if (!M || !set || !d_stats) return cgbk_set_error(CGBK_ERR_INVALID, "NULL argument");
     int rc = check_genome(genome);
     if (rc) return rc;
@@ -615,46 +618,89 @@ extern "C" int cgbk_background_stats(cgbk_model* M, const cgbk_genome* genome, c
     } else {
         n_bins = 1; hist_lo = M->min_score - 1.0; hist_hi = M->max_score + 2.0;
     }
-    cudaStream_t st = (cudaStream_t)stream;
     cgbk_seqset* S = const_cast<cgbk_seqset*>(set);
-    FastWork w;
-    rc = carve(S, M->m, d_work, work_bytes, 0, &w);
+    rc = carve(S, M->m, d_work, work_bytes, 0, &run->w);
     if (rc) return rc;
-    const int threads = fast_threads(M->G, 1);
-    const int sms = device_sms(M->device);
+    run->M = M; run->g = view_of(genome); run->S = S; run->d_stats = d_stats;
+    run->threads = fast_threads(M->G, 1);
+    run->sms = device_sms(M->device);
     // the tiling depends only on (set, m), not on the kernel variant: a score plane written by
     // the stats scan stays addressable after a hit scan of the same set
-    const int L = choose_L(S, M->m, sms * 16);
-    rc = ensure_tiles(S, M->m, L, st);
+    run->L = choose_L(S, M->m, run->sms * 16);
+    rc = ensure_tiles(S, M->m, run->L, st);
     if (rc) return rc;
-    if (d_plane && plane_ints < S->n_tiles * (int64_t)((L / 32 + 1) * 1024))
+    if (d_plane && plane_ints < S->n_tiles * (int64_t)((run->L / 32 + 1) * 1024))
         return cgbk_set_error(CGBK_ERR_INVALID, "score plane of %lld ints is smaller than the %lld required",
                               (long long)plane_ints, (long long)cgbk_score_plane_ints(S, M->m));
-    CUDA_TRY(cudaMemsetAsync(w.counters, 0, 64, st));
+    CUDA_TRY(cudaMemsetAsync(run->w.counters, 0, 64, st));
     if (!accumulate) {
         if (d_hist) CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * n_bins, st));
         CUDA_TRY(cudaMemsetAsync(d_stats, 0, sizeof(double) * CGBK_BG_COUNT, st));
     }
-    const double inv_binw = (double)n_bins / (hist_hi - hist_lo);
-    const int wpb = threads / 32;
-    long long grid = (S->n_tiles + wpb - 1) / wpb;
-    if (grid > sms) grid = sms;
-    if (grid < 1) grid = 1;
-    int launches = 1;
-    if (S->n_tiles > 0) {
-        const StatsParams sp = make_stats_params(M, hist_lo, hist_hi, n_bins, d_hist, d_plane);
-        PROF_START(st);
-        CUDA_TRY(launch_fast_stats(M, view_of(genome), table_of(S), w, L, (int)grid, sp, st));
-        PROF_STOP(st);
-        // exact pass over tiles with non-ACGT bytes; its last block reduces all partial moments
-        CUDA_TRY(launch_dirty_stats(M, view_of(genome), table_of(S), w, L, hist_lo, inv_binw, sp, (int)grid,
-                                    (int)grid + CGBK_DIRTY_STATS_BLOCKS, d_stats, st));
-        launches = 2;
-    } else {
-        CUDA_TRY(launch_bg_finalize(w.partials, 0, d_stats, 1, st));
-    }
-    g_launch_info[0] = launches; g_launch_info[1] = S->n_tiles; g_launch_info[2] = L;
+    run->hist_lo = hist_lo;
+    run->inv_binw = (double)n_bins / (hist_hi - hist_lo);
+    run->sp = make_stats_params(M, hist_lo, hist_hi, n_bins, d_hist, d_plane);
+    run->next_tile = 0; run->n_ranges = 0; run->partials_used = 0;
+    g_launch_info[0] = 0; g_launch_info[1] = S->n_tiles; g_launch_info[2] = run->L;
     return CGBK_OK;
+}
+
+int cgbk_bg_scan_range(BgScan* run, long long bases_ready, int last, cudaStream_t st) {
+    cgbk_seqset* S = run->S;
+    long long t_end = S->n_tiles;
+    if (!last) {
+        // only single-sequence sets are fed in chunks: tile t reads bases [t * stride, t * stride + 32 L)
+        if (S->n_seq != 1) return cgbk_set_error(CGBK_ERR_INVALID, "chunked scans take one sequence");
+        const long long span = 32ll * run->L, stride = span - 32;
+        const long long ready = bases_ready - S->h_off[0];
+        t_end = ready < span ? 0 : (ready - span) / stride + 1;
+        if (t_end > S->n_tiles) t_end = S->n_tiles;
+    }
+    if (t_end <= run->next_tile) return CGBK_OK;
+    if (run->n_ranges >= CGBK_MAX_TILE_RANGES)
+        return cgbk_set_error(CGBK_ERR_INVALID, "more than %d tile ranges", CGBK_MAX_TILE_RANGES);
+    const int wpb = run->threads / 32;
+    long long grid = (t_end - run->next_tile + wpb - 1) / wpb;
+    if (grid > run->sms) grid = run->sms;
+    FastWork w = run->w;
+    w.tile_begin = run->next_tile; w.tile_end = t_end;
+    w.ctr_slot = CGBK_CTR_INTERNAL_TILE + run->n_ranges;
+    w.partial_base = run->partials_used;
+    PROF_START(st);
+    CUDA_TRY(launch_fast_stats(run->M, run->g, table_of(S), w, run->L, (int)grid, run->sp, st));
+    PROF_STOP(st);
+    run->next_tile = t_end;
+    run->n_ranges += 1;
+    run->partials_used += (int)grid;
+    g_launch_info[0] += 1;
+    return CGBK_OK;
+}
+
+int cgbk_bg_scan_end(BgScan* run, cudaStream_t st) {
+    if (run->n_ranges > 0) {
+        // exact pass over tiles with non-ACGT bytes; its last block reduces all partial moments
+        CUDA_TRY(launch_dirty_stats(run->M, run->g, table_of(run->S), run->w, run->L, run->hist_lo,
+                                    run->inv_binw, run->sp, run->partials_used,
+                                    run->partials_used + CGBK_DIRTY_STATS_BLOCKS, run->d_stats, st));
+    } else {
+        CUDA_TRY(launch_bg_finalize(run->w.partials, 0, run->d_stats, 1, st));
+    }
+    g_launch_info[0] += 1;
+    return CGBK_OK;
+}
+
+extern "C" int cgbk_background_stats(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqset* set,
+                                     double hist_lo, double hist_hi, int n_bins, unsigned long long* d_hist,
+                                     double* d_stats, int accumulate, int32_t* d_plane, int64_t plane_ints,
+                                     void* d_work, int64_t work_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    BgScan run;
+    int rc = cgbk_bg_scan_begin(M, genome, set, hist_lo, hist_hi, n_bins, d_hist, d_stats, accumulate, d_plane,
+                                plane_ints, d_work, work_bytes, st, &run);
+    if (rc) return rc;
+    rc = cgbk_bg_scan_range(&run, 0, 1, st);
+    if (rc) return rc;
+    return cgbk_bg_scan_end(&run, st);
 }
 
 extern "C" int cgbk_background_finalize(double* d_stats, void* stream) {

@@ -239,6 +239,50 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     unsigned long long* cand_stage = reinterpret_cast<unsigned long long*>(cand_base);
     unsigned int* cand_cnt = reinterpret_cast<unsigned int*>(cand_base + CGBK_CAND_STAGE * 8);
 
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const uint32_t o16 = (lane & 7) << 4, o8 = (lane & 15) << 3, o4 = lane << 2;
+    if (ONE) B = 1;
+    const int L = 32 * B;
+    const int stride = 32 * L - 32;
+    const long long nwords = g.cap_bases >> 4;
+    const int S = lane * L;                                   // tile-local start of this lane's segment
+
+    // tile -> (packed offset of its sequence, sequence length, first tile of the sequence)
+    auto geometry = [&](long long tile, long long& gbase, long long& seq_len, long long& tile0) {
+        if (seqs.n_seq <= CGBK_INLINE_SEQS) {
+            int sq = 0;
+#pragma unroll
+            for (int i = 1; i < CGBK_INLINE_SEQS; ++i)
+                if (i < seqs.n_seq && seqs.prefix_v[i] <= tile) sq = i;
+            gbase = seqs.off_v[sq]; seq_len = seqs.len_v[sq]; tile0 = seqs.prefix_v[sq];
+        } else {
+            const int sq = find_seq(seqs, tile);
+            gbase = __ldg(seqs.off + sq); seq_len = __ldg(seqs.len + sq); tile0 = __ldg(seqs.tile_prefix + sq);
+        }
+    };
+    // The global loads that open a tile (ambiguity words + first stream words) are issued one
+    // tile ahead: the first tile's before the table fill, the next tile's before the current
+    // tile's tail section, so their DRAM latency never sits on a warp's critical path.
+    uint32_t pre_amb = 0u;
+    uint2 pre_cur = make_uint2(0u, 0u);
+    auto preload = [&](long long tile) {
+        if (tile >= work.tile_end) return;
+        long long gbase, seq_len, tile0;
+        geometry(tile, gbase, seq_len, tile0);
+        const long long p0 = gbase + (tile - tile0) * stride + S;
+        const long long aw = p0 >> 5, left = (g.cap_bases >> 5) - aw;
+        const int n_ok = left < (long long)B ? (left < 0 ? 0 : (int)left) : B;     // B <= 4
+        uint32_t a = 0u;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (b < n_ok) a |= __ldg(g.amb + aw + b);
+        pre_amb = a;
+        pre_cur = ld_stream2(g.bases2, p0 >> 4, nwords);
+    };
+    // this launch covers tiles [work.tile_begin, work.tile_end); every warp's first tile is static
+    long long tile = work.tile_begin + (long long)blockIdx.x * wpb + warp;
+    preload(tile);
+
     fill_tables<NW, Cfg::THREADS>(smem, gtab);
     if (MODE == 1)
         for (int i = threadIdx.x; i < (sp.n_bins + 1) * sp.hist_words; i += blockDim.x)
@@ -246,12 +290,6 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     if (MODE == 0 && (threadIdx.x & 31) == 0) *cand_cnt = 0u;
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const uint32_t o16 = (lane & 7) << 4, o8 = (lane & 15) << 3, o4 = lane << 2;
-    if (ONE) B = 1;
-    const int L = 32 * B;
-    const int stride = 32 * L - 32;
-    const long long nwords = g.cap_bases >> 4;
     // per-warp strip for the partial sums handed to the previous lane: [D][33]
     uint32_t* stash32 = reinterpret_cast<uint32_t*>(stash_base) + warp * (D * 33) + lane;
     uint2* stash64 = reinterpret_cast<uint2*>(stash_base) + warp * (D * 33) + lane;
@@ -269,51 +307,33 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     // Tiles are handed out dynamically (one global atomic per warp tile, fetched one tile
     // ahead): with only a few tiles per warp a static split leaves most warps idle while the
     // unlucky ones run their extra tile.  All outputs are order independent.
-    unsigned long long* tile_ctr = reinterpret_cast<unsigned long long*>(work.counters + CGBK_CTR_INTERNAL_TILE);
-    const long long first_dyn = (long long)gridDim.x * wpb;   // every warp's first tile is static
-    long long prefetched = 0;                                 // lane 0: id of the tile after the current one
+    unsigned long long* tile_ctr = reinterpret_cast<unsigned long long*>(work.counters + work.ctr_slot);
+    const long long first_dyn = work.tile_begin + (long long)gridDim.x * wpb;
+    long long prefetched = 0;                                 // lane 0: id of the tile after the next one
     if (lane == 0) prefetched = first_dyn + (long long)atomicAdd(tile_ctr, 1ull);
     auto advance = [&]() -> long long {
         const long long t = __shfl_sync(0xffffffffu, prefetched, 0);   // fetched one tile ago
         if (lane == 0) prefetched = first_dyn + (long long)atomicAdd(tile_ctr, 1ull);
         return t;
     };
-    for (long long tile = (long long)blockIdx.x * wpb + warp; tile < seqs.n_tiles; tile = advance()) {
+    while (tile < work.tile_end) {
         long long gbase, seq_len, tile0;
-        if (seqs.n_seq <= CGBK_INLINE_SEQS) {
-            int sq = 0;
-#pragma unroll
-            for (int i = 1; i < CGBK_INLINE_SEQS; ++i)
-                if (i < seqs.n_seq && seqs.prefix_v[i] <= tile) sq = i;
-            gbase = seqs.off_v[sq]; seq_len = seqs.len_v[sq]; tile0 = seqs.prefix_v[sq];
-        } else {
-            const int sq = find_seq(seqs, tile);
-            gbase = __ldg(seqs.off + sq); seq_len = __ldg(seqs.len + sq); tile0 = __ldg(seqs.tile_prefix + sq);
-        }
+        geometry(tile, gbase, seq_len, tile0);
         const long long A = (tile - tile0) * stride;
         const long long rem = seq_len - m + 1 - A;            // valid windows from A on
         const int own_n = rem < stride ? (int)rem : stride;   // this tile owns windows [A, A + own_n)
-        const int S = lane * L;                               // tile-local start of this lane's segment
         const long long wbase = (gbase + A + S) >> 4;
 
-        // issue the independent loads of the tile together: ambiguity words + first stream words
-        uint32_t any_amb = 0;
-        {
-            const long long aw = (gbase + A + S) >> 5, naw = g.cap_bases >> 5;
-            const long long left = naw - aw;
-            const int n_ok = left < (long long)B ? (left < 0 ? 0 : (int)left) : B;     // B <= 4
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-                if (b < n_ok) any_amb |= __ldg(g.amb + aw + b);
-        }
-        uint2 cur = ld_stream2(g.bases2, wbase, nwords);
-        if (__any_sync(0xffffffffu, any_amb != 0)) {
+        uint2 cur = pre_cur;
+        if (__any_sync(0xffffffffu, pre_amb != 0)) {
             // tiles touching a non-ACGT byte go to the exact kernels
             if (lane == 0) {
                 const unsigned long long k = atomicAdd(
                     reinterpret_cast<unsigned long long*>(work.counters + CGBK_CTR_DIRTY_TILES), 1ull);
                 work.dirty_tiles[k] = (unsigned int)tile;
             }
+            tile = advance();
+            preload(tile);
             continue;
         }
 
@@ -434,6 +454,8 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 staged = false;
             }
         }
+        const long long next_tile = advance();
+        preload(next_tile);
         // windows straddling into the next lane: add the partial sums it parked for us
         if (D > 0) {
             __syncwarp();
@@ -461,6 +483,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
             const int mine = own_n - S;
             cnt += mine < 0 ? 0 : (mine > L ? L : mine);
         }
+        tile = next_tile;
     }
 
     if (MODE == 1) {
@@ -478,7 +501,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         if (threadIdx.x == 0) {
             // s_i = centre + d_i * q  ->  raw moments
             const double q = sp.q;
-            double* p = work.partials + 3ll * blockIdx.x;
+            double* p = work.partials + 3ll * (work.partial_base + blockIdx.x);
             p[0] = c * sp.c + a * q;
             p[1] = c * sp.c * sp.c + 2.0 * sp.c * q * a + q * q * b2;
             p[2] = c;

@@ -56,7 +56,9 @@ struct GenomeView {
 };
 
 #define CGBK_CTR_INTERNAL_DONE 3   // blocks of the dirty-stats kernel that have finished
-#define CGBK_CTR_INTERNAL_TILE 4   // dynamic tile scheduler of the tiled scan
+#define CGBK_CTR_INTERNAL_TILE 4   // dynamic tile scheduler of the tiled scan (slots 4..7: one per
+                                   // tile range of a chunked background scan)
+#define CGBK_MAX_TILE_RANGES 4
 #define CGBK_INLINE_SEQS 4   // sequence tables this small travel by value in the kernel parameters
 
 struct SeqTable {
@@ -87,6 +89,11 @@ struct FastWork {      // carved out of the caller's workspace
     long long cand_cap;
     double* partials;           // per-block (sum, sumsq, n) triples
     int partial_cap;            // triples available
+    // one launch of the tiled scan covers tiles [tile_begin, tile_end) and hands them out
+    // through counters[ctr_slot]; its blocks write moment partials from partial_base on
+    long long tile_begin, tile_end;
+    int ctr_slot;
+    int partial_base;
 };
 
 cudaError_t launch_pack(const uint8_t* d_ascii, long long n, long long dst_off, uint32_t* b2,
@@ -163,3 +170,30 @@ __host__ __device__ inline long long plane_index(long long tile, int wt, int L, 
 }
 
 int fast_threads(int G, int mode);
+
+// ---------------------------------------------------------------------------
+// background scan in tile ranges (cgbk_api.cu), for callers that feed the genome in chunks
+// (cgbk_pipeline.cu overlaps the H2D of chunk k + 1 with the scan of chunk k):
+//   begin -> validates, clears the accumulators, fixes the tiling
+//   range -> scans the not yet scanned tiles that lie entirely below bases_ready
+//            (all remaining tiles when last != 0); at most CGBK_MAX_TILE_RANGES launches
+//   end   -> exact pass over dirty tiles + reduction of the partial moments into d_stats
+// ---------------------------------------------------------------------------
+struct BgScan {
+    cgbk_model* M;
+    GenomeView g;
+    cgbk_seqset* S;
+    FastWork w;
+    StatsParams sp;
+    int L, sms, threads;
+    double hist_lo, inv_binw;
+    double* d_stats;
+    long long next_tile;
+    int n_ranges, partials_used;
+};
+int cgbk_bg_scan_begin(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqset* set, double hist_lo,
+                       double hist_hi, int n_bins, unsigned long long* d_hist, double* d_stats,
+                       int accumulate, int32_t* d_plane, int64_t plane_ints, void* d_work,
+                       int64_t work_bytes, cudaStream_t st, BgScan* out);
+int cgbk_bg_scan_range(BgScan* run, long long bases_ready, int last, cudaStream_t st);
+int cgbk_bg_scan_end(BgScan* run, cudaStream_t st);

@@ -10,13 +10,49 @@
 // synchronisation, so the host-side cost is one function call instead of a dozen Python /
 // driver round trips.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "cgbk_internal.cuh"
 
 static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
+
+// -DCGBK_PIPE_TRACE (tools/pipeline_trace.py builds that variant): device and host timestamps of
+// the call's phases on stderr.  Compiled out of the shipped library.
+#ifdef CGBK_PIPE_TRACE
+#include <stdio.h>
+#include <time.h>
+struct PipeTrace {
+    const char* name[24]; cudaEvent_t ev[24]; double host_us[24]; int n = 0;
+    static double now_us() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e6 + t.tv_nsec * 1e-3; }
+    void mark(const char* what, cudaStream_t st) {
+        if (n >= 24) return;
+        cudaEventCreate(&ev[n]); cudaEventRecord(ev[n], st); name[n] = what; host_us[n] = now_us(); ++n;
+    }
+    void dump() {
+        const double end = now_us();
+        for (int i = 0; i < n; ++i) {
+            float ms = 0.f; cudaEventElapsedTime(&ms, ev[0], ev[i]);
+            fprintf(stderr, "[pipe] %-12s device +%8.1f us   host enqueue +%8.1f us\n", name[i], ms * 1e3,
+                    host_us[i] - host_us[0]);
+            }
+        fprintf(stderr, "[pipe] %-12s host +%8.1f us\n", "returned", end - host_us[0]);
+        for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+    }
+};
+#define TRACE_DECL PipeTrace trace
+#define TRACE(what) trace.mark(what, st)
+#define TRACE_ON(what, stream) trace.mark(what, stream)
+#define TRACE_DUMP() trace.dump()
+#else
+#define TRACE_DECL
+#define TRACE(what)
+#define TRACE_ON(what, stream)
+#define TRACE_DUMP()
+#endif
 
 struct PipeLayout {
     int64_t cap_bases;
@@ -40,13 +76,63 @@ static PipeLayout pipe_layout(int64_t n_bases, int n_regions, int m, int n_bins)
     p.off_table = o;  o += align256(8 * 4);
     p.off_work = o;   o += p.work_bytes;
     p.off_plane = o;  o += align256(4 * p.plane_ints);
-    p.off_hist = o;   o += align256(8 * (int64_t)(n_bins > 0 ? n_bins : 1));
-    p.off_stats = o;  o += 256;
     p.off_msm = o;    o += 256;
     p.off_desc = o;   o += align256(12 * (int64_t)n_regions);
-    p.off_post = o;   o += align256(8 * (int64_t)n_regions);
+    // results, contiguous so that one D2H can return them: posteriors | stats | histogram
+    p.off_post = o;
+    p.off_stats = p.off_post + 8 * (int64_t)n_regions;
+    p.off_hist = p.off_stats + 8 * CGBK_BG_COUNT;
+    o += align256(8 * (int64_t)n_regions + 8 * CGBK_BG_COUNT + 8 * (int64_t)(n_bins > 0 ? n_bins : 1));
     p.total = o;
     return p;
+}
+
+// side stream + events of the chunked upload, one set per device, created on first use and
+// kept for the life of the process
+#define PIPE_MAX_CHUNKS CGBK_MAX_TILE_RANGES
+struct PipeStreams {
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev[PIPE_MAX_CHUNKS + 1] = {};
+};
+static std::mutex g_pipe_mu;
+static PipeStreams* g_pipe[64] = {};
+
+static PipeStreams* pipe_streams(int device) {
+    if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pipe_mu);
+    if (g_pipe[device]) return g_pipe[device];
+    PipeStreams* p = new PipeStreams;
+    bool ok = cudaStreamCreateWithFlags(&p->copy, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i <= PIPE_MAX_CHUNKS; ++i)
+        ok = cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { delete p; return nullptr; }
+    g_pipe[device] = p;
+    return p;
+}
+
+// Chunk boundaries (multiples of CGBK_SEQ_ALIGN).  Measured on B200 / PCIe 5 (tools/h2d_probe.py,
+// tools/pipeline_trace.py): cutting a pinned upload into 3-4 copies costs ~10 us, kernels
+// running beside the DMA slow it by another ~5 %, and every chunk's scan pays the ~14 us fixed
+// cost of a launch.  At 5 MB that cancels the overlap exactly (202 us either way); at 50 MB the
+// chunked form wins ~5 % (1.17 vs 1.23 ms).  So small replicons go up in one piece and only
+// large ones are pipelined, the last (exposed) chunk being the smallest.
+static int plan_chunks(int64_t n, int64_t* cut) {
+    static const double frac3[3] = {0.50, 0.30, 0.20};
+    static const double frac4[4] = {0.35, 0.30, 0.20, 0.15};
+    int k = n >= (16ll << 20) ? 4 : 1;
+    if (const char* e = getenv("CGBK_PIPE_CHUNKS")) {          // tuning knob: 1, 3 or 4
+        const int want = atoi(e);
+        if (want == 1 || ((want == 3 || want == 4) && n >= 4 * CGBK_SEQ_ALIGN)) k = want;
+    }
+    const double* f = k == 4 ? frac4 : frac3;
+    cut[0] = 0;
+    double acc = 0.0;
+    for (int c = 1; c < k; ++c) {
+        acc += f[c - 1];
+        cut[c] = (int64_t)(acc * (double)n) / CGBK_SEQ_ALIGN * CGBK_SEQ_ALIGN;
+    }
+    cut[k] = n;
+    return k;
 }
 
 extern "C" int64_t cgbk_pipeline_scratch_bytes(int64_t n_bases, int n_regions, int m, int n_bins) {
@@ -77,6 +163,8 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
         return cgbk_set_error(CGBK_ERR_INVALID, "staging buffer too small");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* base = (unsigned char*)d_scratch;
+    TRACE_DECL;
+    TRACE("enter");
 
     // promoter slices -> (packed offset, window count): Chromid.subsequence's Python slice
     // (cgb/chromid.py:94) then len(seq) - m + 1 windows; len(seq) < m raises in the reference
@@ -97,52 +185,98 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
     double* st_msm = (double*)((unsigned char*)h_staging + cgbk_pipeline_staging_bytes(n_regions) - 256);
     st_msm[0] = mu_m; st_msm[1] = std_m;
 
-    // 1. sequence to the device and into the 2-bit planes
+    // 1. The sequence travels in a few chunks on a side stream while the caller's stream packs
+    //    and scans the chunks that have arrived: only the last chunk's pack + scan is left
+    //    after the last byte has crossed PCIe.  The promoter table rides in front of it.
+    TRACE("host prep");
+    PipeStreams* ps = pipe_streams(M->device);
+    if (!ps) return cgbk_set_error(CGBK_ERR_CUDA, "could not create the copy stream");
+    cudaStream_t cs = ps->copy;
     uint8_t* d_ascii = base + P.off_ascii;
-    if (cudaMemcpyAsync(d_ascii, h_ascii, n_bases, cudaMemcpyHostToDevice, st) != cudaSuccess)
-        return cgbk_set_error(CGBK_ERR_CUDA, "H2D of the sequence failed");
+    int64_t cut[PIPE_MAX_CHUNKS + 1];
+    const int n_chunks = plan_chunks(n_bases, cut);
+    cudaError_t ce = cudaEventRecord(ps->ev[PIPE_MAX_CHUNKS], st);       // scratch is free from here on
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(cs, ps->ev[PIPE_MAX_CHUNKS], 0);
+    if (ce == cudaSuccess && n_regions > 0) {
+        ce = cudaMemcpyAsync(base + P.off_desc, h_staging, 12 * (int64_t)n_regions, cudaMemcpyHostToDevice, cs);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(base + P.off_msm, st_msm, 16, cudaMemcpyHostToDevice, cs);
+    }
+    for (int c = 0; c < n_chunks && ce == cudaSuccess; ++c) {
+        ce = cudaMemcpyAsync(d_ascii + cut[c], h_ascii + cut[c], cut[c + 1] - cut[c], cudaMemcpyHostToDevice, cs);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ps->ev[c], cs);
+        TRACE_ON("chunk copied", cs);
+    }
+    if (ce != cudaSuccess) {
+        cudaStreamSynchronize(cs);
+        return cgbk_check_cuda(ce, "H2D of the sequence");
+    }
+    TRACE("h2d issued");
     cgbk_genome G;
     uint32_t* planes = (uint32_t*)(base + P.off_planes);
     G.d_bases2 = planes;
     G.d_amb = planes + P.cap_bases / 16;
     G.d_lower = planes + P.cap_bases / 16 + P.cap_bases / 32;
     G.cap_bases = P.cap_bases;
-    int rc = cgbk_pack_ascii(d_ascii, n_bases, 0, planes, planes + P.cap_bases / 16,
-                             planes + P.cap_bases / 16 + P.cap_bases / 32, P.cap_bases, st);
-    if (rc) return rc;
 
-    // 2. background: stats scan (+ score plane) over all windows
+    // 2. background: stats scan (+ score plane) over all windows, chunk by chunk
     cgbk_seqset* S = nullptr;
     const int64_t zero = 0;
-    rc = cgbk_seqset_create(&zero, &n_bases, 1, M->device, (int64_t*)(base + P.off_table), st, &S);
-    if (rc) return rc;
+    int rc = cgbk_seqset_create(&zero, &n_bases, 1, M->device, (int64_t*)(base + P.off_table), st, &S);
     unsigned long long* d_hist = n_bins > 0 ? (unsigned long long*)(base + P.off_hist) : nullptr;
     double* d_stats = (double*)(base + P.off_stats);
     int32_t* d_plane = n_regions > 0 ? (int32_t*)(base + P.off_plane) : nullptr;
-    rc = cgbk_background_stats(M, &G, S, hist_lo, hist_hi, n_bins, d_hist, d_stats, 0, d_plane, P.plane_ints,
-                               base + P.off_work, P.work_bytes, st);
-    if (rc) { cgbk_seqset_destroy(S); return rc; }
-
+    BgScan run;
+    if (!rc)
+        rc = cgbk_bg_scan_begin(M, &G, S, hist_lo, hist_hi, n_bins, d_hist, d_stats, 0, d_plane, P.plane_ints,
+                                base + P.off_work, P.work_bytes, st, &run);
+    for (int c = 0; c < n_chunks && !rc; ++c) {
+        if (cudaStreamWaitEvent(st, ps->ev[c], 0) != cudaSuccess)
+            rc = cgbk_set_error(CGBK_ERR_CUDA, "stream wait failed");
+        if (!rc)
+            rc = cgbk_pack_ascii(d_ascii + cut[c], cut[c + 1] - cut[c], cut[c], planes, planes + P.cap_bases / 16,
+                                 planes + P.cap_bases / 16 + P.cap_bases / 32,
+                                 P.cap_bases, st);
+        if (!rc) rc = cgbk_bg_scan_range(&run, cut[c + 1], c == n_chunks - 1, st);
+        TRACE("chunk scanned");
+    }
+    if (!rc) rc = cgbk_bg_scan_end(&run, st);
+    if (rc) {
+        // the side stream may still be writing into the caller's scratch: drain both
+        cudaStreamSynchronize(cs);
+        cudaStreamSynchronize(st);
+        if (S) cgbk_seqset_destroy(S);
+        return rc;
+    }
+    TRACE("stats");
     // 3. posteriors of every promoter from the plane, estimator straight from d_stats
     if (n_regions > 0) {
-        cudaError_t e1 = cudaMemcpyAsync(base + P.off_desc, h_staging, 12 * (int64_t)n_regions,
-                                         cudaMemcpyHostToDevice, st);
-        cudaError_t e2 = cudaMemcpyAsync(base + P.off_msm, st_msm, 16, cudaMemcpyHostToDevice, st);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) {
-            cgbk_seqset_destroy(S);
-            return cgbk_set_error(CGBK_ERR_CUDA, "H2D of the promoter table failed");
-        }
         rc = cgbk_posteriors(M, &G, S, d_plane, (const int64_t*)(base + P.off_desc),
                              (const int32_t*)(base + P.off_desc + 8 * (int64_t)n_regions), n_regions,
                              (const double*)(base + P.off_msm), d_stats + CGBK_BG_MEAN, p_motif, alpha,
                              (double*)(base + P.off_post), st);
-        if (rc) { cgbk_seqset_destroy(S); return rc; }
-        cudaMemcpyAsync(h_post, base + P.off_post, 8 * (int64_t)n_regions, cudaMemcpyDeviceToHost, st);
+        if (rc) {
+            cudaStreamSynchronize(st);
+            cgbk_seqset_destroy(S);
+            return rc;
+        }
+        TRACE("posteriors");
     }
-    cudaMemcpyAsync(h_stats, d_stats, sizeof(double) * CGBK_BG_COUNT, cudaMemcpyDeviceToHost, st);
-    if (h_hist && n_bins > 0)
-        cudaMemcpyAsync(h_hist, d_hist, sizeof(unsigned long long) * n_bins, cudaMemcpyDeviceToHost, st);
+    // 4. results back: one copy when the caller's three host buffers are laid out like ours
+    const int64_t post_bytes = 8 * (int64_t)n_regions, stats_bytes = sizeof(double) * CGBK_BG_COUNT;
+    const bool want_hist = h_hist && n_bins > 0;
+    if (n_regions > 0 && (unsigned char*)h_stats == (unsigned char*)h_post + post_bytes &&
+        (!want_hist || (unsigned char*)h_hist == (unsigned char*)h_stats + stats_bytes)) {
+        cudaMemcpyAsync(h_post, base + P.off_post, post_bytes + stats_bytes + (want_hist ? 8 * (int64_t)n_bins : 0),
+                        cudaMemcpyDeviceToHost, st);
+    } else {
+        if (n_regions > 0) cudaMemcpyAsync(h_post, base + P.off_post, post_bytes, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(h_stats, d_stats, stats_bytes, cudaMemcpyDeviceToHost, st);
+        if (want_hist)
+            cudaMemcpyAsync(h_hist, d_hist, sizeof(unsigned long long) * n_bins, cudaMemcpyDeviceToHost, st);
+    }
+    TRACE("d2h");
     cudaError_t e = cudaStreamSynchronize(st);
+    TRACE_DUMP();
     cgbk_seqset_destroy(S);
     if (e != cudaSuccess) return cgbk_check_cuda(e, "regulation pipeline");
     return CGBK_OK;

@@ -142,6 +142,42 @@ def test_config2_full_size(lexa, lexa_weights):
     assert np.max(np.abs(post - exp)) < 1e-6
 
 
+@pytest.mark.parametrize("n,chunks", [(1_600_000, 3), (3_000_001, 4), (17_000_000, None)])
+def test_pipeline_chunked_upload_matches_resident_path(lexa, lexa_weights, n, chunks, monkeypatch):
+    """cgbk_regulation_pipeline uploads large sequences in chunks (4 from 16 MB on; forced here
+    for the small cases through the CGBK_PIPE_CHUNKS tuning knob) and scans each chunk as it
+    arrives: same histogram / count as the resident whole-genome scan, also with non-ACGT runs
+    sitting on the chunk cuts (those tiles go to the exact kernel)."""
+    if chunks:
+        monkeypatch.setenv("CGBK_PIPE_CHUNKS", str(chunks))
+    M = PSSMModel(_collections(lexa), lexa_weights["site_count"])
+    seq = np.frombuffer(O.synthetic_genome(n, 77), dtype=np.uint8).copy()
+    fracs = (0.5, 0.8) if chunks == 3 else (0.35, 0.65, 0.85)
+    for f in fracs:
+        cut = int(f * n) // 512 * 512
+        seq[cut - 7:cut + 9] = ord("N")
+        seq[cut + 3000:cut + 3002] = ord("n")
+    seq[100:140] = np.frombuffer(b"acgtacgtacgtacgtacgtacgtacgtacgtacgtacgt", dtype=np.uint8)   # lower case: repaired
+    n_genes = 500
+    step = n // n_genes
+    start = np.arange(n_genes, dtype=np.int64) * step + step // 3
+    gt = GeneTable(start, start + 900, np.where(np.arange(n_genes) % 2 == 0, 1, -1), n)
+    ps, pe = gt.promoter_region_location(300, 50)
+    prior, alpha = lexa["prior_regulation_probability"], lexa["alpha"]
+    post, stats, hist = M.regulation_pipeline(seq, ps, pe, prior, alpha, n_bins=256)
+    M2 = PSSMModel(_collections(lexa), lexa_weights["site_count"])
+    g = PackedGenome.from_sequences([seq])
+    bg = M2.background_stats(g, n_bins=256, keep_scores=True)
+    M2.fit_background(bg=bg)
+    st2 = bg["stats"].cpu().numpy()
+    assert np.array_equal(hist, bg["hist"].cpu().numpy().astype(np.uint64))
+    assert stats[_cabi.BG_N] == st2[_cabi.BG_N] == n - M.length + 1
+    assert abs(stats[_cabi.BG_MEAN] - st2[_cabi.BG_MEAN]) < 1e-12
+    assert abs(stats[_cabi.BG_STD] - st2[_cabi.BG_STD]) < 1e-12
+    post2 = M2.binding_probabilities(g, ps, pe, prior, alpha).cpu().numpy()
+    assert np.max(np.abs(post - post2)) < 1e-12
+
+
 def test_large_sequence_tiling_invariance(lexa, lexa_weights):
     """Size-independent properties at 200 Mbp (no oracle at this size): the hit list and the
     background record do not depend on how the sequence is cut into chunks / tiles, every window
