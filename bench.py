@@ -285,7 +285,7 @@ def run_ours(args):
     step_ms = [a.elapsed_time(b) for a, b in ev]
     eager_total_ms = float(np.sum(step_ms))
     total_ms = eager_total_ms
-    launches_per_step = 3                           # tiled scan, dirty tiles + moment reduction, posteriors
+    launches_per_step = 2                           # stats scan (exact tiles + moment reduction inside), posteriors
     info = _cabi.last_launch_info()
 
     # ---- the same K steps replayed from a CUDA graph (the step is launch-bound: 3 kernels and

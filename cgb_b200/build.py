@@ -20,7 +20,7 @@ LIB = os.path.join(LIBDIR, "libcgbk.so")
 SOURCES = ["cgbk_api.cu", "cgbk_exact.cu", "cgbk_fast.cu", "cgbk_pipeline.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # exact kernels must not contract a*b+c into FMA: they restate CPU double arithmetic
-EXTRA = {"cgbk_exact.cu": ["-fmad=false"]}
+EXTRA = {"cgbk_exact.cu": ["-fmad=false"], "cgbk_fast.cu": ["-fmad=false"]}
 
 
 def _nvcc():

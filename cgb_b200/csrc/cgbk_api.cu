@@ -260,14 +260,24 @@ extern "C" int cgbk_model_create(const double* lo, int m, int device, cgbk_model
             precise[(size_t)e * 2 * G + 2 * g] = (uint32_t)(int32_t)sf;
             precise[(size_t)e * 2 * G + 2 * g + 1] = (uint32_t)(int32_t)sr;
         }
-    cudaError_t e1 = cudaMalloc(&M->d_exact, sizeof(double) * CGBK_EXACT_DOUBLES);
+    // ... followed by the same tables in ExactTables order: fr[j][b] = (fwd, rc), mean[j] = (f, r)
+    ex.resize(2 * CGBK_EXACT_DOUBLES);
+    for (int i = 0; i < CGBK_MAXM * 4; ++i) {
+        ex[CGBK_EXACT_TAB_OFFSET + 2 * i] = ex[i];
+        ex[CGBK_EXACT_TAB_OFFSET + 2 * i + 1] = ex[CGBK_MAXM * 4 + i];
+    }
+    for (int i = 0; i < CGBK_MAXM; ++i) {
+        ex[CGBK_EXACT_TAB_OFFSET + CGBK_MAXM * 8 + 2 * i] = ex[CGBK_MAXM * 8 + i];
+        ex[CGBK_EXACT_TAB_OFFSET + CGBK_MAXM * 8 + 2 * i + 1] = ex[CGBK_MAXM * 9 + i];
+    }
+    cudaError_t e1 = cudaMalloc(&M->d_exact, sizeof(double) * 2 * CGBK_EXACT_DOUBLES);
     cudaError_t e2 = cudaMalloc(&M->d_precise, sizeof(uint32_t) * 256 * 2 * G);
     cudaError_t e3 = cudaMalloc(&M->d_coarse, sizeof(uint32_t) * 256 * G);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
         cgbk_model_destroy(M);
         return cgbk_set_error(CGBK_ERR_CUDA, "cudaMalloc of model tables failed");
     }
-    cudaError_t c1 = cudaMemcpy(M->d_exact, ex.data(), sizeof(double) * CGBK_EXACT_DOUBLES, cudaMemcpyHostToDevice);
+    cudaError_t c1 = cudaMemcpy(M->d_exact, ex.data(), sizeof(double) * 2 * CGBK_EXACT_DOUBLES, cudaMemcpyHostToDevice);
     std::vector<uint32_t> precise_ch(precise.size());
     chunked_layout(precise.data(), 2 * G, precise_ch.data());
     cudaError_t c2 = cudaMemcpy(M->d_precise, precise_ch.data(), sizeof(uint32_t) * precise_ch.size(), cudaMemcpyHostToDevice);
@@ -637,10 +647,9 @@ int cgbk_bg_scan_begin(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqs
         if (d_hist) CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * n_bins, st));
         CUDA_TRY(cudaMemsetAsync(d_stats, 0, sizeof(double) * CGBK_BG_COUNT, st));
     }
-    run->hist_lo = hist_lo;
-    run->inv_binw = (double)n_bins / (hist_hi - hist_lo);
     run->sp = make_stats_params(M, hist_lo, hist_hi, n_bins, d_hist, d_plane);
-    run->next_tile = 0; run->n_ranges = 0; run->partials_used = 0;
+    run->sp.d_stats = d_stats;
+    run->next_tile = 0; run->n_ranges = 0; run->partials_used = 0; run->finalized = 0;
     g_launch_info[0] = 0; g_launch_info[1] = S->n_tiles; g_launch_info[2] = run->L;
     return CGBK_OK;
 }
@@ -656,7 +665,15 @@ int cgbk_bg_scan_range(BgScan* run, long long bases_ready, int last, cudaStream_
         t_end = ready < span ? 0 : (ready - span) / stride + 1;
         if (t_end > S->n_tiles) t_end = S->n_tiles;
     }
-    if (t_end <= run->next_tile) return CGBK_OK;
+    if (t_end <= run->next_tile) {
+        // nothing new to scan; a last call still owes the reduction of the earlier ranges
+        if (last && run->n_ranges > 0 && !run->finalized) {
+            CUDA_TRY(launch_bg_finalize(run->w.partials, run->partials_used, run->d_stats, 1, st));
+            run->finalized = 1;
+            g_launch_info[0] += 1;
+        }
+        return CGBK_OK;
+    }
     if (run->n_ranges >= CGBK_MAX_TILE_RANGES)
         return cgbk_set_error(CGBK_ERR_INVALID, "more than %d tile ranges", CGBK_MAX_TILE_RANGES);
     const int wpb = run->threads / 32;
@@ -666,9 +683,12 @@ int cgbk_bg_scan_range(BgScan* run, long long bases_ready, int last, cudaStream_
     w.tile_begin = run->next_tile; w.tile_end = t_end;
     w.ctr_slot = CGBK_CTR_INTERNAL_TILE + run->n_ranges;
     w.partial_base = run->partials_used;
+    StatsParams sp = run->sp;
+    sp.finalize = last ? 1 : 0;      // this launch's last block reduces all partial moments
     PROF_START(st);
-    CUDA_TRY(launch_fast_stats(run->M, run->g, table_of(S), w, run->L, (int)grid, run->sp, st));
+    CUDA_TRY(launch_fast_stats(run->M, run->g, table_of(S), w, run->L, (int)grid, sp, st));
     PROF_STOP(st);
+    if (last) run->finalized = 1;
     run->next_tile = t_end;
     run->n_ranges += 1;
     run->partials_used += (int)grid;
@@ -677,15 +697,12 @@ int cgbk_bg_scan_range(BgScan* run, long long bases_ready, int last, cudaStream_
 }
 
 int cgbk_bg_scan_end(BgScan* run, cudaStream_t st) {
-    if (run->n_ranges > 0) {
-        // exact pass over tiles with non-ACGT bytes; its last block reduces all partial moments
-        CUDA_TRY(launch_dirty_stats(run->M, run->g, table_of(run->S), run->w, run->L, run->hist_lo,
-                                    run->inv_binw, run->sp, run->partials_used,
-                                    run->partials_used + CGBK_DIRTY_STATS_BLOCKS, run->d_stats, st));
-    } else {
-        CUDA_TRY(launch_bg_finalize(run->w.partials, 0, run->d_stats, 1, st));
+    if (!run->finalized) {
+        // an empty scan (no tiles at all), or the caller never flagged a last range
+        CUDA_TRY(launch_bg_finalize(run->w.partials, run->partials_used, run->d_stats, 1, st));
+        run->finalized = 1;
+        g_launch_info[0] += 1;
     }
-    g_launch_info[0] += 1;
     return CGBK_OK;
 }
 

@@ -181,3 +181,36 @@ __device__ __forceinline__ void block_reduce3(double& a, double& b, double& c, d
     }
     __syncthreads();
 }
+
+// windows [w_lo, w_hi) owned by a tile and the packed offset of its sequence
+__device__ __forceinline__ void tile_range(const SeqTable& seqs, unsigned int tile, int L, int m,
+                                           long long& gbase, long long& w_lo, long long& w_hi) {
+    const int s = find_seq(seqs, tile);
+    const long long local = (long long)tile - seq_prefix_of(seqs, s);
+    const long long stride = 32ll * L - 32;
+    const long long nwin = seq_len_of(seqs, s) - m + 1;
+    gbase = seq_off_of(seqs, s);
+    w_lo = local * stride;
+    w_hi = w_lo + stride < nwin ? w_lo + stride : nwin;
+}
+
+// block-wide: per-block partial moments (sum, sumsq, n) -> stats record (n, sum, sumsq, mean, std)
+__device__ __forceinline__ void finalize_stats(const double* partials, int n_partials,
+                                               double* stats, int accumulate, double* scratch) {
+    double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) {
+        s1 += partials[3 * i]; s2 += partials[3 * i + 1]; cnt += partials[3 * i + 2];
+    }
+    block_reduce3(s1, s2, cnt, scratch);
+    if (threadIdx.x == 0) {
+        if (accumulate) {
+            cnt += stats[CGBK_BG_N]; s1 += stats[CGBK_BG_SUM]; s2 += stats[CGBK_BG_SUMSQ];
+        }
+        stats[CGBK_BG_N] = cnt; stats[CGBK_BG_SUM] = s1; stats[CGBK_BG_SUMSQ] = s2;
+        const double mean = cnt > 0 ? s1 / cnt : nan("");
+        double var = cnt > 0 ? s2 / cnt - mean * mean : nan("");
+        if (var < 0) var = 0;
+        stats[CGBK_BG_MEAN] = mean;
+        stats[CGBK_BG_STD] = sqrt(var);
+    }
+}

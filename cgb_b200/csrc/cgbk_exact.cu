@@ -143,101 +143,126 @@ cudaError_t launch_score_windows(const cgbk_model* mdl, GenomeView g, const long
 //   x = alpha/(1-alpha) * pdf_m/pdf_bg = c * exp((yb^2 - ym^2)/2),  c = alpha/(1-alpha) * std_bg/std_m
 // The ratio form needs one exp + one log1p per window instead of the two pdfs and two logs
 // of binding_model.py:106-112; it differs from the literal form only where a pdf underflows
-// to 0 (|z| > 38).  Windows whose x is below 1e-4 -- all but the rare high-scoring ones --
-// take a float32 path (|error| < 1e-9 per window).  With a score plane (PLANE) the window's
-// soft-max score comes from the stats scan (fixed point, |error| ~ 1e-6, harmless at
-// x < 1e-4: d term = x * 1.4 * d s); windows with x >= 1e-4 are re-scored exactly.
+// to 0 (|z| > 38).
+//   Re-score path (no plane): every window is scored exactly; x below 1e-4 takes log1pf.
+//   Plane path: the window's soft-max score comes from the stats scan as a fixed-point integer
+//   (|error| ~ 1e-6), and log2 x is a quadratic in it (two DFMA).  Windows with x < 1e-2 --
+//   all but the rare high-scoring ones -- take a float32 series for log1p (|error| < 3e-9 per
+//   window, plus x * 1.4 * 1e-6 from the fixed-point score); the others are re-scored exactly.
 // ---------------------------------------------------------------------------
+#ifndef CGBK_POST_PF
+#define CGBK_POST_PF 2      // plane loads in flight per lane (1, 2, 4, 8 measured: 10.1, 9.4, 9.7, 10.6 us)
+#endif
+
+__device__ __forceinline__ float ex2_approx_f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <bool PLANE>
 __global__ void __launch_bounds__(256) posterior_kernel(
     const double* __restrict__ d_exact, int m, GenomeView g, SeqTable seqs, PlaneView pv,
     const long long* __restrict__ d_start, const int* __restrict__ d_nwin, int n_regions,
     const double* __restrict__ ms_m, const double* __restrict__ ms_bg, double p_motif, double alpha,
-    double* __restrict__ post) {
-    __shared__ ExactTables tab;
-    stage_exact(&tab, d_exact);
+    double nlog1m_alpha /* -log1p(-alpha) */, double* __restrict__ post) {
+    // the re-score path stages the exact tables in shared memory; with a plane only the rare
+    // high-scoring windows need them and they are read in place (device ExactTables, L1 resident)
+    __shared__ ExactTables tab_s;
+    __shared__ double kc[8];
+    const ExactTables* tab = reinterpret_cast<const ExactTables*>(d_exact + CGBK_EXACT_TAB_OFFSET);
+    if (!PLANE) {
+        stage_exact(&tab_s, d_exact);
+        tab = &tab_s;
+    }
+    if (threadIdx.x == 0) {
+        // estimator constants, once per block
+        const double mu_m = ms_m[0], std_m = ms_m[1], mu_bg = ms_bg[0], std_bg = ms_bg[1];
+        const double im = 1.0 / std_m, ib = 1.0 / std_bg, c = alpha / (1 - alpha) * (std_bg / std_m);
+        kc[0] = im; kc[1] = ib; kc[2] = c;
+        // plane path: log2(x) as a quadratic in the fixed-point score sfix (s = sfix * inv_scale):
+        //   log2 x = log2 c + log2(e) * ((s - mu_bg)^2 / (2 std_bg^2) - (s - mu_m)^2 / (2 std_m^2))
+        const double log2e = 1.4426950408889634074;
+        const double q2 = 0.5 * (ib * ib - im * im), q1 = -(mu_bg * ib * ib - mu_m * im * im);
+        const double q0 = 0.5 * (mu_bg * mu_bg * ib * ib - mu_m * mu_m * im * im);
+        kc[3] = log2e * q2 * pv.inv_scale * pv.inv_scale;
+        kc[4] = log2e * q1 * pv.inv_scale;
+        kc[5] = log2e * q0 + log2(c);
+    }
     __syncthreads();
-    const double mu_m = ms_m[0], std_m = ms_m[1], mu_bg = ms_bg[0], std_bg = ms_bg[1];
-    const double inv_std_m = 1.0 / std_m, inv_std_bg = 1.0 / std_bg;
-    const double c = alpha / (1 - alpha) * (std_bg / std_m);
+    const double mu_m = ms_m[0], mu_bg = ms_bg[0];
+    const double inv_std_m = kc[0], inv_std_bg = kc[1], c = kc[2];
+    const double A2 = kc[3], A1 = kc[4], A0 = kc[5];
     const float cf = (float)c;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int stride = 32 * pv.L - 32;
     const int log2L = 31 - __clz(pv.L);                       // L is 32, 64 or 128
-    const int rows_body = pv.L;                               // (L / 32) bodies * 32 rows
     const long long plane_tile = (long long)(pv.L / 32 + 1) * 1024;
+    // one window, exactly: float64 strand sums in the reference's order, double exp / log1p
+    auto exact_term = [&](long long gpos) {
+        double f, r;
+        exact_window(g, tab, m, gpos, false, f, r);
+        const double se = softmax2_f32tail((float)f, (float)r);     // Biopython's float32 strand scores
+        const double ym = (se - mu_m) * inv_std_m, yb = (se - mu_bg) * inv_std_bg;
+        return log1p(c * exp(0.5 * (yb * yb - ym * ym)));
+    };
     for (int reg = blockIdx.x * warps_per_block + (threadIdx.x >> 5); reg < n_regions;
          reg += gridDim.x * warps_per_block) {
         const long long start = __ldg(d_start + reg);
         const int nwin = __ldg(d_nwin + reg);
-        long long tile_r = 0;
-        int wt0 = 0;
+        double acc = 0.0;       // sum of log1p(x_i)
         if (PLANE) {
             const int sq = find_seq_by_offset(seqs, start);
             const long long x0 = start - seq_off_of(seqs, sq);
-            tile_r = x0 / stride;
-            wt0 = (int)(x0 - tile_r * stride);
-            tile_r += seq_prefix_of(seqs, sq);
-        }
-        double acc = 0.0;       // sum of log1p(x_i)
-        if (PLANE) {
-            // pass 1: every window from the plane on the float32 path; windows whose mixture
-            // ratio x reaches 1e-2 are only marked (bit k = this lane's k-th window)
+            long long tile = x0 < 0x7fffffffll ? (long long)((unsigned)x0 / (unsigned)stride) : x0 / stride;
+            int wt = (int)(x0 - tile * stride) + lane;            // this lane's window, tile-local
+            tile += seq_prefix_of(seqs, sq);
+            if (wt >= stride) { wt -= stride; ++tile; }
+            const int* tp = pv.plane + tile * plane_tile;
+            // Pass 1: every window from the plane on the float32 path; windows whose mixture
+            // ratio x reaches 1e-2 are only marked (bit k = this lane's k-th window).  The plane
+            // row of a window at position `within` of its scan lane's segment is within + D.
             unsigned long long marked = 0ull;
-#ifndef CGBK_POST_PF
-#define CGBK_POST_PF 1
-#endif
-            constexpr int PF = CGBK_POST_PF;   // plane loads issued ahead per lane (measured: 1, 4, 12 are within 2 us of each other)
+            constexpr int PF = CGBK_POST_PF;
             for (int base = 0, k0 = 0; base < nwin; base += 32 * PF, k0 += PF) {
                 int sfix[PF];
 #pragma unroll
                 for (int j = 0; j < PF; ++j) {              // all loads first: independent L2 round trips
-                    const int w = base + lane + 32 * j;
-                    int wt = wt0 + w;
-                    long long tile = tile_r;
-                    while (wt >= stride) { wt -= stride; ++tile; }
-                    const int ln = wt >> log2L, within = wt & (pv.L - 1);
-                    const int row = within < pv.L - pv.D ? within + pv.D : rows_body + (within - (pv.L - pv.D));
-                    sfix[j] = w < nwin ? __ldg(pv.plane + tile * plane_tile + row * 32 + ln) : 0;
+                    const int off = (((wt & (pv.L - 1)) + pv.D) << 5) + (wt >> log2L);
+                    sfix[j] = base + lane + 32 * j < nwin ? __ldg(tp + off) : 0;
+                    wt += 32;
+                    if (wt >= stride) { wt -= stride; tp += plane_tile; }
                 }
+                float part = 0.0f;
 #pragma unroll
                 for (int j = 0; j < PF; ++j) {
                     const int w = base + lane + 32 * j;
-                    const double s = (double)sfix[j] * pv.inv_scale;
-                    const double ym = (s - mu_m) * inv_std_m, yb = (s - mu_bg) * inv_std_bg;
-                    const float ef = (float)(0.5 * (yb * yb - ym * ym));
-                    // x = c * exp(e); below e = -60 x < 1e-26 adds nothing
-                    float xf = ef < -60.0f ? 0.0f : cf * __expf(ef);
-                    if (w >= nwin) xf = 0.0f;
-                    if (xf < 1e-2f) {
+                    const double sd = (double)sfix[j];
+                    float t = (float)(fma(fma(A2, sd, A1), sd, A0));      // log2 x
+                    if (w >= nwin) t = -200.0f;
+                    if (t < -6.6438562f) {                               // x < 1e-2
                         // log1p(x) = x - x^2/2 + x^3/3 - ... : |error| < 3e-9 for x < 1e-2
-                        acc += (double)(xf * (1.0f - xf * (0.5f - xf * (1.0f / 3.0f))));
+                        const float xf = ex2_approx_f(t);                // 0 below 2^-126
+                        part += xf * (1.0f - xf * (0.5f - xf * (1.0f / 3.0f)));
                     } else if (k0 + j < 64) {
                         marked |= 1ull << (k0 + j);
                     } else {
-                        double f, r;                           // regions longer than 2048 windows
-                        exact_window(g, &tab, m, start + w, false, f, r);
-                        const double se = softmax2_f32tail((float)f, (float)r);
-                        const double ym2 = (se - mu_m) * inv_std_m, yb2 = (se - mu_bg) * inv_std_bg;
-                        acc += log1p(c * exp(0.5 * (yb2 * yb2 - ym2 * ym2)));
+                        acc += exact_term(start + w);                    // regions longer than 2048 windows
                     }
                 }
+                acc += (double)part;
             }
-            // pass 2: the marked windows, exactly (float64 strand sums in the reference's order)
+            // pass 2: the marked windows, exactly
             while (marked) {
                 const int kk = __ffsll((long long)marked) - 1;
                 marked &= marked - 1;
-                double f, r;
-                exact_window(g, &tab, m, start + lane + 32 * kk, false, f, r);
-                const double se = softmax2_f32tail((float)f, (float)r);
-                const double ym2 = (se - mu_m) * inv_std_m, yb2 = (se - mu_bg) * inv_std_bg;
-                acc += log1p(c * exp(0.5 * (yb2 * yb2 - ym2 * ym2)));
+                acc += exact_term(start + lane + 32 * kk);
             }
         } else {
             for (int w = lane; w < nwin; w += 32) {
                 double f, r;
-                exact_window(g, &tab, m, start + w, false, f, r);
+                exact_window(g, tab, m, start + w, false, f, r);
                 const double s = softmax2_f32tail((float)f, (float)r);   // Biopython's float32 strand scores
                 const double ym = (s - mu_m) * inv_std_m, yb = (s - mu_bg) * inv_std_bg;
                 const double e = 0.5 * (yb * yb - ym * ym);
@@ -258,7 +283,7 @@ __global__ void __launch_bounds__(256) posterior_kernel(
             if (nwin <= 0) {
                 res = nan("");      // the reference raises inside Biopython for len(seq) < m
             } else {
-                const double lh_ratio = exp(-(double)nwin * log1p(-alpha) - acc);
+                const double lh_ratio = exp((double)nwin * nlog1m_alpha - acc);
                 res = 1 / (1 + lh_ratio * (1 - p_motif) / p_motif);
             }
             post[reg] = res;
@@ -277,10 +302,12 @@ cudaError_t launch_posteriors(const cgbk_model* mdl, GenomeView g, SeqTable seqs
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (pv.plane)
         posterior_kernel<true><<<blocks, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, pv, d_start, d_nwin,
-                                                      n_regions, d_ms_m, d_ms_bg, p_motif, alpha, d_post);
+                                                      n_regions, d_ms_m, d_ms_bg, p_motif, alpha,
+                                                      -log1p(-alpha), d_post);
     else
         posterior_kernel<false><<<blocks, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, pv, d_start, d_nwin,
-                                                       n_regions, d_ms_m, d_ms_bg, p_motif, alpha, d_post);
+                                                       n_regions, d_ms_m, d_ms_bg, p_motif, alpha,
+                                                       -log1p(-alpha), d_post);
     return cudaGetLastError();
 }
 
@@ -343,17 +370,6 @@ __global__ void __launch_bounds__(128) rescore_kernel(const double* __restrict__
 
 // tile geometry shared with cgbk_fast.cu: a warp tile covers 32*L lookup positions and
 // owns the windows [A, A + 32*L - 32) of its sequence.
-__device__ __forceinline__ void tile_range(const SeqTable& seqs, unsigned int tile, int L, int m,
-                                           long long& gbase, long long& w_lo, long long& w_hi) {
-    const int s = find_seq(seqs, tile);
-    const long long local = (long long)tile - seq_prefix_of(seqs, s);
-    const long long stride = 32ll * L - 32;
-    const long long nwin = seq_len_of(seqs, s) - m + 1;
-    gbase = seq_off_of(seqs, s);
-    w_lo = local * stride;
-    w_hi = w_lo + stride < nwin ? w_lo + stride : nwin;
-}
-
 __global__ void __launch_bounds__(128) dirty_hits_kernel(const double* __restrict__ d_exact, int m,
                                                          GenomeView g, SeqTable seqs, FastWork w,
                                                          int L, double thr, int flags,
@@ -394,89 +410,9 @@ cudaError_t launch_rescore(const cgbk_model* mdl, GenomeView g, SeqTable seqs, F
 }
 
 // ---------------------------------------------------------------------------
-// background statistics: dirty tiles (exact, ambiguity aware), then -- in the block that
-// finishes last -- the deterministic reduction of every per-block partial into d_stats
+// background statistics: reduction of per-block partial moments (empty scans, and after the
+// cross-rank all-reduce of the raw sums)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void finalize_stats(const double* __restrict__ partials, int n_partials,
-                                               double* stats, int accumulate, double* scratch) {
-    double s1 = 0.0, s2 = 0.0, cnt = 0.0;
-    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) {
-        s1 += partials[3 * i]; s2 += partials[3 * i + 1]; cnt += partials[3 * i + 2];
-    }
-    block_reduce3(s1, s2, cnt, scratch);
-    if (threadIdx.x == 0) {
-        if (accumulate) {
-            cnt += stats[CGBK_BG_N]; s1 += stats[CGBK_BG_SUM]; s2 += stats[CGBK_BG_SUMSQ];
-        }
-        stats[CGBK_BG_N] = cnt; stats[CGBK_BG_SUM] = s1; stats[CGBK_BG_SUMSQ] = s2;
-        const double mean = cnt > 0 ? s1 / cnt : nan("");
-        double var = cnt > 0 ? s2 / cnt - mean * mean : nan("");
-        if (var < 0) var = 0;
-        stats[CGBK_BG_MEAN] = mean;
-        stats[CGBK_BG_STD] = sqrt(var);
-    }
-}
-
-__global__ void __launch_bounds__(128) dirty_stats_kernel(const double* __restrict__ d_exact, int m,
-                                                          GenomeView g, SeqTable seqs, FastWork w,
-                                                          int L, int D, double hist_lo, double inv_binw,
-                                                          StatsParams sp, int partial_base,
-                                                          int n_partials, double* d_stats) {
-    __shared__ ExactTables tab;
-    __shared__ double scratch[96];
-    __shared__ int is_last;
-    double s1 = 0.0, s2 = 0.0, cnt = 0.0;
-    const long long nd = w.counters[CGBK_CTR_DIRTY_TILES];
-    // only as many blocks as there are dirty tiles take part (one when there is none, the
-    // usual case: it just reduces the scan's partial moments)
-    const int n_part = nd < 1 ? 1 : (nd < (long long)gridDim.x ? (int)nd : (int)gridDim.x);
-    if ((int)blockIdx.x >= n_part) return;
-    if (nd > 0) {
-        stage_exact(&tab, d_exact);
-        __syncthreads();
-    }
-    for (long long d = blockIdx.x; d < nd; d += n_part) {
-        long long gbase, lo, hi;
-        const unsigned int tile = w.dirty_tiles[d];
-        tile_range(seqs, tile, L, m, gbase, lo, hi);
-        for (long long x = lo + threadIdx.x; x < hi; x += blockDim.x) {
-            double f, r;
-            exact_window(g, &tab, m, gbase + x, false, f, r);
-            const double s = softmax2_f64((double)(float)f, (double)(float)r);
-            s1 += s; s2 += s * s; cnt += 1.0;
-            if (sp.d_hist) {
-                int bin = (int)floor((s - hist_lo) * inv_binw);
-                bin = bin < 0 ? 0 : (bin >= sp.n_bins ? sp.n_bins - 1 : bin);
-                atomicAdd(sp.d_hist + bin, 1ull);
-            }
-            if (sp.plane) sp.plane[plane_index(tile, (int)(x - lo), L, D)] = (int)llrint(s * (double)sp.scale);
-        }
-    }
-    block_reduce3(s1, s2, cnt, scratch);
-    if (threadIdx.x == 0) {
-        double* p = w.partials + 3ll * (partial_base + blockIdx.x);
-        p[0] = s1; p[1] = s2; p[2] = cnt;
-        __threadfence();
-        const unsigned long long done =
-            atomicAdd(reinterpret_cast<unsigned long long*>(w.counters + CGBK_CTR_INTERNAL_DONE), 1ull);
-        is_last = (done == (unsigned long long)(n_part - 1));
-    }
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        finalize_stats(w.partials, partial_base + n_part, d_stats, 1, scratch);
-    }
-}
-
-cudaError_t launch_dirty_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
-                               int L, double hist_lo, double inv_binw, const StatsParams& sp,
-                               int partial_base, int n_partials, double* d_stats, cudaStream_t st) {
-    dirty_stats_kernel<<<CGBK_DIRTY_STATS_BLOCKS, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, w, L,
-                                                               4 * (mdl->G - 1), hist_lo, inv_binw, sp,
-                                                               partial_base, n_partials, d_stats);
-    return cudaGetLastError();
-}
-
 __global__ void __launch_bounds__(256) bg_finalize_kernel(const double* __restrict__ partials,
                                                           int n_partials, double* stats,
                                                           int accumulate) {

@@ -207,6 +207,41 @@ __device__ __noinline__ void flush_candidates(unsigned long long* stage, unsigne
     __syncwarp();
 }
 
+// Stats scan, rare path: a tile that holds a byte outside ACGT is scored by the warp that drew
+// it with the reference's exact arithmetic (PSSMModel._calculate repair included), straight from
+// the device ExactTables (L1 resident, 5 KB).  Deliberately NOT inlined: the hot loop keeps its
+// registers.  Moments go to three per-block doubles in shared memory, the histogram to global.
+__device__ __noinline__ void exact_tile_stats(const ExactTables* tab, const uint32_t* bases2, const uint32_t* amb,
+                                              const uint32_t* lower, long long cap_bases, long long gbase,
+                                              long long w_lo, long long w_hi, int m, long long tile, int L, int D,
+                                              unsigned long long* d_hist, int n_bins, double hist_lo,
+                                              double inv_binw, int* plane, double scale, double* acc3) {
+    GenomeView g;
+    g.bases2 = bases2; g.amb = amb; g.lower = lower; g.cap_bases = cap_bases;
+    double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+    for (long long x = w_lo + (threadIdx.x & 31); x < w_hi; x += 32) {
+        double f, r;
+        exact_window(g, tab, m, gbase + x, false, f, r);
+        const double s = softmax2_f64((double)(float)f, (double)(float)r);
+        s1 += s; s2 += s * s; cnt += 1.0;
+        if (d_hist) {
+            int bin = (int)floor((s - hist_lo) * inv_binw);
+            bin = bin < 0 ? 0 : (bin >= n_bins ? n_bins - 1 : bin);
+            atomicAdd(d_hist + bin, 1ull);
+        }
+        if (plane) plane[plane_index(tile, (int)(x - w_lo), L, D)] = (int)llrint(s * scale);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_down_sync(0xffffffffu, s1, o);
+        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(acc3, s1); atomicAdd(acc3 + 1, s2); atomicAdd(acc3 + 2, cnt);
+    }
+}
+
 template <int G, int MODE>
 struct FastCfg {
     static constexpr int THREADS = MODE == 0 ? CGBK_FILTER_THREADS : (G <= 6 ? CGBK_STATS_THREADS : 256);
@@ -234,6 +269,8 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     unsigned char* stash_base = smem + TL::BYTES;
     unsigned int* hist = reinterpret_cast<unsigned int*>(smem + TL::BYTES + Cfg::STASH_BYTES);
     __shared__ double red_scratch[96];
+    __shared__ double exact_acc[3];     // MODE 1: moments of the exactly scored (non-ACGT) tiles
+    __shared__ int is_last_block;
     // MODE 0: this warp's candidate staging buffer and its fill count
     unsigned char* cand_base = smem + TL::BYTES + Cfg::STASH_BYTES + (threadIdx.x >> 5) * (CGBK_CAND_STAGE * 8 + 16);
     unsigned long long* cand_stage = reinterpret_cast<unsigned long long*>(cand_base);
@@ -288,6 +325,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         for (int i = threadIdx.x; i < (sp.n_bins + 1) * sp.hist_words; i += blockDim.x)
             hist[i] = 0u;                                    // row n_bins = discard bin
     if (MODE == 0 && (threadIdx.x & 31) == 0) *cand_cnt = 0u;
+    if (MODE == 1 && threadIdx.x < 3) exact_acc[threadIdx.x] = 0.0;
     __syncthreads();
 
     // per-warp strip for the partial sums handed to the previous lane: [D][33]
@@ -326,11 +364,20 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
 
         uint2 cur = pre_cur;
         if (__any_sync(0xffffffffu, pre_amb != 0)) {
-            // tiles touching a non-ACGT byte go to the exact kernels
-            if (lane == 0) {
-                const unsigned long long k = atomicAdd(
-                    reinterpret_cast<unsigned long long*>(work.counters + CGBK_CTR_DIRTY_TILES), 1ull);
-                work.dirty_tiles[k] = (unsigned int)tile;
+            // a tile touching a non-ACGT byte: exact arithmetic (filter: listed for the exact
+            // hit kernel; stats: scored right here, out of line)
+            if (MODE == 0) {
+                if (lane == 0) {
+                    const unsigned long long k = atomicAdd(
+                        reinterpret_cast<unsigned long long*>(work.counters + CGBK_CTR_DIRTY_TILES), 1ull);
+                    work.dirty_tiles[k] = (unsigned int)tile;
+                }
+            } else {
+                if (lane == 0)
+                    atomicAdd(reinterpret_cast<unsigned long long*>(work.counters + CGBK_CTR_DIRTY_TILES), 1ull);
+                exact_tile_stats(static_cast<const ExactTables*>(sp.exact_tab), g.bases2, g.amb, g.lower,
+                                 g.cap_bases, gbase, A, A + (own_n > 0 ? own_n : 0), m, tile, L, D, sp.d_hist,
+                                 sp.n_bins, sp.hist_lo_d, sp.inv_binw_d, sp.plane, (double)sp.scale, exact_acc);
             }
             tile = advance();
             preload(tile);
@@ -499,12 +546,22 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         double a = (double)sum_d, b2 = sum_d2, c = (double)cnt;
         block_reduce3(a, b2, c, red_scratch);
         if (threadIdx.x == 0) {
-            // s_i = centre + d_i * q  ->  raw moments
+            // s_i = centre + d_i * q  ->  raw moments; plus the exactly scored tiles
             const double q = sp.q;
             double* p = work.partials + 3ll * (work.partial_base + blockIdx.x);
-            p[0] = c * sp.c + a * q;
-            p[1] = c * sp.c * sp.c + 2.0 * sp.c * q * a + q * q * b2;
-            p[2] = c;
+            p[0] = c * sp.c + a * q + exact_acc[0];
+            p[1] = c * sp.c * sp.c + 2.0 * sp.c * q * a + q * q * b2 + exact_acc[1];
+            p[2] = c + exact_acc[2];
+            __threadfence();
+            const unsigned long long done =
+                atomicAdd(reinterpret_cast<unsigned long long*>(work.counters + CGBK_CTR_INTERNAL_DONE), 1ull);
+            is_last_block = sp.finalize && done + 1 == (unsigned long long)(work.partial_base + gridDim.x);
+        }
+        __syncthreads();
+        if (is_last_block) {
+            // every block of this and of the earlier tile ranges has published its partial
+            __threadfence();
+            finalize_stats(work.partials, work.partial_base + (int)gridDim.x, sp.d_stats, 1, red_scratch);
         }
     }
 }
@@ -573,6 +630,11 @@ StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist
     sp.bin_shift = k;
     sp.n_bins = n_bins;
     sp.hist_words = n_bins <= 256 ? 32 : 1;
+    sp.exact_tab = mdl->d_exact + CGBK_EXACT_TAB_OFFSET;
+    sp.hist_lo_d = hist_lo;
+    sp.inv_binw_d = (double)n_bins / (hist_hi - hist_lo);
+    sp.d_stats = nullptr;
+    sp.finalize = 0;
     const double centre = 0.5 * (mdl->min_score + mdl->max_score);
     sp.c_fix = (int)llrint(centre * scale);
     sp.c = (double)sp.c_fix / scale;

@@ -47,6 +47,9 @@ struct cgbk_seqset {
 };
 
 #define CGBK_EXACT_DOUBLES (CGBK_MAXM * 4 * 2 + CGBK_MAXM * 2)
+// d_exact holds the plain tables (CGBK_EXACT_DOUBLES doubles) followed by the same numbers in
+// ExactTables order (strands interleaved), which kernels without a staging step read in place
+#define CGBK_EXACT_TAB_OFFSET CGBK_EXACT_DOUBLES
 
 struct GenomeView {
     const uint32_t* bases2;
@@ -55,7 +58,7 @@ struct GenomeView {
     long long cap_bases;
 };
 
-#define CGBK_CTR_INTERNAL_DONE 3   // blocks of the dirty-stats kernel that have finished
+#define CGBK_CTR_INTERNAL_DONE 3   // blocks of the stats scan that have written their partial moments
 #define CGBK_CTR_INTERNAL_TILE 4   // dynamic tile scheduler of the tiled scan (slots 4..7: one per
                                    // tile range of a chunked background scan)
 #define CGBK_MAX_TILE_RANGES 4
@@ -121,16 +124,8 @@ cudaError_t launch_rescore(const cgbk_model* mdl, GenomeView g, SeqTable seqs, F
                            double thr, int flags, cgbk_hit* hits, long long hit_cap, int L,
                            cudaStream_t st);
 
-// exact scoring of the dirty tiles of a stats scan, then (last block done) the reduction of
-// all per-block partial moments [0, n_partials) into d_stats
-cudaError_t launch_dirty_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
-                               int L, double hist_lo, double inv_binw, const StatsParams& sp,
-                               int partial_base, int n_partials, double* d_stats, cudaStream_t st);
-
 cudaError_t launch_bg_finalize(const double* partials, int n_partials, double* d_stats,
                                int accumulate, cudaStream_t st);
-
-#define CGBK_DIRTY_STATS_BLOCKS 148
 
 cudaError_t launch_fast_filter(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
                                int L, int grid, cudaStream_t st);
@@ -152,6 +147,14 @@ struct StatsParams {
     double q;              // moment unit in score units: 2^-(kexp - sh)
     unsigned long long* d_hist;
     int* plane;            // optional score plane [tile][(B + 1) * 32 rows][32 lanes]
+    // tiles with non-ACGT bytes are scored exactly inside the scan (device ExactTables)
+    const void* exact_tab;
+    double hist_lo_d;      // histogram lower edge and 1 / bin width in score units
+    double inv_binw_d;
+    // the block that finishes last in the launch flagged `finalize` reduces every per-block
+    // partial moment written so far into d_stats (n, sum, sumsq accumulate; mean, std derived)
+    double* d_stats;
+    int finalize;
 };
 
 StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist_hi, int n_bins,
@@ -177,7 +180,8 @@ int fast_threads(int G, int mode);
 //   begin -> validates, clears the accumulators, fixes the tiling
 //   range -> scans the not yet scanned tiles that lie entirely below bases_ready
 //            (all remaining tiles when last != 0); at most CGBK_MAX_TILE_RANGES launches
-//   end   -> exact pass over dirty tiles + reduction of the partial moments into d_stats
+//   end   -> makes sure the partial moments were reduced into d_stats (the last range's
+//            last block does it; an empty scan needs the tiny finalize kernel)
 // ---------------------------------------------------------------------------
 struct BgScan {
     cgbk_model* M;
@@ -186,10 +190,9 @@ struct BgScan {
     FastWork w;
     StatsParams sp;
     int L, sms, threads;
-    double hist_lo, inv_binw;
     double* d_stats;
     long long next_tile;
-    int n_ranges, partials_used;
+    int n_ranges, partials_used, finalized;
 };
 int cgbk_bg_scan_begin(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqset* set, double hist_lo,
                        double hist_hi, int n_bins, unsigned long long* d_hist, double* d_stats,

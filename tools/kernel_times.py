@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""CUDA-event time of each stage of the config-2 step (stats scan call, posterior call, hit scan
-call), warm L2, many repetitions.  For A/B-ing kernel variants (CGBK_LIB=...)."""
+"""Device time of each stage of the config-2 step (stats scan call, posterior call), warm L2, replayed
+from a CUDA graph so that host overhead does not count.  For A/B-ing kernel variants (CGBK_LIB=...)."""
 import json
 import os
 import sys
@@ -33,17 +33,29 @@ def main():
     post = torch.empty(bench.N_GENES, dtype=torch.float64, device=dev)
     reps = 200
 
-    def timeit(fn):
-        for _ in range(10):
+    def timeit(fn, per_graph=20):
+        """``per_graph`` calls captured into one CUDA graph and replayed: the host (Python +
+        driver, ~12 us per call) is out of the picture, what is left is device time per call."""
+        for _ in range(5):
             fn()
         torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
+        side = torch.cuda.Stream()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
             fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps * 1e3
+            side.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(per_graph):
+                    fn()
+            graph.replay()
+            side.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(side)
+            for _ in range(reps // per_graph):
+                graph.replay()
+            b.record(side)
+            side.synchronize()
+        return a.elapsed_time(b) / (reps // per_graph * per_graph) * 1e3
 
     out = {
         "stats_call_us": timeit(lambda: M.background_stats(g, out=bg, keep_scores=True)),
