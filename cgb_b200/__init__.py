@@ -10,6 +10,8 @@ from .genome_buffer import PackedGenome
 from .pssm_model import PSSMModel, scan_hits_many
 from .site_collection import SiteCollection
 from .site_search import Site, calculate_regulation_probabilities, identify_sites
+from .genome import Chromid, Genome
+from . import genbank, operons
 
 __all__ = ["TFBindingModel", "PSSMModel", "SiteCollection", "PackedGenome", "GeneTable",
-           "Site", "identify_sites", "scan_hits_many", "calculate_regulation_probabilities", "python_slice_bounds"]
+           "Site", "Genome", "Chromid", "genbank", "operons", "identify_sites", "scan_hits_many", "calculate_regulation_probabilities", "python_slice_bounds"]

@@ -19,7 +19,7 @@ class GeneTable:
     exclusive, as Biopython FeatureLocation) and strand (+1 / -1)."""
 
     def __init__(self, start, end, strand, chrom_len, seq_index=0, locus_tag=None, protein_id=None,
-                 product=None):
+                 product=None, index=None, name=None, product_type=None):
         self.start = np.asarray(start, dtype=np.int64)
         self.end = np.asarray(end, dtype=np.int64)
         self.strand = np.asarray(strand, dtype=np.int64)
@@ -27,29 +27,47 @@ class GeneTable:
         self.seq_index = int(seq_index)
         # optional annotation columns of the identified_sites report (genome.py:470-493)
         self.locus_tag, self.protein_id, self.product = locus_tag, protein_id, product
+        self.name, self.product_type = name, product_type
         if not (len(self.start) == len(self.end) == len(self.strand)):
             raise ValueError("start/end/strand must have equal lengths")
+        # Gene._index (chromid.py:101-121): the running number of the 'gene' FEATURE, which
+        # keeps counting over the compound-location genes the reference leaves out of the
+        # list.  Gene.upstream_gene indexes the (shorter) list with it, so after a skipped
+        # gene "the previous gene" is really a later one.  Default: list position.
+        self.index = np.arange(len(self.start), dtype=np.int64) if index is None else np.asarray(index, dtype=np.int64)
+        if len(self.index) != len(self.start):
+            raise ValueError("index must have one entry per gene")
 
     def __len__(self):
         return len(self.start)
 
-    # gene.py:57-70: previous gene for forward genes, next gene for reverse genes
+    # gene.py:57-70: genes[_index - 1] for forward genes with _index > 0, genes[_index + 1] for
+    # reverse genes with _index < len(genes) - 1, else None
     def _upstream(self):
         n = len(self)
         fwd = self.strand == 1
-        idx = np.where(fwd, np.arange(n) - 1, np.arange(n) + 1)
-        has = np.where(fwd, np.arange(n) > 0, np.arange(n) < n - 1)
+        idx = np.where(fwd, self.index - 1, self.index + 1)
+        has = np.where(fwd, self.index > 0, self.index < n - 1)
+        if np.any(has & (idx >= n)):
+            # the reference's list lookup fails the same way (forward gene after enough
+            # skipped compound genes)
+            raise IndexError("list index out of range (Gene.upstream_gene, cgb/gene.py:66)")
         idx = np.clip(idx, 0, max(n - 1, 0))
         return idx, has
+
+    def upstream_gene(self):
+        """Row of each gene's upstream gene (gene.py:57-70), -1 where there is none."""
+        idx, has = self._upstream()
+        return np.where(has, idx, -1)
 
     def upstream_noncoding_region_location(self, up=None, down=50):
         """gene.py:72-104.  ``if up:`` means 0 behaves like None."""
         fwd = self.strand == 1
-        uidx, has = self._upstream()
         if up:
             f_start = np.maximum(0, self.start - up)
             r_end = np.minimum(self.chrom_len, self.end + up)
         else:
+            uidx, has = self._upstream()          # only looked up on this branch (gene.py:85-88)
             f_start = np.where(has, np.minimum(self.end[uidx] - down, self.start), 0)
             r_end = np.where(has, np.maximum(self.start[uidx] + down, self.end), self.chrom_len)
         f_end = self.start + down

@@ -84,7 +84,8 @@ def calculate_regulation_probabilities(model, genome, gene_table, prior, alpha,
 CSV_HEADER = ['score', 'site', 'chromid', 'start', 'end', 'strand', 'distance', 'category',
               'gene_strand', 'gene_start', 'gene_end', 'gene_locus_tag', 'protein_id', 'gene_product']
 
-_COMPLEMENT = str.maketrans("ACGTacgtNn", "TGCAtgcaNn")
+# Bio.Seq complement table (IUPAC ambiguity codes included, case kept)
+_COMPLEMENT = str.maketrans("ACGTMRWSYKVHDBNacgtmrwsykvhdbn", "TGCAKYWSRMBDHVNtgcakywsrmbdhvn")
 
 
 def relative_distance_to_start(gene_start, gene_end, gene_strand, site_start, site_end):

@@ -417,35 +417,63 @@ def binding_probability(model, seq, p_motif, alpha=1 / 350.0, softmax="legacy64"
 OGene = namedtuple("OGene", "start end strand")      # strand +1 / -1
 
 
-def upstream_gene(genes, idx):
-    """gene.py:58-70."""
+def upstream_gene(genes, idx, index=None):
+    """gene.py:58-70.  ``index[idx]`` is the gene's ``_index`` (chromid.py:101-121): the running
+    number of its 'gene' feature, which also counts the compound-location genes left out of the
+    list -- the reference indexes the shortened list with it (IndexError past its end)."""
     g = genes[idx]
-    if g.strand == 1 and idx > 0:
-        return genes[idx - 1]
-    if g.strand != 1 and idx < len(genes) - 1:
-        return genes[idx + 1]
+    k = idx if index is None else index[idx]
+    if g.strand == 1 and k > 0:
+        return genes[k - 1]
+    if g.strand != 1 and k < len(genes) - 1:
+        return genes[k + 1]
     return None
 
 
-def upstream_noncoding_region_location(genes, idx, chrom_len, up=None, down=50):
+def upstream_noncoding_region_location(genes, idx, chrom_len, up=None, down=50, index=None):
     """gene.py:72-104 (``if up:`` treats 0 like None)."""
     g = genes[idx]
-    ug = upstream_gene(genes, idx)
     if g.strand == 1:
         if up:
             loc_start = max(0, g.start - up)
-        elif ug:
-            loc_start = min(ug.end - down, g.start)
+        elif upstream_gene(genes, idx, index):
+            loc_start = min(upstream_gene(genes, idx, index).end - down, g.start)
         else:
             loc_start = 0
         return loc_start, g.start + down
     if up:
         loc_end = min(chrom_len, g.end + up)
-    elif ug:
-        loc_end = max(ug.start + down, g.end)
+    elif upstream_gene(genes, idx, index):
+        loc_end = max(upstream_gene(genes, idx, index).start + down, g.end)
     else:
         loc_end = chrom_len
     return g.end - down, loc_end
+
+
+def genes_from_features(features):
+    """Chromid.genes (cgb/chromid.py:99-122) over plain feature dicts
+    ``{type, start, end, strand, compound, qualifiers}``: rows
+    ``(index, start, end, strand, locus_tag, product_type, product, protein_id)``."""
+    rows, index = [], 0
+    for f, next_f in zip(features, features[1:]):
+        if f["type"] == "gene":
+            locus_tag = f["qualifiers"]["locus_tag"]
+            next_locus_tag = next_f["qualifiers"].get("locus_tag")
+            product_f = next_f if locus_tag == next_locus_tag else None
+            if f["compound"]:
+                index += 1
+                continue
+            ptype = product_f["type"] if product_f else ""
+            try:
+                product = product_f["qualifiers"]["product"][0]
+            except (TypeError, KeyError):
+                product = ""
+            protein = ""
+            if ptype == "CDS":
+                protein = product_f["qualifiers"].get("protein_id", [""])[0]
+            rows.append((index, f["start"], f["end"], f["strand"], locus_tag[0], ptype, product, protein))
+            index += 1
+    return rows
 
 
 def promoter_region_location(gene, chrom_len, up=300, down=50):
@@ -476,7 +504,7 @@ def reverse_complement(seq):
 OSite = namedtuple("OSite", "start end strand score gene")
 
 
-def identify_sites(model, sequence, genes, up=None, down=50, threshold=None):
+def identify_sites(model, sequence, genes, up=None, down=50, threshold=None, index=None):
     """Hit loop of genome.py:419-448 over one chromid.  ``gene`` in the result
     is the gene index.  float32 score vs float64 threshold (pinned numpy)."""
     if threshold is None:
@@ -485,7 +513,7 @@ def identify_sites(model, sequence, genes, up=None, down=50, threshold=None):
     L = len(sequence)
     sites = []
     for gi in range(len(genes)):
-        start, end = upstream_noncoding_region_location(genes, gi, L, up, down)
+        start, end = upstream_noncoding_region_location(genes, gi, L, up, down, index)
         seq = subsequence(sequence, start, end)
         if len(seq) < m:
             continue   # the reference would raise inside Biopython here

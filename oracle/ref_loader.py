@@ -131,3 +131,100 @@ def lexa_collections(ns, test_input_json=None):
     with open(path) as f:
         d = json.load(f)
     return [ns.SiteCollection(mo["sites"], _TF(), mo["name"]) for mo in d["motifs"]]
+
+
+# ---------------------------------------------------------------------------
+# the genome-side stack: gene.py, operon.py, chromid.py, genome.py, bio_utils.py VERBATIM
+# ---------------------------------------------------------------------------
+class FakePosition(object):
+    """Bio.SeqFeature position: the reference reads ``.position`` (gene.py:25,30)."""
+
+    def __init__(self, position):
+        self.position = int(position)
+
+
+class FeatureLocation(object):
+    """Stand-in for Bio.SeqFeature.FeatureLocation (0-based start, exclusive end)."""
+
+    def __init__(self, start, end, strand):
+        self.start, self.end, self.strand = FakePosition(start), FakePosition(end), strand
+
+
+class CompoundLocation(object):
+    """Stand-in for Bio.SeqFeature.CompoundLocation: chromid.py:108 skips genes whose
+    location is not a plain FeatureLocation."""
+
+    def __init__(self, parts, strand):
+        self.parts, self.strand = parts, strand
+
+
+class FakeFeature(object):
+    def __init__(self, type_, location, qualifiers):
+        self.type, self.location, self.qualifiers = type_, location, qualifiers
+
+    @property
+    def strand(self):
+        return self.location.strand
+
+
+class FakeRecord(object):
+    """What chromid.py reads of a Biopython SeqRecord: id, description, seq, features."""
+
+    def __init__(self, accession, description, sequence, features):
+        self.id, self.description, self.seq, self.features = accession, description, sequence, features
+
+
+_RECORDS = {}
+
+
+def register_record(record):
+    """Makes ``Chromid(accession, genome)`` of the verbatim chromid.py find this record
+    (entrez_utils.get_genome_record / SeqIO.read are the stubbed network + parser)."""
+    _RECORDS[record.id] = record
+
+
+def load_genome_stack():
+    """Namespace of ``load()`` extended with the verbatim Genome / Chromid / Gene / Operon."""
+    ns = load()
+    if hasattr(ns, "Genome"):
+        return ns
+    import io
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    mod("cStringIO", StringIO=io.StringIO)
+    bio = sys.modules["Bio"]
+    bio.SeqIO = mod("Bio.SeqIO", read=lambda handle, fmt: _RECORDS[handle.getvalue()])
+    bio.SeqFeature = mod("Bio.SeqFeature", FeatureLocation=FeatureLocation, CompoundLocation=CompoundLocation)
+    bio.SeqRecord = mod("Bio.SeqRecord", SeqRecord=FakeRecord)
+    blast_mod = mod("Bio.Blast")
+    blast_mod.__path__ = []
+    blast_mod.NCBIXML = mod("Bio.Blast.NCBIXML")
+    mod("cgb_ref.entrez_utils", get_genome_record=lambda acc: acc, get_protein_record=lambda acc: acc)
+
+    def load_verbatim(name):
+        path = os.path.join(REFERENCE_ROOT, "cgb", name + ".py")
+        spec = importlib.util.spec_from_file_location("cgb_ref." + name, path)
+        m = importlib.util.module_from_spec(spec)
+        sys.modules["cgb_ref." + name] = m
+        m.__dict__["sum"] = plain_sum
+        spec.loader.exec_module(m)
+        return m
+
+    bio_utils = load_verbatim("bio_utils")          # replaces the weblogo-only stub
+    ns.pssm_model.weblogo = bio_utils.weblogo
+    blast = load_verbatim("blast")
+    protein = load_verbatim("protein")
+    gene = load_verbatim("gene")
+    operon = load_verbatim("operon")
+    chromid = load_verbatim("chromid")
+    genome = load_verbatim("genome")
+    genome.tqdm = lambda it: it                     # progress bar only
+    ns.bio_utils, ns.gene, ns.operon, ns.chromid, ns.genome = bio_utils, gene, operon, chromid, genome
+    ns.Genome, ns.Chromid, ns.Gene, ns.Operon = genome.Genome, chromid.Chromid, gene.Gene, operon.Operon
+    del blast, protein
+    return ns

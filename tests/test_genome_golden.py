@@ -1,0 +1,180 @@
+"""Genome-side rows of SURVEY.md §8 against the reference run verbatim (CPU, no GPU needed).
+
+tests/golden/genome_vectors.json holds what the unmodified cgb/genome.py, chromid.py, gene.py and
+operon.py produce on a small synthetic annotated genome (tests/golden/make_genome_golden.py).
+Checked here: the GenBank parser + gene-selection rules, the coordinate rules (product and
+oracle), the oracle's identify_sites / report rows / posterior, and operon prediction + CSVs.
+"""
+import csv
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cgb_b200 import GeneTable, genbank, operons, python_slice_bounds
+from oracle import np_oracle as O
+from genbank_writer import genbank_text
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def gv():
+    with open(os.path.join(HERE, "golden", "genome_vectors.json")) as f:
+        return json.load(f)
+
+
+def _table(gold, k=0):
+    rows = gold["rows"]
+    col = lambda name: [r[name] for r in rows]
+    return GeneTable(col("start"), col("end"), col("strand"), gold["length"], seq_index=k,
+                     locus_tag=col("locus_tag"), protein_id=col("protein_id"), product=col("product"),
+                     index=col("index"), name=col("name"), product_type=col("product_type"))
+
+
+def _csv_text(rows):
+    buf = io.StringIO(newline="")
+    w = csv.writer(buf)
+    for r in rows:
+        w.writerow(r)
+    return buf.getvalue()
+
+
+def test_genbank_parse_matches_reference_gene_table(gv):
+    """GenBank text -> sequence + GeneTable == what Chromid.genes derives from the same features."""
+    for rep, gold in zip(gv["replicons"], gv["genes"]):
+        rec = genbank.read(genbank_text(rep))
+        assert rec.id == rep["accession"] and rec.description == rep["description"]
+        assert rec.sequence.decode() == rep["sequence"].upper()       # Biopython upper-cases ORIGIN
+        assert len(rec.features) == len(rep["features"])
+        gt = rec.gene_table()
+        rows = gold["rows"]
+        assert len(gt) == len(rows)
+        for name in ("index", "start", "end", "strand"):
+            assert getattr(gt, name).tolist() == [r[name] for r in rows], name
+        for name in ("locus_tag", "name", "product_type", "product", "protein_id"):
+            assert list(getattr(gt, name)) == [r[name] for r in rows], name
+        # the oracle's restatement of chromid.py:99-122 on the raw feature dicts
+        orows = O.genes_from_features(rep["features"])
+        assert [(r["index"], r["start"], r["end"], r["strand"], r["locus_tag"], r["product_type"], r["product"],
+                 r["protein_id"]) for r in rows] == orows
+
+
+def test_genbank_location_forms():
+    f = genbank.parse_location
+    assert f("123..456") == (122, 456, 1, False)
+    assert f("complement(123..456)") == (122, 456, -1, False)
+    assert f("<123..>456") == (122, 456, 1, False)
+    assert f("77") == (76, 77, 1, False)
+    assert f("join(1..10,20..30)")[3] and f("complement(join(1..10,\n 20..30))")[2:] == (-1, True)
+    assert f("order(5..9,12..14)")[3]
+    assert f("J00194.1:100..202") == (99, 202, 1, False)
+    with pytest.raises(ValueError):
+        genbank.read("no records here")
+    with pytest.raises(ValueError):
+        rep = {"accession": "X.1", "description": "d", "sequence": "ACGT", "features": []}
+        genbank.read(genbank_text(rep) + genbank_text(rep))
+
+
+def test_coordinate_rules_match_reference(gv):
+    up, dw = gv["promoter_up_distance"], gv["promoter_dw_distance"]
+    for k, (rep, gold) in enumerate(zip(gv["replicons"], gv["genes"])):
+        gt = _table(gold, k)
+        rows = gold["rows"]
+        tags = [r["locus_tag"] for r in rows]
+        ug = gt.upstream_gene()
+        assert [tags[i] if i >= 0 else None for i in ug] == [r["upstream_gene"] for r in rows]
+        s, e = gt.upstream_noncoding_region_location(None, dw)
+        assert [[int(a), int(b)] for a, b in zip(s, e)] == [r["upstream_noncoding_none"] for r in rows]
+        s, e = gt.upstream_noncoding_region_location(up, dw)
+        assert [[int(a), int(b)] for a, b in zip(s, e)] == [r["upstream_noncoding_up"] for r in rows]
+        s, e = gt.promoter_region_location(up, dw)
+        s, e = python_slice_bounds(s, e, gold["length"])
+        assert [rep["sequence"][int(a):int(b)] for a, b in zip(s, e)] == [r["promoter_region"] for r in rows]
+        # the oracle's scalar rules
+        genes = [O.OGene(r["start"], r["end"], r["strand"]) for r in rows]
+        index = [r["index"] for r in rows]
+        for i, r in enumerate(rows):
+            assert list(O.upstream_noncoding_region_location(genes, i, gold["length"], None, dw, index)) == \
+                r["upstream_noncoding_none"]
+            assert list(O.upstream_noncoding_region_location(genes, i, gold["length"], up, dw, index)) == \
+                r["upstream_noncoding_up"]
+            a, b = O.promoter_region_location(genes[i], gold["length"], up, dw)
+            assert O.subsequence(rep["sequence"], a, b) == r["promoter_region"]
+
+
+def test_upstream_gene_index_error_like_reference():
+    # a forward gene whose feature number points past the shortened list: genes[_index - 1] raises
+    gt = GeneTable([100, 900], [500, 1300], [1, 1], 5000, index=[0, 4])
+    with pytest.raises(IndexError):
+        gt.upstream_noncoding_region_location(None, 50)
+    s, e = gt.upstream_noncoding_region_location(300, 50)          # never looks the neighbour up
+    assert s.tolist() == [0, 600] and e.tolist() == [150, 950]
+
+
+def _oracle_model(gv, lexa):
+    om = O.OracleModel([mo["sites"] for mo in lexa["motifs"]], gv["weights"])
+    est = gv["estimator"]
+    om._mu_m, om._std_m, om._mu_bg, om._std_bg = est["mu_m"], est["std_m"], est["mu_bg"], est["std_bg"]
+    return om
+
+
+def test_oracle_identify_sites_and_report_match_reference(gv, lexa):
+    """Pins the oracle's hit loop and report rows (genome.py:394-494) to the verbatim run:
+    same sites in the same order, CSV text byte for byte."""
+    om = _oracle_model(gv, lexa)
+    assert om.threshold() == gv["estimator"]["threshold"]
+    up, dw = gv["promoter_up_distance"], gv["promoter_dw_distance"]
+    for scen, use_up in (("scan_to_upstream_gene", None), ("scan_up_distance", up)):
+        sites, rows = [], []
+        for rep, gold in zip(gv["replicons"], gv["genes"]):
+            genes = [O.OGene(r["start"], r["end"], r["strand"]) for r in gold["rows"]]
+            index = [r["index"] for r in gold["rows"]]
+            ann = [(r["locus_tag"], r["protein_id"], r["product"]) for r in gold["rows"]]
+            ss = O.identify_sites(om, rep["sequence"], genes, use_up, dw, index=index)
+            sites.extend((rep, genes, ann, s) for s in ss)
+        sites.sort(key=lambda t: t[3].score, reverse=True)          # genome.py:448 over all chromids
+        want = gv["scenarios"][scen]["sites"]
+        assert len(sites) == len(want)
+        for (rep, genes, ann, s), w in zip(sites, want):
+            assert (rep["accession"], s.start, s.end, s.strand, float(s.score)) == \
+                (w["chromid"], w["start"], w["end"], w["strand"], w["score"])
+            assert ann[s.gene][0] == w["gene"]
+            rows.extend(O.identified_sites_rows([s], rep["sequence"], genes, up, rep["accession"], ann))
+        from cgb_b200.site_search import CSV_HEADER
+        assert _csv_text([CSV_HEADER] + rows) == gv["scenarios"][scen]["sites_csv"]
+
+
+def test_oracle_posteriors_match_reference(gv, lexa):
+    om = _oracle_model(gv, lexa)
+    for rep, gold, want in zip(gv["replicons"], gv["genes"], gv["regulation_probability"]):
+        got = [O.binding_probability(om, r["promoter_region"], gv["prior"], gv["alpha"], softmax="nep50")
+               for r in gold["rows"]]
+        assert got == want
+
+
+@pytest.mark.parametrize("name", ["split_0.5_sigma_1.0", "nosplit_sigma_1.0", "split_0.2_sigma_1.5"])
+def test_operon_prediction_matches_reference(gv, name):
+    """Directons, adaptive distance threshold, posterior-driven splitting, operon ids and the
+    two CSV reports (chromid.py:140-243, genome.py:74-152,335-378), from the reference's own
+    posteriors."""
+    want = gv["operons"][name]
+    tables = [_table(g, k) for k, g in enumerate(gv["genes"])]
+    accs = [g["accession"] for g in gv["genes"]]
+    probs = [np.array(p) for p in gv["regulation_probability"]]
+    assert operons.intergenic_distance_threshold(tables, want["sigma"]) == want["distance_threshold"]
+    oprs = operons.predict_operons_genome(tables, want["probability_th"], want["sigma"], probs, accs)
+    assert len(oprs) == len(want["operons"])
+    for o, w in zip(oprs, want["operons"]):
+        gt = tables[o.seq_index]
+        assert (o.operon_id, o.chromid, o.start, o.end, o.strand) == \
+            (w["id"], w["chromid"], w["start"], w["end"], w["strand"])
+        assert [gt.locus_tag[g] for g in o.genes] == w["genes"]
+        assert gt.locus_tag[o.first_gene] == w["first_gene"]
+        assert o.regulation_probability == w["regulation_probability"]
+    assert _csv_text(operons.operons_rows(oprs, tables)) == want["operons_csv"]
+    results, regulons = operons.infer_regulons(oprs, 0.5)
+    assert _csv_text(operons.regulon_rows(results, tables)) == want["regulons_csv"]
+    assert [[tables[o.seq_index].locus_tag[g] for g in o.genes] for o in regulons] == want["regulons"]

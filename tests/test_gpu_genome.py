@@ -1,0 +1,101 @@
+"""The Genome mirror end to end on the GPU against the reference run verbatim
+(tests/golden/genome_vectors.json): background fit, identified sites + CSV, posteriors of
+regulation, operon prediction with posterior-driven splitting, regulon report."""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+
+from cgb_b200 import Chromid, Genome, GeneTable, SiteCollection
+from genbank_writer import genbank_text
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def gv():
+    with open(os.path.join(HERE, "golden", "genome_vectors.json")) as f:
+        return json.load(f)
+
+
+def _genome(gv):
+    chromids = []
+    for k, (rep, gold) in enumerate(zip(gv["replicons"], gv["genes"])):
+        rows = gold["rows"]
+        col = lambda name: [r[name] for r in rows]
+        gt = GeneTable(col("start"), col("end"), col("strand"), gold["length"], seq_index=k,
+                       locus_tag=col("locus_tag"), protein_id=col("protein_id"), product=col("product"),
+                       index=col("index"), name=col("name"), product_type=col("product_type"))
+        chromids.append(Chromid(rep["accession"], rep["description"], rep["sequence"].encode(), gt))
+    return Genome("synthetic_strain", chromids)
+
+
+def _read(path):
+    with open(path, newline="") as f:
+        return f.read()
+
+
+def test_genome_pipeline_matches_reference(gv, lexa, tmp_path):
+    colls = [SiteCollection(mo["sites"], None, mo["name"]) for mo in lexa["motifs"]]
+    genome = _genome(gv)
+    genome.build_PSSM_model(colls, gv["weights"])
+    M, est = genome.TF_binding_model, gv["estimator"]
+    assert M.threshold() == est["threshold"]
+    assert abs(M._mu_m - est["mu_m"]) < 1e-6 and abs(M._std_m - est["std_m"]) < 1e-6
+    # the fixture's soft-max ran with float32 pow (numpy 2); the pinned numpy 1.x, which the
+    # kernels follow, differs by < 2e-7 per score
+    assert abs(M._mu_bg - est["mu_bg"]) < 1e-6 and abs(M._std_bg - est["std_bg"]) < 1e-6
+    up, dw = gv["promoter_up_distance"], gv["promoter_dw_distance"]
+    for scen, use_up in (("scan_to_upstream_gene", False), ("scan_up_distance", True)):
+        ui = types.SimpleNamespace(promoter_up_distance=up, promoter_dw_distance=dw, alpha=gv["alpha"],
+                                   use_up_dist_site_scan=use_up)
+        path = str(tmp_path / ("sites_%s.csv" % scen))
+        genome.identify_sites(ui, path)
+        want = gv["scenarios"][scen]["sites"]
+        got = genome.putative_sites
+        assert len(got) == len(want)
+        for s, w in zip(got, want):
+            gt = genome.gene_tables[s.chromid]
+            assert (genome.chromids[s.chromid].accession_number, s.start, s.end, s.strand, float(s.score),
+                    gt.locus_tag[s.gene]) == (w["chromid"], w["start"], w["end"], w["strand"], w["score"], w["gene"])
+        assert _read(path) == gv["scenarios"][scen]["sites_csv"]          # byte for byte
+    ui = types.SimpleNamespace(promoter_up_distance=up, promoter_dw_distance=dw, alpha=gv["alpha"],
+                               use_up_dist_site_scan=False)
+    probs = genome.calculate_regulation_probabilities(gv["prior"], ui)
+    for got, want in zip(probs, gv["regulation_probability"]):
+        assert np.max(np.abs(got - np.array(want))) < 1e-6
+    for name, want in gv["operons"].items():
+        genome.operon_prediction(want["probability_th"], want["sigma"])
+        assert genome.num_operons == len(want["operons"])
+        for o, w in zip(genome.operons, want["operons"]):
+            gt = genome.gene_tables[o.seq_index]
+            assert (o.operon_id, o.chromid, [gt.locus_tag[g] for g in o.genes]) == (w["id"], w["chromid"], w["genes"])
+            assert abs(o.regulation_probability - w["regulation_probability"]) < 1e-6
+        p1, p2 = str(tmp_path / "operons.csv"), str(tmp_path / "regulons.csv")
+        genome.operons_to_csv(p1)
+        regulons = genome.infer_regulons(0.5, p2)
+        assert _read(p1) == want["operons_csv"]
+        assert _read(p2) == want["regulons_csv"]
+        assert [[genome.gene_tables[o.seq_index].locus_tag[g] for g in o.genes] for o in regulons] == want["regulons"]
+
+
+def test_genome_from_genbank(gv, lexa):
+    """GenBank text in (upper-cased by the format), same gene tables and a working scan."""
+    texts = [genbank_text(rep) for rep in gv["replicons"]]
+    genome = Genome.from_genbank("synthetic_strain", texts)
+    assert [c.accession_number for c in genome.chromids] == [r["accession"] for r in gv["replicons"]]
+    for gt, gold in zip(genome.gene_tables, gv["genes"]):
+        assert gt.start.tolist() == [r["start"] for r in gold["rows"]]
+        assert list(gt.locus_tag) == [r["locus_tag"] for r in gold["rows"]]
+    colls = [SiteCollection(mo["sites"], None, mo["name"]) for mo in lexa["motifs"]]
+    genome.build_PSSM_model(colls, gv["weights"])
+    ui = types.SimpleNamespace(promoter_up_distance=300, promoter_dw_distance=50, alpha=gv["alpha"],
+                               use_up_dist_site_scan=True)
+    genome.identify_sites(ui)
+    # the planted sites are found whatever the case of the surrounding sequence
+    top = genome.putative_sites[0]
+    assert abs(float(top.score) - gv["scenarios"]["scan_up_distance"]["sites"][0]["score"]) < 1e-4
+    assert repr(genome).startswith("synthetic_strain: ['SYNA01.1'")
