@@ -7,11 +7,11 @@ Importing the package does not need a GPU; any scoring call does (no CPU fallbac
 from .binding_model import TFBindingModel
 from .gene_regions import GeneTable, python_slice_bounds
 from .genome_buffer import PackedGenome
-from .pssm_model import PSSMModel, scan_hits_many
+from .pssm_model import PSSMModel, prepare_thresholds, scan_hits_many
 from .site_collection import SiteCollection
 from .site_search import Site, calculate_regulation_probabilities, identify_sites
-from .genome import Chromid, Genome
+from .genome import Chromid, Genome, get_prior
 from . import genbank, operons
 
 __all__ = ["TFBindingModel", "PSSMModel", "SiteCollection", "PackedGenome", "GeneTable",
-           "Site", "Genome", "Chromid", "genbank", "operons", "identify_sites", "scan_hits_many", "calculate_regulation_probabilities", "python_slice_bounds"]
+           "Site", "Genome", "Chromid", "get_prior", "prepare_thresholds", "genbank", "operons", "identify_sites", "scan_hits_many", "calculate_regulation_probabilities", "python_slice_bounds"]

@@ -38,6 +38,8 @@ SYMBOLS = {
     "cgbk_version": (C.c_int, []),
     "cgbk_last_error": (C.c_char_p, []),
     "cgbk_patser_threshold": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 4),
+    "cgbk_patser_threshold_batch": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int] +
+                                    [C.POINTER(C.c_double)] * 4 + [C.POINTER(C.c_int)]),
     "cgbk_bases2_words": (C.c_int64, [C.c_int64]),
     "cgbk_pack_ascii": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_void_p]),

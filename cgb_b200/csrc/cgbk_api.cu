@@ -6,6 +6,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "cgbk_internal.cuh"
@@ -155,6 +158,53 @@ extern "C" int cgbk_patser_threshold(const double* lo, int m, int precision, dou
         prob += dens[i];
     }
     *threshold = min_score + (double)i * step;
+    return CGBK_OK;
+}
+
+// Motif batches (JASPAR-scale sets, BASELINE configs[4]): the same DP for n motifs, spread over
+// host threads.  Each motif's arithmetic is exactly cgbk_patser_threshold's (one thread per
+// motif, no shared accumulation), so the results are identical to n single calls.
+extern "C" int cgbk_patser_threshold_batch(const double* logodds, const int* m, int n, int precision,
+                                           int n_threads, double* threshold, double* ic,
+                                           double* min_score, double* max_score, int* status) {
+    if (!logodds || !m || n < 0) return cgbk_set_error(CGBK_ERR_INVALID, "NULL argument");
+    std::vector<long long> off(n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        if (m[i] <= 0) return cgbk_set_error(CGBK_ERR_INVALID, "motif %d has length %d", i, m[i]);
+        off[i + 1] = off[i] + 4ll * m[i];
+    }
+    if (n_threads < 1) {
+        n_threads = (int)std::thread::hardware_concurrency();
+        if (n_threads < 1) n_threads = 1;
+    }
+    if (n_threads > n) n_threads = n > 0 ? n : 1;
+    std::vector<int> rc(n, CGBK_OK);
+    std::vector<std::string> msg(n);
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= n) break;
+            double t = 0, a = 0, b = 0, c = 0;
+            rc[i] = cgbk_patser_threshold(logodds + off[i], m[i], precision, threshold ? &t : nullptr, &a, &b, &c);
+            if (rc[i] != CGBK_OK) msg[i] = g_err;               // thread-local text of this worker
+            if (threshold) threshold[i] = t;
+            if (ic) ic[i] = a;
+            if (min_score) min_score[i] = b;
+            if (max_score) max_score[i] = c;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    int first_bad = -1;
+    for (int i = 0; i < n; ++i) {
+        if (status) status[i] = rc[i];
+        if (rc[i] != CGBK_OK && first_bad < 0) first_bad = i;
+    }
+    if (first_bad >= 0)
+        return cgbk_set_error(rc[first_bad], "motif %d: %s", first_bad, msg[first_bad].c_str());
     return CGBK_OK;
 }
 

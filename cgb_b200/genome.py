@@ -133,8 +133,14 @@ class Genome(object):
         return _operons.intergenic_distance_threshold(self.gene_tables, sigma)
 
     def operon_prediction(self, probability_th, sigma):
+        probs = self._regulation_probability
+        if probs is None:                      # fine as long as splitting is off (get_prior)
+            if probability_th != 1.0:
+                raise AttributeError("calculate_regulation_probabilities has not been run "
+                                     "(Gene._regulation_probability, cgb/gene.py:144)")
+            probs = [None] * len(self._chromids)
         self._operons = _operons.predict_operons_genome(
-            self.gene_tables, probability_th, sigma, self._regulation_probability,
+            self.gene_tables, probability_th, sigma, probs,
             [c.accession_number for c in self._chromids])
 
     @property
@@ -160,3 +166,15 @@ class Genome(object):
 
     def __repr__(self):
         return self._strain_name + ': ' + str([c.accession_number for c in self._chromids])
+
+
+def get_prior(genome, user_input):
+    """cgb/__init__.py:293-350: the user's prior probability of regulation or, without one, the
+    expected number of sites G / 2^IC (one per regulated operon) over the number of operons
+    predicted with splitting switched off."""
+    if user_input.prior_regulation_probability:
+        return user_input.prior_regulation_probability
+    genome.operon_prediction(1, user_input.operon_prediction_distance_tuning_parameter)
+    prior = (genome.length / 2 ** genome.TF_binding_model.IC / genome.num_operons)
+    genome.remove_operons()
+    return prior

@@ -85,6 +85,16 @@ const char* cgbk_last_error(void);
 int cgbk_patser_threshold(const double* logodds, int m, int precision,
                           double* threshold, double* ic, double* min_score, double* max_score);
 
+/* The same for a batch of n motifs (PSSMModel.IC / .patser_threshold of every model of a
+ * JASPAR-scale set, cgb/pssm_model.py:57-70): logodds holds the [m_i][4] tables back to back,
+ * outputs are arrays of n (any may be NULL).  Motifs are spread over n_threads host threads
+ * (<= 0: all hardware threads); each motif's arithmetic is that of the single call, so the
+ * numbers are identical.  status[i] (optional) receives the per-motif status; the call returns
+ * the first failure, if any. */
+int cgbk_patser_threshold_batch(const double* logodds, const int* m, int n, int precision, int n_threads,
+                                double* threshold, double* ic, double* min_score, double* max_score,
+                                int* status);
+
 /* ---- packing ("str(record.seq)" -> HBM planes) ----------------------------- */
 
 /* Words (uint32) the bases2 plane needs for cap_bases bases; amb/lower need half. */

@@ -210,6 +210,14 @@ def main():
             "regulons": [[g.locus_tag for g in o.genes] for o in regulons]}
         genome.remove_operons() if False else None      # the reference's remove_operons mutates a temp list
 
+    # --- get_prior (cgb/__init__.py:320-350; that file is Python-2-only syntax, so its three
+    # lines are spelled out here over the verbatim Genome): operons without splitting, then
+    # G / 2^IC expected sites over the number of operons
+    genome.operon_prediction(1, 1.0)
+    out["inferred_prior"] = {"sigma": 1.0, "IC": float(model.IC), "genome_length": genome.length,
+                             "num_operons": genome.num_operons,
+                             "prior": genome.length / 2 ** genome.TF_binding_model.IC / genome.num_operons}
+
     with open(os.path.join(HERE, "genome_vectors.json"), "w") as f:
         json.dump(out, f, indent=1)
     n_genes = sum(len(c["rows"]) for c in out["genes"])

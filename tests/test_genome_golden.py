@@ -178,3 +178,38 @@ def test_operon_prediction_matches_reference(gv, name):
     results, regulons = operons.infer_regulons(oprs, 0.5)
     assert _csv_text(operons.regulon_rows(results, tables)) == want["regulons_csv"]
     assert [[tables[o.seq_index].locus_tag[g] for g in o.genes] for o in regulons] == want["regulons"]
+
+
+def test_get_prior_matches_reference(gv):
+    """cgb/__init__.py:320-350 over the Genome mirror (host only: IC + operons without splitting)."""
+    import types
+    from cgb_b200 import Chromid, Genome, get_prior
+    chromids = [Chromid(g["accession"], "", rep["sequence"].encode(), _table(g, k))
+                for k, (rep, g) in enumerate(zip(gv["replicons"], gv["genes"]))]
+    genome = Genome("synthetic_strain", chromids)
+    want = gv["inferred_prior"]
+    genome._TF_binding_model = types.SimpleNamespace(IC=want["IC"])
+    ui = types.SimpleNamespace(prior_regulation_probability=None,
+                               operon_prediction_distance_tuning_parameter=want["sigma"])
+    assert genome.length == want["genome_length"]
+    assert get_prior(genome, ui) == want["prior"]
+    assert genome.num_operons == 0                                    # removed again, as the reference does
+    ui.prior_regulation_probability = 0.03
+    assert get_prior(genome, ui) == 0.03
+    with pytest.raises(AttributeError):
+        genome.operon_prediction(0.5, 1.0)                            # needs the posteriors first
+
+
+def test_batched_patser_thresholds_equal_single_calls():
+    from cgb_b200 import PSSMModel, SiteCollection, prepare_thresholds
+    rng = np.random.default_rng(3)
+    models, singles = [], []
+    for k in range(24):
+        m = int(rng.integers(8, 31))
+        cols = rng.dirichlet([0.5] * 4, size=m)
+        sites = ["".join("ACGT"[rng.choice(4, p=cols[j])] for j in range(m)) for _ in range(20)]
+        singles.append(PSSMModel([SiteCollection(sites)], [1.0]).threshold())
+        models.append(PSSMModel([SiteCollection(sites)], [1.0]))
+    prepare_thresholds(models, n_threads=4)
+    assert all("patser_threshold" in M.__dict__ for M in models)
+    assert [M.threshold() for M in models] == singles
