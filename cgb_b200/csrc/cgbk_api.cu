@@ -694,8 +694,15 @@ int cgbk_bg_scan_begin(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqs
                               (long long)plane_ints, (long long)cgbk_score_plane_ints(S, M->m));
     CUDA_TRY(cudaMemsetAsync(run->w.counters, 0, 64, st));
     if (!accumulate) {
-        if (d_hist) CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * n_bins, st));
-        CUDA_TRY(cudaMemsetAsync(d_stats, 0, sizeof(double) * CGBK_BG_COUNT, st));
+        // one memset when the histogram sits right behind the stats record (as the pipeline and
+        // the Python wrapper lay them out)
+        if (d_hist && (unsigned char*)d_hist == (unsigned char*)d_stats + sizeof(double) * CGBK_BG_COUNT) {
+            CUDA_TRY(cudaMemsetAsync(d_stats, 0, sizeof(double) * CGBK_BG_COUNT +
+                                                  sizeof(unsigned long long) * n_bins, st));
+        } else {
+            if (d_hist) CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * n_bins, st));
+            CUDA_TRY(cudaMemsetAsync(d_stats, 0, sizeof(double) * CGBK_BG_COUNT, st));
+        }
     }
     run->sp = make_stats_params(M, hist_lo, hist_hi, n_bins, d_hist, d_plane);
     run->sp.d_stats = d_stats;

@@ -4,11 +4,11 @@
 // (cgb/__init__.py:686-695): Genome.build_PSSM_model's background fit (genome.py:215-226,
 // over ALL windows) followed by Genome.calculate_regulation_probabilities
 // (genome.py:330-333 -> gene.py:129-146 -> binding_model.py:94-113), behind ONE C-ABI call
-// that takes HOST buffers.  Everything is enqueued on the caller's stream (H2D of the
-// sequence, pack, stats scan, dirty tiles + moment reduction, H2D of the promoter
-// descriptors, posteriors, D2H of the results) and the call returns after one stream
-// synchronisation, so the host-side cost is one function call instead of a dozen Python /
-// driver round trips.
+// that takes HOST buffers.  The call enqueues the upload of the sequence (one copy, or chunks
+// on a side stream for large replicons), the pack, the stats scan, the upload of the promoter
+// descriptors (side stream), the posteriors and ONE download of the results, and returns after
+// one stream synchronisation: the host-side cost is one function call instead of a dozen
+// Python / driver round trips.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -92,7 +92,7 @@ static PipeLayout pipe_layout(int64_t n_bases, int n_regions, int m, int n_bins)
 #define PIPE_MAX_CHUNKS CGBK_MAX_TILE_RANGES
 struct PipeStreams {
     cudaStream_t copy = nullptr;
-    cudaEvent_t ev[PIPE_MAX_CHUNKS + 1] = {};
+    cudaEvent_t ev[PIPE_MAX_CHUNKS + 2] = {};   // chunk c arrived | scratch free | promoter table arrived
 };
 static std::mutex g_pipe_mu;
 static PipeStreams* g_pipe[64] = {};
@@ -103,7 +103,7 @@ static PipeStreams* pipe_streams(int device) {
     if (g_pipe[device]) return g_pipe[device];
     PipeStreams* p = new PipeStreams;
     bool ok = cudaStreamCreateWithFlags(&p->copy, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; ok && i <= PIPE_MAX_CHUNKS; ++i)
+    for (int i = 0; ok && i < PIPE_MAX_CHUNKS + 2; ++i)
         ok = cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { delete p; return nullptr; }
     g_pipe[device] = p;
@@ -165,6 +165,21 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
     unsigned char* base = (unsigned char*)d_scratch;
     TRACE_DECL;
     TRACE("enter");
+    PipeStreams* ps = pipe_streams(M->device);
+    if (!ps) return cgbk_set_error(CGBK_ERR_CUDA, "could not create the copy stream");
+    cudaStream_t cs = ps->copy;
+    uint8_t* d_ascii = base + P.off_ascii;
+    int64_t cut[PIPE_MAX_CHUNKS + 1];
+    const int n_chunks = plan_chunks(n_bases, cut);
+    // whatever the caller's stream still has queued may use the scratch: the side stream starts
+    // behind it
+    if (cudaEventRecord(ps->ev[PIPE_MAX_CHUNKS], st) != cudaSuccess ||
+        cudaStreamWaitEvent(cs, ps->ev[PIPE_MAX_CHUNKS], 0) != cudaSuccess)
+        return cgbk_set_error(CGBK_ERR_CUDA, "stream hand-over failed");
+    // one-piece upload: start the DMA now, prepare the promoter table while it runs
+    const bool early = n_chunks == 1;
+    if (early && cudaMemcpyAsync(d_ascii, h_ascii, n_bases, cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return cgbk_set_error(CGBK_ERR_CUDA, "H2D of the sequence failed");
 
     // promoter slices -> (packed offset, window count): Chromid.subsequence's Python slice
     // (cgb/chromid.py:94) then len(seq) - m + 1 windows; len(seq) < m raises in the reference
@@ -176,38 +191,37 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
         e = e < 0 ? (e + n_bases > 0 ? e + n_bases : 0) : (e < n_bases ? e : n_bases);
         if (e < s) e = s;
         const int64_t nw = e - s - m + 1;
-        if (nw < 1)
+        if (nw < 1) {
+            cudaStreamSynchronize(st);              // the upload may be in flight
             return cgbk_set_error(CGBK_ERR_INVALID, "region %d is shorter than the motif "
                                   "(negative dimensions are not allowed)", i);
+        }
         st_start[i] = s;           // sequence 0 starts at packed offset 0
         st_nwin[i] = (int32_t)nw;
     }
     double* st_msm = (double*)((unsigned char*)h_staging + cgbk_pipeline_staging_bytes(n_regions) - 256);
     st_msm[0] = mu_m; st_msm[1] = std_m;
 
-    // 1. The sequence travels in a few chunks on a side stream while the caller's stream packs
-    //    and scans the chunks that have arrived: only the last chunk's pack + scan is left
-    //    after the last byte has crossed PCIe.  The promoter table rides in front of it.
+    // 1. Upload.  A small replicon goes up in ONE copy on the caller's stream (issued before the
+    //    host-side preparation above, see `early`), the promoter table beside it on a side stream.
+    //    A large one travels in chunks on the side stream while the caller's stream packs and
+    //    scans the chunks that have arrived: only the last chunk's pack + scan is left after the
+    //    last byte has crossed PCIe.
     TRACE("host prep");
-    PipeStreams* ps = pipe_streams(M->device);
-    if (!ps) return cgbk_set_error(CGBK_ERR_CUDA, "could not create the copy stream");
-    cudaStream_t cs = ps->copy;
-    uint8_t* d_ascii = base + P.off_ascii;
-    int64_t cut[PIPE_MAX_CHUNKS + 1];
-    const int n_chunks = plan_chunks(n_bases, cut);
-    cudaError_t ce = cudaEventRecord(ps->ev[PIPE_MAX_CHUNKS], st);       // scratch is free from here on
-    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(cs, ps->ev[PIPE_MAX_CHUNKS], 0);
-    if (ce == cudaSuccess && n_regions > 0) {
-        ce = cudaMemcpyAsync(base + P.off_desc, h_staging, 12 * (int64_t)n_regions, cudaMemcpyHostToDevice, cs);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(base + P.off_msm, st_msm, 16, cudaMemcpyHostToDevice, cs);
-    }
-    for (int c = 0; c < n_chunks && ce == cudaSuccess; ++c) {
+    cudaError_t ce = cudaSuccess;
+    for (int c = 0; c < n_chunks && !early && ce == cudaSuccess; ++c) {
         ce = cudaMemcpyAsync(d_ascii + cut[c], h_ascii + cut[c], cut[c + 1] - cut[c], cudaMemcpyHostToDevice, cs);
         if (ce == cudaSuccess) ce = cudaEventRecord(ps->ev[c], cs);
         TRACE_ON("chunk copied", cs);
     }
+    if (ce == cudaSuccess && n_regions > 0) {
+        ce = cudaMemcpyAsync(base + P.off_desc, h_staging, 12 * (int64_t)n_regions, cudaMemcpyHostToDevice, cs);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(base + P.off_msm, st_msm, 16, cudaMemcpyHostToDevice, cs);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ps->ev[PIPE_MAX_CHUNKS + 1], cs);
+    }
     if (ce != cudaSuccess) {
         cudaStreamSynchronize(cs);
+        cudaStreamSynchronize(st);
         return cgbk_check_cuda(ce, "H2D of the sequence");
     }
     TRACE("h2d issued");
@@ -230,7 +244,7 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
         rc = cgbk_bg_scan_begin(M, &G, S, hist_lo, hist_hi, n_bins, d_hist, d_stats, 0, d_plane, P.plane_ints,
                                 base + P.off_work, P.work_bytes, st, &run);
     for (int c = 0; c < n_chunks && !rc; ++c) {
-        if (cudaStreamWaitEvent(st, ps->ev[c], 0) != cudaSuccess)
+        if (!early && cudaStreamWaitEvent(st, ps->ev[c], 0) != cudaSuccess)
             rc = cgbk_set_error(CGBK_ERR_CUDA, "stream wait failed");
         if (!rc)
             rc = cgbk_pack_ascii(d_ascii + cut[c], cut[c + 1] - cut[c], cut[c], planes, planes + P.cap_bases / 16,
@@ -250,11 +264,18 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
     TRACE("stats");
     // 3. posteriors of every promoter from the plane, estimator straight from d_stats
     if (n_regions > 0) {
+        if (cudaStreamWaitEvent(st, ps->ev[PIPE_MAX_CHUNKS + 1], 0) != cudaSuccess) {
+            cudaStreamSynchronize(cs);
+            cudaStreamSynchronize(st);
+            cgbk_seqset_destroy(S);
+            return cgbk_set_error(CGBK_ERR_CUDA, "stream wait failed");
+        }
         rc = cgbk_posteriors(M, &G, S, d_plane, (const int64_t*)(base + P.off_desc),
                              (const int32_t*)(base + P.off_desc + 8 * (int64_t)n_regions), n_regions,
                              (const double*)(base + P.off_msm), d_stats + CGBK_BG_MEAN, p_motif, alpha,
                              (double*)(base + P.off_post), st);
         if (rc) {
+            cudaStreamSynchronize(cs);
             cudaStreamSynchronize(st);
             cgbk_seqset_destroy(S);
             return rc;

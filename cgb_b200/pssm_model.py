@@ -294,8 +294,11 @@ class PSSMModel(TFBindingModel):
             n_bins = int(hist.numel())
             plane = out.get("plane") if out.get("genome") is genome else None
         elif accumulate_into is None:
-            stats = torch.zeros(_cabi.BG_COUNT, dtype=torch.float64, device=dev)
-            hist = torch.zeros(n_bins, dtype=torch.int64, device=dev)
+            # one allocation, stats record followed by the histogram: the library clears both
+            # with a single memset
+            rec = torch.empty(_cabi.BG_COUNT + n_bins, dtype=torch.int64, device=dev)
+            stats = rec[:_cabi.BG_COUNT].view(torch.float64)
+            hist = rec[_cabi.BG_COUNT:]
             acc = 0
         else:
             stats, hist = accumulate_into["stats"], accumulate_into["hist"]
