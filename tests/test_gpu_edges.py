@@ -1,0 +1,79 @@
+"""Edge cases of the CUDA path against the oracle: ragged sequence sets (shorter than, equal to and
+just above the motif length), all-ambiguous and all-lower-case sequences, promoter slices with
+negative / overshooting bounds, histogram bin counts at both ends, an empty promoter list."""
+import numpy as np
+import pytest
+
+from cgb_b200 import PackedGenome, PSSMModel, SiteCollection, _cabi
+from oracle import c_oracle, np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pair(lexa, lexa_weights):
+    M = PSSMModel([SiteCollection(mo["sites"], None, mo["name"]) for mo in lexa["motifs"]], lexa_weights["site_count"])
+    om = O.OracleModel([mo["sites"] for mo in lexa["motifs"]], lexa_weights["site_count"])
+    return M, om
+
+
+def _ragged(m):
+    rng = np.random.default_rng(9)
+    dna = lambda n: bytes(rng.choice(list(b"ACGT"), size=n).astype(np.uint8))
+    site = b"AAATCGAACATGTGTTCGAGTA"
+    return [dna(m - 1), dna(m), dna(m + 1), dna(3), b"N" * 700, dna(900).lower(), site, dna(100) + site + dna(31),
+            dna(1023), dna(1024), dna(1025), dna(40000)]
+
+
+def test_ragged_set_hits_and_background(pair):
+    M, om = pair
+    m = M.length
+    seqs = _ragged(m)
+    g = PackedGenome.from_sequences(seqs)
+    assert g.total_windows(m) == sum(max(0, len(s) - m + 1) for s in seqs)
+    thr = 2.0                                       # low: plenty of hits in every sequence
+    seq_i, pos, strand, score = M.scan_hits(g, thr)
+    for k, s in enumerate(seqs):
+        sel = seq_i == k
+        if len(s) < m:
+            assert not sel.any()
+            continue
+        ep, es, ev = c_oracle.scan_hits(om, s, thr)
+        assert np.array_equal(pos[sel], ep) and np.array_equal(strand[sel], es) and np.array_equal(score[sel], ev), k
+    b = np.concatenate([c_oracle.score_seq(om, s)[2] for s in seqs if len(s) >= m])
+    for bins in (1, 256, 257, 4096):
+        bg = M.background_stats(g, n_bins=bins)
+        st = bg["stats"].cpu().numpy()
+        assert st[_cabi.BG_N] == len(b) and int(bg["hist"].sum()) == len(b)
+        assert abs(st[_cabi.BG_MEAN] - b.mean()) < 1e-6 and abs(st[_cabi.BG_STD] - b.std()) < 1e-6
+    # a set with no window at all: n = 0, mean / std undefined
+    g0 = PackedGenome.from_sequences([seqs[0], seqs[3]])
+    st = M.background_stats(g0)["stats"].cpu().numpy()
+    assert st[_cabi.BG_N] == 0 and np.isnan(st[_cabi.BG_MEAN])
+    assert len(M.scan_hits(g0, thr)[1]) == 0
+
+
+def test_slice_bounds_and_short_regions(pair, lexa):
+    M, om = pair
+    m = M.length
+    seq = O.synthetic_genome(5000, 71, n_frac=0.002)
+    g = PackedGenome.from_sequences([seq])
+    M.fit_background(g)
+    b = c_oracle.score_seq(om, seq)[2]
+    O.build_bayesian_estimator(om, b)
+    prior, alpha = lexa["prior_regulation_probability"], lexa["alpha"]
+    # Python-slice semantics of Chromid.subsequence: negative start wraps once, end clamps
+    starts = np.array([0, -300, 4800, 100, 4978, -22])
+    ends = np.array([350, 5000, 6000, 100 + m, 5000, 5000])
+    got = M.binding_probabilities(g, starts, ends, prior, alpha).cpu().numpy()
+    for s, e, p in zip(starts, ends, got):
+        sub = seq[int(s):int(e)]
+        assert len(sub) >= m
+        exp = c_oracle.binding_probability(om, sub, om._mu_m, om._std_m, om._mu_bg, om._std_bg, prior, alpha)
+        assert abs(p - exp) < 1e-6, (s, e)
+    with pytest.raises(ValueError):                                  # shorter than the motif
+        M.binding_probabilities(g, [10], [10 + m - 1], prior, alpha)
+    # no promoters at all: the pipeline still returns the background record
+    post, stats, hist = M.regulation_pipeline(seq, [], [], prior, alpha)
+    assert len(post) == 0 and stats[_cabi.BG_N] == len(b) and hist.sum() == len(b)
+    assert abs(stats[_cabi.BG_MEAN] - b.mean()) < 1e-6
