@@ -38,6 +38,27 @@ def main():
         t.append((time.perf_counter() - t0) * 1e6)
     out["pipeline_us_median"] = float(np.median(t))
     out["pipeline_us_p10"] = float(np.percentile(t, 10))
+    # the C call alone (arguments marshalled once): what the Python wrapper adds on top
+    from cgb_b200 import _cabi
+    lib = _cabi.lib()
+    starts = np.ascontiguousarray(ps, dtype=np.int64)
+    ends = np.ascontiguousarray(pe, dtype=np.int64)
+    n = len(starts)
+    scratch, host = M._pipe_scratch, M._pipe_host
+    stage_bytes = int(lib.cgbk_pipeline_staging_bytes(n))
+    hp = host.data_ptr()
+    lo, hi = M._score_bounds
+    args = (M._model(), pinned.data_ptr(), bp, starts.ctypes.data, ends.ctypes.data, n, float(M._mu_m),
+            float(M._std_m), float(prior), float(alpha), float(lo), float(hi), 256, scratch.data_ptr(),
+            scratch.numel(), hp, stage_bytes, hp + stage_bytes, hp + stage_bytes + 8 * n,
+            hp + stage_bytes + 8 * n + 64, M._stream())
+    t = []
+    for _ in range(200):
+        t0 = time.perf_counter()
+        rc = lib.cgbk_regulation_pipeline(*args)
+        t.append((time.perf_counter() - t0) * 1e6)
+    assert rc == 0
+    out["c_call_us_median"] = float(np.median(t))
     # the bare H2D of the same bytes, for scale
     t = []
     for _ in range(100):
