@@ -562,6 +562,14 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
             // every block of this and of the earlier tile ranges has published its partial
             __threadfence();
             finalize_stats(work.partials, work.partial_base + (int)gridDim.x, sp.d_stats, 1, red_scratch);
+            if (sp.host_stats) {
+                // every block flushed its histogram before it bumped the counter: the record is final
+                __syncthreads();
+                if (threadIdx.x < CGBK_BG_COUNT) sp.host_stats[threadIdx.x] = __ldcg(sp.d_stats + threadIdx.x);
+                if (sp.host_hist && sp.d_hist)
+                    for (int i = threadIdx.x; i < sp.n_bins; i += blockDim.x)
+                        sp.host_hist[i] = __ldcg(sp.d_hist + i);
+            }
         }
     }
 }
@@ -635,6 +643,8 @@ StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist
     sp.inv_binw_d = (double)n_bins / (hist_hi - hist_lo);
     sp.d_stats = nullptr;
     sp.finalize = 0;
+    sp.host_stats = nullptr;
+    sp.host_hist = nullptr;
     const double centre = 0.5 * (mdl->min_score + mdl->max_score);
     sp.c_fix = (int)llrint(centre * scale);
     sp.c = (double)sp.c_fix / scale;

@@ -155,6 +155,10 @@ struct StatsParams {
     // partial moment written so far into d_stats (n, sum, sumsq accumulate; mean, std derived)
     double* d_stats;
     int finalize;
+    // optional device-visible aliases of pinned host buffers: the finalizing block also
+    // stores the finished record (and histogram) there, sparing the caller a D2H copy
+    double* host_stats;
+    unsigned long long* host_hist;
 };
 
 StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist_hi, int n_bins,

@@ -110,6 +110,18 @@ static PipeStreams* pipe_streams(int device) {
     return p;
 }
 
+// device-visible alias of a pinned host pointer (false for pageable memory)
+static bool device_alias(const void* h, void** d) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+    *d = at.devicePointer;
+    return true;
+}
+
 // Chunk boundaries (multiples of CGBK_SEQ_ALIGN).  Measured on B200 / PCIe 5 (tools/h2d_probe.py,
 // tools/pipeline_trace.py): cutting a pinned upload into 3-4 copies costs ~10 us, kernels
 // running beside the DMA slow it by another ~5 %, and every chunk's scan pays the ~14 us fixed
@@ -243,6 +255,19 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
     if (!rc)
         rc = cgbk_bg_scan_begin(M, &G, S, hist_lo, hist_hi, n_bins, d_hist, d_stats, 0, d_plane, P.plane_ints,
                                 base + P.off_work, P.work_bytes, st, &run);
+    // Results straight into the caller's buffers when those are pinned (and therefore visible to
+    // the device under unified addressing): the finalizing block of the scan stores the record
+    // and the histogram, the posterior kernel its posteriors -- no D2H copy at all.  Pageable
+    // buffers (or a sequence without a single window) take the copy below.
+    const bool want_hist = h_hist && n_bins > 0;
+    void *a_post = nullptr, *a_stats = nullptr, *a_hist = nullptr;
+    const bool direct = !rc && S->n_tiles > 0 && device_alias(h_stats, &a_stats) &&
+                        (n_regions == 0 || device_alias(h_post, &a_post)) &&
+                        (!want_hist || device_alias(h_hist, &a_hist));
+    if (direct) {
+        run.sp.host_stats = (double*)a_stats;
+        run.sp.host_hist = (unsigned long long*)a_hist;
+    }
     for (int c = 0; c < n_chunks && !rc; ++c) {
         if (!early && cudaStreamWaitEvent(st, ps->ev[c], 0) != cudaSuccess)
             rc = cgbk_set_error(CGBK_ERR_CUDA, "stream wait failed");
@@ -273,7 +298,7 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
         rc = cgbk_posteriors(M, &G, S, d_plane, (const int64_t*)(base + P.off_desc),
                              (const int32_t*)(base + P.off_desc + 8 * (int64_t)n_regions), n_regions,
                              (const double*)(base + P.off_msm), d_stats + CGBK_BG_MEAN, p_motif, alpha,
-                             (double*)(base + P.off_post), st);
+                             direct ? (double*)a_post : (double*)(base + P.off_post), st);
         if (rc) {
             cudaStreamSynchronize(cs);
             cudaStreamSynchronize(st);
@@ -282,11 +307,13 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
         }
         TRACE("posteriors");
     }
-    // 4. results back: one copy when the caller's three host buffers are laid out like ours
+    // 4. results back (unless the kernels stored them in place): one copy when the caller's
+    //    three host buffers are laid out like ours
     const int64_t post_bytes = 8 * (int64_t)n_regions, stats_bytes = sizeof(double) * CGBK_BG_COUNT;
-    const bool want_hist = h_hist && n_bins > 0;
-    if (n_regions > 0 && (unsigned char*)h_stats == (unsigned char*)h_post + post_bytes &&
-        (!want_hist || (unsigned char*)h_hist == (unsigned char*)h_stats + stats_bytes)) {
+    if (direct) {
+        // nothing to copy
+    } else if (n_regions > 0 && (unsigned char*)h_stats == (unsigned char*)h_post + post_bytes &&
+               (!want_hist || (unsigned char*)h_hist == (unsigned char*)h_stats + stats_bytes)) {
         cudaMemcpyAsync(h_post, base + P.off_post, post_bytes + stats_bytes + (want_hist ? 8 * (int64_t)n_bins : 0),
                         cudaMemcpyDeviceToHost, st);
     } else {

@@ -77,3 +77,31 @@ def test_slice_bounds_and_short_regions(pair, lexa):
     post, stats, hist = M.regulation_pipeline(seq, [], [], prior, alpha)
     assert len(post) == 0 and stats[_cabi.BG_N] == len(b) and hist.sum() == len(b)
     assert abs(stats[_cabi.BG_MEAN] - b.mean()) < 1e-6
+
+
+def test_pipeline_pageable_result_buffers(pair, lexa):
+    """cgbk_regulation_pipeline writes results in place when the caller's buffers are pinned
+    (the Python wrapper's case) and copies them back otherwise: same numbers either way."""
+    import ctypes as C
+    import torch
+    M, om = pair
+    seq = O.synthetic_genome(300000, 72, n_frac=0.001)
+    starts = np.arange(0, 290000, 1000, dtype=np.int64)
+    ends = starts + 350
+    prior, alpha = lexa["prior_regulation_probability"], lexa["alpha"]
+    post, stats, hist = M.regulation_pipeline(seq, starts, ends, prior, alpha)          # pinned buffers
+    lib = _cabi.lib()
+    n, n_bins = len(starts), 256
+    seq_arr = np.frombuffer(seq, dtype=np.uint8)                                       # pageable input too
+    scratch = torch.empty(int(lib.cgbk_pipeline_scratch_bytes(len(seq), n, M.length, n_bins)), dtype=torch.uint8,
+                          device="cuda")
+    stage = torch.empty(int(lib.cgbk_pipeline_staging_bytes(n)), dtype=torch.uint8).pin_memory()
+    p2, s2, h2 = np.empty(n), np.empty(_cabi.BG_COUNT), np.empty(n_bins, dtype=np.uint64)   # separate, pageable
+    lo, hi = M._score_bounds
+    _cabi.check(lib.cgbk_regulation_pipeline(
+        M._model(), seq_arr.ctypes.data, len(seq), starts.ctypes.data, ends.ctypes.data, n, float(M._mu_m),
+        float(M._std_m), float(prior), float(alpha), float(lo), float(hi), n_bins, scratch.data_ptr(),
+        scratch.numel(), stage.data_ptr(), stage.numel(), p2.ctypes.data, s2.ctypes.data, h2.ctypes.data,
+        M._stream()))
+    assert np.array_equal(h2, hist) and s2[_cabi.BG_N] == stats[_cabi.BG_N]
+    assert abs(s2[_cabi.BG_MEAN] - stats[_cabi.BG_MEAN]) < 1e-12 and np.max(np.abs(p2 - post)) < 1e-12
