@@ -409,12 +409,12 @@ static int ensure_coarse(cgbk_model* M, double thr, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // sequence sets and tiling
 // ---------------------------------------------------------------------------
-extern "C" int64_t cgbk_seqset_table_ints(int n_seq) { return 3 * (int64_t)n_seq + 1; }
+extern "C" int64_t cgbk_seqset_table_ints(int n_seq) { return 4 * (int64_t)n_seq + 2; }
 
 extern "C" int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len, int n_seq, int device,
                                   int64_t* d_table, void* stream, cgbk_seqset** out) {
     if (!seq_off || !seq_len || !out || n_seq < 1) return cgbk_set_error(CGBK_ERR_INVALID, "bad sequence table");
-    if (!d_table) return cgbk_set_error(CGBK_ERR_INVALID, "d_table (device int64[3 * n_seq + 1]) is NULL");
+    if (!d_table) return cgbk_set_error(CGBK_ERR_INVALID, "d_table (device int64[cgbk_seqset_table_ints(n_seq)]) is NULL");
     for (int i = 0; i < n_seq; ++i) {
         if (seq_off[i] < 0 || seq_off[i] % CGBK_SEQ_ALIGN != 0 || seq_len[i] < 0)
             return cgbk_set_error(CGBK_ERR_INVALID, "sequence %d: offset must be a multiple of %d", i, CGBK_SEQ_ALIGN);
@@ -428,11 +428,15 @@ extern "C" int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len
     S->h_len = (int64_t*)malloc(sizeof(int64_t) * n_seq);
     memcpy(S->h_off, seq_off, sizeof(int64_t) * n_seq);
     memcpy(S->h_len, seq_len, sizeof(int64_t) * n_seq);
-    S->h_tile_prefix = (int64_t*)calloc(n_seq + 1, sizeof(int64_t));
-    // caller-owned device block: off[n] | len[n] | tile_prefix[n + 1]; no cudaMalloc / cudaFree
+    // caller-owned device block: off[n] | len[n] | 2 x tile_prefix[n + 1]; no cudaMalloc / cudaFree
     // (both synchronise the device) on the per-genome path
     int64_t* block = d_table;
-    S->d_off = block; S->d_len = block + n_seq; S->d_tile_prefix = block + 2 * n_seq;
+    S->d_off = block; S->d_len = block + n_seq;
+    for (int k = 0; k < 2; ++k) {
+        S->tiling[k].h_tile_prefix = (int64_t*)calloc(n_seq + 1, sizeof(int64_t));
+        S->tiling[k].d_tile_prefix = block + 2 * n_seq + k * (n_seq + 1);
+        S->tiling[k].cached_m = -1; S->tiling[k].cached_L = -1; S->tiling[k].n_tiles = 0;
+    }
     cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
     if (n_seq > CGBK_INLINE_SEQS) {     // small tables travel in the kernel parameters instead
         e1 = cudaMemcpyAsync(S->d_off, S->h_off, sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice,
@@ -444,14 +448,14 @@ extern "C" int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len
         cgbk_seqset_destroy(S);
         return cgbk_set_error(CGBK_ERR_CUDA, "upload of sequence table failed");
     }
-    S->cached_m = -1; S->cached_L = -1;
     *out = S;
     return CGBK_OK;
 }
 
 extern "C" void cgbk_seqset_destroy(cgbk_seqset* S) {
     if (!S) return;
-    free(S->h_off); free(S->h_len); free(S->h_tile_prefix);   // the device table is the caller's
+    free(S->h_off); free(S->h_len);                           // the device table is the caller's
+    free(S->tiling[0].h_tile_prefix); free(S->tiling[1].h_tile_prefix);
     free(S);
 }
 
@@ -472,10 +476,11 @@ static int64_t count_tiles(const cgbk_seqset* S, int m, int L) {
     return t;
 }
 
-static int ensure_tiles(cgbk_seqset* S, int m, int L, cudaStream_t st) {
-    if (S->cached_m == m && S->cached_L == L) return CGBK_OK;
+static int ensure_tiles(cgbk_seqset* S, int slot, int m, int L, cudaStream_t st) {
+    cgbk_seqset::Tiling& T = S->tiling[slot];
+    if (T.cached_m == m && T.cached_L == L) return CGBK_OK;
     const int64_t stride = 32ll * L - 32;
-    int64_t* prefix = S->h_tile_prefix;
+    int64_t* prefix = T.h_tile_prefix;
     prefix[0] = 0;
     for (int i = 0; i < S->n_seq; ++i) {
         const int64_t nwin = S->h_len[i] - m + 1;
@@ -484,10 +489,10 @@ static int ensure_tiles(cgbk_seqset* S, int m, int L, cudaStream_t st) {
     // stream-ordered after any earlier scan of this set on the same stream; small tables
     // travel in the kernel parameters instead
     if (S->n_seq > CGBK_INLINE_SEQS)
-        CUDA_TRY(cudaMemcpyAsync(S->d_tile_prefix, prefix, sizeof(int64_t) * (S->n_seq + 1),
+        CUDA_TRY(cudaMemcpyAsync(T.d_tile_prefix, prefix, sizeof(int64_t) * (S->n_seq + 1),
                                  cudaMemcpyHostToDevice, st));
-    S->n_tiles = prefix[S->n_seq];
-    S->cached_m = m; S->cached_L = L;
+    T.n_tiles = prefix[S->n_seq];
+    T.cached_m = m; T.cached_L = L;
     return CGBK_OK;
 }
 
@@ -500,12 +505,28 @@ static int device_sms(int device) {
     return cached > 0 ? cached : 148;
 }
 
-// lane segment length: the longest of 128/64/32 bases that still leaves >= 2 tiles per warp
-static int choose_L(const cgbk_seqset* S, int m, int warps_total) {
-    for (int L = 128; L > 32; L >>= 1)
-        if (count_tiles(S, m, L) >= 2ll * warps_total) return L;
-    return 32;
+// Lane segment length L (32, 64, 96 or 128 bases; a warp tile owns 32 L - 32 windows).
+// A tile costs a warp ~(1.8 + 0.093 L) us in the stats scan (measured on B200: 4.8 us at
+// L = 32, 13.7 us at L = 128 -- the per-tile part is the hand-over of the straddling windows
+// and the tile bookkeeping), and tiles are dealt to `warps_total` resident warps in rounds.
+// Large inputs want the longest segment (least overhead per window); small ones want the
+// tiling whose last round is not mostly empty: 5 Mbp is ONE round at L = 96 (10.7 us) but
+// three at L = 32 (14.4 us).  The constants are per scan kind (below).
+static int choose_L(const cgbk_seqset* S, int m, int warps_total, double per_tile_us, double per_base_us) {
+    int best_L = 128;
+    double best = 0.0;
+    for (int L = 128; L >= 32; L -= 32) {
+        const int64_t tiles = count_tiles(S, m, L);
+        const int64_t rounds = (tiles + warps_total - 1) / warps_total;
+        const double cost = (double)rounds * (per_tile_us + per_base_us * L);
+        if (L == 128 || cost < best * 0.999) { best = cost; best_L = L; }
+    }
+    return best_L;
 }
+// stats scan: 12 warps per SM, 4.8 us per tile at L = 32 and 13.7 us at L = 128
+static int choose_L_stats(const cgbk_seqset* S, int m, int sms) { return choose_L(S, m, sms * 12, 1.8, 0.093); }
+// hit filter: 20 warps per SM, 2.5 us per tile at L = 32 and 10.8 us at L = 128
+static int choose_L_hits(const cgbk_seqset* S, int m, int sms) { return choose_L(S, m, sms * 20, 1.0, 0.0865); }
 
 #define PARTIAL_CAP 1024
 #define WORK_HEADER (64 + 3 * 8 * PARTIAL_CAP)
@@ -565,7 +586,7 @@ extern "C" int cgbk_score_windows(const cgbk_model* M, const cgbk_genome* genome
     return CGBK_OK;
 }
 
-static SeqTable table_of(const cgbk_seqset* S);
+static SeqTable table_of(const cgbk_seqset* S, int slot);
 
 extern "C" int cgbk_posteriors(const cgbk_model* M, const cgbk_genome* genome, const cgbk_seqset* set,
                                const int32_t* d_plane, const int64_t* d_start, const int32_t* d_nwin,
@@ -581,11 +602,11 @@ extern "C" int cgbk_posteriors(const cgbk_model* M, const cgbk_genome* genome, c
     SeqTable seqs = {};
     if (d_plane) {
         if (!set) return cgbk_set_error(CGBK_ERR_INVALID, "a score plane needs the sequence set it was written for");
-        if (set->cached_m != M->m)
+        if (set->tiling[CGBK_TILING_STATS].cached_m != M->m)
             return cgbk_set_error(CGBK_ERR_INVALID, "the score plane was not written for this motif length "
                                   "(run cgbk_background_stats with d_plane first)");
-        pv.plane = d_plane; pv.L = set->cached_L;
-        seqs = table_of(set);
+        pv.plane = d_plane; pv.L = set->tiling[CGBK_TILING_STATS].cached_L;
+        seqs = table_of(set, CGBK_TILING_STATS);
     }
     CUDA_TRY(launch_posteriors(M, view_of(genome), seqs, pv, (const long long*)d_start, d_nwin, n_regions,
                                d_ms_m, d_ms_bg, p_motif, alpha, d_post, (cudaStream_t)stream));
@@ -596,15 +617,16 @@ extern "C" int cgbk_posteriors(const cgbk_model* M, const cgbk_genome* genome, c
 // ---------------------------------------------------------------------------
 // tiled scans
 // ---------------------------------------------------------------------------
-static SeqTable table_of(const cgbk_seqset* S) {
+static SeqTable table_of(const cgbk_seqset* S, int slot) {
+    const cgbk_seqset::Tiling& T = S->tiling[slot];
     SeqTable t;
     t.off = (const long long*)S->d_off; t.len = (const long long*)S->d_len;
-    t.tile_prefix = (const long long*)S->d_tile_prefix; t.n_seq = S->n_seq; t.n_tiles = S->n_tiles;
+    t.tile_prefix = (const long long*)T.d_tile_prefix; t.n_seq = S->n_seq; t.n_tiles = T.n_tiles;
     for (int i = 0; i < CGBK_INLINE_SEQS; ++i) {
         const bool have = i < S->n_seq && S->n_seq <= CGBK_INLINE_SEQS;
         t.off_v[i] = have ? S->h_off[i] : 0;
         t.len_v[i] = have ? S->h_len[i] : 0;
-        t.prefix_v[i] = have ? S->h_tile_prefix[i] : 0;
+        t.prefix_v[i] = have ? T.h_tile_prefix[i] : 0;
     }
     return t;
 }
@@ -628,26 +650,27 @@ extern "C" int cgbk_scan_hits(cgbk_model* M, const cgbk_genome* genome, const cg
     const int sms = device_sms(M->device);
     // the tiling depends only on (set, m), not on the kernel variant: a score plane written by
     // the stats scan stays addressable after a hit scan of the same set
-    const int L = choose_L(S, M->m, sms * 16);
-    rc = ensure_tiles(S, M->m, L, st);
+    const int L = choose_L_hits(S, M->m, sms);
+    rc = ensure_tiles(S, CGBK_TILING_HITS, M->m, L, st);
     if (rc) return rc;
     rc = ensure_coarse(M, threshold, st);
     if (rc) return rc;
-    w.tile_end = S->n_tiles;
+    const int64_t n_tiles = S->tiling[CGBK_TILING_HITS].n_tiles;
+    w.tile_end = n_tiles;
     CUDA_TRY(cudaMemsetAsync(w.counters, 0, 64, st));
     int launches = 0;
-    if (S->n_tiles > 0) {
+    if (n_tiles > 0) {
         const int wpb = threads / 32;
-        long long grid = (S->n_tiles + wpb - 1) / wpb;
+        long long grid = (n_tiles + wpb - 1) / wpb;
         if (grid > sms) grid = sms;
         PROF_START(st);
-        CUDA_TRY(launch_fast_filter(M, view_of(genome), table_of(S), w, L, (int)grid, st));
+        CUDA_TRY(launch_fast_filter(M, view_of(genome), table_of(S, CGBK_TILING_HITS), w, L, (int)grid, st));
         PROF_STOP(st);
-        CUDA_TRY(launch_rescore(M, view_of(genome), table_of(S), w, threshold, flags, d_hits, hit_cap, L, st));
+        CUDA_TRY(launch_rescore(M, view_of(genome), table_of(S, CGBK_TILING_HITS), w, threshold, flags, d_hits, hit_cap, L, st));
         launches = 3;
     }
     CUDA_TRY(cudaMemcpyAsync(d_counters, w.counters, 64, cudaMemcpyDeviceToDevice, st));
-    g_launch_info[0] = launches; g_launch_info[1] = S->n_tiles; g_launch_info[2] = L;
+    g_launch_info[0] = launches; g_launch_info[1] = n_tiles; g_launch_info[2] = L;
     return CGBK_OK;
 }
 
@@ -655,7 +678,7 @@ extern "C" int cgbk_scan_hits(cgbk_model* M, const cgbk_genome* genome, const cg
 extern "C" int64_t cgbk_score_plane_ints(const cgbk_seqset* S, int m) {
     if (!S) return 0;
     int64_t best = 0;
-    for (int L = 32; L <= 128; L <<= 1) {
+    for (int L = 32; L <= 128; L += 32) {
         const int64_t need = count_tiles(S, m, L) * (int64_t)((L / 32 + 1) * 1024);
         if (need > best) best = need;
     }
@@ -686,10 +709,10 @@ int cgbk_bg_scan_begin(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqs
     run->sms = device_sms(M->device);
     // the tiling depends only on (set, m), not on the kernel variant: a score plane written by
     // the stats scan stays addressable after a hit scan of the same set
-    run->L = choose_L(S, M->m, run->sms * 16);
-    rc = ensure_tiles(S, M->m, run->L, st);
+    run->L = choose_L_stats(S, M->m, run->sms);
+    rc = ensure_tiles(S, CGBK_TILING_STATS, M->m, run->L, st);
     if (rc) return rc;
-    if (d_plane && plane_ints < S->n_tiles * (int64_t)((run->L / 32 + 1) * 1024))
+    if (d_plane && plane_ints < S->tiling[CGBK_TILING_STATS].n_tiles * (int64_t)((run->L / 32 + 1) * 1024))
         return cgbk_set_error(CGBK_ERR_INVALID, "score plane of %lld ints is smaller than the %lld required",
                               (long long)plane_ints, (long long)cgbk_score_plane_ints(S, M->m));
     CUDA_TRY(cudaMemsetAsync(run->w.counters, 0, 64, st));
@@ -707,20 +730,20 @@ int cgbk_bg_scan_begin(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqs
     run->sp = make_stats_params(M, hist_lo, hist_hi, n_bins, d_hist, d_plane);
     run->sp.d_stats = d_stats;
     run->next_tile = 0; run->n_ranges = 0; run->partials_used = 0; run->finalized = 0;
-    g_launch_info[0] = 0; g_launch_info[1] = S->n_tiles; g_launch_info[2] = run->L;
+    g_launch_info[0] = 0; g_launch_info[1] = S->tiling[CGBK_TILING_STATS].n_tiles; g_launch_info[2] = run->L;
     return CGBK_OK;
 }
 
 int cgbk_bg_scan_range(BgScan* run, long long bases_ready, int last, cudaStream_t st) {
     cgbk_seqset* S = run->S;
-    long long t_end = S->n_tiles;
+    long long t_end = S->tiling[CGBK_TILING_STATS].n_tiles;
     if (!last) {
         // only single-sequence sets are fed in chunks: tile t reads bases [t * stride, t * stride + 32 L)
         if (S->n_seq != 1) return cgbk_set_error(CGBK_ERR_INVALID, "chunked scans take one sequence");
         const long long span = 32ll * run->L, stride = span - 32;
         const long long ready = bases_ready - S->h_off[0];
         t_end = ready < span ? 0 : (ready - span) / stride + 1;
-        if (t_end > S->n_tiles) t_end = S->n_tiles;
+        if (t_end > S->tiling[CGBK_TILING_STATS].n_tiles) t_end = S->tiling[CGBK_TILING_STATS].n_tiles;
     }
     if (t_end <= run->next_tile) {
         // nothing new to scan; a last call still owes the reduction of the earlier ranges
@@ -743,7 +766,7 @@ int cgbk_bg_scan_range(BgScan* run, long long bases_ready, int last, cudaStream_
     StatsParams sp = run->sp;
     sp.finalize = last ? 1 : 0;      // this launch's last block reduces all partial moments
     PROF_START(st);
-    CUDA_TRY(launch_fast_stats(run->M, run->g, table_of(S), w, run->L, (int)grid, sp, st));
+    CUDA_TRY(launch_fast_stats(run->M, run->g, table_of(S, CGBK_TILING_STATS), w, run->L, (int)grid, sp, st));
     PROF_STOP(st);
     if (last) run->finalized = 1;
     run->next_tile = t_end;

@@ -197,7 +197,6 @@ __global__ void __launch_bounds__(256) posterior_kernel(
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int stride = 32 * pv.L - 32;
-    const int log2L = 31 - __clz(pv.L);                       // L is 32, 64 or 128
     const long long plane_tile = (long long)(pv.L / 32 + 1) * 1024;
     // one window, exactly: float64 strand sums in the reference's order, double exp / log1p
     auto exact_term = [&](long long gpos) {
@@ -220,6 +219,7 @@ __global__ void __launch_bounds__(256) posterior_kernel(
             tile += seq_prefix_of(seqs, sq);
             if (wt >= stride) { wt -= stride; ++tile; }
             const int* tp = pv.plane + tile * plane_tile;
+            int ln = wt / pv.L, within = wt - ln * pv.L;          // scan lane and position in its segment
             // Pass 1: every window from the plane on the float32 path; windows whose mixture
             // ratio x reaches 1e-2 are only marked (bit k = this lane's k-th window).  The plane
             // row of a window at position `within` of its scan lane's segment is within + D.
@@ -229,10 +229,11 @@ __global__ void __launch_bounds__(256) posterior_kernel(
                 int sfix[PF];
 #pragma unroll
                 for (int j = 0; j < PF; ++j) {              // all loads first: independent L2 round trips
-                    const int off = (((wt & (pv.L - 1)) + pv.D) << 5) + (wt >> log2L);
+                    const int off = ((within + pv.D) << 5) + ln;
                     sfix[j] = base + lane + 32 * j < nwin ? __ldg(tp + off) : 0;
-                    wt += 32;
-                    if (wt >= stride) { wt -= stride; tp += plane_tile; }
+                    wt += 32; within += 32;
+                    if (within >= pv.L) { within -= pv.L; ++ln; }
+                    if (wt >= stride) { wt -= stride; tp += plane_tile; ln = 0; within = wt; }
                 }
                 float part = 0.0f;
 #pragma unroll

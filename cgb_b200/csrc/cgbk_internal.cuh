@@ -39,12 +39,18 @@ struct cgbk_seqset {
     int64_t* h_len;
     int64_t* d_off;       // [n_seq]
     int64_t* d_len;       // [n_seq]
-    // tile prefix tables are built per (m, lane segment) on demand and cached
-    int cached_m, cached_L;
-    int64_t* d_tile_prefix;  // [n_seq + 1]
-    int64_t* h_tile_prefix;  // [n_seq + 1] (staging for the async upload; inline copy source)
-    int64_t n_tiles;
+    // Tile prefix tables are built per (m, lane segment) on demand and cached, one slot per scan
+    // kind: the stats scan (whose tiling also addresses the score plane) and the hit scan have
+    // different numbers of resident warps and therefore different best tilings.
+    struct Tiling {
+        int cached_m, cached_L;
+        int64_t* d_tile_prefix;  // [n_seq + 1]
+        int64_t* h_tile_prefix;  // [n_seq + 1] (staging for the async upload; inline copy source)
+        int64_t n_tiles;
+    } tiling[2];
 };
+#define CGBK_TILING_STATS 0
+#define CGBK_TILING_HITS 1
 
 #define CGBK_EXACT_DOUBLES (CGBK_MAXM * 4 * 2 + CGBK_MAXM * 2)
 // d_exact holds the plain tables (CGBK_EXACT_DOUBLES doubles) followed by the same numbers in

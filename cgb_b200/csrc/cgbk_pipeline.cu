@@ -73,7 +73,7 @@ static PipeLayout pipe_layout(int64_t n_bases, int n_regions, int m, int n_bins)
     int64_t o = 0;
     p.off_ascii = o;  o += align256(n_bases);
     p.off_planes = o; o += align256(padded / 2);                // bases2 (cap/4) + amb + lower (cap/8 each)
-    p.off_table = o;  o += align256(8 * 4);
+    p.off_table = o;  o += align256(8 * 6);                      // cgbk_seqset_table_ints(1) int64
     p.off_work = o;   o += p.work_bytes;
     p.off_plane = o;  o += align256(4 * p.plane_ints);
     p.off_msm = o;    o += 256;
@@ -261,7 +261,7 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
     // buffers (or a sequence without a single window) take the copy below.
     const bool want_hist = h_hist && n_bins > 0;
     void *a_post = nullptr, *a_stats = nullptr, *a_hist = nullptr;
-    const bool direct = !rc && S->n_tiles > 0 && device_alias(h_stats, &a_stats) &&
+    const bool direct = !rc && S->tiling[CGBK_TILING_STATS].n_tiles > 0 && device_alias(h_stats, &a_stats) &&
                         (n_regions == 0 || device_alias(h_post, &a_post)) &&
                         (!want_hist || device_alias(h_hist, &a_hist));
     if (direct) {
