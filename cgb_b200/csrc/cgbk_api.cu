@@ -715,16 +715,25 @@ int cgbk_bg_scan_begin(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqs
     if (d_plane && plane_ints < S->tiling[CGBK_TILING_STATS].n_tiles * (int64_t)((run->L / 32 + 1) * 1024))
         return cgbk_set_error(CGBK_ERR_INVALID, "score plane of %lld ints is smaller than the %lld required",
                               (long long)plane_ints, (long long)cgbk_score_plane_ints(S, M->m));
-    CUDA_TRY(cudaMemsetAsync(run->w.counters, 0, 64, st));
-    if (!accumulate) {
-        // one memset when the histogram sits right behind the stats record (as the pipeline and
-        // the Python wrapper lay them out)
-        if (d_hist && (unsigned char*)d_hist == (unsigned char*)d_stats + sizeof(double) * CGBK_BG_COUNT) {
-            CUDA_TRY(cudaMemsetAsync(d_stats, 0, sizeof(double) * CGBK_BG_COUNT +
-                                                  sizeof(unsigned long long) * n_bins, st));
+    // Clearing the accumulators: ONE memset when the caller laid out
+    // stats record | histogram | workspace (the workspace begins with the scan's counters), as
+    // the pipeline and the Python wrapper do; separate ones otherwise.
+    {
+        unsigned char* rec = (unsigned char*)d_stats;
+        const size_t rec_bytes = sizeof(double) * CGBK_BG_COUNT;
+        const size_t hist_bytes = d_hist ? sizeof(unsigned long long) * n_bins : 0;
+        const bool hist_adj = d_hist && (unsigned char*)d_hist == rec + rec_bytes;
+        const bool ctr_adj = hist_adj && (unsigned char*)run->w.counters == rec + rec_bytes + hist_bytes;
+        if (!accumulate && ctr_adj) {
+            CUDA_TRY(cudaMemsetAsync(rec, 0, rec_bytes + hist_bytes + 64, st));
         } else {
-            if (d_hist) CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * n_bins, st));
-            CUDA_TRY(cudaMemsetAsync(d_stats, 0, sizeof(double) * CGBK_BG_COUNT, st));
+            CUDA_TRY(cudaMemsetAsync(run->w.counters, 0, 64, st));
+            if (!accumulate && hist_adj) {
+                CUDA_TRY(cudaMemsetAsync(rec, 0, rec_bytes + hist_bytes, st));
+            } else if (!accumulate) {
+                if (d_hist) CUDA_TRY(cudaMemsetAsync(d_hist, 0, hist_bytes, st));
+                CUDA_TRY(cudaMemsetAsync(d_stats, 0, rec_bytes, st));
+            }
         }
     }
     run->sp = make_stats_params(M, hist_lo, hist_hi, n_bins, d_hist, d_plane);

@@ -74,15 +74,18 @@ static PipeLayout pipe_layout(int64_t n_bases, int n_regions, int m, int n_bins)
     p.off_ascii = o;  o += align256(n_bases);
     p.off_planes = o; o += align256(padded / 2);                // bases2 (cap/4) + amb + lower (cap/8 each)
     p.off_table = o;  o += align256(8 * 6);                      // cgbk_seqset_table_ints(1) int64
-    p.off_work = o;   o += p.work_bytes;
     p.off_plane = o;  o += align256(4 * p.plane_ints);
     p.off_msm = o;    o += 256;
     p.off_desc = o;   o += align256(12 * (int64_t)n_regions);
-    // results, contiguous so that one D2H can return them: posteriors | stats | histogram
+    // results, contiguous so that one D2H can return them: posteriors | stats | histogram; the
+    // scan workspace (counters first) follows directly so that one memset clears record,
+    // histogram and counters
     p.off_post = o;
     p.off_stats = p.off_post + 8 * (int64_t)n_regions;
     p.off_hist = p.off_stats + 8 * CGBK_BG_COUNT;
-    o += align256(8 * (int64_t)n_regions + 8 * CGBK_BG_COUNT + 8 * (int64_t)(n_bins > 0 ? n_bins : 1));
+    p.off_work = p.off_hist + 8 * (int64_t)(n_bins > 0 ? n_bins : 1);
+    o = p.off_work + p.work_bytes;
+    o = align256(o);
     p.total = o;
     return p;
 }

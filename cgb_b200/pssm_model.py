@@ -289,16 +289,21 @@ class PSSMModel(TFBindingModel):
         if hist_hi is None:
             hist_hi = self._score_bounds[1]
         plane = None
+        work = None
         if out is not None:
             stats, hist, acc = out["stats"], out["hist"], 0
             n_bins = int(hist.numel())
             plane = out.get("plane") if out.get("genome") is genome else None
+            if out.get("work_key") == (id(genome), m):
+                work = out["work"]
         elif accumulate_into is None:
-            # one allocation, stats record followed by the histogram: the library clears both
-            # with a single memset
-            rec = torch.empty(_cabi.BG_COUNT + n_bins, dtype=torch.int64, device=dev)
+            # one allocation: stats record | histogram | scan workspace (whose first words are
+            # the scan's counters) -- the library clears all three with a single memset
+            wbytes = int(_cabi.lib().cgbk_scan_workspace_bytes(genome.seqset, m, 0))
+            rec = torch.empty(_cabi.BG_COUNT + n_bins + (wbytes + 7) // 8, dtype=torch.int64, device=dev)
             stats = rec[:_cabi.BG_COUNT].view(torch.float64)
-            hist = rec[_cabi.BG_COUNT:]
+            hist = rec[_cabi.BG_COUNT:_cabi.BG_COUNT + n_bins]
+            work = rec[_cabi.BG_COUNT + n_bins:].view(torch.uint8)
             acc = 0
         else:
             stats, hist = accumulate_into["stats"], accumulate_into["hist"]
@@ -308,14 +313,17 @@ class PSSMModel(TFBindingModel):
             plane = torch.empty(max(n_ints, 1), dtype=torch.int32, device=dev)
         if not keep_scores:
             plane = None
-        work = genome.workspace(m, 0)
+        own_work = work is not None
+        if work is None:
+            work = genome.workspace(m, 0)
         _cabi.check(_cabi.lib().cgbk_background_stats(
             model, genome.struct_ref(), genome.seqset, float(hist_lo), float(hist_hi), int(n_bins),
             hist.data_ptr(), stats.data_ptr(), acc,
             plane.data_ptr() if plane is not None else None, int(plane.numel()) if plane is not None else 0,
             work.data_ptr(), work.numel(), self._stream()))
         return {"stats": stats, "hist": hist, "hist_lo": float(hist_lo), "hist_hi": float(hist_hi),
-                "n_bins": int(n_bins), "plane": plane, "genome": genome if plane is not None else None}
+                "n_bins": int(n_bins), "plane": plane, "genome": genome if plane is not None else None,
+                "work": work if own_work else None, "work_key": (id(genome), m) if own_work else None}
 
     def fit_background(self, genome=None, bg=None, sync=True, keep_scores=True):
         """build_bayesian_estimator (binding_model.py:71-92) with the background
