@@ -359,8 +359,8 @@ def run_ours(args):
             "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one
-            # `ncu --set full` capture (profiles/r1_ncu_stats_bench.csv): 1.956 MB read + 256 B written per launch
-            "traffic": 1955840, "algorithmic_bytes": alg_bytes,
+            # `ncu --set full` capture (profiles/r1_ncu_stats_bench.csv): 1.956 MB read + 10.8 KB written per launch
+            "traffic": 1966592, "algorithmic_bytes": alg_bytes,
             "peak_source": peak_src, "kernel_ms": k_ms,
             "issue": {"achieved": lookup_adds / (k_ms * 1e-3), "peak": issue_peak, "unit": "lookup-add/s",
                       "frac": lookup_adds / (k_ms * 1e-3) / issue_peak,
