@@ -108,112 +108,112 @@ def _quote_closed(value):
     return len(value) >= 2 and value.endswith('"') and value.count('"') % 2 == 0
 
 
-def _finish_qualifier(quals, key, value):
-    if key is None:
-        return
-    if value is None:
-        v = ""
-    else:
-        v = value
-        if v.startswith('"'):
-            v = v[1:-1] if v.endswith('"') and len(v) >= 2 else v[1:]
-            v = v.replace('""', '"')
-        if key == "translation":
-            v = v.replace(" ", "")
-    quals.setdefault(key, []).append(v)
+_FEATURE_START = re.compile(r"^ {5}(?=\S)", re.M)
+_QUALIFIER_START = re.compile(r"\n {21}/")
+_CONTINUATION = re.compile(r"\n\s*")
 
 
-def _parse_features(lines):
+def _parse_features(block):
+    """Feature table text (without its header line) -> [Feature].  The table is cut at feature
+    keys (column 6) and at qualifier starts (column 22, '/') by regular expressions; a '/' that
+    opens a continuation line INSIDE a quoted value is glued back."""
     feats = []
-    ftype, loc_parts, quals = None, [], None
-    qkey, qval, in_quote = None, None, False
-
-    def close_feature():
-        nonlocal ftype, loc_parts, quals, qkey, qval, in_quote
-        if ftype is not None:
-            _finish_qualifier(quals, qkey, qval)
-            start, end, strand, compound = parse_location("".join(loc_parts))
-            feats.append(Feature(ftype, start, end, strand, compound, quals))
-        ftype, loc_parts, quals, qkey, qval, in_quote = None, [], None, None, None, False
-
-    for line in lines:
-        key = line[5:20].strip()
-        body = line[21:].rstrip()
-        if key and not line[:5].strip():
-            close_feature()
-            ftype, loc_parts, quals = key, [body.strip()], {}
-            continue
-        if ftype is None:
-            continue
-        text = body.strip()
-        if in_quote:
-            qval += text if qkey == "translation" else " " + text
-            in_quote = not _quote_closed(qval)
-            continue
-        if text.startswith("/"):
-            _finish_qualifier(quals, qkey, qval)
-            if "=" in text:
-                qkey, qval = text[1:].split("=", 1)
-                in_quote = qval.startswith('"') and not _quote_closed(qval)
-            else:
-                qkey, qval = text[1:], None
-            continue
-        if qkey is None:
-            loc_parts.append(text)                  # location continued over several lines
+    for chunk in _FEATURE_START.split(block)[1:]:
+        chunk = chunk.rstrip()
+        parts = _QUALIFIER_START.split(chunk)
+        head = parts[0]
+        sp = head.find(" ")
+        if sp < 0:
+            ftype, loc = head.strip(), ""
         else:
-            qval = (qval or "") + " " + text        # unquoted continuation
-    close_feature()
+            ftype, loc = head[:sp], head[sp:]
+        start, end, strand, compound = parse_location(loc)
+        quals = {}
+        i, n = 1, len(parts)
+        while i < n:
+            q = parts[i]
+            i += 1
+            eq = q.find("=")
+            if eq < 0:
+                quals.setdefault(q.strip(), []).append("")          # flag qualifier (/pseudo)
+                continue
+            key, value = q[:eq], q[eq + 1:]
+            if value.startswith('"'):
+                while not _quote_closed(value.rstrip()) and i < n:  # a '/' line inside the quotes
+                    value += "\n" + " " * 21 + "/" + parts[i]
+                    i += 1
+            if "\n" in value:
+                value = _CONTINUATION.sub("" if key == "translation" else " ", value)
+            value = value.rstrip()
+            if value.startswith('"'):
+                value = value[1:-1] if value.endswith('"') and len(value) >= 2 else value[1:]
+                if '""' in value:
+                    value = value.replace('""', '"')
+            if key == "translation" and " " in value:
+                value = value.replace(" ", "")
+            quals.setdefault(key, []).append(value)
+        feats.append(Feature(ftype, start, end, strand, compound, quals))
     return feats
 
 
 def parse(text):
-    """All records of a GenBank flat file (``str`` or ``bytes``)."""
-    if isinstance(text, bytes):
-        text = text.decode("ascii", "replace")
+    """All records of a GenBank flat file (``str`` or ``bytes``).  The three big blocks of a
+    record (header, feature table, ORIGIN) are cut out with ``find`` and the sequence is
+    cleaned with one ``bytes.translate``: only the feature table is walked line by line."""
+    if isinstance(text, str):
+        text = text.encode("ascii", "replace")
     records = []
-    lines = text.splitlines()
-    i, n = 0, len(lines)
-    while i < n:
-        while i < n and not lines[i].startswith("LOCUS"):
-            i += 1
-        if i >= n:
+    pos, n = 0, len(text)
+    while True:
+        start = 0 if text.startswith(b"LOCUS", pos) and pos == 0 else text.find(b"\nLOCUS", pos)
+        if start < 0:
             break
-        locus_name = lines[i].split()[1] if len(lines[i].split()) > 1 else ""
-        accession, version, definition = "", "", []
-        feat_lines, seq_parts = [], []
+        if text[start:start + 1] == b"\n":
+            start += 1
+        end = text.find(b"\n//", start)
+        if end < 0:
+            end = n
+        rec = text[start:end]
+        pos = end + 3
+        f0 = rec.find(b"\nFEATURES")
+        o0 = rec.find(b"\nORIGIN")
+        header = rec[:f0 if f0 >= 0 else (o0 if o0 >= 0 else len(rec))].decode("ascii", "replace")
+        locus_name, accession, version, definition = "", "", "", []
         section = None
-        i += 1
-        while i < n and not lines[i].startswith("//"):
-            line = lines[i]
+        for line in header.splitlines():
             head = line[:12].strip() if line[:1] != " " else ""
             if head:
                 section = head
                 rest = line[12:].strip()
-                if head == "DEFINITION":
+                if head == "LOCUS":
+                    locus_name = rest.split()[0] if rest else ""
+                elif head == "DEFINITION":
                     definition = [rest]
                 elif head == "ACCESSION" and rest:
                     accession = rest.split()[0]
                 elif head == "VERSION" and rest:
                     version = rest.split()[0]
-                elif head.startswith("FEATURES"):
-                    section = "FEATURES"
-                elif head.startswith("ORIGIN"):
-                    section = "ORIGIN"
             elif section == "DEFINITION":
                 definition.append(line.strip())
-            elif section == "FEATURES":
-                feat_lines.append(line)
-            elif section == "ORIGIN":
-                seq_parts.append(line)
-            i += 1
-        i += 1
-        raw = "".join(seq_parts).encode("ascii")
-        sequence = raw.translate(_UPPER, b" 0123456789\t\r\n")
+        feat_block = ""
+        if f0 >= 0:
+            block = rec[f0 + 1:o0 if o0 > f0 else len(rec)].decode("ascii", "replace")
+            nl = block.find("\n")
+            feat_block = block[nl + 1:] if nl >= 0 else ""       # drop the FEATURES header line
+            # anything after the table that starts in column 1 (CONTIG, BASE COUNT) is not a feature
+            mt = re.search(r"^\S", feat_block, re.M)
+            if mt:
+                feat_block = feat_block[:mt.start()]
+        sequence = b""
+        if o0 >= 0:
+            nl = rec.find(b"\n", o0 + 1)
+            if nl >= 0:
+                sequence = rec[nl + 1:].translate(_UPPER, b" 0123456789\t\r\n")
         description = " ".join(definition)
         if description.endswith("."):
             description = description[:-1]
         records.append(GenBankRecord(version or accession or locus_name, description, sequence,
-                                     _parse_features(feat_lines)))
+                                     _parse_features(feat_block)))
     return records
 
 

@@ -213,3 +213,53 @@ def test_batched_patser_thresholds_equal_single_calls():
     prepare_thresholds(models, n_threads=4)
     assert all("patser_threshold" in M.__dict__ for M in models)
     assert [M.threshold() for M in models] == singles
+
+
+def test_genbank_awkward_feature_tables():
+    """Multi-line locations, a '/' opening a continuation line inside a quoted value, doubled
+    quotes, flag qualifiers, a CONTIG line after the table, lower-case ORIGIN."""
+    text = """LOCUS       TEST0001                  60 bp    DNA     linear   BCT 01-JAN-2020
+DEFINITION  Awkward test record, with a second
+            definition line.
+ACCESSION   TEST0001
+VERSION     TEST0001.2
+FEATURES             Location/Qualifiers
+     source          1..60
+                     /organism="Test organism"
+     gene            complement(join(1..10,
+                     20..30))
+                     /locus_tag="T_0001"
+     gene            11..40
+                     /locus_tag="T_0002"
+                     /note="a note that wraps and then has a line starting with
+                     /slash inside the quotes, and a ""quoted"" word"
+                     /pseudo
+     CDS             11..40
+                     /locus_tag="T_0002"
+                     /product="two-line
+                     product name"
+                     /protein_id="WP_1.1"
+                     /translation="MKV
+                     LLA"
+     gene            41..50
+                     /locus_tag="T_0003"
+     misc_feature    45..46
+CONTIG      join(TEST0001.2:1..60)
+ORIGIN
+        1 acgtacgtac gtacgtacgt acgtacgtac gtacgtacgt acgtacgtac gtacgtacgn
+//
+"""
+    rec = genbank.read(text)
+    assert rec.id == "TEST0001.2" and rec.description == "Awkward test record, with a second definition line"
+    assert rec.sequence == b"ACGT" * 14 + b"ACGN" and rec.length == 60
+    assert [f.type for f in rec.features] == ["source", "gene", "gene", "CDS", "gene", "misc_feature"]
+    g1, g2, cds = rec.features[1], rec.features[2], rec.features[3]
+    assert g1.compound and g1.strand == -1
+    assert (g2.start, g2.end, g2.strand, g2.compound) == (10, 40, 1, False)
+    assert g2.qualifiers["note"] == ['a note that wraps and then has a line starting with /slash inside the '
+                                     'quotes, and a "quoted" word']
+    assert g2.qualifiers["pseudo"] == [""]
+    assert cds.qualifiers["product"] == ["two-line product name"] and cds.qualifiers["translation"] == ["MKVLLA"]
+    gt = rec.gene_table()
+    assert list(gt.locus_tag) == ["T_0002", "T_0003"] and gt.index.tolist() == [1, 2]   # the join gene is skipped
+    assert list(gt.product) == ["two-line product name", ""] and list(gt.protein_id) == ["WP_1.1", ""]
