@@ -11,6 +11,11 @@ Parity status
   VERBATIM (``oracle/ref_loader.py``) in the build container to generate the
   golden vectors under ``tests/golden/``; the restatement in
   ``oracle/np_oracle.py`` is checked bit-for-bit against those vectors.
+* ``genome.py`` / ``chromid.py`` / ``gene.py`` / ``operon.py`` / ``bio_utils.py`` are executed
+  VERBATIM the same way (``ref_loader.load_genome_stack``; network, BLAST and the GenBank
+  parser stubbed) on a synthetic annotated genome: gene selection, coordinate rules,
+  identified sites + CSV text, posteriors per gene, operons and regulon reports are recorded in
+  ``tests/golden/genome_vectors.json`` and pin the oracle's and the product's genome side.
 * The arithmetic that lives in Biopython 1.76 (``Bio.motifs``; not vendored in
   ``/root/reference``, not installed, no network) is restated from its
   published algorithm.  The reference ships no tests or golden outputs for
