@@ -398,6 +398,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel()) + 12 * N_GENES + 16,
                     "d2h_bytes_per_step": N_GENES * 8 + 64 + 256 * 8, "ms_per_step": e2e_ms / args.steps,
                     "call": "PSSMModel.regulation_pipeline -> cgbk_regulation_pipeline (host buffers)",
+                    "d2h": "posteriors + stats + histogram land in the pinned host buffer inside the call "
+                           "(stored over PCIe by the finalising kernels; a D2H copy for pageable buffers)",
                     "multi_call_ms_per_step": 1e3 * e2e_multi_s / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks, "wall_s_timed_loop": wall, "at_scale": scale,
