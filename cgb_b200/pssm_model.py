@@ -262,13 +262,20 @@ class PSSMModel(TFBindingModel):
                                         max(n_hits, (n_cand + 3) // 4) + 1024)
         self.last_scan_counters = {"candidates": n_cand, "hits": n_hits,
                                    "dirty_tiles": int(c[_cabi.CTR_DIRTY_TILES])}
-        rec = pending["hits"][:2 * n_hits].cpu().numpy().view(
+        # Sort on the device (by packed offset, + strand first: the (seq, pos, strand) order, as
+        # sequence offsets grow with the sequence index) and bring the records over once; low-
+        # information motifs produce millions of hits and a host lexsort would dominate.
+        dev_rec = pending["hits"][:2 * n_hits].view(n_hits, 2)
+        if n_hits > 1:
+            minus = (dev_rec[:, 1] & 0xffffffff) != 1            # low word of the second int64 = strand
+            order = torch.argsort(dev_rec[:, 0] * 2 + minus.to(torch.int64))
+            dev_rec = dev_rec[order]
+        rec = dev_rec.cpu().numpy().reshape(-1).view(
             np.dtype([("gpos", "<i8"), ("strand", "<i4"), ("score", "<f4")]))
-        gpos, strand, score = rec["gpos"].copy(), rec["strand"].copy(), rec["score"].copy()
+        gpos = rec["gpos"]
         seq = np.searchsorted(genome.seq_off, gpos, side="right") - 1
         pos = gpos - genome.seq_off[seq]
-        order = np.lexsort((-strand, pos, seq))
-        return seq[order], pos[order], strand[order], score[order]
+        return seq, pos, rec["strand"].copy(), rec["score"].copy()
 
     def background_stats(self, genome, n_bins=256, hist_lo=None, hist_hi=None, accumulate_into=None,
                          out=None, keep_scores=False):
