@@ -105,3 +105,28 @@ def test_pipeline_pageable_result_buffers(pair, lexa):
         M._stream()))
     assert np.array_equal(h2, hist) and s2[_cabi.BG_N] == stats[_cabi.BG_N]
     assert abs(s2[_cabi.BG_MEAN] - stats[_cabi.BG_MEAN]) < 1e-12 and np.max(np.abs(p2 - post)) < 1e-12
+
+
+def test_long_regions_beyond_the_marked_window_bitmask(pair, lexa):
+    """Regions longer than 2 048 windows: high-scoring windows past the 64 x 32 positions the
+    posterior kernel can merely mark are re-scored on the spot."""
+    M, om = pair
+    m = M.length
+    seq = bytearray(O.synthetic_genome(30000, 73))
+    site = b"AAATCGAACATGTGTTCGAGTA"
+    for at in (150, 2500, 7000, 11990, 20000, 29900):
+        seq[at:at + m] = site
+    seq = bytes(seq)
+    g = PackedGenome.from_sequences([seq])
+    M.fit_background(g)
+    b = c_oracle.score_seq(om, seq)[2]
+    O.build_bayesian_estimator(om, b)
+    prior, alpha = lexa["prior_regulation_probability"], lexa["alpha"]
+    starts = np.array([0, 100, 5000, 0])
+    ends = np.array([30000, 12100, 25000, 2100])
+    for use_plane in (True, False):
+        got = M.binding_probabilities(g, starts, ends, prior, alpha, use_plane=use_plane).cpu().numpy()
+        for s, e, p in zip(starts, ends, got):
+            exp = c_oracle.binding_probability(om, seq[int(s):int(e)], om._mu_m, om._std_m, om._mu_bg, om._std_bg,
+                                               prior, alpha)
+            assert abs(p - exp) < 1e-6, (use_plane, s, e, p, exp)
