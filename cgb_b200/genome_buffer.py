@@ -51,7 +51,7 @@ class PackedGenome:
         # one allocation: bases2 | amb | lower | sequence table.  Every word of the planes is
         # written by the pack kernel (padding included), so nothing is zeroed here.
         c16, c32 = self.cap_bases // 16, self.cap_bases // 32
-        n_table = 2 * (3 * n + 1)                       # int64[3n + 1] as int32 pairs
+        n_table = 2 * int(lib.cgbk_seqset_table_ints(n))   # the set's device table (int64) as int32 pairs
         self._storage = torch.empty(c16 + 2 * c32 + n_table, dtype=torch.int32, device=self.device)
         self.bases2 = self._storage[:c16]
         self.amb = self._storage[c16:c16 + c32]

@@ -31,6 +31,8 @@ def test_ragged_set_hits_and_background(pair):
     seqs = _ragged(m)
     g = PackedGenome.from_sequences(seqs)
     assert g.total_windows(m) == sum(max(0, len(s) - m + 1) for s in seqs)
+    # more than CGBK_INLINE_SEQS sequences: the set's tables live in the caller-owned device block
+    assert g._table.numel() * 4 == 8 * int(_cabi.lib().cgbk_seqset_table_ints(len(seqs)))
     thr = 2.0                                       # low: plenty of hits in every sequence
     seq_i, pos, strand, score = M.scan_hits(g, thr)
     for k, s in enumerate(seqs):
