@@ -132,3 +132,28 @@ def test_long_regions_beyond_the_marked_window_bitmask(pair, lexa):
             exp = c_oracle.binding_probability(om, seq[int(s):int(e)], om._mu_m, om._std_m, om._mu_bg, om._std_bg,
                                                prior, alpha)
             assert abs(p - exp) < 1e-6, (use_plane, s, e, p, exp)
+
+
+@pytest.mark.parametrize("n,lane", [(1_200_000, 32), (2_500_000, 64), (5_000_000, 96), (7_000_000, 128)])
+def test_every_lane_segment_length_against_the_oracle(pair, lexa, n, lane):
+    """The tiling is picked by a cost model (lane segments of 32 / 64 / 96 / 128 bases); the score
+    plane, the histogram and the hit list must not care.  Sizes chosen to land on each."""
+    M, om = pair
+    seq = O.synthetic_genome(n, 80 + lane, n_frac=0.0002)
+    g = PackedGenome.from_sequences([seq])
+    M.fit_background(g, keep_scores=True)
+    assert _cabi.last_launch_info()["lane_bases"] == lane
+    b = c_oracle.score_seq(om, seq)[2]
+    O.build_bayesian_estimator(om, b)
+    assert abs(M._mu_bg - om._mu_bg) < 1e-6 and abs(M._std_bg - om._std_bg) < 1e-6
+    rng = np.random.default_rng(lane)
+    starts = np.sort(rng.integers(0, n - 400, size=300))
+    ends = starts + rng.integers(M.length, 400, size=300)
+    prior, alpha = lexa["prior_regulation_probability"], lexa["alpha"]
+    got = M.binding_probabilities(g, starts, ends, prior, alpha).cpu().numpy()
+    exp = np.array([c_oracle.binding_probability(om, seq[int(s):int(e)], om._mu_m, om._std_m, om._mu_bg,
+                                                 om._std_bg, prior, alpha) for s, e in zip(starts, ends)])
+    assert np.max(np.abs(got - exp)) < 1e-6
+    _, pos, strand, score = M.scan_hits(g)
+    ep, es, ev = c_oracle.scan_hits(om, seq, om.threshold())
+    assert np.array_equal(pos, ep) and np.array_equal(strand, es) and np.array_equal(score, ev)
