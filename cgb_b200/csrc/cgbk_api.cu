@@ -506,27 +506,28 @@ static int device_sms(int device) {
 }
 
 // Lane segment length L (32, 64, 96 or 128 bases; a warp tile owns 32 L - 32 windows).
-// A tile costs a warp ~(1.8 + 0.093 L) us in the stats scan (measured on B200: 4.8 us at
-// L = 32, 13.7 us at L = 128 -- the per-tile part is the hand-over of the straddling windows
-// and the tile bookkeeping), and tiles are dealt to `warps_total` resident warps in rounds.
-// Large inputs want the longest segment (least overhead per window); small ones want the
-// tiling whose last round is not mostly empty: 5 Mbp is ONE round at L = 96 (10.7 us) but
-// three at L = 32 (14.4 us).  The constants are per scan kind (below).
-static int choose_L(const cgbk_seqset* S, int m, int warps_total, double per_tile_us, double per_base_us) {
+// Tiles are dealt to the resident warps in rounds and a round costs about the same however
+// full it is, so the tiling is picked to minimise rounds x (time of one round), with the round
+// times measured on B200 under full load (tools/scan_scale.py over 0.1 Mbp - 1 Gbp,
+// profiles/r1_scan_sizes.md): large inputs want the longest segment (least overhead per
+// window), small ones the tiling whose last round is not mostly empty -- 5 Mbp is ONE round at
+// L = 96 in the stats scan but three at L = 32.
+static int choose_L(const cgbk_seqset* S, int m, int warps_total, const double (&round_us)[4]) {
     int best_L = 128;
     double best = 0.0;
     for (int L = 128; L >= 32; L -= 32) {
         const int64_t tiles = count_tiles(S, m, L);
         const int64_t rounds = (tiles + warps_total - 1) / warps_total;
-        const double cost = (double)rounds * (per_tile_us + per_base_us * L);
+        const double cost = (double)rounds * round_us[L / 32 - 1];
         if (L == 128 || cost < best * 0.999) { best = cost; best_L = L; }
     }
     return best_L;
 }
-// stats scan: 12 warps per SM, 4.8 us per tile at L = 32 and 13.7 us at L = 128
-static int choose_L_stats(const cgbk_seqset* S, int m, int sms) { return choose_L(S, m, sms * 12, 1.8, 0.093); }
-// hit filter: 20 warps per SM, 2.5 us per tile at L = 32 and 10.8 us at L = 128
-static int choose_L_hits(const cgbk_seqset* S, int m, int sms) { return choose_L(S, m, sms * 20, 1.0, 0.0865); }
+// stats scan: 12 warps per SM; hit filter: 20 warps per SM.  Microseconds per round at L = 32, 64, 96, 128.
+static const double kStatsRoundUs[4] = {4.6, 9.8, 12.6, 14.0};
+static const double kHitsRoundUs[4] = {3.8, 6.3, 8.6, 10.7};
+static int choose_L_stats(const cgbk_seqset* S, int m, int sms) { return choose_L(S, m, sms * 12, kStatsRoundUs); }
+static int choose_L_hits(const cgbk_seqset* S, int m, int sms) { return choose_L(S, m, sms * 20, kHitsRoundUs); }
 
 #define PARTIAL_CAP 1024
 #define WORK_HEADER (64 + 3 * 8 * PARTIAL_CAP)

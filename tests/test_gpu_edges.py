@@ -134,7 +134,7 @@ def test_long_regions_beyond_the_marked_window_bitmask(pair, lexa):
             assert abs(p - exp) < 1e-6, (use_plane, s, e, p, exp)
 
 
-@pytest.mark.parametrize("n,lane", [(1_200_000, 32), (2_500_000, 64), (5_000_000, 96), (7_000_000, 128)])
+@pytest.mark.parametrize("n,lane", [(1_200_000, 32), (3_550_000, 64), (5_000_000, 96), (7_000_000, 128)])
 def test_every_lane_segment_length_against_the_oracle(pair, lexa, n, lane):
     """The tiling is picked by a cost model (lane segments of 32 / 64 / 96 / 128 bases); the score
     plane, the histogram and the hit list must not care.  Sizes chosen to land on each."""
