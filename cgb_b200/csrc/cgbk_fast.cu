@@ -559,16 +559,46 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         }
         __syncthreads();
         if (is_last_block) {
-            // every block of this and of the earlier tile ranges has published its partial
+            // Every block of this and of the earlier tile ranges has published its partial and
+            // flushed its histogram.  All global loads of the finalisation are issued together
+            // (partials, the record being accumulated into, the histogram for the host copy):
+            // one L2 round trip instead of three dependent ones.
             __threadfence();
-            finalize_stats(work.partials, work.partial_base + (int)gridDim.x, sp.d_stats, 1, red_scratch);
-            if (sp.host_stats) {
-                // every block flushed its histogram before it bumped the counter: the record is final
-                __syncthreads();
-                if (threadIdx.x < CGBK_BG_COUNT) sp.host_stats[threadIdx.x] = __ldcg(sp.d_stats + threadIdx.x);
-                if (sp.host_hist && sp.d_hist)
-                    for (int i = threadIdx.x; i < sp.n_bins; i += blockDim.x)
-                        sp.host_hist[i] = __ldcg(sp.d_hist + i);
+            const int n_part = work.partial_base + (int)gridDim.x;
+            double s1 = 0.0, s2 = 0.0, cn = 0.0;
+            for (int i = threadIdx.x; i < n_part; i += blockDim.x) {
+                s1 += __ldcg(work.partials + 3 * i); s2 += __ldcg(work.partials + 3 * i + 1);
+                cn += __ldcg(work.partials + 3 * i + 2);
+            }
+            double prev = 0.0;                                   // n, sum, sumsq accumulated so far
+            if (threadIdx.x < 3) prev = __ldcg(sp.d_stats + threadIdx.x);
+            unsigned long long hcopy = 0ull;                     // n_bins <= blockDim.x in the common case
+            const bool copy_hist = sp.host_stats && sp.host_hist && sp.d_hist;
+            if (copy_hist && (int)threadIdx.x < sp.n_bins) hcopy = __ldcg(sp.d_hist + threadIdx.x);
+            block_reduce3(s1, s2, cn, red_scratch);
+            // thread 0 holds the totals; threads 0..2 hold the previous n / sum / sumsq
+            const double prev_n = __shfl_sync(0xffffffffu, prev, 0), prev_s1 = __shfl_sync(0xffffffffu, prev, 1),
+                         prev_s2 = __shfl_sync(0xffffffffu, prev, 2);
+            if (threadIdx.x == 0) {
+                cn += prev_n; s1 += prev_s1; s2 += prev_s2;
+                const double mean = cn > 0 ? s1 / cn : nan("");
+                double var = cn > 0 ? s2 / cn - mean * mean : nan("");
+                if (var < 0) var = 0;
+                const double sd = sqrt(var);
+                double* st = sp.d_stats;
+                st[CGBK_BG_N] = cn; st[CGBK_BG_SUM] = s1; st[CGBK_BG_SUMSQ] = s2;
+                st[CGBK_BG_MEAN] = mean; st[CGBK_BG_STD] = sd;
+                if (sp.host_stats) {
+                    double* hs = sp.host_stats;
+                    hs[CGBK_BG_N] = cn; hs[CGBK_BG_SUM] = s1; hs[CGBK_BG_SUMSQ] = s2;
+                    hs[CGBK_BG_MEAN] = mean; hs[CGBK_BG_STD] = sd;
+                    for (int k = CGBK_BG_STD + 1; k < CGBK_BG_COUNT; ++k) hs[k] = 0.0;
+                }
+            }
+            if (copy_hist) {
+                if ((int)threadIdx.x < sp.n_bins) sp.host_hist[threadIdx.x] = hcopy;
+                for (int i = threadIdx.x + blockDim.x; i < sp.n_bins; i += blockDim.x)
+                    sp.host_hist[i] = __ldcg(sp.d_hist + i);
             }
         }
     }
