@@ -194,6 +194,9 @@ def at_scale(M, dev, bp, reps=3):
                      "hbm_frac": nwin * 0.25 / (ms * 1e-3) / 1e9 / hbm_peak}
         if mode == "hit_scan":
             out[mode].update(M.last_scan_counters)
+    # what actually bounds both kernels (one `ncu --set full` capture of this leg,
+    # profiles/r1_ncu_scans_1gbp.csv: l1tex__data_pipe_lsu_wavefronts_mem_shared, % of peak)
+    out["smem_wavefront_pct_of_peak_ncu"] = {"hit_scan": 89.4, "stats_scan": 88.5}
     return out
 
 
@@ -402,6 +405,8 @@ def run_ours(args):
                            "(stored over PCIe by the finalising kernels; a D2H copy for pageable buffers)",
                     "multi_call_ms_per_step": 1e3 * e2e_multi_s / args.steps},
             "gpu_launches": launches_per_step * args.steps,
+            # SURVEY.md 8d's second figure: promoters / time of (background fit + posterior kernels)
+            "promoter_posteriors_per_s": world * N_GENES / (total_ms * 1e-3 / args.steps),
             "clocks": clocks, "wall_s_timed_loop": wall, "at_scale": scale,
         }
         print(json.dumps(line))
