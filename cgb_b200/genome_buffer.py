@@ -137,6 +137,39 @@ class PackedGenome:
             self._work = {key: w}
         return w
 
+    # --------------------------------------------------- packed on-disk form
+    # a replicon set stored the way the kernels read it (2-bit bases +
+    # ambiguity + lower-case planes, 0.5 byte per base) loads with one H2D copy and no pack
+    # kernel, instead of parsing and uploading 1 byte per base.
+    FILE_MAGIC = "cgbk-packed-genome-1"
+
+    def save(self, path, names=None):
+        """Write the packed planes and the sequence table to ``path`` (numpy ``.npz``, not
+        compressed: the planes are already 4 bits per base).  Every sequence must have been
+        packed.  ``names``: optional accession per sequence."""
+        if not bool(self._packed.all()):
+            raise ValueError("some sequences have not been packed yet")
+        torch.cuda.current_stream(self.device).synchronize()
+        planes = self._storage[:self.cap_bases // 16 + 2 * (self.cap_bases // 32)].cpu().numpy()
+        with open(path, "wb") as f:
+            np.savez(f, magic=np.array(self.FILE_MAGIC), seq_len=self.seq_len, planes=planes,
+                     names=np.array(list(names) if names is not None else [""] * self.n_seq))
+
+    @classmethod
+    def load(cls, path, device=None):
+        """Inverse of :meth:`save`: returns ``(genome, names)``."""
+        with np.load(path, allow_pickle=False) as z:
+            if str(z["magic"]) != cls.FILE_MAGIC:
+                raise ValueError("%s is not a packed genome file" % path)
+            seq_len, planes, names = z["seq_len"], z["planes"], [str(x) for x in z["names"]]
+        g = cls(seq_len, device)
+        want = g.cap_bases // 16 + 2 * (g.cap_bases // 32)
+        if planes.dtype != np.int32 or planes.shape != (want,):
+            raise ValueError("%s: planes do not match the sequence table" % path)
+        g._storage[:want].copy_(torch.from_numpy(planes), non_blocking=False)
+        g._packed[:] = True
+        return g, names
+
     def __del__(self):
         try:
             if getattr(self, "_seqset", None) is not None and self._seqset.value:

@@ -157,3 +157,26 @@ def test_every_lane_segment_length_against_the_oracle(pair, lexa, n, lane):
     _, pos, strand, score = M.scan_hits(g)
     ep, es, ev = c_oracle.scan_hits(om, seq, om.threshold())
     assert np.array_equal(pos, ep) and np.array_equal(strand, es) and np.array_equal(score, ev)
+
+
+def test_packed_genome_file_round_trip(pair, tmp_path):
+    """PackedGenome.save / load: the on-disk packed form scans exactly like the freshly packed one
+    (hits incl. the ambiguity repair, background record)."""
+    M, om = pair
+    seqs = [O.synthetic_genome(300000, 91, n_frac=0.001), b"acgtnACGT" * 50, O.synthetic_genome(70001, 92)]
+    g = PackedGenome.from_sequences(seqs)
+    path = str(tmp_path / "genome.npz")
+    g.save(path, names=["chr", "tiny", "plasmid"])
+    g2, names = PackedGenome.load(path)
+    assert names == ["chr", "tiny", "plasmid"] and g2.seq_len.tolist() == g.seq_len.tolist()
+    a, b = M.scan_hits(g, 3.0), M.scan_hits(g2, 3.0)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[1]) > 100
+    sa, sb = M.background_stats(g), M.background_stats(g2)
+    assert torch_equal(sa["hist"], sb["hist"]) and torch_equal(sa["stats"][:1], sb["stats"][:1])
+    with pytest.raises(ValueError):
+        PackedGenome([10, 20]).save(path)                       # nothing packed yet
+
+
+def torch_equal(a, b):
+    import torch
+    return bool(torch.equal(a, b))
