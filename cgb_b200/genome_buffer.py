@@ -82,6 +82,21 @@ class PackedGenome:
             lens = [int(p.numel()) for p in pinned]
         g = cls(lens, device)
         stream = torch.cuda.current_stream(g.device)
+        if pinned is None and len(lens) > 1 and g.cap_bases <= (64 << 20):
+            # Many host sequences (e.g. the 164 sites of score_self): build the padded image of
+            # the whole buffer on the host -- padding as 'A', which packs to the same zero words
+            # the per-sequence path writes -- and pack it with ONE copy and ONE launch.
+            image = np.full(g.cap_bases, ord("A"), dtype=np.uint8)
+            for k, r in enumerate(raw):
+                if lens[k]:
+                    image[g.seq_off[k]:g.seq_off[k] + lens[k]] = np.frombuffer(r, dtype=np.uint8)
+            dev = torch.from_numpy(image).to(g.device, non_blocking=True)
+            _cabi.check(_cabi.lib().cgbk_pack_ascii(
+                dev.data_ptr(), g.cap_bases, 0, g.bases2.data_ptr(), g.amb.data_ptr(), g.lower.data_ptr(),
+                g.cap_bases, stream.cuda_stream))
+            dev.record_stream(stream)
+            g._packed[:] = True
+            return g
         for k in range(len(lens)):
             if pinned is not None:
                 host = pinned[k]

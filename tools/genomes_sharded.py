@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""BASELINE configs[2] at full size: 100 genomes x 4 Mbp x 3 derived PSWMs, genomes sharded over
+the ranks (no collective: every genome has its own background fit).  Per (genome, PSWM): the
+one-call pipeline (background of all windows + posteriors of every promoter) and the thresholded
+hit scan.  Launch under torchrun; rank 0 prints a JSON line.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29540 tools/genomes_sharded.py [--genomes 100] [--bp 4000000]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import bench
+    from cgb_b200 import GeneTable, PackedGenome, PSSMModel, SiteCollection, prepare_thresholds
+    from cgb_b200 import dist as cdist
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--genomes", type=int, default=100)
+    ap.add_argument("--bp", type=int, default=4_000_000)
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    d, site_lists, weights = bench.lexa()
+    prior, alpha = d["prior_regulation_probability"], d["alpha"]
+    colls = [SiteCollection(s) for s in site_lists]
+    mine = cdist.assign_genomes([args.bp] * args.genomes, world)[rank]
+    n_genes = args.bp // 1667
+    gs, ge, gstrand = bench.gene_layout(args.bp, n_genes)
+    ps, pe = GeneTable(gs, ge, gstrand, args.bp).promoter_region_location(bench.UP, bench.DOWN)
+    # inputs (outside the timed span): pinned ASCII per genome, three PSWMs per genome
+    genomes, models = [], []
+    for gi in mine:
+        genomes.append(torch.from_numpy(bench.synthetic_genome(args.bp, 100 + gi)).pin_memory())
+        rng = np.random.default_rng(gi)
+        ws = [[1.0 / len(colls)] * len(colls), weights, rng.dirichlet([1.0] * len(colls)).tolist()]
+        models.append([PSSMModel(colls, w, device=dev) for w in ws])
+    prepare_thresholds([M for ms in models for M in ms])
+    for M in models[0]:                                   # warm-up: context, allocator, tables
+        M.regulation_pipeline(genomes[0], ps, pe, prior, alpha)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    n_hits = 0
+    post_sum = 0.0
+    for seq, ms in zip(genomes, models):
+        packed = PackedGenome.from_sequences([None], dev, pinned=[seq])
+        for M in ms:
+            post, stats, hist = M.regulation_pipeline(seq, ps, pe, prior, alpha)
+            _, pos, strand, score = M.scan_hits(packed)
+            n_hits += len(pos)
+            post_sum += float(post.sum())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt, float(n_hits), float(len(mine))], dtype=torch.float64, device=dev)
+    tmax = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        wall = float(tmax[0].item())
+        units = args.genomes * 3 * (args.bp - 21)
+        print(json.dumps({
+            "workload": "configs[2]: %d genomes x %d bp x 3 PSWMs, genomes sharded over %d ranks, per (genome, "
+                        "PSWM): background fit + %d promoter posteriors (one-call pipeline from pinned ASCII) + "
+                        "hit scan" % (args.genomes, args.bp, world, n_genes),
+            "n_gpus": world, "wall_s_max_over_ranks": wall, "genome_pswm_pairs": args.genomes * 3,
+            "pairs_per_s": args.genomes * 3 / wall, "bp_motif_per_s": units / wall,
+            "hits_total": int(t[1].item()), "genomes_on_rank0": len(mine)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
