@@ -320,13 +320,18 @@ extern "C" int cgbk_model_create(const double* lo, int m, int device, cgbk_model
         ex[CGBK_EXACT_TAB_OFFSET + CGBK_MAXM * 8 + 2 * i] = ex[CGBK_MAXM * 8 + i];
         ex[CGBK_EXACT_TAB_OFFSET + CGBK_MAXM * 8 + 2 * i + 1] = ex[CGBK_MAXM * 9 + i];
     }
-    cudaError_t e1 = cudaMalloc(&M->d_exact, sizeof(double) * 2 * CGBK_EXACT_DOUBLES);
-    cudaError_t e2 = cudaMalloc(&M->d_precise, sizeof(uint32_t) * 256 * 2 * G);
-    cudaError_t e3 = cudaMalloc(&M->d_coarse, sizeof(uint32_t) * 256 * G);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    // one device block per model: exact tables | int32 group tables | 16-bit filter tables
+    const size_t exact_bytes = (sizeof(double) * 2 * CGBK_EXACT_DOUBLES + 255) / 256 * 256;
+    const size_t precise_bytes = (sizeof(uint32_t) * 256 * 2 * G + 255) / 256 * 256;
+    const size_t coarse_bytes = sizeof(uint32_t) * 256 * G;
+    unsigned char* block = nullptr;
+    if (cudaMalloc((void**)&block, exact_bytes + precise_bytes + coarse_bytes) != cudaSuccess) {
         cgbk_model_destroy(M);
         return cgbk_set_error(CGBK_ERR_CUDA, "cudaMalloc of model tables failed");
     }
+    M->d_exact = (double*)block;
+    M->d_precise = (uint32_t*)(block + exact_bytes);
+    M->d_coarse = (uint32_t*)(block + exact_bytes + precise_bytes);
     cudaError_t c1 = cudaMemcpy(M->d_exact, ex.data(), sizeof(double) * 2 * CGBK_EXACT_DOUBLES, cudaMemcpyHostToDevice);
     std::vector<uint32_t> precise_ch(precise.size());
     chunked_layout(precise.data(), 2 * G, precise_ch.data());
@@ -342,9 +347,7 @@ extern "C" int cgbk_model_create(const double* lo, int m, int device, cgbk_model
 
 extern "C" void cgbk_model_destroy(cgbk_model* M) {
     if (!M) return;
-    if (M->d_exact) cudaFree(M->d_exact);
-    if (M->d_precise) cudaFree(M->d_precise);
-    if (M->d_coarse) cudaFree(M->d_coarse);
+    if (M->d_exact) cudaFree(M->d_exact);      // one block: d_precise and d_coarse live inside it
     free(M);
 }
 
