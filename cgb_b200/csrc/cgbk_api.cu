@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -136,18 +137,32 @@ extern "C" int cgbk_patser_threshold(const double* lo, int m, int precision, dou
     if (start < 0) start += n_points;            // Python negative index
     if (start < 0 || start >= n_points) return cgbk_set_error(CGBK_ERR_INVALID, "degenerate score range");
     dens[start] = 1.0;
+    // Same additions in the same order as the reference's loops (letters outer, i ascending,
+    // target index clamped to the grid), restricted to the support of the density -- adding the
+    // +0.0 of an empty cell changes nothing -- and with the clamped ends peeled off so that the
+    // interior is a plain shifted accumulate.
+    long long s_lo = start, s_hi = start;
     for (int pos = 0; pos < m; ++pos) {
         std::fill(next.begin(), next.end(), 0.0);
+        long long n_lo = n_points - 1, n_hi = 0;
         for (int k = 0; k < 4; ++k) {             // letters in alphabet order
             const long long d = index_diff(lo[pos * 4 + k]);
-            for (long long i = 0; i < n_points; ++i) {
-                long long j = i + d;
-                if (j < 0) j = 0;
-                if (j > n_points - 1) j = n_points - 1;
-                next[j] += dens[i] * 0.25;
-            }
+            const double* src = dens.data();
+            double* dst = next.data();
+            long long i = s_lo;
+            const long long below_end = std::min(s_hi, -d - 1);            // i + d < 0  -> cell 0
+            for (; i <= below_end; ++i) dst[0] += src[i] * 0.25;
+            const long long in_end = std::min(s_hi, n_points - 1 - d);     // 0 <= i + d <= n - 1
+            for (; i <= in_end; ++i) dst[i + d] += src[i] * 0.25;
+            for (; i <= s_hi; ++i) dst[n_points - 1] += src[i] * 0.25;     // i + d > n - 1 -> last cell
+            long long a = s_lo + d, b = s_hi + d;
+            a = a < 0 ? 0 : (a > n_points - 1 ? n_points - 1 : a);
+            b = b < 0 ? 0 : (b > n_points - 1 ? n_points - 1 : b);
+            if (a < n_lo) n_lo = a;
+            if (b > n_hi) n_hi = b;
         }
         dens.swap(next);
+        s_lo = n_lo; s_hi = n_hi;
     }
     const double fpr = pow(2.0, -ic);
     long long i = n_points;
