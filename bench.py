@@ -388,7 +388,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32 fixed point (2^-24) + f64 moments/posterior",
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32 fixed point (2^-24 for this motif) + f64 moments/posterior",
             "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "genome_bp": GENOME_BP, "promoters": N_GENES, "posterior_windows": n_post_windows,

@@ -303,8 +303,8 @@ extern "C" int cgbk_model_create(const double* lo, int m, int device, cgbk_model
     memcpy(ex.data() + CGBK_MAXM * 4, M->rc, sizeof(M->rc));
     memcpy(ex.data() + CGBK_MAXM * 8, M->mean_f, sizeof(M->mean_f));
     memcpy(ex.data() + CGBK_MAXM * 8 + CGBK_MAXM, M->mean_r, sizeof(M->mean_r));
-    // int32 fixed-point tables: scale 2^kexp with |any window sum| < 2^30
-    int kexp = 24;
+    // int32 fixed-point tables: scale 2^kexp (at most 2^28) with |any window sum| < 2^30
+    int kexp = 28;
     if (R > 0) {
         const int k2 = (int)floor(log2(1073741824.0 / R));
         if (k2 < kexp) kexp = k2;
@@ -313,6 +313,21 @@ extern "C" int cgbk_model_create(const double* lo, int m, int device, cgbk_model
     const double scale = ldexp(1.0, kexp);
     std::vector<long long> qf(4 * m), qr(4 * m);
     for (int i = 0; i < 4 * m; ++i) { qf[i] = llrint(M->fwd[i] * scale); qr[i] = llrint(M->rc[i] * scale); }
+    // Each entry is off by up to half a unit.  Over a window the m errors add up, and when many
+    // entries share one value (a motif built from a few sites: most log-odds are the
+    // pseudocount's) they all lean the same way -- 12 x 0.45 units = 3e-7 on EVERY window of a
+    // 12-bp motif at 2^-24, straight into the background mean (tools/fuzz_parity.py, seed 56).
+    // The expected sum of the errors under a uniform base composition is therefore taken out
+    // again, as a whole number of units, at position 0 of each strand.
+    {
+        double bias_f = 0.0, bias_r = 0.0;
+        for (int i = 0; i < 4 * m; ++i) {
+            bias_f += ((double)qf[i] - M->fwd[i] * scale) * 0.25;
+            bias_r += ((double)qr[i] - M->rc[i] * scale) * 0.25;
+        }
+        const long long shift_f = llrint(bias_f), shift_r = llrint(bias_r);
+        for (int b = 0; b < 4; ++b) { qf[b] -= shift_f; qr[b] -= shift_r; }
+    }
     const int G = M->G;
     std::vector<uint32_t> precise((size_t)256 * 2 * G);
     for (int e = 0; e < 256; ++e)

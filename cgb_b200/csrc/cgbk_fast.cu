@@ -678,7 +678,16 @@ StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist
     const double centre = 0.5 * (mdl->min_score + mdl->max_score);
     sp.c_fix = (int)llrint(centre * scale);
     sp.c = (double)sp.c_fix / scale;
-    sp.sh = mdl->kexp > 18 ? mdl->kexp - 18 : 0;
+    // Moment unit 2^-(kexp - sh): the finest the integer accumulators allow.  A body adds 32
+    // re-centred scores in an int32 (|d| < 2^26) and a tile up to 128 squares in an int64
+    // (|d| < 2^28).  For LexA (score range 70 bits, kexp 24) that is 2^-20; a motif with a
+    // narrow range gets an exact sum.  (With a fixed 2^-18 a degenerate 2-bp motif -- 14
+    // distinct scores, so the rounding does not average out -- was off by 9e-7 in the mean,
+    // which its 3 000-window posteriors amplify past 1e-6; found by tools/fuzz_parity.py.)
+    const double half_range_fix = (0.5 * (mdl->max_score - mdl->min_score) + 1.0) * scale + 1.0;  // soft-max <= max + 1
+    int need = 0;
+    while (need < 30 && ldexp(1.0, 26 + need) <= half_range_fix) ++need;
+    sp.sh = need;
     sp.half = sp.sh > 0 ? (1 << (sp.sh - 1)) : 0;
     sp.q = ldexp(1.0, -(mdl->kexp - sp.sh));
     sp.d_hist = d_hist;

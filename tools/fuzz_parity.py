@@ -1,0 +1,120 @@
+#!/usr/bin/env python
+"""Randomised parity run of the CUDA path against the C/numpy oracle (not a pytest: runs for a time
+budget and reports the first mismatch with its seed).  Random motif lengths 1-32, several
+sequences per set from a handful of bases to a few Mbp, N runs, lower-case stretches, random
+thresholds, random promoter slices.
+
+    python tools/fuzz_parity.py [--seconds 120] [--seed 0]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def random_sequence(rng, n):
+    seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n)
+    if n > 50 and rng.random() < 0.6:
+        for _ in range(int(rng.integers(1, 6))):
+            at = int(rng.integers(0, n - 10)); ln = int(rng.integers(1, 40))
+            seq[at:at + ln] = ord("N") if rng.random() < 0.7 else ord(rng.choice(list("RYKMSWn")))
+    if n > 200 and rng.random() < 0.4:
+        at = int(rng.integers(0, n - 100)); ln = int(rng.integers(1, 100))
+        seq[at:at + ln] |= 0x20                     # lower case
+    return seq.tobytes()
+
+
+def one_case(seed):
+    from cgb_b200 import PackedGenome, PSSMModel, SiteCollection, _cabi
+    from oracle import c_oracle, np_oracle as O
+    rng = np.random.default_rng(seed)
+    m = int(rng.integers(1, 33))
+    cols = rng.dirichlet([rng.choice([0.3, 0.5, 1.0, 3.0])] * 4, size=m)
+    sites = ["".join("ACGT"[rng.choice(4, p=cols[j])] for j in range(m)) for _ in range(int(rng.integers(5, 40)))]
+    M = PSSMModel([SiteCollection(sites)], [1.0])
+    om = O.OracleModel([sites], [1.0])
+    sizes = [int(rng.choice([m - 1 if m > 1 else 1, m, m + 1, 100, 1000, 1023, 1024, 1025, 5000, 33000]))
+             for _ in range(int(rng.integers(0, 4)))]
+    sizes.append(int(rng.choice([20000, 150000, 600000, 1500000, 2500000, 3600000])))
+    rng.shuffle(sizes)
+    seqs = [random_sequence(rng, n) for n in sizes]
+    g = PackedGenome.from_sequences(seqs)
+    info = {"seed": seed, "m": m, "sizes": sizes}
+    # hits at a random operating point
+    allb = np.concatenate([c_oracle.score_seq(om, s)[2] for s in seqs if len(s) >= m])
+    thr = float(np.quantile(allb, rng.choice([0.9, 0.99, 0.999, 0.9999])))
+    seq_i, pos, strand, score = M.scan_hits(g, thr)
+    for k, s in enumerate(seqs):
+        sel = seq_i == k
+        if len(s) < m:
+            assert not sel.any(), info
+            continue
+        ep, es, ev = c_oracle.scan_hits(om, s, thr)
+        assert np.array_equal(pos[sel], ep) and np.array_equal(strand[sel], es) and np.array_equal(score[sel], ev), \
+            (info, "hits", k)
+    # background record
+    bins = int(rng.choice([1, 64, 256, 300, 1024]))
+    bg = M.background_stats(g, n_bins=bins, keep_scores=True)
+    st = bg["stats"].cpu().numpy()
+    assert st[_cabi.BG_N] == len(allb) and int(bg["hist"].sum()) == len(allb), (info, "count")
+    assert abs(st[_cabi.BG_MEAN] - allb.mean()) < 1e-6 and abs(st[_cabi.BG_STD] - allb.std()) < 1e-6, (info, "moments")
+    if allb.std() < 1e-3:
+        return info
+    # posteriors of random slices of the largest sequence, from the plane and re-scored
+    M.fit_background(bg=bg)
+    O.build_bayesian_estimator(om, allb)
+    if om._std_m < 1e-3:
+        # all sites identical: the reference's own posterior hinges on exact float equality of a
+        # window score with the site mean (pdf of a zero-width normal); not a meaningful target
+        return info
+    k = int(np.argmax(sizes))
+    n = sizes[k]
+    starts = rng.integers(0, max(1, n - 2 * m - 2), size=40)
+    ends = np.minimum(n, starts + rng.integers(m, min(n, 3000) + 1, size=40))
+    keep = ends - starts >= m
+    starts, ends = starts[keep], ends[keep]
+    exp = np.array([c_oracle.binding_probability(om, seqs[k][int(a):int(b)], om._mu_m, om._std_m, om._mu_bg,
+                                                 om._std_bg, 0.03, 1 / 350.0) for a, b in zip(starts, ends)])
+    ok = np.isfinite(exp)
+    if not ok.any():
+        return info
+    # the same with the GPU's own background estimate: separates the posterior kernel's error
+    # from the sensitivity of a posterior to the (1e-6-accurate) background mean / std
+    exp_own = np.array([c_oracle.binding_probability(om, seqs[k][int(a):int(b)], om._mu_m, om._std_m, M._mu_bg,
+                                                     M._std_bg, 0.03, 1 / 350.0) for a, b in zip(starts, ends)])
+    for use_plane in (True, False):
+        got = M.binding_probabilities(g, starts, ends, 0.03, 1 / 350.0, seq_index=k, use_plane=use_plane).cpu().numpy()
+        err = float(np.max(np.abs(got[ok] - exp[ok])))
+        err_own = float(np.max(np.abs(got[ok] - exp_own[ok])))
+        info["posterior_err_plane" if use_plane else "posterior_err_rescore"] = (err, err_own)
+        assert err < 1e-6, (info, "posterior", use_plane, err, "kernel alone", err_own,
+                            "mu_bg diff", M._mu_bg - om._mu_bg, "std_bg diff", M._std_bg - om._std_bg)
+    return info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=120.0)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    t0 = time.time()
+    n, seed = 0, args.seed
+    worst = {"plane": 0.0, "rescore": 0.0}
+    while time.time() - t0 < args.seconds:
+        info = one_case(seed)
+        worst["plane"] = max(worst["plane"], info.get("posterior_err_plane", (0.0, 0.0))[0])
+        worst["rescore"] = max(worst["rescore"], info.get("posterior_err_rescore", (0.0, 0.0))[0])
+        seed += 1
+        n += 1
+    print(json.dumps({"cases": n, "first_seed": args.seed, "last_seed": seed - 1, "mismatches": 0,
+                      "worst_posterior_error": worst, "seconds": round(time.time() - t0, 1)}))
+
+
+if __name__ == "__main__":
+    main()
