@@ -98,16 +98,92 @@ def one_case(seed):
     return info
 
 
+def sites_case(seed):
+    """identify_sites / calculate_regulation_probabilities / regulation_pipeline on random gene
+    tables (overlapping genes, regions running off either end, regions shorter than the motif)
+    against the oracle's per-gene loops."""
+    from cgb_b200 import (GeneTable, PackedGenome, PSSMModel, SiteCollection, calculate_regulation_probabilities,
+                          identify_sites)
+    from oracle import c_oracle, np_oracle as O
+    rng = np.random.default_rng(seed)
+    m = int(rng.integers(4, 31))
+    cols = rng.dirichlet([0.5] * 4, size=m)
+    sites = ["".join("ACGT"[rng.choice(4, p=cols[j])] for j in range(m)) for _ in range(int(rng.integers(8, 40)))]
+    M = PSSMModel([SiteCollection(sites)], [1.0])
+    om = O.OracleModel([sites], [1.0])
+    info = {"seed": seed, "m": m}
+    if om.IC < 2.0:
+        return info                                   # threshold near the bulk: millions of sites
+    seqs, tables, ogenes = [], [], []
+    for k in range(int(rng.integers(1, 4))):
+        n = int(rng.integers(2000, 60000))
+        seq = random_sequence(rng, n)
+        genes, pos, strand = [], int(rng.integers(0, 200)), 1
+        while pos + 60 < n:
+            glen = int(rng.integers(30, 900))
+            genes.append(O.OGene(pos, min(n, pos + glen), strand))
+            pos += glen + int(rng.integers(-20, 400))
+            pos = max(0, pos)
+            if rng.random() < 0.4:
+                strand = -strand
+        seqs.append(seq); ogenes.append(genes)
+        tables.append(GeneTable([x.start for x in genes], [x.end for x in genes], [x.strand for x in genes], n,
+                                seq_index=k))
+    g = PackedGenome.from_sequences(seqs)
+    up = int(rng.choice([0, 50, 300, 1000])); dw = int(rng.integers(0, 80)); use_up = bool(rng.random() < 0.5)
+    got = identify_sites(M, g, tables, up, dw, use_up)
+    want = []
+    for k, (seq, genes) in enumerate(zip(seqs, ogenes)):
+        want.extend((k, s) for s in O.identify_sites(om, seq, genes, up if use_up else None, dw))
+    want.sort(key=lambda t: t[1].score, reverse=True)
+    assert len(got) == len(want), (info, len(got), len(want))
+    for a, (k, b) in zip(got, want):
+        assert (a.chromid, a.start, a.end, a.strand, float(a.score), a.gene) == \
+            (k, b.start, b.end, b.strand, float(b.score), b.gene), (info, a, b)
+    info["sites"] = len(got)
+    # posteriors of every gene with a promoter at least one motif long + the one-call pipeline
+    allb = np.concatenate([c_oracle.score_seq(om, s)[2] for s in seqs])
+    M.fit_background(g)
+    O.build_bayesian_estimator(om, allb)
+    if om._std_m < 1e-3 or up + dw < m:
+        return info
+    for k, (seq, genes, gt) in enumerate(zip(seqs, ogenes, tables)):
+        ps, pe = gt.promoter_region_location(up, dw)
+        lens = np.array([len(seq[int(a):int(b)]) for a, b in zip(ps, pe)])
+        if (lens < m).any():
+            continue                                  # the reference raises for such a gene
+        got_p = calculate_regulation_probabilities(M, g, gt, 0.03, 1 / 350.0, up, dw).cpu().numpy()
+        exp = np.array([c_oracle.binding_probability(om, seq[int(a):int(b)], om._mu_m, om._std_m, om._mu_bg,
+                                                     om._std_bg, 0.03, 1 / 350.0) for a, b in zip(ps, pe)])
+        ok = np.isfinite(exp)
+        assert np.max(np.abs(got_p[ok] - exp[ok]), initial=0.0) < 1e-6, (info, "posterior", k)
+    # one-call pipeline on the first replicon alone (it refits the model's estimator to that
+    # replicon's background, so it comes last)
+    seq, gt = seqs[0], tables[0]
+    ps, pe = gt.promoter_region_location(up, dw)
+    if all(len(seq[int(a):int(b)]) >= m for a, b in zip(ps, pe)):
+        b0 = c_oracle.score_seq(om, seq)[2]
+        O.build_bayesian_estimator(om, b0)
+        p2, st2, h2 = M.regulation_pipeline(seq, ps, pe, 0.03, 1 / 350.0)
+        assert int(h2.sum()) == len(b0) and abs(st2[3] - b0.mean()) < 1e-6 and abs(st2[4] - b0.std()) < 1e-6, info
+        exp = np.array([c_oracle.binding_probability(om, seq[int(a):int(b)], om._mu_m, om._std_m, om._mu_bg,
+                                                     om._std_bg, 0.03, 1 / 350.0) for a, b in zip(ps, pe)])
+        ok = np.isfinite(exp)
+        assert np.max(np.abs(p2[ok] - exp[ok]), initial=0.0) < 1e-6, (info, "pipeline posterior")
+    return info
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=120.0)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--mode", choices=["kernels", "sites"], default="kernels")
     args = ap.parse_args()
     t0 = time.time()
     n, seed = 0, args.seed
     worst = {"plane": 0.0, "rescore": 0.0}
     while time.time() - t0 < args.seconds:
-        info = one_case(seed)
+        info = one_case(seed) if args.mode == "kernels" else sites_case(seed)
         worst["plane"] = max(worst["plane"], info.get("posterior_err_plane", (0.0, 0.0))[0])
         worst["rescore"] = max(worst["rescore"], info.get("posterior_err_rescore", (0.0, 0.0))[0])
         seed += 1
