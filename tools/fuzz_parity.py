@@ -173,17 +173,61 @@ def sites_case(seed):
     return info
 
 
+def chunks_case(seed):
+    """The chunked upload of cgbk_regulation_pipeline (tile-range scans as chunks arrive) against
+    the resident whole-sequence path: random sizes, 3 or 4 chunks forced through the tuning
+    knob, non-ACGT runs scattered around (some of them on the cuts)."""
+    from cgb_b200 import PackedGenome, PSSMModel, SiteCollection, _cabi
+    rng = np.random.default_rng(seed)
+    m = int(rng.integers(2, 33))
+    cols = rng.dirichlet([0.5] * 4, size=m)
+    sites = ["".join("ACGT"[rng.choice(4, p=cols[j])] for j in range(m)) for _ in range(20)]
+    n = int(rng.choice([rng.integers(2100, 9000), rng.integers(9000, 200000), rng.integers(200000, 2600000)]))
+    chunks = int(rng.choice([3, 4]))
+    seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n)
+    fr = (0.5, 0.8) if chunks == 3 else (0.35, 0.65, 0.85)
+    for f in fr:
+        cut = int(f * n) // 512 * 512
+        if rng.random() < 0.7 and cut > 40:
+            a = cut + int(rng.integers(-30, 30)); seq[max(0, a):a + int(rng.integers(1, 50))] = ord("N")
+    for _ in range(int(rng.integers(0, 4))):
+        a = int(rng.integers(0, n)); seq[a:a + int(rng.integers(1, 30))] = ord("n")
+    seq = seq.tobytes()
+    n_reg = int(rng.integers(0, 60))
+    starts = np.sort(rng.integers(0, max(1, n - 2 * m - 400), size=n_reg)).astype(np.int64)
+    ends = np.minimum(n, starts + rng.integers(m, 400 + m, size=n_reg)).astype(np.int64)
+    os.environ["CGBK_PIPE_CHUNKS"] = str(chunks)
+    try:
+        M = PSSMModel([SiteCollection(sites)], [1.0])
+        post, stats, hist = M.regulation_pipeline(seq, starts, ends, 0.03, 1 / 350.0)
+    finally:
+        os.environ.pop("CGBK_PIPE_CHUNKS", None)
+    M2 = PSSMModel([SiteCollection(sites)], [1.0])
+    g = PackedGenome.from_sequences([seq])
+    bg = M2.background_stats(g, keep_scores=True)
+    M2.fit_background(bg=bg)
+    st2 = bg["stats"].cpu().numpy()
+    info = {"seed": seed, "m": m, "n": n, "chunks": chunks, "regions": n_reg}
+    assert np.array_equal(hist, bg["hist"].cpu().numpy().astype(np.uint64)), (info, "hist")
+    assert stats[_cabi.BG_N] == st2[_cabi.BG_N] == n - m + 1, (info, "n")
+    assert abs(stats[_cabi.BG_MEAN] - st2[_cabi.BG_MEAN]) < 1e-12 and abs(stats[_cabi.BG_STD] - st2[_cabi.BG_STD]) < 1e-12, info
+    if n_reg and M2._std_m > 1e-3:
+        post2 = M2.binding_probabilities(g, starts, ends, 0.03, 1 / 350.0).cpu().numpy()
+        assert np.max(np.abs(post - post2)) < 1e-12, (info, "posterior", float(np.max(np.abs(post - post2))))
+    return info
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=120.0)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--mode", choices=["kernels", "sites"], default="kernels")
+    ap.add_argument("--mode", choices=["kernels", "sites", "chunks"], default="kernels")
     args = ap.parse_args()
     t0 = time.time()
     n, seed = 0, args.seed
     worst = {"plane": 0.0, "rescore": 0.0}
     while time.time() - t0 < args.seconds:
-        info = one_case(seed) if args.mode == "kernels" else sites_case(seed)
+        info = {"kernels": one_case, "sites": sites_case, "chunks": chunks_case}[args.mode](seed)
         worst["plane"] = max(worst["plane"], info.get("posterior_err_plane", (0.0, 0.0))[0])
         worst["rescore"] = max(worst["rescore"], info.get("posterior_err_rescore", (0.0, 0.0))[0])
         seed += 1
