@@ -202,9 +202,15 @@ int cgbk_background_finalize(double* d_stats, void* stream);
  *                         is CGBK_ERR_INVALID (the reference raises there too)
  *   mu_m, std_m           motif score distribution (binding_model.py:85)
  *   d_scratch             device, >= cgbk_pipeline_scratch_bytes(n_bases, n, m, n_bins)
- *   h_staging             pinned host, >= cgbk_pipeline_staging_bytes(n)
- *   h_post[n]             posteriors; h_stats[CGBK_BG_COUNT]; h_hist[n_bins] (or NULL)
- * Enqueues everything on `stream` and returns after one stream synchronisation. */
+ *   h_staging             host, >= cgbk_pipeline_staging_bytes(n) (pinned: asynchronous upload)
+ *   h_post[n]             posteriors; h_stats[CGBK_BG_COUNT]; h_hist[n_bins] (or NULL).  When
+ *                         these three are pinned the kernels store the results straight into
+ *                         them; otherwise they are copied back (one copy if the buffers are
+ *                         laid out post | stats | hist)
+ * The sequence goes up in one copy on `stream`, or -- from 16 MB on -- in four chunks on an
+ * internal side stream while `stream` packs and scans the chunks that have arrived.  Returns
+ * after one synchronisation of `stream`; the model's estimator is NOT touched (the caller passes
+ * mu_m / std_m and reads mean / std of the background from h_stats). */
 int64_t cgbk_pipeline_scratch_bytes(int64_t n_bases, int n_regions, int m, int n_bins);
 int64_t cgbk_pipeline_staging_bytes(int n_regions);
 int cgbk_regulation_pipeline(cgbk_model* model, const uint8_t* h_ascii, int64_t n_bases,
