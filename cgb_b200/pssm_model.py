@@ -239,6 +239,17 @@ class PSSMModel(TFBindingModel):
             # expected hits at the Patser operating point, with head-room
             nwin = genome.total_windows(m)
             hit_cap = int(2 * nwin * 2.0 ** (-max(self.IC, 0.0)) * 4) + 4096
+        # 16 bytes per hit + 4 x 8 bytes per candidate slot: never ask for more than half of what
+        # the device has free (a low-information motif on a Gbp sequence would otherwise request
+        # hundreds of GB up front; the two-phase retry in _collect_scan still grows the buffers
+        # to the real count, and fails with a clear message if that cannot fit)
+        free_bytes, _ = torch.cuda.mem_get_info(dev)
+        max_cap = max(4096, int(free_bytes // 2 // 48))
+        if hit_cap > max_cap:
+            if getattr(self, "_hit_cap_needed", 0) > max_cap:
+                raise MemoryError("the hit list needs %d entries, the device has room for %d"
+                                  % (self._hit_cap_needed, max_cap))
+            hit_cap = max_cap
         flags = _cabi.RC_REVSEQ_ORDER if revseq_order else _cabi.RC_MATRIX_ORDER
         counters = torch.empty(_cabi.CTR_COUNT, dtype=torch.int64, device=dev)
         cand_cap = 4 * hit_cap
@@ -258,8 +269,10 @@ class PSSMModel(TFBindingModel):
             n_cand, n_hits = int(c[_cabi.CTR_CANDIDATES]), int(c[_cabi.CTR_HITS])
             if n_cand <= pending["cand_cap"] and n_hits <= pending["hit_cap"]:
                 break
+            self._hit_cap_needed = max(n_hits, (n_cand + 3) // 4) + 1024
             pending = self._launch_scan(genome, pending["threshold"], pending["revseq_order"],
-                                        max(n_hits, (n_cand + 3) // 4) + 1024)
+                                        self._hit_cap_needed)
+            self._hit_cap_needed = 0
         self.last_scan_counters = {"candidates": n_cand, "hits": n_hits,
                                    "dirty_tiles": int(c[_cabi.CTR_DIRTY_TILES])}
         # Sort on the device (by packed offset, + strand first: the (seq, pos, strand) order, as
