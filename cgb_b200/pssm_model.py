@@ -243,13 +243,14 @@ class PSSMModel(TFBindingModel):
         # the device has free (a low-information motif on a Gbp sequence would otherwise request
         # hundreds of GB up front; the two-phase retry in _collect_scan still grows the buffers
         # to the real count, and fails with a clear message if that cannot fit)
-        free_bytes, _ = torch.cuda.mem_get_info(dev)
-        max_cap = max(4096, int(free_bytes // 2 // 48))
-        if hit_cap > max_cap:
-            if getattr(self, "_hit_cap_needed", 0) > max_cap:
-                raise MemoryError("the hit list needs %d entries, the device has room for %d"
-                                  % (self._hit_cap_needed, max_cap))
-            hit_cap = max_cap
+        if hit_cap * 48 > (1 << 30):                   # the query costs ~0.1 ms: only for big requests
+            free_bytes, _ = torch.cuda.mem_get_info(dev)
+            max_cap = max(4096, int(free_bytes // 2 // 48))
+            if hit_cap > max_cap:
+                if getattr(self, "_hit_cap_needed", 0) > max_cap:
+                    raise MemoryError("the hit list needs %d entries, the device has room for %d"
+                                      % (self._hit_cap_needed, max_cap))
+                hit_cap = max_cap
         flags = _cabi.RC_REVSEQ_ORDER if revseq_order else _cabi.RC_MATRIX_ORDER
         counters = torch.empty(_cabi.CTR_COUNT, dtype=torch.int64, device=dev)
         cand_cap = 4 * hit_cap
