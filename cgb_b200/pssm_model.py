@@ -559,5 +559,19 @@ def scan_hits_many(models, genome, thresholds=None, revseq_order=True):
     if thresholds is None:
         prepare_thresholds(models)
         thresholds = [None] * len(models)
-    pending = [M._launch_scan(genome, thr, revseq_order) for M, thr in zip(models, thresholds)]
-    return [M._collect_scan(genome, p) for M, p in zip(models, pending)]
+    # launched scans hold their hit buffers until collected: keep at most a quarter of the
+    # device's memory in flight (a Gbp sequence x low-information motifs is GBs per scan)
+    budget = torch.cuda.get_device_properties(genome.device).total_memory // 4
+    results = [None] * len(models)
+    in_flight, held = [], 0
+    for k, (M, thr) in enumerate(zip(models, thresholds)):
+        p = M._launch_scan(genome, thr, revseq_order)
+        in_flight.append((k, M, p))
+        held += p["hits"].numel() * 8
+        while held > budget and len(in_flight) > 1:
+            j, Mj, pj = in_flight.pop(0)
+            held -= pj["hits"].numel() * 8
+            results[j] = Mj._collect_scan(genome, pj)
+    for j, Mj, pj in in_flight:
+        results[j] = Mj._collect_scan(genome, pj)
+    return results
