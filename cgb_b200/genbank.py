@@ -200,10 +200,14 @@ def parse(text):
             block = rec[f0 + 1:o0 if o0 > f0 else len(rec)].decode("ascii", "replace")
             nl = block.find("\n")
             feat_block = block[nl + 1:] if nl >= 0 else ""       # drop the FEATURES header line
-            # anything after the table that starts in column 1 (CONTIG, BASE COUNT) is not a feature
-            mt = re.search(r"^\S", feat_block, re.M)
-            if mt:
-                feat_block = feat_block[:mt.start()]
+            # anything after the table that starts in column 1 (CONTIG, BASE COUNT, ...) is not a
+            # feature: feature lines are indented, so the table ends at the first such line
+            cut = len(feat_block)
+            for word in ("\nCONTIG", "\nBASE COUNT", "\nWGS", "\nCOMMENT"):
+                k = feat_block.find(word)
+                if 0 <= k < cut:
+                    cut = k + 1
+            feat_block = feat_block[:cut]
         sequence = b""
         if o0 >= 0:
             nl = rec.find(b"\n", o0 + 1)
