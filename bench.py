@@ -12,8 +12,8 @@ mean/std -> posterior of regulation of all 3 000 promoters.
 
 value      bp*motif/s with the packed genome already resident in HBM (per-step CUDA
            events; L2 flushed between steps, flush outside the timed span)
-e2e        the same through the public API from pinned HOST bytes: H2D of the
-           ASCII genome + pack + scan + posteriors + D2H of the posteriors
+e2e        the same through the public API from pinned HOST bytes (one C call): H2D of the
+           ASCII genome + pack + scan + posteriors, results landing in pinned host memory
 roofline   the tiled stats-scan kernel (dominant): algorithmic bytes and lookup-adds
            per launch over its CUDA-event duration (cgbk_profile_*)
 at_scale   (N = 1) the two tiled kernels on a 1 Gbp synthetic sequence, i.e. at the
@@ -291,8 +291,8 @@ def run_ours(args):
     launches_per_step = 2                           # stats scan (exact tiles + moment reduction inside), posteriors
     info = _cabi.last_launch_info()
 
-    # ---- the same K steps replayed from a CUDA graph (the step is launch-bound: 3 kernels and
-    # 3 memsets of ~50 us in total).  `value` is taken from these replays; the eager loop above
+    # ---- the same K steps replayed from a CUDA graph (the step is launch-bound: one memset and
+    # two kernels, ~37 us in total).  `value` is taken from these replays; the eager loop above
     # provides the per-kernel CUDA-event time for the roofline.
     graph_mode = "eager"
     if not args.no_graph:
