@@ -27,6 +27,17 @@ class Genome(C.Structure):
                 ("cap_bases", C.c_int64)]
 
 
+class PipelineArgs(C.Structure):
+    """cgbk_pipeline_args (include/cgbk.h)."""
+    _fields_ = [("model", C.c_void_p), ("h_ascii", C.c_void_p), ("n_bases", C.c_int64),
+                ("h_start", C.c_void_p), ("h_end", C.c_void_p), ("n_regions", C.c_int32), ("n_bins", C.c_int32),
+                ("mu_m", C.c_double), ("std_m", C.c_double), ("p_motif", C.c_double), ("alpha", C.c_double),
+                ("hist_lo", C.c_double), ("hist_hi", C.c_double),
+                ("d_scratch", C.c_void_p), ("scratch_bytes", C.c_int64),
+                ("h_staging", C.c_void_p), ("staging_bytes", C.c_int64),
+                ("h_post", C.c_void_p), ("h_stats", C.c_void_p), ("h_hist", C.c_void_p), ("stream", C.c_void_p)]
+
+
 class CgbkError(RuntimeError):
     pass
 
@@ -71,6 +82,7 @@ SYMBOLS = {
                                             C.c_double, C.c_double, C.c_int,
                                             C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cgbk_regulation_pipeline_args": (C.c_int, [C.c_void_p]),
     "cgbk_last_launch_info": (C.c_int, [C.POINTER(C.c_int64)]),
     "cgbk_profile_enable": (C.c_int, [C.c_int]),
     "cgbk_profile_last_ms": (C.c_int, [C.POINTER(C.c_float)]),

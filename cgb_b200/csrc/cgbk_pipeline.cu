@@ -332,3 +332,11 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
     if (e != cudaSuccess) return cgbk_check_cuda(e, "regulation pipeline");
     return CGBK_OK;
 }
+
+extern "C" int cgbk_regulation_pipeline_args(const cgbk_pipeline_args* a) {
+    if (!a) return cgbk_set_error(CGBK_ERR_INVALID, "NULL argument struct");
+    return cgbk_regulation_pipeline(a->model, a->h_ascii, a->n_bases, a->h_start, a->h_end, a->n_regions, a->mu_m,
+                                    a->std_m, a->p_motif, a->alpha, a->hist_lo, a->hist_hi, a->n_bins,
+                                    a->d_scratch, a->scratch_bytes, a->h_staging, a->staging_bytes, a->h_post,
+                                    a->h_stats, a->h_hist, a->stream);
+}

@@ -510,19 +510,27 @@ class PSSMModel(TFBindingModel):
                 self._pipe_host = host
             arr = host.numpy()
             hp = host.data_ptr()
-            plan = {"key": key, "fn": lib.cgbk_regulation_pipeline, "model": self._model(),
-                    "scratch_ptr": scratch.data_ptr(), "scratch_bytes": scratch.numel(), "hp": hp,
-                    "stage_bytes": stage_bytes, "p_post": hp + stage_bytes, "p_stats": hp + stage_bytes + 8 * n,
-                    "p_hist": (hp + stage_bytes + 8 * n + 64) if n_bins > 0 else None,
+            args = _cabi.PipelineArgs()
+            args.model = self._model().value
+            args.n_bases, args.n_regions, args.n_bins = n_bases, n, int(n_bins)
+            args.d_scratch, args.scratch_bytes = scratch.data_ptr(), scratch.numel()
+            args.h_staging, args.staging_bytes = hp, stage_bytes
+            args.h_post, args.h_stats = hp + stage_bytes, hp + stage_bytes + 8 * n
+            args.h_hist = (hp + stage_bytes + 8 * n + 64) if n_bins > 0 else None
+            plan = {"key": key, "fn": lib.cgbk_regulation_pipeline_args, "args": args, "ref": C.addressof(args),
                     "post": arr[stage_bytes:stage_bytes + 8 * n].view(np.float64),
                     "stats": arr[stage_bytes + 8 * n:stage_bytes + 8 * n + 64].view(np.float64),
                     "hist": arr[stage_bytes + 8 * n + 64:stage_bytes + 8 * n + 64 + 8 * n_bins].view(np.uint64)}
             self._pipe_plan = plan
-        _cabi.check(plan["fn"](
-            plan["model"], seq_t.data_ptr(), n_bases, starts.ctypes.data, ends.ctypes.data, n,
-            float(self._mu_m), float(self._std_m), float(p_motif), float(alpha),
-            float(hist_lo), float(hist_hi), int(n_bins), plan["scratch_ptr"], plan["scratch_bytes"],
-            plan["hp"], plan["stage_bytes"], plan["p_post"], plan["p_stats"], plan["p_hist"], self._stream()))
+        # one struct, rewritten in place: the call itself passes a single pointer
+        args = plan["args"]
+        args.h_ascii = seq_t.data_ptr()
+        args.h_start, args.h_end = starts.ctypes.data, ends.ctypes.data
+        args.mu_m, args.std_m = float(self._mu_m), float(self._std_m)
+        args.p_motif, args.alpha = float(p_motif), float(alpha)
+        args.hist_lo, args.hist_hi = float(hist_lo), float(hist_hi)
+        args.stream = self._stream()
+        _cabi.check(plan["fn"](plan["ref"]))
         post, stats, hist = plan["post"].copy(), plan["stats"].copy(), plan["hist"].copy()
         self._mu_bg, self._std_bg = float(stats[_cabi.BG_MEAN]), float(stats[_cabi.BG_STD])
         self._dev_ms_bg = None                         # re-uploaded lazily by _require_estimator

@@ -222,6 +222,29 @@ int cgbk_regulation_pipeline(cgbk_model* model, const uint8_t* h_ascii, int64_t 
                              double* h_post, double* h_stats, unsigned long long* h_hist,
                              void* stream);
 
+/* The same call with its arguments in one struct: a binding keeps the struct alive and only
+ * rewrites the fields that change between calls (a ctypes call with 21 scalar arguments costs
+ * several microseconds of marshalling; with one pointer it costs one). */
+typedef struct {
+    cgbk_model* model;
+    const uint8_t* h_ascii;
+    int64_t n_bases;
+    const int64_t* h_start;
+    const int64_t* h_end;
+    int32_t n_regions;
+    int32_t n_bins;
+    double mu_m, std_m, p_motif, alpha, hist_lo, hist_hi;
+    void* d_scratch;
+    int64_t scratch_bytes;
+    void* h_staging;
+    int64_t staging_bytes;
+    double* h_post;
+    double* h_stats;
+    unsigned long long* h_hist;
+    void* stream;
+} cgbk_pipeline_args;
+int cgbk_regulation_pipeline_args(const cgbk_pipeline_args* args);
+
 /* Launch statistics of the calling thread's last tiled-scan call (for bench.py):
  * out[0] = kernels launched, out[1] = tiles, out[2] = bases per lane segment. */
 int cgbk_last_launch_info(int64_t* out3);
