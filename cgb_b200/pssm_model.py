@@ -483,8 +483,14 @@ class PSSMModel(TFBindingModel):
         if getattr(self, "_mu_m", None) is None:
             pssm_scores = self.score_self()
             self._mu_m, self._std_m = np.mean(pssm_scores), np.std(pssm_scores)
-        starts = np.ascontiguousarray(starts, dtype=np.int64)
-        ends = np.ascontiguousarray(ends, dtype=np.int64)
+        # the same int64 arrays passed again (a loop over genomes sharing one gene layout, the
+        # benchmark): their addresses are remembered with the plan.  Only arrays that needed no
+        # conversion qualify, so in-place edits by the caller are still seen.
+        plan = getattr(self, "_pipe_plan", None)
+        reuse_ptrs = plan is not None and plan.get("starts") is starts and plan.get("ends") is ends
+        if not reuse_ptrs:
+            starts = np.ascontiguousarray(starts, dtype=np.int64)
+            ends = np.ascontiguousarray(ends, dtype=np.int64)
         n = len(starts)
         if hist_lo is None:
             hist_lo = self._score_bounds[0]
@@ -493,8 +499,8 @@ class PSSMModel(TFBindingModel):
         # buffers, pointers and result views for this problem size are set up once and reused:
         # the per-call host work is argument marshalling + three small copies
         key = (n_bases, n, int(n_bins))
-        plan = getattr(self, "_pipe_plan", None)
         if plan is None or plan["key"] != key:
+            reuse_ptrs = False
             lib = _cabi.lib()
             dev = self._dev()
             need = int(lib.cgbk_pipeline_scratch_bytes(n_bases, n, self.length, n_bins))
@@ -525,7 +531,9 @@ class PSSMModel(TFBindingModel):
         # one struct, rewritten in place: the call itself passes a single pointer
         args = plan["args"]
         args.h_ascii = seq_t.data_ptr()
-        args.h_start, args.h_end = starts.ctypes.data, ends.ctypes.data
+        if not reuse_ptrs:
+            args.h_start, args.h_end = starts.ctypes.data, ends.ctypes.data
+            plan["starts"], plan["ends"] = starts, ends                 # keep them alive
         args.mu_m, args.std_m = float(self._mu_m), float(self._std_m)
         args.p_motif, args.alpha = float(p_motif), float(alpha)
         args.hist_lo, args.hist_hi = float(hist_lo), float(hist_hi)
