@@ -1,30 +1,38 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json headline metric on BASELINE configs[1].
+"""bench.py -- BASELINE.json headline metric: PSWM scan bp*motif/s (both strands) at 1/2/4/8 B200,
+and promoter posteriors/s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload ("config2"): LexA 22-bp PSWM (site-count-weighted mix of the six
-test_input.json collections), a synthetic 5 Mbp genome (i.i.d. uniform ACGT,
-PCG64 seed 2 + rank), 3 000 genes laid out every ~1 667 bp on alternating strands,
-promoters = Gene.promoter_region(300, 50).  One step = the hot path over one
-genome: genome-wide both-strand scan -> soft-max background histogram + moments ->
-mean/std -> posterior of regulation of all 3 000 promoters.
+Headline workload (BASELINE configs[4], "config5" of SURVEY.md 8d): a motif set of 500 JASPAR-scale
+PSWMs (length ~U{8..30}, 20 sites each drawn from a Dirichlet(0.5)-column PWM, pseudocount 1,
+seed 5) over ONE synthetic 1 Gbp sequence (i.i.d. uniform ACGT, counter-based generator keyed by
+the global position block, so every rank count sees the same sequence).  The sequence is
+SHARDED over the N ranks (strong scaling): rank r owns the windows that start in its slice and
+carries the (m_max - 1)-base halo; every motif is capped at the shard's own windows.
 
-value      bp*motif/s with the packed genome already resident in HBM (per-step CUDA
-           events; L2 flushed between steps, flush outside the timed span)
-e2e        the same through the public API from pinned HOST bytes (one C call): H2D of the
-           ASCII genome + pack + scan + posteriors, results landing in pinned host memory
-roofline   the tiled stats-scan kernel (dominant): algorithmic bytes and lookup-adds
-           per launch over its CUDA-event duration (cgbk_profile_*)
-at_scale   (N = 1) the two tiled kernels on a 1 Gbp synthetic sequence, i.e. at the
-           size where launch ramp and tile quantisation no longer matter
-N > 1      one genome per rank (BASELINE configs[2] style sharding, no collective)
+One step = for every motif ONE pass of the fused scan over the rank's shard -- background
+histogram + moments of all windows (genome.py:215-226) AND the thresholded both-strand site list at
+the motif's Patser threshold (genome.py:433-445; candidates re-scored exactly, sorted on the
+device) -- followed by ONE NCCL all-reduce of {n, sum, sumsq, histogram} of all motifs and the
+recomputation of mean / std on every rank.
+
+value      bp*motif/s = (sum over motifs of windows) / step time, shard packed and resident in
+           HBM, site lists produced (compacted, sorted) in HBM; CUDA events, max over ranks
+e2e        the same from HOST memory: pinned ASCII shard -> H2D -> pack -> scan -> every site
+           record and every background record back in host memory (+ the all-reduce)
+roofline   the scan kernel over the whole motif set: 2m lookup-adds per bp*motif against
+           SMs * 128 lanes * f_max (the binding bound), HBM bytes nested
+posteriors BASELINE configs[1] (LexA 22 bp, one 5 Mbp genome per rank, 3000 promoters): background
+           fit + posteriors, promoter posteriors/s; its own e2e through cgbk_regulation_pipeline
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import subprocess
 import sys
 import time
 
@@ -34,14 +42,61 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+METRIC = "PSWM scan bp*motif/s (both strands): background record + thresholded sites per motif, sequence-sharded"
+UNIT = "bp*motif/s"
+MOTIF_SEED = 5
+GEN_BLOCK = 1 << 26          # bases per generator block (seeded by the global block number)
+
+# config 2 (the `posteriors` sub-object)
 GENOME_BP = 5_000_000
 N_GENES = 3000
 UP, DOWN = 300, 50
-M_LEN = 22
-METRIC = "PSWM scan bp*motif/s (both strands): background fit + promoter posteriors"
-UNIT = "bp*motif/s"
-WORKLOAD = ("config2: LexA 22-bp PSWM, synthetic 5 Mbp genome per GPU, 3000 promoters x 350 bp "
-            "(background histogram+moments, then posteriors)")
+
+
+def workload_name(n_motifs, bp):
+    return ("config5: %d synthetic JASPAR-scale motifs (8-30 bp, seed %d) x one %d bp synthetic sequence, "
+            "sequence-sharded over the ranks with an (m_max - 1)-base halo; per motif background histogram + "
+            "moments and the Patser-threshold site list in one fused pass; one all-reduce per step"
+            % (n_motifs, MOTIF_SEED, bp))
+
+
+# ----------------------------------------------------------------------------- inputs
+def motif_site_lists(n, seed=MOTIF_SEED):
+    """length ~U{8..30}, 20 sites from a Dirichlet(0.5)-column PWM."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        m = int(rng.integers(8, 31))
+        cols = rng.dirichlet([0.5] * 4, size=m)
+        out.append(["".join("ACGT"[rng.choice(4, p=cols[j])] for j in range(m)) for _ in range(20)])
+    return out
+
+
+def shard_bounds(bp, m_max, world, rank):
+    """Rank's slice of window START positions [lo, lo + cap) and the bases it must hold."""
+    own = (bp + world - 1) // world
+    lo = min(bp, rank * own)
+    cap = max(0, min(own, bp - lo))
+    hi = min(bp, lo + cap + m_max - 1)
+    return lo, cap, hi
+
+
+def generate_bases(lo, hi, dev=None):
+    """ASCII bases [lo, hi) of THE benchmark sequence (a function of the position only)."""
+    import torch
+    if dev is None:
+        gen_dev = torch.device("cpu")
+    else:
+        gen_dev = dev
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=gen_dev)
+    out = torch.empty(hi - lo, dtype=torch.uint8, device=gen_dev)
+    for b0 in range(lo // GEN_BLOCK * GEN_BLOCK, hi, GEN_BLOCK):
+        gen = torch.Generator(device=gen_dev)
+        gen.manual_seed(1000 + b0 // GEN_BLOCK)
+        vals = lut[torch.randint(0, 4, (GEN_BLOCK,), device=gen_dev, generator=gen)]
+        a, b = max(b0, lo), min(b0 + GEN_BLOCK, hi)
+        out[a - lo:b - lo] = vals[a - b0:b - b0]
+    return out
 
 
 def lexa():
@@ -75,7 +130,117 @@ def peaks():
     return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
 
 
+def git_head():
+    try:
+        return subprocess.check_output(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT,
+                                       stderr=subprocess.DEVNULL).decode().strip()
+    except Exception:
+        return None
+
+
+def ncu_traffic(kernel_key):
+    """DRAM traffic per launch of the dominant kernel from the committed ncu capture
+    (profiles/r2_ncu_traffic.json, written from an `ncu --set full` run; null when absent)."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        d = json.load(f)
+    e = d.get(kernel_key)
+    if not e:
+        return None, None
+    return e.get("dram_bytes_per_launch"), {k: e.get(k) for k in ("captured_at_commit", "workload", "source")}
+
+
+def spread(ms):
+    ms = np.asarray(ms, dtype=np.float64)
+    return {"min": float(ms.min()), "median": float(np.median(ms)), "max": float(ms.max())}
+
+
 # ----------------------------------------------------------------------------- CPU arms
+def cpu_motif_job(args):
+    """Reference CPU path for a list of motifs over one sample of the sequence: per motif the
+    background scores of every window (score_seq both strands -> mean / std / histogram) and the
+    thresholded site loop on both strands (genome.py:433-445), oracle/py_port.py."""
+    site_lists, thresholds, seq = args
+    from oracle import np_oracle as O
+    from oracle.py_port import PortModel
+    units = 0
+    hits = 0
+    for sites, thr in zip(site_lists, thresholds):
+        om = O.OracleModel([sites], [1.0])
+        port = PortModel(om)
+        bg = port.score_seq(seq)                                 # soft-max of every window
+        np.mean(bg), np.std(bg)
+        np.histogram(bg, bins=256)
+        hits += len(port.region_hits(seq, 0, thr))
+        units += len(bg)
+    return units, hits
+
+
+def cpu_sample_thresholds(site_lists):
+    """Patser thresholds through the product's host C code (float64, no GPU): the CPU arm times
+    the scan, not the once-per-model threshold DP."""
+    from cgb_b200 import PSSMModel, SiteCollection, prepare_thresholds
+    models = [PSSMModel([SiteCollection(s)], [1.0]) for s in site_lists]
+    prepare_thresholds(models)
+    return [M.threshold() for M in models]
+
+
+_REF_SEQ = None
+
+
+def _ref_worker(args):
+    site_lists, thresholds = args
+    return cpu_motif_job((site_lists, thresholds, _REF_SEQ))
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (Python port with the C inner scan,
+    oracle/py_port.py; the reference tree itself cannot travel to the GPU box and is pinned to the
+    port in the container tests) on all host cores, on a bounded sample of the same workload per
+    step: all motifs x the first `--ref-sample-bp` bases of the same sequence."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import c_oracle
+    c_oracle.build()
+    cores = os.cpu_count() or 1
+    site_lists = motif_site_lists(args.motifs)
+    thresholds = cpu_sample_thresholds(site_lists)
+    global _REF_SEQ
+    _REF_SEQ = generate_bases(0, args.ref_sample_bp).numpy().tobytes()
+    jobs = [(site_lists[c::cores], thresholds[c::cores]) for c in range(cores) if site_lists[c::cores]]
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(len(jobs)) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_ref_worker, jobs)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    units = sum(r[0] for r in res)
+    total = float(np.sum(times))
+    value = units * len(times) / total
+    sample = ("per step all %d motifs x the first %d bases of the benchmark sequence (%d bp*motif), "
+              "%d processes" % (args.motifs, args.ref_sample_bp, units, len(jobs)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "step_ms": spread(np.array(times) * 1e3),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.motifs, args.bp), "motifs": args.motifs, "sequence_bp": args.bp,
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": len(jobs), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
 def cpu_config2(seq_bytes, promoters, bg_slice, lexa_d, site_lists, weights):
     """One config-2 step of the reference's CPU path (oracle/py_port.py) on one core."""
     from oracle import np_oracle as O
@@ -90,121 +255,43 @@ def cpu_config2(seq_bytes, promoters, bg_slice, lexa_d, site_lists, weights):
     return time.perf_counter() - t0, nwin, nprom
 
 
-_REF_SEQ = None     # genome bytes, inherited by the forked workers (not pickled per step)
-
-
-def _ref_worker(args):
-    promoters, bg_slice = args
-    d, site_lists, weights = lexa()
-    t, nwin, nprom = cpu_config2(_REF_SEQ, promoters, bg_slice, d, site_lists, weights)
-    return nwin, nprom
-
-
-def run_reference(args):
-    """--impl reference: the reference's CPU path (Python port, oracle/py_port.py; the
-    reference tree itself cannot travel to the GPU box) on all host cores, on a bounded
-    sample of the same workload per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    import multiprocessing as mp
-    from oracle import c_oracle
-    from cgb_b200.gene_regions import GeneTable, python_slice_bounds
-    c_oracle.build()
-    cores = os.cpu_count() or 1
-    global _REF_SEQ
-    _REF_SEQ = synthetic_genome(GENOME_BP, 2).tobytes()
-    gs, ge, gstrand = gene_layout(GENOME_BP, N_GENES)
-    gt = GeneTable(gs, ge, gstrand, GENOME_BP)
-    ps, pe = python_slice_bounds(*gt.promoter_region_location(UP, DOWN), GENOME_BP)
-    # per step: a 1/10 sample of config 2 (500 kbp of background windows + 300 promoters),
-    # split evenly over the cores
-    sample_bp, sample_prom = GENOME_BP // 10, N_GENES // 10
-    per_bp = sample_bp // cores
-    jobs = []
-    for c in range(cores):
-        lo = c * per_bp
-        proms = [(int(ps[i]), int(pe[i])) for i in range(c, sample_prom, cores)]
-        jobs.append((proms, (lo, lo + per_bp + M_LEN - 1)))
-    ctx = mp.get_context("fork")
-    times = []
-    with ctx.Pool(cores) as pool:
-        for it in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            res = pool.map(_ref_worker, jobs)
-            dt = time.perf_counter() - t0
-            if it >= args.warmup:
-                times.append(dt)
-    nwin = sum(r[0] for r in res)
-    total = float(np.sum(times))
-    value = nwin * len(times) / total
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "sample": "per step 1/10 of config 2: %d background windows + %d promoters" % (nwin, sample_prom)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "1/10 of config 2 per step, %d processes" % cores},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line))
+# ----------------------------------------------------------------------------- host binding
+def bind_to_gpu_numa(dev_index):
+    """Pin this process (and therefore the pages its pinned staging buffers are first touched on)
+    to the CPUs of the GPU's NUMA node.  Returns a description of what was pinned."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(dev_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(dev_index).pci_domain_id
+        devn = torch.cuda.get_device_properties(dev_index).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, devn)
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "no NUMA information for the GPU (single node)"
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return "NUMA node %d has no CPU this process may use" % node
+        os.sched_setaffinity(0, allowed)
+        return "process + pinned staging buffers on NUMA node %d (%d CPUs)" % (node, len(allowed))
+    except Exception as exc:
+        return "not pinned (%s)" % str(exc)[:60]
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def at_scale(M, dev, bp, reps=3):
-    """The two tiled kernels on one `bp`-base synthetic sequence (kernel CUDA-event time)."""
-    import torch
-
-    from cgb_b200 import PackedGenome, _cabi
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(4)
-    g = PackedGenome([bp], dev)
-    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
-    ascii_all = torch.empty(bp, dtype=torch.uint8, device=dev)
-    chunk = 1 << 28
-    for off in range(0, bp, chunk):
-        n = min(chunk, bp - off)
-        ascii_all[off:off + n] = lut[torch.randint(0, 4, (n,), device=dev, generator=gen)]
-    g.pack_into(0, ascii_all)
-    torch.cuda.synchronize()
-    del ascii_all
-    nwin = g.total_windows(M.length)
-    sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    hbm_peak, sm_max, _ = peaks()
-    issue_peak = sms * 128 * sm_max * 1e6
-    out = {"bp": bp, "motif_len": M.length}
-    thr = M.threshold()
-    for mode in ("hit_scan", "stats_scan"):
-        times = []
-        for rep in range(reps + 2):
-            if mode == "hit_scan":
-                M.scan_hits(g, thr)
-            else:
-                M.background_stats(g)
-                torch.cuda.synchronize()
-            if rep >= 2:
-                times.append(_cabi.profile_last_ms())
-        ms = float(np.mean(times))
-        rate = nwin / (ms * 1e-3)
-        out[mode] = {"kernel_ms": ms, "bp_motif_per_s": rate,
-                     "issue_frac": rate * 2 * M.length / issue_peak,
-                     "hbm_frac": nwin * 0.25 / (ms * 1e-3) / 1e9 / hbm_peak}
-        if mode == "hit_scan":
-            out[mode].update(M.last_scan_counters)
-    # what actually bounds both kernels (one `ncu --set full` capture of this leg,
-    # profiles/r1_ncu_scans_1gbp.csv: l1tex__data_pipe_lsu_wavefronts_mem_shared, % of peak)
-    out["smem_wavefront_pct_of_peak_ncu"] = {"hit_scan": 89.4, "stats_scan": 88.5}
-    return out
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from cgb_b200 import GeneTable, PackedGenome, PSSMModel, SiteCollection, _cabi
+    from cgb_b200 import GeneTable, PackedGenome, PSSMModel, SiteCollection, _cabi, prepare_thresholds
+    from cgb_b200 import dist as cdist
+    from cgb_b200 import motif_batch as mb
     from tools.clock_sampler import ClockSampler
 
     rank = int(os.environ.get("RANK", "0"))
@@ -212,8 +299,280 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor(x, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+
+    def sum_over_ranks(x):
+        t = torch.tensor(x, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    # ---- the motif set: tables of all models in one device block, thresholds by the host DP
+    site_lists = motif_site_lists(args.motifs)
+    models = [PSSMModel([SiteCollection(s)], [1.0], device=dev) for s in site_lists]
+    t0 = time.perf_counter()
+    batch = mb.ModelBatch(models, dev)
+    prepare_thresholds(models)
+    thr = [M.threshold() for M in models]
+    setup_s = time.perf_counter() - t0
+    m_len = np.array([M.length for M in models])
+    m_max = int(m_len.max())
+    K = len(models)
+
+    # ---- this rank's shard of THE sequence, packed and resident
+    bp = args.bp
+    lo, cap, hi = shard_bounds(bp, m_max, world, rank)
+    ascii_dev = generate_bases(lo, hi, dev)
+    g = PackedGenome([hi - lo], dev)
+    g.pack_into(0, ascii_dev)
+    torch.cuda.synchronize()
+    pinned = None
+    if not args.no_e2e:
+        pinned = torch.empty(hi - lo, dtype=torch.uint8).pin_memory()
+        pinned.copy_(ascii_dev)
+    del ascii_dev
+    torch.cuda.empty_cache()
+    win_rank = np.array([max(0, min(cap, bp - lo - m + 1)) for m in m_len], dtype=np.float64)   # windows this rank scores
+    win_total = np.array([bp - m + 1 for m in m_len], dtype=np.float64)
+    units_total = float(win_total.sum())
+    exp_hits = np.array([mb.expected_hits(M, cap) * 1.25 + 4096 for M in models])
+    hit_cap = int(min(exp_hits.sum() * 1.05, 1.5e9))
+
+    kern_acc = np.zeros(K)
+
+    def step():
+        res = mb.scan_batch(models, g, thr, n_bins=args.bins, win_cap=cap, to_host=False, recycle=True,
+                            hit_cap=hit_cap, kernel_ms=kern_acc if timing_kernels[0] else None)
+        nbytes = 0
+        if world > 1:
+            nbytes = cdist.allreduce_batch(res["stats"], res["hist"])
+        return res, nbytes
+
+    timing_kernels = [False]
+    # ---- warm-up + the in-run checks (outside the timed region)
+    for _ in range(args.warmup):
+        res, ar_bytes = step()
+    torch.cuda.synchronize()
+    stats = res["stats"].cpu().numpy()
+    hist = res["hist"].cpu().numpy() if res["hist"] is not None else None
+    hits_rank = np.array(res["hits"], dtype=np.float64)
+    hits_all = sum_over_ranks(hits_rank)
+    checks = {"n_equals_bp_minus_m_plus_1": bool(np.array_equal(stats[:, _cabi.BG_N], win_total)),
+              "hist_sums_to_n": bool(hist is None or np.array_equal(hist.sum(axis=1), stats[:, _cabi.BG_N])),
+              "hits_total": float(hits_all.sum())}
+    assert checks["n_equals_bp_minus_m_plus_1"], "window counts after the all-reduce are wrong"
+    assert checks["hist_sums_to_n"], "histograms do not sum to the window counts"
+    if world > 1 and not args.no_check:
+        # rank 0 scans the first motifs over the WHOLE sequence on its own: the sharded, all-reduced
+        # records and the summed site counts must match the one-GPU ones
+        P = min(args.check_motifs, K)
+        ok = 1.0
+        if rank == 0:
+            whole = PackedGenome([bp], dev)
+            whole.pack_into(0, generate_bases(0, bp, dev))
+            one = mb.scan_batch(models[:P], whole, thr[:P], n_bins=args.bins, to_host=False, recycle=True,
+                                hit_cap=int(min(exp_hits[:P].sum() * world * 1.1 + 1e6, 1.5e9)))
+            s1 = one["stats"].cpu().numpy()
+            same_n = np.array_equal(s1[:, _cabi.BG_N], stats[:P, _cabi.BG_N])
+            same_hist = hist is None or np.array_equal(one["hist"].cpu().numpy(), hist[:P])
+            same_hits = np.array_equal(np.array(one["hits"], dtype=np.float64), hits_all[:P])
+            dmean = float(np.max(np.abs(s1[:, _cabi.BG_MEAN] - stats[:P, _cabi.BG_MEAN])))
+            dstd = float(np.max(np.abs(s1[:, _cabi.BG_STD] - stats[:P, _cabi.BG_STD])))
+            checks["sharded_vs_one_gpu"] = {"motifs": P, "same_n": bool(same_n), "same_histogram": bool(same_hist),
+                                            "same_hit_counts": bool(same_hits), "max_abs_dmean": dmean,
+                                            "max_abs_dstd": dstd}
+            ok = float(same_n and same_hist and same_hits and dmean < 1e-9 and dstd < 1e-9)
+            del whole, one
+            mb.release_buffers(dev)
+            torch.cuda.empty_cache()
+        ok = float(max_over_ranks([1.0 - ok])[0] == 0.0)
+        assert ok == 1.0, "sharded run differs from the one-GPU run: %s" % checks.get("sharded_vs_one_gpu")
+
+    # ---- timed: K steps, device-resident
+    sampler = ClockSampler(dev, period_s=0.005)
+    if rank == 0:
+        sampler.start()
+    # every motif's scan kernel is bracketed by its own CUDA event pair on the launching stream
+    # (two event records per ~ms kernel): the roofline's kernel time comes from the timed steps
+    _cabi.profile_enable(2)
+    timing_kernels[0] = True
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        ev[i][0].record()
+        res, ar_bytes = step()
+        ev[i][1].record()
+        launches += res["launches"] + (1 if world > 1 else 0)
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    _cabi.profile_enable(False)
+    timing_kernels[0] = False
+    kern_ms = kern_acc / args.steps
+
+    # all-reduce alone (the collective of the step, same buffer)
+    ar_us = None
+    if world > 1:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        cdist.allreduce_batch(res["stats"].clone(), res["hist"].clone() if res["hist"] is not None else None)
+        barrier()
+        st2, h2 = res["stats"].clone(), (res["hist"].clone() if res["hist"] is not None else None)
+        a.record()
+        for _ in range(reps):
+            cdist.allreduce_batch(st2, h2)
+        b.record()
+        torch.cuda.synchronize()
+        ar_us = float(max_over_ranks([a.elapsed_time(b) / reps * 1e3])[0])
+
+    # ---- end to end from host memory
+    e2e = None
+    if not args.no_e2e:
+        sink_count = [0]
+
+        def sink(k, rec):
+            sink_count[0] += len(rec)
+
+        def e2e_step():
+            gg = PackedGenome.from_sequences(None, dev, pinned=[pinned])        # H2D + pack
+            r = mb.scan_batch(models, gg, thr, n_bins=args.bins, win_cap=cap, to_host=True, sink=sink)
+            if world > 1:
+                rec = np.concatenate([r["stats"][:, :3], r["hist"].astype(np.float64)], axis=1) \
+                    if r["hist"] is not None else r["stats"][:, :3].copy()
+                t = torch.from_numpy(rec).to(dev)
+                dist.all_reduce(t)
+                rec = t.cpu().numpy()
+            return r
+
+        e2e_steps = min(args.steps, args.e2e_steps)
+        for _ in range(min(2, args.warmup)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        sink_count[0] = 0
+        for _ in range(e2e_steps):
+            r = e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_ms = float(max_over_ranks([e2e_s * 1e3 / e2e_steps])[0])
+        d2h = sink_count[0] / e2e_steps * 8 + K * (8 * _cabi.BG_COUNT + 8 * args.bins + 8 * _cabi.CTR_COUNT)
+        d2h_all = float(sum_over_ranks([d2h])[0])
+        h2d_all = float(sum_over_ranks([float(hi - lo)])[0])
+        e2e = {"value": units_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),
+               "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "call": "PackedGenome.from_sequences(pinned ASCII) + motif_batch.scan_batch(to_host=True) "
+                       "-> cgbk_pack_ascii / cgbk_scan_batch / cgbk_sort_hits",
+               "d2h": "every site record (8 B, sorted per motif) and every background record lands in pinned host "
+                      "memory; the sites of one sub-batch cross PCIe while the next sub-batch is scanned",
+               "host_binding": numa}
+        del pinned
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_ms = float(max_over_ranks([float(step_ms.sum())])[0])
+    step_ms_max = max_over_ranks(step_ms.tolist())
+    kern_rank = float(np.nansum(kern_ms))
+    la_rank = float(np.nansum(2.0 * m_len * win_rank * (~np.isnan(kern_ms))))
+
+    # ---- config 2 (posteriors/s), every rank its own genome, no collective
+    post = None
+    if not args.no_posteriors:
+        mb.release_buffers(dev)
+        torch.cuda.empty_cache()
+        post = posteriors_leg(args, dev, rank, world, barrier, max_over_ranks)
+
+    if rank == 0:
+        hbm_peak, sm_max, peak_src = peaks()
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_peak = sms * 128 * sm_max * 1e6
+        value = units_total * args.steps / (total_ms * 1e-3)
+        by_g = {}
+        for G in sorted(set(((m_len + 3) // 4).tolist())):
+            sel = ((m_len + 3) // 4 == G) & ~np.isnan(kern_ms)
+            if sel.any():
+                t = float(kern_ms[sel].sum()) * 1e-3
+                by_g["G%d" % G] = {"motifs": int(sel.sum()), "kernel_ms_mean": float(kern_ms[sel].mean()),
+                                   "bp_motif_per_s": float(win_rank[sel].sum() / t),
+                                   "issue_frac": float((2.0 * m_len[sel] * win_rank[sel]).sum() / t / issue_peak)}
+        traffic, traffic_src = ncu_traffic("fused_scan_1gbp_m22")
+        roofline = {
+            "bound": "issue", "kernel": "fast_scan_kernel<G, hist+moments+candidates> (fused scan), all %d motifs" % K,
+            "achieved": la_rank / (kern_rank * 1e-3), "peak": issue_peak, "unit": "lookup-add/s",
+            "frac": la_rank / (kern_rank * 1e-3) / issue_peak,
+            "definition": "algorithmic 2*m lookup-adds per bp*motif (SURVEY 8d) x windows of this rank's shard, over the "
+                          "CUDA-event time of the scan kernels alone (one event pair per motif, on the launching stream); "
+                          "peak = SMs x 128 lanes x f_max; north_star's scan roofline is the slower of this and HBM, "
+                          "this one binds",
+            "kernel_ms_per_step": kern_rank, "kernel_share_of_step": kern_rank / (float(step_ms.mean())),
+            "traffic": traffic, "traffic_source": traffic_src,
+            "hbm": {"achieved": float(np.nansum(0.25 * win_rank * (~np.isnan(kern_ms)))) / (kern_rank * 1e-3) / 1e9,
+                    "peak": hbm_peak, "unit": "GB/s",
+                    "frac": float(np.nansum(0.25 * win_rank * (~np.isnan(kern_ms)))) / (kern_rank * 1e-3) / 1e9 / hbm_peak,
+                    "algorithmic_bytes_per_step": float(0.25 * win_rank.sum())},
+            "by_group_count": by_g, "peak_source": peak_src,
+        }
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu:
+            from oracle import c_oracle
+            c_oracle.build()
+            n_s = args.cpu_sample_bp
+            seq_s = generate_bases(0, n_s).numpy().tobytes()
+            t0 = time.perf_counter()
+            units_cpu, hits_cpu = cpu_motif_job((site_lists, thr, seq_s))
+            t_cpu = time.perf_counter() - t0
+            cpu_baseline = {"value": units_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": "all %d motifs x the first %d bases of the benchmark sequence once "
+                                      "(%d bp*motif, %.1f s on one core)" % (K, n_s, units_cpu, t_cpu)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "step_ms": spread(step_ms_max),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int32 fixed point (2^-21..2^-28 per motif) scan, f64 exact re-score of site candidates, f64 moments",
+            "data": "synthetic",
+            "config": {"workload": workload_name(K, bp), "motifs": K, "sequence_bp": bp,
+                       "motif_lengths": "8-30 (mean %.1f)" % float(m_len.mean()), "hist_bins": args.bins,
+                       "windows_x_motifs_per_step": units_total, "shard_bp_per_rank": int(hi - lo),
+                       "halo_bases": m_max - 1,
+                       "collective": "one all-reduce(SUM) of float64 [%d][3 + %d] per step (%d bytes)"
+                                     % (K, args.bins, int(ar_bytes)) if world > 1 else "none (one rank)",
+                       "allreduce_us": ar_us,
+                       "l2": "inputs larger than L2 (packed shard %.0f MB per pass, %d passes per step)"
+                             % ((hi - lo) / 4e6, K),
+                       "timing": "per-step CUDA events on the launching stream, barrier + synchronize on both sides, "
+                                 "max over ranks",
+                       "hit_buffer_records": hit_cap,
+                       "sites_per_step": checks["hits_total"], "model_setup_s": setup_s},
+            "checks": checks, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": int(launches), "posteriors": post,
+            "clocks": clocks, "wall_s_timed_loop": wall, "commit": git_head(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    del batch
+
+
+def posteriors_leg(args, dev, rank, world, barrier, max_over_ranks):
+    """BASELINE configs[1]: LexA 22-bp PSWM, one synthetic 5 Mbp genome per rank, 3000 promoters x
+    350 bp: genome-wide background histogram + moments, then the posterior of every promoter."""
+    import torch
+
+    from cgb_b200 import GeneTable, PackedGenome, PSSMModel, SiteCollection, _cabi
 
     d, site_lists, weights = lexa()
     prior, alpha = d["prior_regulation_probability"], d["alpha"]
@@ -223,210 +582,124 @@ def run_ours(args):
     gs, ge, gstrand = gene_layout(GENOME_BP, N_GENES)
     gt = GeneTable(gs, ge, gstrand, GENOME_BP)
     ps, pe = gt.promoter_region_location(UP, DOWN)
-
     g = PackedGenome.from_sequences(None, dev, pinned=[pinned])
     desc = M.promoter_descriptors(g, ps, pe)
     n_windows = g.total_windows(M.length)
-    n_post_windows = int(desc[1].sum().item())
     bg = M.background_stats(g, n_bins=256, keep_scores=True)
-    M.fit_background(bg=bg, sync=True)            # also scores the model's own sites once (mu_m, std_m)
+    M.fit_background(bg=bg, sync=True)
     post = torch.empty(N_GENES, dtype=torch.float64, device=dev)
-    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    _cabi.profile_enable(True)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step():
         M.background_stats(g, out=bg, keep_scores=True)
         M.fit_background(bg=bg, sync=False)
         M.binding_probabilities(g, None, None, prior, alpha, out=post, region_tensors=desc)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    # per-kernel time of the stats scan (eager launches, CUDA events inside the library)
+    _cabi.profile_enable(1)
+    kern = []
+    for i in range(8):
+        step()
         torch.cuda.synchronize()
-
-    post_host = torch.empty(N_GENES, dtype=torch.float64).pin_memory()
-    stats_host = torch.empty(_cabi.BG_COUNT, dtype=torch.float64).pin_memory()
-
-    def e2e_step():
-        # the reference-facing host-buffer call (cgbk_regulation_pipeline through
-        # PSSMModel.regulation_pipeline): pinned host ASCII + promoter slices in, host
-        # posteriors / background moments / histogram out
-        return M.regulation_pipeline(pinned, ps, pe, prior, alpha, n_bins=256)
-
-    def e2e_step_multi_call():
-        # the same through the individual batched calls (pack, stats, posteriors)
-        gg = PackedGenome.from_sequences(None, dev, pinned=[pinned])
-        b = M.background_stats(gg, n_bins=256, keep_scores=True)
-        M.fit_background(bg=b, sync=False)
-        p = M.binding_probabilities(gg, ps, pe, prior, alpha, out=post)
-        post_host.copy_(p, non_blocking=True)
-        stats_host.copy_(b["stats"], non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        return post_host, stats_host
-
-    for _ in range(args.warmup):
-        step()
+        if i >= 3:
+            kern.append(_cabi.profile_last_ms())
         flush.zero_()
-    for _ in range(max(3, args.warmup)):
-        e2e_step()
-    barrier()
-    sampler = ClockSampler(dev)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kern_ms = []
-    barrier()
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        ev[i][0].record()
-        step()
-        ev[i][1].record()
-        kern_ms.append(_cabi.profile_last_ms())     # syncs on the scan kernel's stop event
-        flush.zero_()                               # L2 flush, outside the timed span
-    barrier()
-    wall = time.perf_counter() - t_wall0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    eager_total_ms = float(np.sum(step_ms))
-    total_ms = eager_total_ms
-    launches_per_step = 2                           # stats scan (exact tiles + moment reduction inside), posteriors
-    info = _cabi.last_launch_info()
-
-    # ---- the same K steps replayed from a CUDA graph (the step is launch-bound: one memset and
-    # two kernels, ~37 us in total).  `value` is taken from these replays; the eager loop above
-    # provides the per-kernel CUDA-event time for the roofline.
-    graph_mode = "eager"
-    if not args.no_graph:
-        try:
-            _cabi.profile_enable(False)             # event records are not wanted inside the graph
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                step()
-            torch.cuda.current_stream(dev).wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                step()
-            for _ in range(3):
-                graph.replay()
-                flush.zero_()
-            barrier()
-            for i in range(args.steps):
-                ev[i][0].record()
-                graph.replay()
-                ev[i][1].record()
-                flush.zero_()
-            barrier()
-            total_ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
-            graph_mode = "cuda_graph"
-        except Exception as exc:                    # keep the eager number
-            graph_mode = "eager (graph capture failed: %s)" % str(exc)[:80]
-            total_ms = eager_total_ms
-        finally:
-            _cabi.profile_enable(True)
-
-    # ---- end to end through the public API, from pinned host memory (no profiling events)
     _cabi.profile_enable(False)
+    # the step replayed from a CUDA graph (one memset + two kernels): `inner` replays per timed
+    # step, L2 flushed before each timed step
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        step()
+    cold, warm = [], []
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(3 + args.post_steps):
+        flush.zero_()
+        a.record(); graph.replay(); b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            cold.append(a.elapsed_time(b))
+    inner = 200
+    for i in range(2 + 5):
+        a.record()
+        for _ in range(inner):
+            graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            warm.append(a.elapsed_time(b) / inner)
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    # end to end through the host-buffer call
+    for _ in range(5):
+        M.regulation_pipeline(pinned, ps, pe, prior, alpha, n_bins=256)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    for _ in range(3):
-        e2e_step_multi_call()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step_multi_call()
-    torch.cuda.synchronize()
-    e2e_multi_s = time.perf_counter() - t0
-    _cabi.profile_enable(True)
-    clocks = sampler.stop() if rank == 0 else None
-
-    tt = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(tt[0].item()), float(tt[1].item())
-
+    e2e_ms = []
+    for _ in range(args.post_steps):
+        t0 = time.perf_counter()
+        M.regulation_pipeline(pinned, ps, pe, prior, alpha, n_bins=256)
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    barrier()
+    cold_med = float(max_over_ranks([float(np.median(cold))])[0])
+    warm_med = float(max_over_ranks([float(np.median(warm))])[0])
+    e2e_med = float(max_over_ranks([float(np.median(e2e_ms))])[0])
+    out = None
     if rank == 0:
-        units = n_windows * world * args.steps          # bp*motif (1 motif), all ranks
-        value = units / (total_ms * 1e-3)
-        e2e_value = units / (e2e_ms * 1e-3)
-        hbm_peak, sm_max, peak_src = peaks()
-        k_ms = float(np.mean(kern_ms))
-        alg_bytes = n_windows * 0.25                    # 0.25 B per bp per pass
-        lookup_adds = n_windows * 2 * M_LEN             # 2m lookup-adds per bp*motif
+        hbm_peak, sm_max, _ = peaks()
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        issue_peak = sms * 128 * sm_max * 1e6
-        roofline = {
-            "bound": "hbm", "kernel": "fast_scan_kernel<G=6, stats> on one 5 Mbp genome",
-            "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one
-            # `ncu --set full` capture (profiles/r1_ncu_stats_bench.csv): 1.956 MB read + 10.8 KB written per launch
-            "traffic": 1966592, "algorithmic_bytes": alg_bytes,
-            "peak_source": peak_src, "kernel_ms": k_ms,
-            "issue": {"achieved": lookup_adds / (k_ms * 1e-3), "peak": issue_peak, "unit": "lookup-add/s",
-                      "frac": lookup_adds / (k_ms * 1e-3) / issue_peak,
-                      "note": "north_star scan roofline = slower of HBM bytes and 2m lookup-adds at "
-                              "SMs*128 lanes*f_max; the issue bound binds"},
+        k_ms = float(np.mean(kern))
+        out = {
+            "workload": "config2: LexA 22-bp PSWM, one synthetic 5 Mbp genome per rank, 3000 promoters x 350 bp "
+                        "(genome-wide background histogram + moments, then posteriors); no collective",
+            "promoter_posteriors_per_s": world * N_GENES / (cold_med * 1e-3),
+            "bp_motif_per_s": world * n_windows / (cold_med * 1e-3),
+            "step_ms_l2_flushed": spread(cold), "step_ms_l2_warm_200_replays": spread(warm),
+            "timing": "CUDA-graph replay of the step (1 memset + 2 kernels), CUDA events; max over ranks of the median",
+            "stats_kernel_us": k_ms * 1e3,
+            "stats_kernel_issue_frac": n_windows * 2 * M.length / (k_ms * 1e-3) / (sms * 128 * sm_max * 1e6),
+            "e2e": {"ms_per_step": e2e_med, "step_ms": spread(e2e_ms),
+                    "promoter_posteriors_per_s": world * N_GENES / (e2e_med * 1e-3),
+                    "bp_motif_per_s": world * n_windows / (e2e_med * 1e-3),
+                    "h2d_bytes_per_step": int(pinned.numel()) + 12 * N_GENES + 16,
+                    "d2h_bytes_per_step": N_GENES * 8 + 64 + 256 * 8,
+                    "call": "PSSMModel.regulation_pipeline -> cgbk_regulation_pipeline (host buffers)"},
         }
-        cpu_baseline = None
-        scale = None
         if world == 1 and not args.no_cpu:
             from oracle import c_oracle
             c_oracle.build()
             s2, e2 = np.clip(ps, 0, GENOME_BP), np.clip(pe, 0, GENOME_BP)
-            t_cpu, nwin_cpu, nprom_cpu = cpu_config2(host.tobytes(), [(int(a), int(b)) for a, b in zip(s2, e2)],
-                                                     None, d, site_lists, weights)
-            cpu_baseline = {"value": nwin_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-                            "sample": "the full config-2 step once (%d windows + %d promoters, %.1f s)"
-                                      % (nwin_cpu, nprom_cpu, t_cpu)}
-        if world == 1 and not args.no_scale:
-            del flush
-            torch.cuda.empty_cache()
-            scale = at_scale(M, dev, args.scale_bp)
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32 fixed point (2^-24 for this motif) + f64 moments/posterior",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "genome_bp": GENOME_BP, "promoters": N_GENES, "posterior_windows": n_post_windows,
-                       "l2": "flushed between steps (512 MiB memset, outside the timed span)",
-                       "timing": "per-step CUDA events, max over ranks; value: %s; roofline kernel time: eager steps"
-                                 % graph_mode,
-                       "eager_ms_per_step": eager_total_ms / args.steps, "tiles": info["tiles"],
-                       "lane_bases": info["lane_bases"], "sharding": "one genome per rank, no collective"},
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel()) + 12 * N_GENES + 16,
-                    "d2h_bytes_per_step": N_GENES * 8 + 64 + 256 * 8, "ms_per_step": e2e_ms / args.steps,
-                    "call": "PSSMModel.regulation_pipeline -> cgbk_regulation_pipeline (host buffers)",
-                    "d2h": "posteriors + stats + histogram land in the pinned host buffer inside the call "
-                           "(stored over PCIe by the finalising kernels; a D2H copy for pageable buffers)",
-                    "multi_call_ms_per_step": 1e3 * e2e_multi_s / args.steps},
-            "gpu_launches": launches_per_step * args.steps,
-            # SURVEY.md 8d's second figure: promoters / time of (background fit + posterior kernels)
-            "promoter_posteriors_per_s": world * N_GENES / (total_ms * 1e-3 / args.steps),
-            "clocks": clocks, "wall_s_timed_loop": wall, "at_scale": scale,
-        }
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+            # a tenth of the step (500 kbp of background windows + 300 promoters) on one core
+            proms = [(int(x), int(y)) for x, y in zip(s2[:N_GENES // 10], e2[:N_GENES // 10])]
+            t_cpu, nwin_cpu, nprom_cpu = cpu_config2(host.tobytes(), proms, (0, GENOME_BP // 10), d, site_lists, weights)
+            out["cpu_baseline"] = {"promoter_posteriors_per_s": nprom_cpu / t_cpu, "bp_motif_per_s": nwin_cpu / t_cpu,
+                                   "cores": 1, "kind": "port",
+                                   "sample": "1/10 of the step (%d windows + %d promoters, %.1f s)"
+                                             % (nwin_cpu, nprom_cpu, t_cpu)}
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-scale", action="store_true", help="skip the at_scale leg")
-    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
-    ap.add_argument("--scale-bp", type=int, default=1_000_000_000)
+    ap.add_argument("--motifs", type=int, default=500)
+    ap.add_argument("--bp", type=int, default=1_000_000_000)
+    ap.add_argument("--bins", type=int, default=256)
+    ap.add_argument("--e2e-steps", type=int, default=3, help="end-to-end steps (each moves every site record to the host)")
+    ap.add_argument("--post-steps", type=int, default=30, help="timed steps of the posteriors leg")
+    ap.add_argument("--check-motifs", type=int, default=8, help="motifs of the sharded-vs-one-GPU check (N > 1)")
+    ap.add_argument("--cpu-sample-bp", type=int, default=20_000)
+    ap.add_argument("--ref-sample-bp", type=int, default=100_000)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
+    ap.add_argument("--no-posteriors", action="store_true", help="skip the config-2 leg")
+    ap.add_argument("--no-check", action="store_true", help="skip the sharded-vs-one-GPU check")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -11,7 +11,8 @@ from .pssm_model import PSSMModel, prepare_thresholds, scan_hits_many
 from .site_collection import SiteCollection
 from .site_search import Site, calculate_regulation_probabilities, identify_sites
 from .genome import Chromid, Genome, get_prior
-from . import genbank, operons
+from . import genbank, operons, motif_batch
+from .motif_batch import ModelBatch, scan_batch, unpack_hits
 
 __all__ = ["TFBindingModel", "PSSMModel", "SiteCollection", "PackedGenome", "GeneTable",
-           "Site", "Genome", "Chromid", "get_prior", "prepare_thresholds", "genbank", "operons", "identify_sites", "scan_hits_many", "calculate_regulation_probabilities", "python_slice_bounds"]
+           "Site", "Genome", "ModelBatch", "scan_batch", "unpack_hits", "motif_batch", "Chromid", "get_prior", "prepare_thresholds", "genbank", "operons", "identify_sites", "scan_hits_many", "calculate_regulation_probabilities", "python_slice_bounds"]

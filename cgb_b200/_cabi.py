@@ -75,6 +75,25 @@ SYMBOLS = {
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_int64, C.c_void_p]),
     "cgbk_background_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cgbk_background_finalize_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "cgbk_profile_batch_ms": (C.c_int, [C.POINTER(C.c_float), C.c_int]),
+    "cgbk_model_batch_create": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p,
+                                           C.POINTER(C.c_void_p)]),
+    "cgbk_model_batch_get": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "cgbk_model_batch_size": (C.c_int, [C.c_void_p]),
+    "cgbk_model_batch_destroy": (None, [C.c_void_p]),
+    "cgbk_score_sites_host": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
+    "cgbk_region_stats_workspace_bytes": (C.c_int64, []),
+    "cgbk_background_stats_regions": (C.c_int, [C.c_void_p, C.POINTER(Genome), C.c_void_p, C.c_void_p, C.c_int,
+                                                 C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                                 C.c_void_p, C.c_int64, C.c_void_p]),
+    "cgbk_scan_batch_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "cgbk_scan_batch": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Genome), C.c_void_p, C.c_int64,
+                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "cgbk_sort_hits_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "cgbk_sort_hits": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "cgbk_pipeline_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int, C.c_int]),
     "cgbk_pipeline_staging_bytes": (C.c_int64, [C.c_int]),
     "cgbk_regulation_pipeline": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int,
@@ -102,7 +121,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.cgbk_version() != 100:
+        if L.cgbk_version() != 200:
             raise CgbkError("libcgbk.so version %d does not match the Python layer" % L.cgbk_version())
         _lib = L
     return _lib
@@ -121,7 +140,14 @@ def check(status):
 
 
 def profile_enable(on=True):
-    check(lib().cgbk_profile_enable(1 if on else 0))
+    """False / True, or 2: per-model kernel times of cgbk_scan_batch as well."""
+    check(lib().cgbk_profile_enable(int(on)))
+
+
+def profile_batch_ms(n):
+    out = (C.c_float * n)()
+    check(lib().cgbk_profile_batch_ms(out, n))
+    return list(out)
 
 
 def profile_last_ms():

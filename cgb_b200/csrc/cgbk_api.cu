@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -49,7 +50,7 @@ extern "C" int cgbk_profile_enable(int on) {
         CUDA_TRY(cudaEventCreate(&g_prof_ev[0]));
         CUDA_TRY(cudaEventCreate(&g_prof_ev[1]));
     }
-    g_prof_on = on ? 1 : 0;
+    g_prof_on = on;
     g_prof_valid = 0;
     return CGBK_OK;
 }
@@ -62,8 +63,78 @@ extern "C" int cgbk_profile_last_ms(float* ms) {
     return CGBK_OK;
 }
 
+// per-launch timing of a batched scan (cgbk_profile_enable(2)): one event pair per model's scan
+// kernel, read back with cgbk_profile_batch_ms
+static thread_local std::vector<cudaEvent_t>* g_prof_pool = nullptr;
+static thread_local int g_prof_pairs = 0;
+
+static cudaError_t prof_pair_event(int pair, int which, cudaStream_t st) {
+    if (!g_prof_pool) g_prof_pool = new std::vector<cudaEvent_t>();
+    const size_t idx = 2 * (size_t)pair + which;
+    while (g_prof_pool->size() <= idx) {
+        cudaEvent_t e;
+        cudaError_t rc = cudaEventCreate(&e);
+        if (rc != cudaSuccess) return rc;
+        g_prof_pool->push_back(e);
+    }
+    return cudaEventRecord((*g_prof_pool)[idx], st);
+}
+
+extern "C" int cgbk_profile_batch_ms(float* ms, int n) {
+    if (!ms || n < 0) return cgbk_set_error(CGBK_ERR_INVALID, "bad argument");
+    if (n > g_prof_pairs) return cgbk_set_error(CGBK_ERR_INVALID, "only %d launches were timed", g_prof_pairs);
+    for (int k = 0; k < n; ++k) {
+        CUDA_TRY(cudaEventSynchronize((*g_prof_pool)[2 * k + 1]));
+        CUDA_TRY(cudaEventElapsedTime(ms + k, (*g_prof_pool)[2 * k], (*g_prof_pool)[2 * k + 1]));
+    }
+    return CGBK_OK;
+}
+
 #define PROF_START(st) do { if (g_prof_on) CUDA_TRY(cudaEventRecord(g_prof_ev[0], (st))); } while (0)
 #define PROF_STOP(st) do { if (g_prof_on) { CUDA_TRY(cudaEventRecord(g_prof_ev[1], (st))); g_prof_valid = 1; } } while (0)
+
+// Multiprocessor count per device, queried once per device (lock-free: a race only repeats the
+// query).  Launch sizes follow the device the handle lives on, not a literal.
+int cgbk_device_sms(int device) {
+    static std::atomic<int> cache[64];
+    if (device < 0 || device >= 64) return 148;
+    int v = cache[device].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        int q = 0;
+        if (cudaDeviceGetAttribute(&q, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || q <= 0) {
+            cudaGetLastError();
+            q = 148;
+        }
+        cache[device].store(q, std::memory_order_relaxed);
+        v = q;
+    }
+    return v;
+}
+
+int cgbk_current_sms() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }
+    return cgbk_device_sms(dev);
+}
+
+// Every entry point that takes a handle runs on the handle's device: if another device is
+// current it is switched for the duration of the call and restored on return.
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) {
+            err = cudaSetDevice(device);
+            changed = err == cudaSuccess;
+        }
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(dev)                                                    \
+    DeviceGuard _guard(dev);                                              \
+    if (_guard.err != cudaSuccess) return cgbk_check_cuda(_guard.err, "selecting the handle's device")
 
 extern "C" int cgbk_version(void) { return CGBK_VERSION; }
 extern "C" const char* cgbk_last_error(void) { return g_err; }
@@ -268,8 +339,14 @@ static void group_partial(const double* tab, int m, int g, int e, double* out) {
     *out = s;
 }
 
-extern "C" int cgbk_model_create(const double* lo, int m, int device, cgbk_model** out) {
-    if (!lo || !out) return cgbk_set_error(CGBK_ERR_INVALID, "NULL argument");
+// Sizes of the three parts of a model's device block: exact tables | int32 group tables |
+// 16-bit filter tables (the last written per threshold by ensure_coarse)
+static size_t model_exact_bytes() { return (sizeof(double) * 2 * CGBK_EXACT_DOUBLES + 255) / 256 * 256; }
+static size_t model_precise_bytes(int G) { return (sizeof(uint32_t) * 256 * 2 * G + 255) / 256 * 256; }
+static size_t model_coarse_bytes(int G) { return (sizeof(uint32_t) * 256 * G + 255) / 256 * 256; }
+static size_t model_block_bytes(int G) { return model_exact_bytes() + model_precise_bytes(G) + model_coarse_bytes(G); }
+
+static int validate_logodds(const double* lo, int m) {
     if (m < 1) return cgbk_set_error(CGBK_ERR_INVALID, "motif length must be >= 1");
     if (m > CGBK_MAX_MOTIF)
         return cgbk_set_error(CGBK_ERR_UNSUPPORTED, "motif length %d exceeds CGBK_MAX_MOTIF=%d", m, CGBK_MAX_MOTIF);
@@ -277,9 +354,13 @@ extern "C" int cgbk_model_create(const double* lo, int m, int device, cgbk_model
         if (!isfinite(lo[i]))
             return cgbk_set_error(CGBK_ERR_INVALID, "non-finite log-odds at position %d (zero probability "
                                   "without pseudocounts is not supported)", i / 4);
-    CUDA_TRY(cudaSetDevice(device));
-    cgbk_model* M = (cgbk_model*)calloc(1, sizeof(cgbk_model));
-    M->m = m; M->G = (m + 3) / 4; M->device = device;
+    return CGBK_OK;
+}
+
+// Host side of a model: float64 tables of both strands, column means, fixed-point scale; and the
+// image of its device block (exact tables + int32 group tables; the filter part stays unwritten).
+static void build_model_host(const double* lo, int m, int device, cgbk_model* M, unsigned char* image) {
+    M->m = m; M->G = (m + 3) / 4; M->device = device; M->sms = cgbk_device_sms(device);
     double ic;
     pssm_stats(lo, m, &ic, &M->min_score, &M->max_score);
     double R = 0.0;
@@ -350,35 +431,172 @@ extern "C" int cgbk_model_create(const double* lo, int m, int device, cgbk_model
         ex[CGBK_EXACT_TAB_OFFSET + CGBK_MAXM * 8 + 2 * i] = ex[CGBK_MAXM * 8 + i];
         ex[CGBK_EXACT_TAB_OFFSET + CGBK_MAXM * 8 + 2 * i + 1] = ex[CGBK_MAXM * 9 + i];
     }
-    // one device block per model: exact tables | int32 group tables | 16-bit filter tables
-    const size_t exact_bytes = (sizeof(double) * 2 * CGBK_EXACT_DOUBLES + 255) / 256 * 256;
-    const size_t precise_bytes = (sizeof(uint32_t) * 256 * 2 * G + 255) / 256 * 256;
-    const size_t coarse_bytes = sizeof(uint32_t) * 256 * G;
+    memcpy(image, ex.data(), sizeof(double) * 2 * CGBK_EXACT_DOUBLES);
+    chunked_layout(precise.data(), 2 * G, (uint32_t*)(image + model_exact_bytes()));
+    M->coarse_valid = 0;
+}
+
+static void bind_model_block(cgbk_model* M, unsigned char* block) {
+    M->d_exact = (double*)block;
+    M->d_precise = (uint32_t*)(block + model_exact_bytes());
+    M->d_coarse = (uint32_t*)(block + model_exact_bytes() + model_precise_bytes(M->G));
+}
+
+extern "C" int cgbk_model_create(const double* lo, int m, int device, cgbk_model** out) {
+    if (!lo || !out) return cgbk_set_error(CGBK_ERR_INVALID, "NULL argument");
+    int rc = validate_logodds(lo, m);
+    if (rc) return rc;
+    ON_DEVICE(device);
+    cgbk_model* M = (cgbk_model*)calloc(1, sizeof(cgbk_model));
+    const int G = (m + 3) / 4;
+    std::vector<unsigned char> image(model_block_bytes(G), 0);
+    build_model_host(lo, m, device, M, image.data());
     unsigned char* block = nullptr;
-    if (cudaMalloc((void**)&block, exact_bytes + precise_bytes + coarse_bytes) != cudaSuccess) {
-        cgbk_model_destroy(M);
+    if (cudaMalloc((void**)&block, model_block_bytes(G)) != cudaSuccess) {
+        free(M);
         return cgbk_set_error(CGBK_ERR_CUDA, "cudaMalloc of model tables failed");
     }
-    M->d_exact = (double*)block;
-    M->d_precise = (uint32_t*)(block + exact_bytes);
-    M->d_coarse = (uint32_t*)(block + exact_bytes + precise_bytes);
-    cudaError_t c1 = cudaMemcpy(M->d_exact, ex.data(), sizeof(double) * 2 * CGBK_EXACT_DOUBLES, cudaMemcpyHostToDevice);
-    std::vector<uint32_t> precise_ch(precise.size());
-    chunked_layout(precise.data(), 2 * G, precise_ch.data());
-    cudaError_t c2 = cudaMemcpy(M->d_precise, precise_ch.data(), sizeof(uint32_t) * precise_ch.size(), cudaMemcpyHostToDevice);
-    if (c1 != cudaSuccess || c2 != cudaSuccess) {
+    M->owns_block = 1;
+    bind_model_block(M, block);
+    if (cudaMemcpy(block, image.data(), model_exact_bytes() + model_precise_bytes(G), cudaMemcpyHostToDevice) !=
+        cudaSuccess) {
         cgbk_model_destroy(M);
         return cgbk_set_error(CGBK_ERR_CUDA, "upload of model tables failed");
     }
-    M->coarse_valid = 0;
     *out = M;
     return CGBK_OK;
 }
 
 extern "C" void cgbk_model_destroy(cgbk_model* M) {
     if (!M) return;
-    if (M->d_exact) cudaFree(M->d_exact);      // one block: d_precise and d_coarse live inside it
-    free(M);
+    if (M->owns_block && M->d_exact) cudaFree(M->d_exact);   // one block: d_precise and d_coarse live inside it
+    if (M->owns_block) free(M);                               // batch members are freed with their batch
+}
+
+// K models of one device: ONE device allocation and ONE upload (ordered on `stream`) instead of
+// K synchronous allocate + copy pairs.  The reference builds one PSSMModel per genome in its
+// go() loop (cgb/__init__.py:673-686, pssm_model.py:31-35); a motif set or a genome batch builds
+// them all here.
+struct cgbk_model_batch {
+    int n;
+    int device;
+    cgbk_model* models;          // [n]
+    unsigned char* d_block;      // all device tables
+    unsigned char* h_image;      // pinned staging of the upload (kept until destroy)
+};
+
+extern "C" int cgbk_model_batch_create(const double* logodds, const int* m, int n, int device, void* stream,
+                                       cgbk_model_batch** out) {
+    if (!logodds || !m || !out || n < 1) return cgbk_set_error(CGBK_ERR_INVALID, "NULL or empty argument");
+    std::vector<size_t> lo_off(n + 1, 0), blk_off(n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        int rc = validate_logodds(logodds + lo_off[i], m[i]);
+        if (rc) {
+            std::string msg = g_err;
+            return cgbk_set_error(rc, "motif %d: %s", i, msg.c_str());
+        }
+        lo_off[i + 1] = lo_off[i] + 4 * (size_t)m[i];
+        blk_off[i + 1] = blk_off[i] + model_block_bytes((m[i] + 3) / 4);
+    }
+    ON_DEVICE(device);
+    cgbk_model_batch* B = (cgbk_model_batch*)calloc(1, sizeof(cgbk_model_batch));
+    B->n = n; B->device = device;
+    B->models = (cgbk_model*)calloc(n, sizeof(cgbk_model));
+    if (cudaMallocHost((void**)&B->h_image, blk_off[n]) != cudaSuccess ||
+        cudaMalloc((void**)&B->d_block, blk_off[n]) != cudaSuccess) {
+        cgbk_model_batch_destroy(B);
+        return cgbk_set_error(CGBK_ERR_CUDA, "allocation of %zu bytes of model tables failed", blk_off[n]);
+    }
+    // table construction is independent per model: spread over host threads when there are many
+    auto build_range = [&](int lo_i, int hi_i) {
+        for (int i = lo_i; i < hi_i; ++i) {
+            build_model_host(logodds + lo_off[i], m[i], device, &B->models[i], B->h_image + blk_off[i]);
+            bind_model_block(&B->models[i], B->d_block + blk_off[i]);
+        }
+    };
+    int n_thr = n >= 64 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (n_thr > 1) {
+        cgbk_device_sms(device);                    // warm the cache before the threads read it
+        std::vector<std::thread> pool;
+        const int per = (n + n_thr - 1) / n_thr;
+        for (int t = 0; t < n_thr; ++t)
+            if (t * per < n) pool.emplace_back(build_range, t * per, std::min(n, (t + 1) * per));
+        for (auto& th : pool) th.join();
+    } else {
+        build_range(0, n);
+    }
+    if (cudaMemcpyAsync(B->d_block, B->h_image, blk_off[n], cudaMemcpyHostToDevice, (cudaStream_t)stream) !=
+        cudaSuccess) {
+        cgbk_model_batch_destroy(B);
+        return cgbk_set_error(CGBK_ERR_CUDA, "upload of model tables failed");
+    }
+    *out = B;
+    return CGBK_OK;
+}
+
+extern "C" cgbk_model* cgbk_model_batch_get(cgbk_model_batch* B, int k) {
+    if (!B || k < 0 || k >= B->n) return nullptr;
+    return &B->models[k];
+}
+
+extern "C" int cgbk_model_batch_size(const cgbk_model_batch* B) { return B ? B->n : 0; }
+
+extern "C" void cgbk_model_batch_destroy(cgbk_model_batch* B) {
+    if (!B) return;
+    if (B->d_block) cudaFree(B->d_block);
+    if (B->h_image) cudaFreeHost(B->h_image);
+    free(B->models);
+    free(B);
+}
+
+// PSSMModel.score_seq for sequences of exactly the motif's length, on the host, in the
+// reference's arithmetic (pssm_model.py:103-133 with Biopython's _pwm.c underneath): double
+// accumulate in position order, float32 store, non-ACGT windows repaired by _calculate
+// (lower-case letters are unknown there, pssm_model.py:96-100; a repaired single-window score
+// stays float64, :117-127), soft-max log2(2**f + 2**r).  This is what score_self() needs (the
+// ~10^2 sites of the collections, pssm_model.py:84-86): a few thousand table look-ups that
+// are not worth a kernel launch.  `sites`: n_sites * m bytes back to back.
+extern "C" int cgbk_score_sites_host(const double* lo, int m, const char* sites, int n_sites, double* fwd_out,
+                                     double* rc_out, double* both_out) {
+    if (!lo || (n_sites > 0 && !sites) || n_sites < 0) return cgbk_set_error(CGBK_ERR_INVALID, "NULL argument");
+    int rc0 = validate_logodds(lo, m);
+    if (rc0) return rc0;
+    auto code = [](unsigned char ch, bool* lower) -> int {
+        *lower = false;
+        switch (ch) {
+            case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3;
+            case 'a': *lower = true; return 0; case 'c': *lower = true; return 1;
+            case 'g': *lower = true; return 2; case 't': *lower = true; return 3;
+            default: return -1;
+        }
+    };
+    for (int s = 0; s < n_sites; ++s) {
+        const unsigned char* w = (const unsigned char*)sites + (size_t)s * m;
+        bool amb = false;
+        for (int j = 0; j < m; ++j) { bool l; if (code(w[j], &l) < 0) amb = true; }
+        double f = 0.0, r = 0.0;
+        for (int j = 0; j < m; ++j) {
+            bool lower;
+            const int b = code(w[j], &lower);
+            if (!amb) {
+                f += lo[j * 4 + b];
+                r += lo[(m - 1 - j) * 4 + (3 - b)];
+            } else {
+                // _calculate: anything that is not an upper-case ACGT key adds the column mean
+                const bool unk = b < 0 || lower;
+                const double mf = (((0 + lo[j * 4]) + lo[j * 4 + 1]) + lo[j * 4 + 2] + lo[j * 4 + 3]) / 4;
+                const double* rcj = lo + (m - 1 - j) * 4;      // rc[j][b] = lo[m-1-j][3-b]
+                const double mr = (((0 + rcj[3]) + rcj[2]) + rcj[1] + rcj[0]) / 4;
+                f += unk ? mf : lo[j * 4 + b];
+                r += unk ? mr : rcj[3 - b];
+            }
+        }
+        const double fs = amb ? f : (double)(float)f, rs = amb ? r : (double)(float)r;
+        if (fwd_out) fwd_out[s] = fs;
+        if (rc_out) rc_out[s] = rs;
+        if (both_out) both_out[s] = log(pow(2.0, fs) + pow(2.0, rs)) / log(2.0);
+    }
+    return CGBK_OK;
 }
 
 // 16-bit filter tables for one threshold (see cgbk_fast.cu header).
@@ -442,7 +660,7 @@ static int ensure_coarse(cgbk_model* M, double thr, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // sequence sets and tiling
 // ---------------------------------------------------------------------------
-extern "C" int64_t cgbk_seqset_table_ints(int n_seq) { return 4 * (int64_t)n_seq + 2; }
+extern "C" int64_t cgbk_seqset_table_ints(int n_seq) { return (2 + CGBK_N_TILINGS) * (int64_t)n_seq + CGBK_N_TILINGS; }
 
 extern "C" int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len, int n_seq, int device,
                                   int64_t* d_table, void* stream, cgbk_seqset** out) {
@@ -461,14 +679,15 @@ extern "C" int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len
     S->h_len = (int64_t*)malloc(sizeof(int64_t) * n_seq);
     memcpy(S->h_off, seq_off, sizeof(int64_t) * n_seq);
     memcpy(S->h_len, seq_len, sizeof(int64_t) * n_seq);
-    // caller-owned device block: off[n] | len[n] | 2 x tile_prefix[n + 1]; no cudaMalloc / cudaFree
+    // caller-owned device block: off[n] | len[n] | CGBK_N_TILINGS x tile_prefix[n + 1]; no cudaMalloc / cudaFree
     // (both synchronise the device) on the per-genome path
     int64_t* block = d_table;
     S->d_off = block; S->d_len = block + n_seq;
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < CGBK_N_TILINGS; ++k) {
         S->tiling[k].h_tile_prefix = (int64_t*)calloc(n_seq + 1, sizeof(int64_t));
         S->tiling[k].d_tile_prefix = block + 2 * n_seq + k * (n_seq + 1);
-        S->tiling[k].cached_m = -1; S->tiling[k].cached_L = -1; S->tiling[k].n_tiles = 0;
+        S->tiling[k].cached_m = -1; S->tiling[k].cached_L = -1; S->tiling[k].cached_wcap = -1;
+        S->tiling[k].n_tiles = 0;
     }
     cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
     if (n_seq > CGBK_INLINE_SEQS) {     // small tables travel in the kernel parameters instead
@@ -488,7 +707,7 @@ extern "C" int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len
 extern "C" void cgbk_seqset_destroy(cgbk_seqset* S) {
     if (!S) return;
     free(S->h_off); free(S->h_len);                           // the device table is the caller's
-    free(S->tiling[0].h_tile_prefix); free(S->tiling[1].h_tile_prefix);
+    for (int k = 0; k < CGBK_N_TILINGS; ++k) free(S->tiling[k].h_tile_prefix);
     free(S);
 }
 
@@ -499,24 +718,36 @@ extern "C" int64_t cgbk_seqset_total_windows(const cgbk_seqset* S, int m) {
     return t;
 }
 
-static int64_t count_tiles(const cgbk_seqset* S, int m, int L) {
+// windows of sequence i that a scan with window cap `wcap` scores (wcap < 0: all of them).  The
+// cap is how a chunk of a longer sequence is scanned with motifs of several lengths: the chunk
+// carries the halo of the longest motif, and every motif stops at the chunk's own windows.
+static inline int64_t windows_of(const cgbk_seqset* S, int i, int m, int64_t wcap) {
+    int64_t nwin = S->h_len[i] - m + 1;
+    if (nwin < 0) nwin = 0;
+    if (wcap >= 0 && nwin > wcap) nwin = wcap;
+    return nwin;
+}
+
+static int64_t count_tiles(const cgbk_seqset* S, int m, int L, int64_t wcap = -1) {
     const int64_t stride = 32ll * L - 32;
     int64_t t = 0;
     for (int i = 0; i < S->n_seq; ++i) {
-        const int64_t nwin = S->h_len[i] - m + 1;
+        const int64_t nwin = windows_of(S, i, m, wcap);
         if (nwin > 0) t += (nwin + stride - 1) / stride;
     }
     return t;
 }
 
-static int ensure_tiles(cgbk_seqset* S, int slot, int m, int L, cudaStream_t st) {
+static int ensure_tiles(cgbk_seqset* S, int slot, int m, int L, cudaStream_t st, int64_t wcap = -1) {
     cgbk_seqset::Tiling& T = S->tiling[slot];
-    if (T.cached_m == m && T.cached_L == L) return CGBK_OK;
+    if (T.cached_m == m && T.cached_L == L && T.cached_wcap == wcap) return CGBK_OK;
+    if (wcap >= 0 && S->n_seq > CGBK_INLINE_SEQS)
+        return cgbk_set_error(CGBK_ERR_INVALID, "a window cap needs a set of at most %d sequences", CGBK_INLINE_SEQS);
     const int64_t stride = 32ll * L - 32;
     int64_t* prefix = T.h_tile_prefix;
     prefix[0] = 0;
     for (int i = 0; i < S->n_seq; ++i) {
-        const int64_t nwin = S->h_len[i] - m + 1;
+        const int64_t nwin = windows_of(S, i, m, wcap);
         prefix[i + 1] = prefix[i] + (nwin > 0 ? (nwin + stride - 1) / stride : 0);
     }
     // stream-ordered after any earlier scan of this set on the same stream; small tables
@@ -525,18 +756,11 @@ static int ensure_tiles(cgbk_seqset* S, int slot, int m, int L, cudaStream_t st)
         CUDA_TRY(cudaMemcpyAsync(T.d_tile_prefix, prefix, sizeof(int64_t) * (S->n_seq + 1),
                                  cudaMemcpyHostToDevice, st));
     T.n_tiles = prefix[S->n_seq];
-    T.cached_m = m; T.cached_L = L;
+    T.cached_m = m; T.cached_L = L; T.cached_wcap = wcap;
     return CGBK_OK;
 }
 
-static int device_sms(int device) {
-    static int cached_dev = -1, cached = 0;
-    if (cached_dev != device) {
-        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, device);
-        cached_dev = device;
-    }
-    return cached > 0 ? cached : 148;
-}
+static int device_sms(int device) { return cgbk_device_sms(device); }
 
 // Lane segment length L (32, 64, 96 or 128 bases; a warp tile owns 32 L - 32 windows).
 // Tiles are dealt to the resident warps in rounds and a round costs about the same however
@@ -545,11 +769,11 @@ static int device_sms(int device) {
 // profiles/r1_scan_sizes.md): large inputs want the longest segment (least overhead per
 // window), small ones the tiling whose last round is not mostly empty -- 5 Mbp is ONE round at
 // L = 96 in the stats scan but three at L = 32.
-static int choose_L(const cgbk_seqset* S, int m, int warps_total, const double (&round_us)[4]) {
+static int choose_L(const cgbk_seqset* S, int m, int warps_total, const double (&round_us)[4], int64_t wcap = -1) {
     int best_L = 128;
     double best = 0.0;
     for (int L = 128; L >= 32; L -= 32) {
-        const int64_t tiles = count_tiles(S, m, L);
+        const int64_t tiles = count_tiles(S, m, L, wcap);
         const int64_t rounds = (tiles + warps_total - 1) / warps_total;
         const double cost = (double)rounds * round_us[L / 32 - 1];
         if (L == 128 || cost < best * 0.999) { best = cost; best_L = L; }
@@ -559,7 +783,9 @@ static int choose_L(const cgbk_seqset* S, int m, int warps_total, const double (
 // stats scan: 12 warps per SM; hit filter: 20 warps per SM.  Microseconds per round at L = 32, 64, 96, 128.
 static const double kStatsRoundUs[4] = {4.6, 9.8, 12.6, 14.0};
 static const double kHitsRoundUs[4] = {3.8, 6.3, 8.6, 10.7};
-static int choose_L_stats(const cgbk_seqset* S, int m, int sms) { return choose_L(S, m, sms * 12, kStatsRoundUs); }
+static int choose_L_stats(const cgbk_seqset* S, int m, int sms, int64_t wcap = -1) {
+    return choose_L(S, m, sms * (fast_threads((m + 3) / 4, 1) / 32), kStatsRoundUs, wcap);
+}
 static int choose_L_hits(const cgbk_seqset* S, int m, int sms) { return choose_L(S, m, sms * 20, kHitsRoundUs); }
 
 #define PARTIAL_CAP 1024
@@ -586,6 +812,7 @@ static int carve(const cgbk_seqset* S, int m, void* d_work, int64_t work_bytes, 
     w->cand_cap = cand_cap;
     w->tile_begin = 0; w->tile_end = 0;          // set by the caller once the tiling is known
     w->ctr_slot = CGBK_CTR_INTERNAL_TILE; w->partial_base = 0;
+    w->hits8 = nullptr; w->hit_cap = 0; w->hit_cursor = nullptr;
     return CGBK_OK;
 }
 
@@ -614,6 +841,7 @@ extern "C" int cgbk_score_windows(const cgbk_model* M, const cgbk_genome* genome
     if (rc) return rc;
     if (n_regions < 0 || total < 0 || (total > 0 && (!d_start || !d_out_off)))
         return cgbk_set_error(CGBK_ERR_INVALID, "bad region table");
+    ON_DEVICE(M->device);
     CUDA_TRY(launch_score_windows(M, view_of(genome), (const long long*)d_start, (const long long*)d_out_off,
                                   n_regions, total, flags, d_f32, d_r32, d_both, d_f64, d_r64,
                                   (cudaStream_t)stream));
@@ -631,6 +859,7 @@ extern "C" int cgbk_posteriors(const cgbk_model* M, const cgbk_genome* genome, c
     if (rc) return rc;
     if (n_regions < 0 || (n_regions > 0 && (!d_start || !d_nwin || !d_post || !d_ms_m || !d_ms_bg)))
         return cgbk_set_error(CGBK_ERR_INVALID, "bad promoter table");
+    ON_DEVICE(M->device);
     PlaneView pv;
     pv.plane = nullptr; pv.L = 32; pv.D = 4 * (M->G - 1); pv.inv_scale = ldexp(1.0, -M->kexp);
     SeqTable seqs = {};
@@ -653,13 +882,15 @@ extern "C" int cgbk_posteriors(const cgbk_model* M, const cgbk_genome* genome, c
 // ---------------------------------------------------------------------------
 static SeqTable table_of(const cgbk_seqset* S, int slot) {
     const cgbk_seqset::Tiling& T = S->tiling[slot];
+    const int64_t wcap = T.cached_wcap;
     SeqTable t;
     t.off = (const long long*)S->d_off; t.len = (const long long*)S->d_len;
     t.tile_prefix = (const long long*)T.d_tile_prefix; t.n_seq = S->n_seq; t.n_tiles = T.n_tiles;
     for (int i = 0; i < CGBK_INLINE_SEQS; ++i) {
         const bool have = i < S->n_seq && S->n_seq <= CGBK_INLINE_SEQS;
         t.off_v[i] = have ? S->h_off[i] : 0;
-        t.len_v[i] = have ? S->h_len[i] : 0;
+        // with a window cap the kernel sees the sequence end where the capped windows end
+        t.len_v[i] = have ? (wcap >= 0 ? std::min<int64_t>(S->h_len[i], wcap + T.cached_m - 1) : S->h_len[i]) : 0;
         t.prefix_v[i] = have ? T.h_tile_prefix[i] : 0;
     }
     return t;
@@ -675,6 +906,7 @@ extern "C" int cgbk_scan_hits(cgbk_model* M, const cgbk_genome* genome, const cg
     if (rc) return rc;
     if (hit_cap < 0 || cand_cap < 1 || (hit_cap > 0 && !d_hits))
         return cgbk_set_error(CGBK_ERR_INVALID, "bad output capacity");
+    ON_DEVICE(M->device);
     cudaStream_t st = (cudaStream_t)stream;
     cgbk_seqset* S = const_cast<cgbk_seqset*>(set);
     FastWork w;
@@ -735,6 +967,7 @@ int cgbk_bg_scan_begin(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqs
     } else {
         n_bins = 1; hist_lo = M->min_score - 1.0; hist_hi = M->max_score + 2.0;
     }
+    run->moments_only = d_hist ? 0 : 1;      // no histogram wanted: the scan without one (MODE 2)
     cgbk_seqset* S = const_cast<cgbk_seqset*>(set);
     rc = carve(S, M->m, d_work, work_bytes, 0, &run->w);
     if (rc) return rc;
@@ -809,7 +1042,10 @@ int cgbk_bg_scan_range(BgScan* run, long long bases_ready, int last, cudaStream_
     StatsParams sp = run->sp;
     sp.finalize = last ? 1 : 0;      // this launch's last block reduces all partial moments
     PROF_START(st);
-    CUDA_TRY(launch_fast_stats(run->M, run->g, table_of(S, CGBK_TILING_STATS), w, run->L, (int)grid, sp, st));
+    if (run->moments_only)
+        CUDA_TRY(launch_fast_moments(run->M, run->g, table_of(S, CGBK_TILING_STATS), w, run->L, (int)grid, sp, st));
+    else
+        CUDA_TRY(launch_fast_stats(run->M, run->g, table_of(S, CGBK_TILING_STATS), w, run->L, (int)grid, sp, st));
     PROF_STOP(st);
     if (last) run->finalized = 1;
     run->next_tile = t_end;
@@ -833,6 +1069,8 @@ extern "C" int cgbk_background_stats(cgbk_model* M, const cgbk_genome* genome, c
                                      double hist_lo, double hist_hi, int n_bins, unsigned long long* d_hist,
                                      double* d_stats, int accumulate, int32_t* d_plane, int64_t plane_ints,
                                      void* d_work, int64_t work_bytes, void* stream) {
+    if (!M) return cgbk_set_error(CGBK_ERR_INVALID, "NULL model");
+    ON_DEVICE(M->device);
     cudaStream_t st = (cudaStream_t)stream;
     BgScan run;
     int rc = cgbk_bg_scan_begin(M, genome, set, hist_lo, hist_hi, n_bins, d_hist, d_stats, accumulate, d_plane,
@@ -843,8 +1081,161 @@ extern "C" int cgbk_background_stats(cgbk_model* M, const cgbk_genome* genome, c
     return cgbk_bg_scan_end(&run, st);
 }
 
+// Background over a region table (the reference's population: cgb/genome.py:215-218)
+extern "C" int64_t cgbk_region_stats_workspace_bytes(void) { return 3 * 8 * PARTIAL_CAP * 2; }
+
+extern "C" int cgbk_background_stats_regions(const cgbk_model* M, const cgbk_genome* genome, const int64_t* d_start,
+                                             const int32_t* d_nwin, int n_regions, double hist_lo, double hist_hi,
+                                             int n_bins, unsigned long long* d_hist, double* d_stats,
+                                             int accumulate, void* d_work, int64_t work_bytes, void* stream) {
+    if (!M || !d_stats) return cgbk_set_error(CGBK_ERR_INVALID, "NULL argument");
+    int rc = check_genome(genome);
+    if (rc) return rc;
+    if (n_regions < 0 || (n_regions > 0 && (!d_start || !d_nwin)))
+        return cgbk_set_error(CGBK_ERR_INVALID, "bad region table");
+    if (d_hist && (n_bins < 1 || n_bins > CGBK_MAX_HIST_BINS || !(hist_hi > hist_lo)))
+        return cgbk_set_error(CGBK_ERR_INVALID, "histogram needs 1..%d bins and hi > lo", CGBK_MAX_HIST_BINS);
+    if (!d_work || work_bytes < cgbk_region_stats_workspace_bytes())
+        return cgbk_set_error(CGBK_ERR_INVALID, "workspace smaller than cgbk_region_stats_workspace_bytes()");
+    ON_DEVICE(M->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!accumulate) {
+        CUDA_TRY(cudaMemsetAsync(d_stats, 0, sizeof(double) * CGBK_BG_COUNT, st));
+        if (d_hist) CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * n_bins, st));
+    }
+    if (!d_hist) { n_bins = 1; hist_lo = 0.0; hist_hi = 1.0; }
+    CUDA_TRY(launch_region_stats(M, view_of(genome), (const long long*)d_start, d_nwin, n_regions, hist_lo, hist_hi,
+                                 n_bins, d_hist, (double*)d_work, PARTIAL_CAP * 2, d_stats, 1, st));
+    g_launch_info[0] = 2;
+    return CGBK_OK;
+}
+
 extern "C" int cgbk_background_finalize(double* d_stats, void* stream) {
     if (!d_stats) return cgbk_set_error(CGBK_ERR_INVALID, "NULL stats");
     CUDA_TRY(launch_bg_finalize(nullptr, 0, d_stats, 1, (cudaStream_t)stream));
+    return CGBK_OK;
+}
+
+extern "C" int cgbk_background_finalize_batch(double* d_stats, int n_records, void* stream) {
+    if (!d_stats || n_records < 0) return cgbk_set_error(CGBK_ERR_INVALID, "bad argument");
+    if (n_records > 0) CUDA_TRY(launch_bg_finalize_batch(d_stats, n_records, (cudaStream_t)stream));
+    return CGBK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// motif batches: K models over one packed buffer in one call
+// ---------------------------------------------------------------------------
+extern "C" int64_t cgbk_scan_batch_workspace_bytes(int64_t cand_cap) {
+    return (3 * 8 * PARTIAL_CAP + 8 * (cand_cap > 0 ? cand_cap : 0) + 255) / 256 * 256;
+}
+
+extern "C" int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cgbk_genome* genome,
+                               const cgbk_seqset* set, int64_t win_cap, const double* thresholds, int flags,
+                               const double* hist_lo, const double* hist_hi, int n_bins,
+                               unsigned long long* d_hist, double* d_stats, uint64_t* d_hits8, int64_t hit_cap,
+                               int64_t* d_counters, void* d_work, int64_t work_bytes, int64_t cand_cap,
+                               void* stream) {
+    if (!models || n_models < 1 || !set || !d_stats || !d_counters)
+        return cgbk_set_error(CGBK_ERR_INVALID, "NULL or empty argument");
+    int rc = check_genome(genome);
+    if (rc) return rc;
+    for (int k = 0; k < n_models; ++k) {
+        if (!models[k]) return cgbk_set_error(CGBK_ERR_INVALID, "model %d is NULL", k);
+        if (models[k]->device != models[0]->device)
+            return cgbk_set_error(CGBK_ERR_INVALID, "model %d lives on another device", k);
+        if (thresholds && isnan(thresholds[k])) return cgbk_set_error(CGBK_ERR_INVALID, "threshold %d is NaN", k);
+    }
+    if (thresholds) {
+        if (hit_cap < 0 || cand_cap < 1 || (hit_cap > 0 && !d_hits8))
+            return cgbk_set_error(CGBK_ERR_INVALID, "bad hit capacity");
+        if (genome->cap_bases >= (1ll << 31))
+            return cgbk_set_error(CGBK_ERR_UNSUPPORTED, "compact hit records address buffers below 2^31 bases "
+                                  "(shard the sequence, or use cgbk_scan_hits)");
+    } else {
+        cand_cap = 0;
+    }
+    if (d_hist && (n_bins < 1 || n_bins > CGBK_MAX_HIST_BINS))
+        return cgbk_set_error(CGBK_ERR_INVALID, "histogram needs 1..%d bins", CGBK_MAX_HIST_BINS);
+    if (!d_work || work_bytes < cgbk_scan_batch_workspace_bytes(cand_cap))
+        return cgbk_set_error(CGBK_ERR_INVALID, "workspace of %lld bytes is smaller than the %lld required",
+                              (long long)work_bytes, (long long)cgbk_scan_batch_workspace_bytes(cand_cap));
+    ON_DEVICE(models[0]->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    cgbk_seqset* S = const_cast<cgbk_seqset*>(set);
+    const GenomeView gv = view_of(genome);
+    // Clearing: ONE memset when the caller laid out stats | histograms | counters back to back
+    // (as the Python wrapper does), separate ones otherwise.
+    {
+        unsigned char* a = (unsigned char*)d_stats;
+        const size_t stats_bytes = sizeof(double) * CGBK_BG_COUNT * (size_t)n_models;
+        const size_t hist_bytes = d_hist ? sizeof(unsigned long long) * (size_t)n_bins * n_models : 0;
+        const size_t ctr_bytes = 64 * (size_t)(n_models + 1);
+        const bool hist_adj = !d_hist || (unsigned char*)d_hist == a + stats_bytes;
+        const bool ctr_adj = hist_adj && (unsigned char*)d_counters == a + stats_bytes + hist_bytes;
+        if (ctr_adj) {
+            CUDA_TRY(cudaMemsetAsync(a, 0, stats_bytes + hist_bytes + ctr_bytes, st));
+        } else {
+            CUDA_TRY(cudaMemsetAsync(d_stats, 0, stats_bytes, st));
+            if (d_hist) CUDA_TRY(cudaMemsetAsync(d_hist, 0, hist_bytes, st));
+            CUDA_TRY(cudaMemsetAsync(d_counters, 0, ctr_bytes, st));
+        }
+    }
+    long long launches = 0, tiles_total = 0;
+    PROF_START(st);
+    for (int k = 0; k < n_models; ++k) {
+        cgbk_model* M = models[k];
+        const int L = choose_L_stats(S, M->m, M->sms, win_cap);
+        rc = ensure_tiles(S, CGBK_TILING_BATCH, M->m, L, st, win_cap);
+        if (rc) return rc;
+        const int64_t n_tiles = S->tiling[CGBK_TILING_BATCH].n_tiles;
+        double lo = hist_lo ? hist_lo[k] : floor(M->min_score), hi = hist_hi ? hist_hi[k] : ceil(M->max_score) + 1.0;
+        unsigned long long* hist_k = d_hist ? d_hist + (size_t)k * n_bins : nullptr;
+        if (hist_k) {
+            if (!(hi > lo) || (hi - lo) * ldexp(1.0, M->kexp) >= 4294967296.0 ||
+                fabs(lo) * ldexp(1.0, M->kexp) >= 2147483648.0)
+                return cgbk_set_error(CGBK_ERR_INVALID, "model %d: bad histogram range", k);
+        } else {
+            lo = M->min_score - 1.0; hi = M->max_score + 2.0;
+        }
+        StatsParams sp = make_stats_params(M, lo, hi, hist_k ? n_bins : 1, hist_k, nullptr);
+        sp.d_stats = d_stats + (size_t)k * CGBK_BG_COUNT;
+        sp.finalize = 1;
+        if (thresholds) set_stats_threshold(&sp, M, thresholds[k], (flags & CGBK_RC_REVSEQ_ORDER) ? 1 : 0);
+        FastWork w;
+        w.counters = (long long*)d_counters + (size_t)k * CGBK_CTR_COUNT;
+        w.partials = (double*)d_work;
+        w.partial_cap = PARTIAL_CAP;
+        w.dirty_tiles = nullptr;
+        w.cands = (unsigned long long*)((unsigned char*)d_work + 3 * 8 * PARTIAL_CAP);
+        w.cand_cap = cand_cap;
+        w.tile_begin = 0; w.tile_end = n_tiles;
+        w.ctr_slot = CGBK_CTR_INTERNAL_TILE; w.partial_base = 0;
+        w.hits8 = thresholds ? (unsigned long long*)d_hits8 : nullptr;
+        w.hit_cap = hit_cap;
+        w.hit_cursor = (long long*)d_counters + (size_t)n_models * CGBK_CTR_COUNT;
+        if (n_tiles > 0) {
+            const int wpb = fast_threads(M->G, 1) / 32;
+            long long grid = (n_tiles + wpb - 1) / wpb;
+            if (grid > M->sms) grid = M->sms;
+            const SeqTable tab = table_of(S, CGBK_TILING_BATCH);
+            if (g_prof_on == 2) CUDA_TRY(prof_pair_event(k, 0, st));
+            if (hist_k) CUDA_TRY(launch_fast_stats(M, gv, tab, w, L, (int)grid, sp, st));
+            else CUDA_TRY(launch_fast_moments(M, gv, tab, w, L, (int)grid, sp, st));
+            if (g_prof_on == 2) CUDA_TRY(prof_pair_event(k, 1, st));
+            ++launches;
+            if (thresholds) {
+                CUDA_TRY(launch_rescore8(M, gv, w, thresholds[k], flags, st));
+                ++launches;
+            }
+        } else {
+            if (g_prof_on == 2) { CUDA_TRY(prof_pair_event(k, 0, st)); CUDA_TRY(prof_pair_event(k, 1, st)); }
+            CUDA_TRY(launch_bg_finalize(nullptr, 0, sp.d_stats, 1, st));    // n = 0, mean = std = NaN
+            ++launches;
+        }
+        tiles_total += n_tiles;
+    }
+    g_prof_pairs = g_prof_on == 2 ? n_models : 0;
+    PROF_STOP(st);
+    g_launch_info[0] = launches; g_launch_info[1] = tiles_total; g_launch_info[2] = 0;
     return CGBK_OK;
 }

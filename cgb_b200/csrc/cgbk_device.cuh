@@ -111,6 +111,32 @@ __device__ __forceinline__ double softmax2_f32tail(float ff, float rf) {
     return (double)mx + (double)log2f(1.0f + exp2f(mn - mx));
 }
 
+// Warp-convergent append of up to two hits per lane (+ strand, - strand) to the compact hit
+// list: ONE atomic on the batch's append position and one on the model's hit counter per warp.
+__device__ __forceinline__ void emit_hits8_warp(unsigned long long* hits8, long long cap, long long* cursor,
+                                                long long* counters, long long gpos, bool hf, float ff,
+                                                bool hr, float rf) {
+    const unsigned int mf = __ballot_sync(0xffffffffu, hf), mr = __ballot_sync(0xffffffffu, hr);
+    const int nf = __popc(mf), tot = nf + __popc(mr);
+    if (tot == 0) return;                                   // warp-uniform
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) {
+        base = atomicAdd(reinterpret_cast<unsigned long long*>(cursor), (unsigned long long)tot);
+        atomicAdd(reinterpret_cast<unsigned long long*>(counters + CGBK_CTR_HITS), (unsigned long long)tot);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const unsigned int lt = (1u << lane) - 1u;
+    if (hf) {
+        const long long k = (long long)base + __popc(mf & lt);
+        if (k < cap) hits8[k] = cgbk_pack_hit8(gpos, 0, __float_as_uint(ff));
+    }
+    if (hr) {
+        const long long k = (long long)base + nf + __popc(mr & lt);
+        if (k < cap) hits8[k] = cgbk_pack_hit8(gpos, 1, __float_as_uint(rf));
+    }
+}
+
 // Sequence table accessors: tables of up to CGBK_INLINE_SEQS sequences travel by value in the
 // kernel parameters (constant bank), larger ones live in device memory.
 __device__ __forceinline__ long long seq_off_of(const SeqTable& s, int k) {

@@ -78,7 +78,8 @@ cudaError_t launch_pack(const uint8_t* d_ascii, long long n, long long dst_off, 
     if (padded == 0) padded = CGBK_SEQ_ALIGN;      // an empty sequence still owns (and zeroes) one block
     const long long n_chunks = padded / 32;
     long long blocks = (n_chunks + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    const long long cap = (long long)cgbk_current_sms() * 32;
+    if (blocks > cap) blocks = cap;
     pack_kernel<<<(int)blocks, 256, 0, st>>>(d_ascii, n, dst_off, b2, amb, lower, n_chunks);
     return cudaGetLastError();
 }
@@ -128,7 +129,7 @@ cudaError_t launch_score_windows(const cgbk_model* mdl, GenomeView g, const long
                                  double* r64, cudaStream_t st) {
     if (total <= 0) return cudaSuccess;
     long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (long long)mdl->sms * 16) blocks = (long long)mdl->sms * 16;
     score_windows_kernel<<<(int)blocks, 256, 0, st>>>(mdl->d_exact, mdl->m, g, d_start, d_out_off,
                                                      n_regions, total, flags, f32, r32, both, f64,
                                                      r64);
@@ -281,8 +282,8 @@ __global__ void __launch_bounds__(256) posterior_kernel(
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
         if (lane == 0) {
             double res;
-            if (nwin <= 0) {
-                res = nan("");      // the reference raises inside Biopython for len(seq) < m
+            if (nwin < 0) {
+                res = nan("");      // the reference raises inside Biopython for len(seq) < m - 1
             } else {
                 const double lh_ratio = exp((double)nwin * nlog1m_alpha - acc);
                 res = 1 / (1 + lh_ratio * (1 - p_motif) / p_motif);
@@ -300,7 +301,7 @@ cudaError_t launch_posteriors(const cgbk_model* mdl, GenomeView g, SeqTable seqs
     // one warp per promoter, 4 warps per block: a few thousand promoters are all resident at once
     // (no partial second wave)
     int blocks = (n_regions + 3) / 4;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > mdl->sms * 16) blocks = mdl->sms * 16;
     if (pv.plane)
         posterior_kernel<true><<<blocks, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, pv, d_start, d_nwin,
                                                       n_regions, d_ms_m, d_ms_bg, p_motif, alpha,
@@ -402,12 +403,112 @@ __global__ void __launch_bounds__(128) dirty_hits_kernel(const double* __restric
 cudaError_t launch_rescore(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
                            double thr, int flags, cgbk_hit* hits, long long hit_cap, int L,
                            cudaStream_t st) {
-    rescore_kernel<<<148 * 2, 128, 0, st>>>(mdl->d_exact, mdl->m, g, w, thr, flags, hits, hit_cap);
+    rescore_kernel<<<mdl->sms * 2, 128, 0, st>>>(mdl->d_exact, mdl->m, g, w, thr, flags, hits, hit_cap);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    dirty_hits_kernel<<<148 * 2, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, w, L, thr, flags, hits,
-                                              hit_cap);
+    dirty_hits_kernel<<<mdl->sms * 2, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, w, L, thr, flags, hits,
+                                                   hit_cap);
     return cudaGetLastError();
+}
+
+// Candidates of the fused stats scan -> compact hit list shared by a batch of models
+// (cgbk_scan_batch): same exact arithmetic and comparison as rescore_kernel.
+__global__ void __launch_bounds__(128) rescore8_kernel(const double* __restrict__ d_exact, int m,
+                                                       GenomeView g, FastWork w, double thr, int flags) {
+    __shared__ ExactTables tab;
+    stage_exact(&tab, d_exact);
+    __syncthreads();
+    const bool revseq = (flags & CGBK_RC_REVSEQ_ORDER) != 0;
+    long long n = w.counters[CGBK_CTR_CANDIDATES];
+    if (n > w.cand_cap) n = w.cand_cap;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < n;
+         i0 += (long long)gridDim.x * blockDim.x) {
+        const long long i = i0 + (threadIdx.x & 31);
+        bool hf = false, hr = false;
+        long long gpos = 0;
+        float ff = 0.f, rf = 0.f;
+        if (i < n) {
+            const unsigned long long rec = w.cands[i];
+            gpos = (long long)(rec & 0x3fffffffffffffffull);
+            double f, r;
+            exact_window(g, &tab, m, gpos, revseq, f, r);
+            ff = (float)f; rf = (float)r;
+            hf = (rec >> 63) && (double)ff >= thr;
+            hr = ((rec >> 62) & 1ull) && (double)rf >= thr;
+        }
+        emit_hits8_warp(w.hits8, w.hit_cap, w.hit_cursor, w.counters, gpos, hf, ff, hr, rf);
+    }
+}
+
+cudaError_t launch_rescore8(const cgbk_model* mdl, GenomeView g, FastWork w, double thr, int flags,
+                            cudaStream_t st) {
+    rescore8_kernel<<<mdl->sms * 4, 128, 0, st>>>(mdl->d_exact, mdl->m, g, w, thr, flags);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// background over a region table: Genome.build_PSSM_model (cgb/genome.py:215-226)
+//   every m-mer of every gene's upstream non-coding region is scored on its own,
+//   score_seq(seq) with len(seq) == m (pssm_model.py:117-127: one window, a repaired score stays
+//   float64), and the scores go to np.mean / np.std.  One warp per region, windows strided over
+//   the lanes; float64 partial sums per block in a fixed order (deterministic), histogram in
+//   shared memory.  Regions may overlap or repeat: every listed window counts.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) region_stats_kernel(
+    const double* __restrict__ d_exact, int m, GenomeView g, const long long* __restrict__ d_start,
+    const int* __restrict__ d_nwin, int n_regions, double hist_lo, double inv_binw, int n_bins,
+    unsigned long long* __restrict__ d_hist, double* __restrict__ partials) {
+    __shared__ ExactTables tab;
+    __shared__ double scratch[96];
+    extern __shared__ unsigned int shist[];
+    stage_exact(&tab, d_exact);
+    if (d_hist)
+        for (int i = threadIdx.x; i < n_bins; i += blockDim.x) shist[i] = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+    for (int reg = blockIdx.x * wpb + (threadIdx.x >> 5); reg < n_regions; reg += gridDim.x * wpb) {
+        const long long start = __ldg(d_start + reg);
+        const int nwin = __ldg(d_nwin + reg);
+        for (int w = lane; w < nwin; w += 32) {
+            double f, r;
+            const bool repaired = exact_window(g, &tab, m, start + w, false, f, r);
+            const double fs = repaired ? f : (double)(float)f, rs = repaired ? r : (double)(float)r;
+            const double s = softmax2_f64(fs, rs);
+            s1 += s; s2 += s * s; cnt += 1.0;
+            if (d_hist) {
+                int bin = (int)floor((s - hist_lo) * inv_binw);
+                bin = bin < 0 ? 0 : (bin >= n_bins ? n_bins - 1 : bin);
+                atomicAdd(shist + bin, 1u);
+            }
+        }
+    }
+    block_reduce3(s1, s2, cnt, scratch);
+    if (threadIdx.x == 0) {
+        partials[3 * blockIdx.x] = s1; partials[3 * blockIdx.x + 1] = s2; partials[3 * blockIdx.x + 2] = cnt;
+    }
+    if (d_hist) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_bins; i += blockDim.x)
+            if (shist[i]) atomicAdd(d_hist + i, (unsigned long long)shist[i]);
+    }
+}
+
+cudaError_t launch_region_stats(const cgbk_model* mdl, GenomeView g, const long long* d_start, const int* d_nwin,
+                                int n_regions, double hist_lo, double hist_hi, int n_bins,
+                                unsigned long long* d_hist, double* partials, int partial_cap, double* d_stats,
+                                int accumulate, cudaStream_t st) {
+    int blocks = (n_regions + 3) / 4;
+    if (blocks > mdl->sms * 8) blocks = mdl->sms * 8;
+    if (blocks > partial_cap) blocks = partial_cap;
+    if (blocks > 0) {
+        region_stats_kernel<<<blocks, 128, d_hist ? 4 * (size_t)n_bins : 0, st>>>(
+            mdl->d_exact, mdl->m, g, d_start, d_nwin, n_regions, hist_lo, (double)n_bins / (hist_hi - hist_lo),
+            n_bins, d_hist, partials);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return launch_bg_finalize(partials, blocks, d_stats, accumulate, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -419,6 +520,24 @@ __global__ void __launch_bounds__(256) bg_finalize_kernel(const double* __restri
                                                           int accumulate) {
     __shared__ double scratch[96];
     finalize_stats(partials, n_partials, stats, accumulate, scratch);
+}
+
+// mean / std of many records at once (after the all-reduce of a motif batch): one block per record
+__global__ void __launch_bounds__(32) bg_finalize_batch_kernel(double* stats) {
+    if (threadIdx.x == 0) {
+        double* s = stats + (size_t)blockIdx.x * CGBK_BG_COUNT;
+        const double cnt = s[CGBK_BG_N], s1 = s[CGBK_BG_SUM], s2 = s[CGBK_BG_SUMSQ];
+        const double mean = cnt > 0 ? s1 / cnt : nan("");
+        double var = cnt > 0 ? s2 / cnt - mean * mean : nan("");
+        if (var < 0) var = 0;
+        s[CGBK_BG_MEAN] = mean;
+        s[CGBK_BG_STD] = sqrt(var);
+    }
+}
+
+cudaError_t launch_bg_finalize_batch(double* d_stats, int n_records, cudaStream_t st) {
+    bg_finalize_batch_kernel<<<n_records, 32, 0, st>>>(d_stats);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_bg_finalize(const double* partials, int n_partials, double* d_stats,

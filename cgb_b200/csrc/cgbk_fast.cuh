@@ -1,4 +1,6 @@
-// Tiled PSWM scan kernels for sm_100a (the throughput path).
+// Tiled PSWM scan kernel for sm_100a (the throughput path), as a template that the three
+// translation units cgbk_fast_filter.cu / cgbk_fast_stats.cu / cgbk_fast_moments.cu instantiate
+// (one per MODE, so that they compile side by side).
 //
 // What is computed (reference: cgb/pssm_model.py:103-133 through Biopython's
 // _pwm.c calculate()):  for every window i of a sequence,
@@ -32,12 +34,31 @@
 //  * MODE 1 ("stats"): int32 fixed point (2^-kexp) per strand, soft-max
 //    log2(2^f + 2^r) = max + log2(1 + 2^-|f-r|) on the MUFU unit, per-block
 //    shared-memory histogram, and integer moments (sum d, sum d^2 of the score
-//    re-centred and rounded to 2^-18: order independent, hence deterministic).
-//    Optionally every window's fixed-point soft-max score is written to a "score
-//    plane" laid out [tile][row][lane] so that each position is one coalesced 128-byte
-//    store; cgbk_posteriors reads it back instead of re-scoring the promoters;
-//  * tiles that contain a byte outside ACGTacgt are not scored here: their ids are
-//    appended to a list the exact kernels walk (ambiguity repair, pssm_model.py:88-101).
+//    re-centred and rounded to the finest unit the accumulators allow: order
+//    independent, hence deterministic).  Optionally every window's fixed-point soft-max
+//    score is written to a "score plane" laid out [tile][row][lane] so that each position
+//    is one coalesced 128-byte store; cgbk_posteriors reads it back instead of re-scoring
+//    the promoters;
+//  * MODE 2 ("moments"): MODE 1 without the histogram (the reference's estimator only ever
+//    uses mean and std, binding_model.py:85-87);
+//  * MODE 1 / 2 with a threshold ("fused" scan): the fixed-point strand scores are exact to a
+//    few units of 2^-kexp, so the same pass also finds the site-search candidates
+//    (genome.py:433-445): one compare per window against the fixed-point threshold minus
+//    its error bound, the rare candidates parked and flushed like the filter's.  One pass
+//    over the sequence then yields the background record AND the hit candidates;
+//  * VAR 2 ("peeled"): the first 32-position body of a lane segment is its own code copy
+//    without the epilogues of the D windows that belong to the previous lane (they are
+//    only parked), the following bodies a second copy without the parking: no work is
+//    spent on windows that are not the lane's own.  VAR 0 keeps one body for both
+//    (half the code: better when a warp runs a single small tile);
+//  * tiles that contain a byte outside ACGTacgt are not scored on the table path: the
+//    filter lists them for the exact kernels, the stats modes score them in place with the
+//    reference's float64 arithmetic (ambiguity repair, pssm_model.py:88-101).
+#pragma once
+
+#include <mutex>
+#include <type_traits>
+
 #include "cgbk_device.cuh"
 
 // Threads per CTA (one CTA per SM).  Measured on B200 at 1 Gbp / 5 Mbp, LexA m = 22, stats kernel:
@@ -45,6 +66,9 @@
 // 512: 4.76e11 / 26.3 (128 registers, spills), 640: 4.08e11.
 #ifndef CGBK_STATS_THREADS
 #define CGBK_STATS_THREADS 384
+#endif
+#ifndef CGBK_STATS_THREADS_SMALLG      // G <= 2 (motifs of up to 8 bases): fewer registers, more warps
+#define CGBK_STATS_THREADS_SMALLG 384
 #endif
 #ifndef CGBK_STATS_EW
 #define CGBK_STATS_EW 4
@@ -150,11 +174,6 @@ __device__ __forceinline__ uint2 ld_stream2(const uint32_t* __restrict__ b2, lon
     return make_uint2(wi < nw ? __ldg(b2 + wi) : 0u, 0u);
 }
 
-// Rare path of the filter kernel, deliberately NOT inlined (it would otherwise be replicated
-// at each of the 52 completion sites of the unrolled body and push the hot loop out of the
-// instruction cache): examine 4 consecutive windows wt0..wt0+3 of this lane whose flag OR was
-// non-zero and append those that are the tile's own to the candidate list.
-//
 // Candidates are first parked in a small per-warp shared-memory buffer (one shared-memory
 // atomic each) and moved to the global list by flush_candidates() at warp-convergent points
 // with ONE global atomic per flush and coalesced stores: with low-information motifs ~1 % of
@@ -162,7 +181,24 @@ __device__ __forceinline__ uint2 ld_stream2(const uint32_t* __restrict__ b2, lon
 // serialise the whole scan.  A full buffer falls back to the direct global append.
 #define CGBK_CAND_STAGE 96      // entries per warp
 
-__device__ __noinline__ void emit_candidates4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int wt0,
+__device__ __forceinline__ void park_candidate(unsigned long long rec, unsigned long long* stage,
+                                               unsigned int* stage_cnt, long long* counters,
+                                               unsigned long long* cands, long long cand_cap) {
+    const unsigned int idx = atomicAdd(stage_cnt, 1u);
+    if (idx < CGBK_CAND_STAGE) {
+        stage[idx] = rec;
+    } else {
+        const unsigned long long slot =
+            atomicAdd(reinterpret_cast<unsigned long long*>(counters + CGBK_CTR_CANDIDATES), 1ull);
+        if ((long long)slot < cand_cap) cands[slot] = rec;
+    }
+}
+
+// Rare path of the filter kernel, deliberately NOT inlined (it would otherwise be replicated
+// at each of the 52 completion sites of the unrolled body and push the hot loop out of the
+// instruction cache): examine 4 consecutive windows wt0..wt0+3 of this lane whose flag OR was
+// non-zero and append those that are the tile's own to the candidate list.
+static __device__ __noinline__ void emit_candidates4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int wt0,
                                               int lane_first, int own_n, long long gpos0,
                                               unsigned long long* stage, unsigned int* stage_cnt,
                                               long long* counters, unsigned long long* cands,
@@ -175,20 +211,37 @@ __device__ __noinline__ void emit_candidates4(uint32_t a0, uint32_t a1, uint32_t
             const unsigned long long rec = (unsigned long long)(gpos0 + wt) |
                                            ((unsigned long long)(a[k] >> 31) << 63) |
                                            ((unsigned long long)((a[k] >> 15) & 1u) << 62);
-            const unsigned int idx = atomicAdd(stage_cnt, 1u);
-            if (idx < CGBK_CAND_STAGE) {
-                stage[idx] = rec;
-            } else {
-                const unsigned long long slot =
-                    atomicAdd(reinterpret_cast<unsigned long long*>(counters + CGBK_CTR_CANDIDATES), 1ull);
-                if ((long long)slot < cand_cap) cands[slot] = rec;
-            }
+            park_candidate(rec, stage, stage_cnt, counters, cands, cand_cap);
+        }
+    }
+}
+
+// The same for the fused stats scan: the four windows' fixed-point strand scores against the
+// fixed-point candidate threshold.  The staging buffer is found from the shared-memory window
+// (no pointer is kept live in the hot loop).
+static __device__ __noinline__ void emit_candidates4_fix(int f0, int f1, int f2, int f3, int r0, int r1, int r2, int r3,
+                                                  int thr_fix, int wt0, int lane_first, int own_n,
+                                                  long long gpos0, unsigned char* cand_base,
+                                                  long long* counters, unsigned long long* cands,
+                                                  long long cand_cap) {
+    unsigned long long* stage = reinterpret_cast<unsigned long long*>(cand_base);
+    unsigned int* stage_cnt = reinterpret_cast<unsigned int*>(cand_base + CGBK_CAND_STAGE * 8);
+    const int f[4] = {f0, f1, f2, f3}, r[4] = {r0, r1, r2, r3};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int wt = wt0 + k;
+        const bool cf = f[k] >= thr_fix, cr = r[k] >= thr_fix;
+        if ((cf || cr) && wt >= lane_first && wt < own_n) {
+            const unsigned long long rec = (unsigned long long)(gpos0 + wt) |
+                                           ((unsigned long long)(cf ? 1u : 0u) << 63) |
+                                           ((unsigned long long)(cr ? 1u : 0u) << 62);
+            park_candidate(rec, stage, stage_cnt, counters, cands, cand_cap);
         }
     }
 }
 
 // warp-convergent: move this warp's parked candidates to the global list
-__device__ __noinline__ void flush_candidates(unsigned long long* stage, unsigned int* stage_cnt, int lane,
+static __device__ __noinline__ void flush_candidates(unsigned long long* stage, unsigned int* stage_cnt, int lane,
                                                  long long* counters, unsigned long long* cands,
                                                  long long cand_cap) {
     __syncwarp();
@@ -211,25 +264,56 @@ __device__ __noinline__ void flush_candidates(unsigned long long* stage, unsigne
 // it with the reference's exact arithmetic (PSSMModel._calculate repair included), straight from
 // the device ExactTables (L1 resident, 5 KB).  Deliberately NOT inlined: the hot loop keeps its
 // registers.  Moments go to three per-block doubles in shared memory, the histogram to global.
-__device__ __noinline__ void exact_tile_stats(const ExactTables* tab, const uint32_t* bases2, const uint32_t* amb,
+// In a fused scan (thr finite) the tile's hits are final right here and go to the compact hit
+// list (one atomic per warp step); the minus strand is then scored a second time in the
+// site-search order when that order is asked for (genome.py:440-445).
+struct ExactHitSink {
+    unsigned long long* hits8;      // compact records (NULL: no hit search)
+    long long hit_cap;
+    long long* hit_cursor;          // shared append position of the batch
+    long long* counters;            // this model's counters (CGBK_CTR_HITS)
+    double thr;
+    int revseq;
+};
+
+static __device__ __noinline__ void exact_tile_stats(const ExactTables* tab, const uint32_t* bases2, const uint32_t* amb,
                                               const uint32_t* lower, long long cap_bases, long long gbase,
                                               long long w_lo, long long w_hi, int m, long long tile, int L, int D,
                                               unsigned long long* d_hist, int n_bins, double hist_lo,
-                                              double inv_binw, int* plane, double scale, double* acc3) {
+                                              double inv_binw, int* plane, double scale, double* acc3,
+                                              const ExactHitSink* sink) {
     GenomeView g;
     g.bases2 = bases2; g.amb = amb; g.lower = lower; g.cap_bases = cap_bases;
     double s1 = 0.0, s2 = 0.0, cnt = 0.0;
-    for (long long x = w_lo + (threadIdx.x & 31); x < w_hi; x += 32) {
-        double f, r;
-        exact_window(g, tab, m, gbase + x, false, f, r);
-        const double s = softmax2_f64((double)(float)f, (double)(float)r);
-        s1 += s; s2 += s * s; cnt += 1.0;
-        if (d_hist) {
-            int bin = (int)floor((s - hist_lo) * inv_binw);
-            bin = bin < 0 ? 0 : (bin >= n_bins ? n_bins - 1 : bin);
-            atomicAdd(d_hist + bin, 1ull);
+    const int lane = threadIdx.x & 31;
+    for (long long x0 = w_lo; x0 < w_hi; x0 += 32) {        // warp-uniform trip count
+        const long long x = x0 + lane;
+        bool hf = false, hr = false;
+        float ff = 0.f, rf = 0.f;
+        if (x < w_hi) {
+            double f, r;
+            exact_window(g, tab, m, gbase + x, false, f, r);
+            ff = (float)f; rf = (float)r;
+            const double s = softmax2_f64((double)ff, (double)rf);
+            s1 += s; s2 += s * s; cnt += 1.0;
+            if (d_hist) {
+                int bin = (int)floor((s - hist_lo) * inv_binw);
+                bin = bin < 0 ? 0 : (bin >= n_bins ? n_bins - 1 : bin);
+                atomicAdd(d_hist + bin, 1ull);
+            }
+            if (plane) plane[plane_index(tile, (int)(x - w_lo), L, D)] = (int)llrint(s * scale);
+            if (sink->hits8) {
+                if (sink->revseq) {
+                    double f2, r2;
+                    exact_window(g, tab, m, gbase + x, true, f2, r2);
+                    rf = (float)r2;
+                }
+                hf = (double)ff >= sink->thr;
+                hr = (double)rf >= sink->thr;
+            }
         }
-        if (plane) plane[plane_index(tile, (int)(x - w_lo), L, D)] = (int)llrint(s * scale);
+        if (sink->hits8)
+            emit_hits8_warp(sink->hits8, sink->hit_cap, sink->hit_cursor, sink->counters, gbase + x, hf, ff, hr, rf);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -237,44 +321,58 @@ __device__ __noinline__ void exact_tile_stats(const ExactTables* tab, const uint
         s2 += __shfl_down_sync(0xffffffffu, s2, o);
         cnt += __shfl_down_sync(0xffffffffu, cnt, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         atomicAdd(acc3, s1); atomicAdd(acc3 + 1, s2); atomicAdd(acc3 + 2, cnt);
     }
 }
 
+__host__ __device__ constexpr int fast_threads_of(int G, int MODE) {
+    return MODE == 0 ? CGBK_FILTER_THREADS
+                     : (G <= 2 ? CGBK_STATS_THREADS_SMALLG : (G <= 6 ? CGBK_STATS_THREADS : 256));
+}
+
 template <int G, int MODE>
 struct FastCfg {
-    static constexpr int THREADS = MODE == 0 ? CGBK_FILTER_THREADS : (G <= 6 ? CGBK_STATS_THREADS : 256);
+    static constexpr int THREADS = fast_threads_of(G, MODE);
     static constexpr int NW = MODE == 0 ? G : 2 * G;
     static constexpr int D = 4 * (G - 1);
     static constexpr int STASH_BYTES = ((THREADS / 32) * D * 33 * (MODE == 0 ? 4 : 8) + 15) / 16 * 16;
-    // MODE 0: per-warp candidate staging [CGBK_CAND_STAGE] u64 + one counter word (padded to 16 B)
-    static constexpr int CAND_BYTES = MODE == 0 ? (THREADS / 32) * (CGBK_CAND_STAGE * 8 + 16) : 0;
+    // per-warp candidate staging [CGBK_CAND_STAGE] u64 + one counter word (padded to 16 B)
+    static constexpr int CAND_BYTES = (THREADS / 32) * (CGBK_CAND_STAGE * 8 + 16);
 };
 
-template <int G, int MODE, bool ONE>
+#define CGBK_VAR_UNIFIED 0   // one 32-position body for every part of a lane segment
+#define CGBK_VAR_ONE 1       // lane segments of exactly 32 positions (filter only)
+#define CGBK_VAR_PEEL 2      // first body and following bodies as separate code copies (stats modes)
+
+template <int G, int MODE, int VAR>
 __global__ void __launch_bounds__((FastCfg<G, MODE>::THREADS), 1)
 fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs, FastWork work, int m,
                  int B, StatsParams sp) {
     using Cfg = FastCfg<G, MODE>;
     constexpr int NW = Cfg::NW;
     constexpr int D = Cfg::D;
+    constexpr bool ONE = VAR == CGBK_VAR_ONE;
+    constexpr bool PEEL = VAR == CGBK_VAR_PEEL;
+    constexpr bool HIST = MODE == 1;
     // completed windows are handled in groups: 4 for the filter's deferred flag test, CGBK_STATS_EW
     // for the stats epilogue (its dependent chains run side by side)
     constexpr int EW = MODE == 0 ? 4 : CGBK_STATS_EW;
+    static_assert(MODE == 0 || CGBK_STATS_EW == 4, "the fused candidate test examines 4 windows at a time");
     // stream positions whose table look-ups are issued together before their accumulation
     constexpr int SB = MODE == 0 ? CGBK_FILTER_BATCH : CGBK_STATS_BATCH;
     using TL = TableLayout<NW>;
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char* stash_base = smem + TL::BYTES;
-    unsigned int* hist = reinterpret_cast<unsigned int*>(smem + TL::BYTES + Cfg::STASH_BYTES);
+    // this warp's candidate staging buffer and its fill count (found again on demand: no pointer
+    // is kept live through the hot loop), then (MODE 1) the histogram
+    auto cand_ptr = [&]() -> unsigned char* {
+        return smem + TL::BYTES + Cfg::STASH_BYTES + (threadIdx.x >> 5) * (CGBK_CAND_STAGE * 8 + 16);
+    };
+    unsigned int* hist = reinterpret_cast<unsigned int*>(smem + TL::BYTES + Cfg::STASH_BYTES + Cfg::CAND_BYTES);
     __shared__ double red_scratch[96];
-    __shared__ double exact_acc[3];     // MODE 1: moments of the exactly scored (non-ACGT) tiles
+    __shared__ double exact_acc[3];     // stats modes: moments of the exactly scored (non-ACGT) tiles
     __shared__ int is_last_block;
-    // MODE 0: this warp's candidate staging buffer and its fill count
-    unsigned char* cand_base = smem + TL::BYTES + Cfg::STASH_BYTES + (threadIdx.x >> 5) * (CGBK_CAND_STAGE * 8 + 16);
-    unsigned long long* cand_stage = reinterpret_cast<unsigned long long*>(cand_base);
-    unsigned int* cand_cnt = reinterpret_cast<unsigned int*>(cand_base + CGBK_CAND_STAGE * 8);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const uint32_t o16 = (lane & 7) << 4, o8 = (lane & 15) << 3, o4 = lane << 2;
@@ -321,21 +419,21 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     preload(tile);
 
     fill_tables<NW, Cfg::THREADS>(smem, gtab);
-    if (MODE == 1)
-        for (int i = threadIdx.x; i < (sp.n_bins + 1) * sp.hist_words; i += blockDim.x)
-            hist[i] = 0u;                                    // row n_bins = discard bin
-    if (MODE == 0 && (threadIdx.x & 31) == 0) *cand_cnt = 0u;
-    if (MODE == 1 && threadIdx.x < 3) exact_acc[threadIdx.x] = 0.0;
+    if (HIST)
+        for (int i = threadIdx.x; i < sp.n_bins * sp.hist_words; i += blockDim.x) hist[i] = 0u;
+    if ((threadIdx.x & 31) == 0) *reinterpret_cast<unsigned int*>(cand_ptr() + CGBK_CAND_STAGE * 8) = 0u;
+    if (MODE != 0 && threadIdx.x < 3) exact_acc[threadIdx.x] = 0.0;
     __syncthreads();
 
     // per-warp strip for the partial sums handed to the previous lane: [D][33]
     uint32_t* stash32 = reinterpret_cast<uint32_t*>(stash_base) + warp * (D * 33) + lane;
     uint2* stash64 = reinterpret_cast<uint2*>(stash_base) + warp * (D * 33) + lane;
-    const int n_bins = sp.n_bins, last_bin = sp.n_bins - 1;
+    const int last_bin = sp.n_bins - 1;
 
-    long long sum_d = 0;          // exact integer sum of re-centred scores (2^-18 units)
+    long long sum_d = 0;          // exact integer sum of re-centred scores (moment units)
     double sum_d2 = 0.0;          // sum of their squares
     long long cnt = 0;
+    int filler = 0;               // completions counted into the centre bin that are no real windows
 
     // histogram row of bin b starts at b * hist_words words; with 32 words per row every lane
     // counts into its own bank (conflict free), with 1 word per row lanes share the counters
@@ -353,6 +451,12 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         const long long t = __shfl_sync(0xffffffffu, prefetched, 0);   // fetched one tile ago
         if (lane == 0) prefetched = first_dyn + (long long)atomicAdd(tile_ctr, 1ull);
         return t;
+    };
+    auto flush_staged = [&]() {
+        unsigned char* cb = cand_ptr();
+        flush_candidates(reinterpret_cast<unsigned long long*>(cb),
+                         reinterpret_cast<unsigned int*>(cb + CGBK_CAND_STAGE * 8), lane, work.counters,
+                         work.cands, work.cand_cap);
     };
     while (tile < work.tile_end) {
         long long gbase, seq_len, tile0;
@@ -375,9 +479,14 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
             } else {
                 if (lane == 0)
                     atomicAdd(reinterpret_cast<unsigned long long*>(work.counters + CGBK_CTR_DIRTY_TILES), 1ull);
+                ExactHitSink sink;
+                sink.hits8 = sp.thr_fix != CGBK_NO_THRESHOLD ? work.hits8 : nullptr;
+                sink.hit_cap = work.hit_cap; sink.hit_cursor = work.hit_cursor; sink.counters = work.counters;
+                sink.thr = sp.thr; sink.revseq = sp.revseq;
                 exact_tile_stats(static_cast<const ExactTables*>(sp.exact_tab), g.bases2, g.amb, g.lower,
                                  g.cap_bases, gbase, A, A + (own_n > 0 ? own_n : 0), m, tile, L, D, sp.d_hist,
-                                 sp.n_bins, sp.hist_lo_d, sp.inv_binw_d, sp.plane, (double)sp.scale, exact_acc);
+                                 sp.n_bins, sp.hist_lo_d, sp.inv_binw_d, sp.plane, (double)sp.scale, exact_acc,
+                                 &sink);
             }
             tile = advance();
             preload(tile);
@@ -387,17 +496,22 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         uint32_t sa[32], sb[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) { sa[i] = 0u; sb[i] = 0u; }
-        int acc_d = 0;                 // per-body integer sum (MODE 1)
-        long long acc_d2 = 0;          // per-tile integer sum of squares (MODE 1)
+        int acc_d = 0;                 // per-body integer sum (stats modes)
+        long long acc_d2 = 0;          // per-tile integer sum of squares (stats modes)
         // score plane rows of this tile: [(B + 1) * 32][32] ints, row = body*32 + t (last: the tail)
-        int* prow = sp.plane ? sp.plane + tile * (long long)((B + 1) * 1024) + lane : nullptr;
+        int* prow = (MODE != 0 && sp.plane) ? sp.plane + tile * (long long)((B + 1) * 1024) + lane : nullptr;
 
-        // one completed window: accumulators (a, b), tile-local window index wt, plane row
         uint32_t flag_or = 0u, pend[EW], pendb[EW];            // the last (up to) EW completed windows
 #pragma unroll
         for (int i = 0; i < EW; ++i) { pend[i] = 0u; pendb[i] = 0u; }
-        bool staged = false;                                   // MODE 0: this lane parked candidates
-        auto complete = [&](uint32_t a, uint32_t b, int wt, bool live, int row, int q /* window % 4 */) {
+        bool staged = false;                                   // this lane parked candidates
+        // one completed window: accumulators (a, b); its tile-local index is wbase_t + wrel with
+        // wrel a compile-time constant, and it is one of the tile's own iff wrel < lim (lim =
+        // own_n - wbase_t, one subtraction per body); plane row; `live` is false for the partial
+        // sums of the previous lane's windows (unified body only)
+        auto complete = [&](uint32_t a, uint32_t b, int wbase_t, int wrel, int lim, bool live, int row,
+                            int q /* window % EW */) {
+            const int wt = wbase_t + wrel;
             if (MODE == 0) {
                 // Filter: only OR the two flag bits here (one LOP3).  Every 4th window the OR is
                 // tested and, in the rare case it is set, the four windows are examined out of
@@ -407,26 +521,40 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 pend[q] = a;
                 if (q == 3) {
                     if (flag_or) {
-                        emit_candidates4(pend[0], pend[1], pend[2], pend[3], wt - 3, S, own_n, gbase + A,
-                                         cand_stage, cand_cnt, work.counters, work.cands, work.cand_cap);
+                        unsigned char* cb = cand_ptr();
+                        emit_candidates4(pend[0], pend[1], pend[2], pend[3], wt - 3, S, own_n, (wbase << 4) - S,
+                                         reinterpret_cast<unsigned long long*>(cb),
+                                         reinterpret_cast<unsigned int*>(cb + CGBK_CAND_STAGE * 8),
+                                         work.counters, work.cands, work.cand_cap);
                         staged = true;      // something may be parked: flush at the next convergent point
                     }
                     flag_or = 0u;
                 }
             } else {
                 // Stats: the soft-max / histogram / moment epilogue is one long dependent chain
-                // (max, I2F, EX2, LG2, F2I, mul-hi, select, RED: ~170 cycles).  Four windows are
+                // (max, I2F, EX2, LG2, F2I, mul-hi, RED: ~170 cycles).  Four windows are
                 // therefore collected and their chains run side by side, stage by stage.
                 pend[q] = a;
                 pendb[q] = b;
                 if (q == EW - 1) {
                     int mx[EW], sfix[EW];
                     float u[EW];
+                    bool any_cand = false;
 #pragma unroll
                     for (int k = 0; k < EW; ++k) {
                         const int fq = (int)pend[k], rq = (int)pendb[k];
                         mx[k] = max(fq, rq);
                         u[k] = (float)(mx[k] - min(fq, rq)) * sp.neg_inv_scale;
+                        any_cand |= mx[k] >= sp.thr_fix;
+                    }
+                    if (any_cand) {
+                        // rare: some window of the four may reach the hit threshold (examined out of
+                        // line; the strand scores are not needed past this point)
+                        emit_candidates4_fix((int)pend[0], (int)pend[1], (int)pend[2], (int)pend[3], (int)pendb[0],
+                                             (int)pendb[1], (int)pendb[2], (int)pendb[3], sp.thr_fix, wt - 3, S,
+                                             own_n, (wbase << 4) - S, cand_ptr(), work.counters, work.cands,
+                                             work.cand_cap);
+                        staged = true;
                     }
 #pragma unroll
                     for (int k = 0; k < EW; ++k) u[k] = ex2_approx(u[k]);                 // 2^-|f-r|
@@ -436,29 +564,36 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                     for (int k = 0; k < EW; ++k) sfix[k] = mx[k] + __float2int_rn(u[k] * sp.scale);   // fixed point
 #pragma unroll
                     for (int k = 0; k < EW; ++k) {
-                        const bool valid = live && (wt - (EW - 1) + k < own_n);
-                        int bin = min((int)(__umulhi((unsigned)max(sfix[k] - sp.lo_fix, 0), sp.bin_mul) >> sp.bin_shift),
-                                      last_bin);
-                        bin = valid ? bin : n_bins;
-                        // plain shared-memory reduction (atomicAdd(.., 1) would be wrapped in a
-                        // warp-collective region by ptxas)
-                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_saddr + hist_row_bytes * (unsigned)bin),
-                                     "r"(1u));
-                        int dq = (sfix[k] - sp.c_fix + sp.half) >> sp.sh;
-                        dq = valid ? dq : 0;
+                        if (prow) prow[(row - (EW - 1) + k) * 32] = sfix[k];
+                        // Validity is ONE select, not a branch: a window that is not the tile's own
+                        // takes the moment centre as its score.  It then adds nothing to the
+                        // moments and lands in the centre's histogram bin, from which the block's
+                        // count of such windows is taken out again before the flush.
+                        const bool valid = live && (wrel - (EW - 1) + k < lim);
+                        const int sv = valid ? sfix[k] : sp.c_fix;
+                        if (HIST) {
+                            const int bin = min((int)(__umulhi((unsigned)max(sv - sp.lo_fix, 0), sp.bin_mul) >> sp.bin_shift),
+                                                last_bin);
+                            // plain shared-memory reduction (atomicAdd(.., 1) would be wrapped in a
+                            // warp-collective region by ptxas)
+                            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_saddr + hist_row_bytes * (unsigned)bin),
+                                         "r"(1u));
+                        }
+                        const int dq = (sv - sp.c_fix + sp.half) >> sp.sh;
                         acc_d += dq;
                         acc_d2 += (long long)dq * dq;
-                        if (prow) prow[(row - (EW - 1) + k) * 32] = sfix[k];
                     }
                 }
             }
         };
 
-        for (int b = 0; b < B; ++b) {
-            const uint2 nxt = ld_stream2(g.bases2, wbase + 2 * (b + 1), nwords);
-            const uint32_t w0 = cur.x, w1 = cur.y, w2 = nxt.x;
+        // one 32-position body.  FM 0: `first` known at run time (unified code), FM 1: the first
+        // body of the lane segment, FM 2: a later body (peeled code copies).
+        auto body = [&](auto fm_tag, int b, uint32_t w0, uint32_t w1, uint32_t w2) {
+            constexpr int FM = decltype(fm_tag)::value;
             const int Sb = S + 32 * b;
-            const bool first = ONE || (b == 0);
+            const int lim = own_n - Sb;
+            const bool first = FM == 0 ? (ONE || b == 0) : (FM == 1);
 #pragma unroll
             for (int t0 = 0; t0 < 32; t0 += SB) {
               // look up SB consecutive positions first (independent LDS in flight together) ...
@@ -484,21 +619,43 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 if (t < D) {
                     // first body: partial sums of the PREVIOUS lane's last D windows -> strip;
                     // later bodies: a window that started in the previous body completes
-                    if (first) {
+                    if (FM != 2 && first) {
                         if (MODE == 0) stash32[t * 33] = sa[sc];
                         else stash64[t * 33] = make_uint2(sa[sc], sb[sc]);
                     }
-                    if (!ONE) complete(sa[sc], sb[sc], Sb + t - D, !first, b * 32 + t, (t - D) & (EW - 1));
+                    if (FM == 2) complete(sa[sc], sb[sc], Sb, t - D, lim, true, b * 32 + t, (t - D) & (EW - 1));
+                    else if (FM == 0 && !ONE) complete(sa[sc], sb[sc], Sb, t - D, lim, !first, b * 32 + t, (t - D) & (EW - 1));
                 } else {
-                    complete(sa[sc], sb[sc], Sb + t - D, true, b * 32 + t, (t - D) & (EW - 1));
+                    complete(sa[sc], sb[sc], Sb, t - D, lim, true, b * 32 + t, (t - D) & (EW - 1));
                 }
               }
             }
-            cur = nxt;
-            if (MODE == 1) { sum_d += acc_d; acc_d = 0; }
-            if (MODE == 0 && __any_sync(0xffffffffu, staged)) {     // a vote, no memory access, when idle
-                flush_candidates(cand_stage, cand_cnt, lane, work.counters, work.cands, work.cand_cap);
+        };
+        auto after_body = [&]() {
+            if (MODE != 0) { sum_d += acc_d; acc_d = 0; }
+            if (__any_sync(0xffffffffu, staged)) {     // a vote, no memory access, when idle
+                flush_staged();
                 staged = false;
+            }
+        };
+
+        if (PEEL) {
+            uint2 nxt = ld_stream2(g.bases2, wbase + 2, nwords);
+            body(std::integral_constant<int, 1>(), 0, cur.x, cur.y, nxt.x);
+            cur = nxt;
+            after_body();
+            for (int b = 1; b < B; ++b) {
+                nxt = ld_stream2(g.bases2, wbase + 2 * (b + 1), nwords);
+                body(std::integral_constant<int, 2>(), b, cur.x, cur.y, nxt.x);
+                cur = nxt;
+                after_body();
+            }
+        } else {
+            for (int b = 0; b < B; ++b) {
+                const uint2 nxt = ld_stream2(g.bases2, wbase + 2 * (b + 1), nwords);
+                body(std::integral_constant<int, 0>(), b, cur.x, cur.y, nxt.x);
+                cur = nxt;
+                after_body();
             }
         }
         const long long next_tile = advance();
@@ -516,26 +673,38 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                     const uint2 q = stash64[j * 33 + 1];
                     ia = q.x; ib = q.y;
                 }
-                complete(sa[si] + ia, sb[si] + ib, S + L - D + j, true, B * 32 + j, (32 - D + j) & (EW - 1));
+                complete(sa[si] + ia, sb[si] + ib, S + L, j - D, own_n - (S + L), true, B * 32 + j, (32 - D + j) & (EW - 1));
             }
             __syncwarp();
-            if (MODE == 0 && __any_sync(0xffffffffu, staged)) {
-                flush_candidates(cand_stage, cand_cnt, lane, work.counters, work.cands, work.cand_cap);
+            if (__any_sync(0xffffffffu, staged)) {
+                flush_staged();
                 staged = false;
             }
         }
-        if (MODE == 1) {
+        if (MODE != 0) {
             sum_d += acc_d;
             sum_d2 += (double)acc_d2;
             const int mine = own_n - S;
-            cnt += mine < 0 ? 0 : (mine > L ? L : mine);
+            const int mine_c = mine < 0 ? 0 : (mine > L ? L : mine);
+            cnt += mine_c;
+            // completions of this tile that were not the lane's own windows (they sit in the
+            // centre's histogram bin): L per table-scored tile, plus the D junk completions of
+            // the unified first body
+            filler += L + (PEEL ? 0 : D) - mine_c;
         }
         tile = next_tile;
     }
 
-    if (MODE == 1) {
+    if (MODE != 0) {
+        if (HIST) {
+            // the filler completions leave the centre's bin again (every lane's own bank word when
+            // the rows are 32 words wide, one shared word otherwise)
+            const int cbin = min((int)(__umulhi((unsigned)max(sp.c_fix - sp.lo_fix, 0), sp.bin_mul) >> sp.bin_shift),
+                                 last_bin);
+            if (filler) atomicSub(hist + cbin * sp.hist_words + (sp.hist_words == 32 ? lane : 0), (unsigned)filler);
+        }
         __syncthreads();
-        if (sp.d_hist)
+        if (HIST && sp.d_hist)
             for (int i = threadIdx.x; i < sp.n_bins; i += blockDim.x) {
                 unsigned int v = 0;
                 for (int l = 0; l < sp.hist_words; ++l)       // rotate the start: no bank conflict
@@ -573,7 +742,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
             double prev = 0.0;                                   // n, sum, sumsq accumulated so far
             if (threadIdx.x < 3) prev = __ldcg(sp.d_stats + threadIdx.x);
             unsigned long long hcopy = 0ull;                     // n_bins <= blockDim.x in the common case
-            const bool copy_hist = sp.host_stats && sp.host_hist && sp.d_hist;
+            const bool copy_hist = HIST && sp.host_stats && sp.host_hist && sp.d_hist;
             if (copy_hist && (int)threadIdx.x < sp.n_bins) hcopy = __ldcg(sp.d_hist + threadIdx.x);
             block_reduce3(s1, s2, cn, red_scratch);
             // thread 0 holds the totals; threads 0..2 hold the previous n / sum / sumsq
@@ -604,98 +773,31 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     }
 }
 
-template <int G, int MODE, bool ONE>
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of the function: one flag
+// per (template instance, device), set under a lock (a host may drive several GPUs from one
+// process, from several threads).
+#define CGBK_MAX_DEVICES 64
+
+template <int G, int MODE, int VAR>
 static cudaError_t launch_one(const uint32_t* gtab, GenomeView g, SeqTable seqs, FastWork w, int m, int L,
-                              int grid, StatsParams sp, cudaStream_t st) {
+                              int grid, StatsParams sp, int device, cudaStream_t st) {
     using Cfg = FastCfg<G, MODE>;
     const size_t fixed = TableLayout<Cfg::NW>::BYTES + Cfg::STASH_BYTES + Cfg::CAND_BYTES;
     // histogram: (n_bins + 1) rows of 1 word (<= 4096 bins) or of 32 words (<= 256 bins, conflict free)
     const size_t smem_max = fixed + (MODE == 1 ? (size_t)(256 + 1) * 128 : 0);
     const size_t smem = fixed + (MODE == 1 ? ((size_t)sp.n_bins + 1) * 4 * sp.hist_words : 0);
-    static bool configured = false;   // per template instance
-    auto kern = fast_scan_kernel<G, MODE, ONE>;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-        if (e != cudaSuccess) return e;
-        configured = true;
+    static std::mutex mu;
+    static bool configured[CGBK_MAX_DEVICES] = {};   // per template instance
+    auto kern = fast_scan_kernel<G, MODE, VAR>;
+    if (device < 0 || device >= CGBK_MAX_DEVICES) return cudaErrorInvalidDevice;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!configured[device]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+            if (e != cudaSuccess) return e;
+            configured[device] = true;
+        }
     }
     kern<<<grid, Cfg::THREADS, smem, st>>>(gtab, g, seqs, w, m, L / 32, sp);
     return cudaGetLastError();
-}
-
-template <int MODE>
-static cudaError_t dispatch(int G, const uint32_t* gtab, GenomeView g, SeqTable seqs, FastWork w, int m,
-                            int L, int grid, StatsParams sp, cudaStream_t st) {
-#define CGBK_CASE(GG)                                                                               \
-    case GG:                                                                                        \
-        return L == 32 ? launch_one<GG, MODE, true>(gtab, g, seqs, w, m, L, grid, sp, st)           \
-                       : launch_one<GG, MODE, false>(gtab, g, seqs, w, m, L, grid, sp, st);
-    switch (G) {
-        CGBK_CASE(1) CGBK_CASE(2) CGBK_CASE(3) CGBK_CASE(4)
-        CGBK_CASE(5) CGBK_CASE(6) CGBK_CASE(7) CGBK_CASE(8)
-        default: return cudaErrorInvalidValue;
-    }
-#undef CGBK_CASE
-}
-
-int fast_threads(int G, int mode) {
-    if (mode == 0) return CGBK_FILTER_THREADS;
-    return G <= 6 ? CGBK_STATS_THREADS : 256;
-}
-
-cudaError_t launch_fast_filter(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, int L,
-                               int grid, cudaStream_t st) {
-    StatsParams sp = {};
-    return dispatch<0>(mdl->G, mdl->d_coarse, g, seqs, w, mdl->m, L, grid, sp, st);
-}
-
-StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist_hi, int n_bins,
-                              unsigned long long* d_hist, int* plane) {
-    StatsParams sp;
-    const double scale = ldexp(1.0, mdl->kexp);
-    sp.neg_inv_scale = (float)(-1.0 / scale);
-    sp.scale = (float)scale;
-    sp.inv_scale_d = 1.0 / scale;
-    sp.lo_fix = (int)llrint(hist_lo * scale);
-    const double range_fix = (hist_hi - hist_lo) * scale;
-    // bin = (u * n_bins / range_fix) as umulhi(u, M) >> k with M = floor(2^(32+k) n_bins / range_fix)
-    // scaled up to just below 2^32, i.e. bin edges exact to a relative 2^-31
-    double mul = 4294967296.0 * (double)n_bins / range_fix;
-    int k = 0;
-    while (k < 24 && mul * 2.0 < 4294967295.0) { mul *= 2.0; ++k; }
-    if (mul > 4294967295.0) mul = 4294967295.0;
-    sp.bin_mul = (unsigned int)mul;
-    sp.bin_shift = k;
-    sp.n_bins = n_bins;
-    sp.hist_words = n_bins <= 256 ? 32 : 1;
-    sp.exact_tab = mdl->d_exact + CGBK_EXACT_TAB_OFFSET;
-    sp.hist_lo_d = hist_lo;
-    sp.inv_binw_d = (double)n_bins / (hist_hi - hist_lo);
-    sp.d_stats = nullptr;
-    sp.finalize = 0;
-    sp.host_stats = nullptr;
-    sp.host_hist = nullptr;
-    const double centre = 0.5 * (mdl->min_score + mdl->max_score);
-    sp.c_fix = (int)llrint(centre * scale);
-    sp.c = (double)sp.c_fix / scale;
-    // Moment unit 2^-(kexp - sh): the finest the integer accumulators allow.  A body adds 32
-    // re-centred scores in an int32 (|d| < 2^26) and a tile up to 128 squares in an int64
-    // (|d| < 2^28).  For LexA (score range 70 bits, kexp 24) that is 2^-20; a motif with a
-    // narrow range gets an exact sum.  (With a fixed 2^-18 a degenerate 2-bp motif -- 14
-    // distinct scores, so the rounding does not average out -- was off by 9e-7 in the mean,
-    // which its 3 000-window posteriors amplify past 1e-6; found by tools/fuzz_parity.py.)
-    const double half_range_fix = (0.5 * (mdl->max_score - mdl->min_score) + 1.0) * scale + 1.0;  // soft-max <= max + 1
-    int need = 0;
-    while (need < 30 && ldexp(1.0, 26 + need) <= half_range_fix) ++need;
-    sp.sh = need;
-    sp.half = sp.sh > 0 ? (1 << (sp.sh - 1)) : 0;
-    sp.q = ldexp(1.0, -(mdl->kexp - sp.sh));
-    sp.d_hist = d_hist;
-    sp.plane = plane;
-    return sp;
-}
-
-cudaError_t launch_fast_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, int L,
-                              int grid, const StatsParams& sp, cudaStream_t st) {
-    return dispatch<1>(mdl->G, mdl->d_precise, g, seqs, w, mdl->m, L, grid, sp, st);
 }

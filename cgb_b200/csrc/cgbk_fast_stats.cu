@@ -1,0 +1,105 @@
+// MODE 1 of the tiled scan (cgbk_fast.cuh): soft-max histogram + moments (+ score plane,
+// + hit candidates when a threshold is set), and the parameters of that epilogue.
+#include <math.h>
+#include <stdlib.h>
+
+#include "cgbk_fast.cuh"
+
+// Code variant of the stats modes for a lane segment of L bases: the peeled copies waste no
+// epilogue on the previous lane's windows but are twice the code, which a warp that runs a
+// single small tile pays for in cold instruction fetch.  CGBK_STATS_VARIANT=0|2 overrides.
+int stats_variant(int L) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("CGBK_STATS_VARIANT");
+        forced = e ? atoi(e) : -1;
+    }
+    if (forced == CGBK_VAR_UNIFIED || forced == CGBK_VAR_PEEL) return forced;
+    return (L == 32 || L == 128) ? CGBK_VAR_PEEL : CGBK_VAR_UNIFIED;
+}
+
+static cudaError_t dispatch_stats(int G, const uint32_t* gtab, GenomeView g, SeqTable seqs, FastWork w, int m,
+                                  int L, int grid, StatsParams sp, int device, cudaStream_t st) {
+    const bool peel = stats_variant(L) == CGBK_VAR_PEEL;
+#define CGBK_CASE(GG)                                                                                              \
+    case GG:                                                                                                       \
+        return peel ? launch_one<GG, 1, CGBK_VAR_PEEL>(gtab, g, seqs, w, m, L, grid, sp, device, st)               \
+                    : launch_one<GG, 1, CGBK_VAR_UNIFIED>(gtab, g, seqs, w, m, L, grid, sp, device, st);
+    switch (G) {
+        CGBK_CASE(1) CGBK_CASE(2) CGBK_CASE(3) CGBK_CASE(4)
+        CGBK_CASE(5) CGBK_CASE(6) CGBK_CASE(7) CGBK_CASE(8)
+        default: return cudaErrorInvalidValue;
+    }
+#undef CGBK_CASE
+}
+
+StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist_hi, int n_bins,
+                              unsigned long long* d_hist, int* plane) {
+    StatsParams sp;
+    const double scale = ldexp(1.0, mdl->kexp);
+    sp.neg_inv_scale = (float)(-1.0 / scale);
+    sp.scale = (float)scale;
+    sp.inv_scale_d = 1.0 / scale;
+    sp.lo_fix = (int)llrint(hist_lo * scale);
+    const double range_fix = (hist_hi - hist_lo) * scale;
+    // bin = (u * n_bins / range_fix) as umulhi(u, M) >> k with M = floor(2^(32+k) n_bins / range_fix)
+    // scaled up to just below 2^32, i.e. bin edges exact to a relative 2^-31
+    double mul = 4294967296.0 * (double)n_bins / range_fix;
+    int k = 0;
+    while (k < 24 && mul * 2.0 < 4294967295.0) { mul *= 2.0; ++k; }
+    if (mul > 4294967295.0) mul = 4294967295.0;
+    sp.bin_mul = (unsigned int)mul;
+    sp.bin_shift = k;
+    sp.n_bins = n_bins;
+    sp.hist_words = n_bins <= 256 ? 32 : 1;
+    sp.exact_tab = mdl->d_exact + CGBK_EXACT_TAB_OFFSET;
+    sp.hist_lo_d = hist_lo;
+    sp.inv_binw_d = (double)n_bins / (hist_hi - hist_lo);
+    sp.d_stats = nullptr;
+    sp.finalize = 0;
+    sp.host_stats = nullptr;
+    sp.host_hist = nullptr;
+    const double centre = 0.5 * (mdl->min_score + mdl->max_score);
+    sp.c_fix = (int)llrint(centre * scale);
+    sp.c = (double)sp.c_fix / scale;
+    // Moment unit 2^-(kexp - sh): the finest the integer accumulators allow.  A body adds 32
+    // re-centred scores in an int32 (|d| < 2^26) and a tile up to 128 squares in an int64
+    // (|d| < 2^28).  For LexA (score range 70 bits, kexp 24) that is 2^-20; a motif with a
+    // narrow range gets an exact sum.  (With a fixed 2^-18 a degenerate 2-bp motif -- 14
+    // distinct scores, so the rounding does not average out -- was off by 9e-7 in the mean,
+    // which its 3 000-window posteriors amplify past 1e-6; found by tools/fuzz_parity.py.)
+    const double half_range_fix = (0.5 * (mdl->max_score - mdl->min_score) + 1.0) * scale + 1.0;  // soft-max <= max + 1
+    int need = 0;
+    while (need < 30 && ldexp(1.0, 26 + need) <= half_range_fix) ++need;
+    sp.sh = need;
+    sp.half = sp.sh > 0 ? (1 << (sp.sh - 1)) : 0;
+    sp.q = ldexp(1.0, -(mdl->kexp - sp.sh));
+    sp.d_hist = d_hist;
+    sp.plane = plane;
+    sp.thr_fix = CGBK_NO_THRESHOLD;
+    sp.thr = 0.0;
+    sp.revseq = 0;
+    return sp;
+}
+
+// Fused scan: candidate threshold in fixed point.  A hit is (double)(float)score >= thr with the
+// exact float64 score; the fixed-point strand sum differs from score * 2^kexp by at most m
+// units (m table entries rounded to half a unit each, plus the whole-unit bias shift of at
+// most m / 2), and the float32 rounding can lift a score by half an ulp of float32 (< 2^-18
+// for |score| < 64, relative 2^-24 beyond).  Everything at or above the bound is a candidate
+// and is decided by the exact re-score: no false negatives.
+void set_stats_threshold(StatsParams* sp, const cgbk_model* mdl, double thr, int revseq) {
+    const double scale = ldexp(1.0, mdl->kexp);
+    const double slack = 1e-5 + fabs(thr) * 1.2e-7;
+    double t = floor((thr - slack) * scale) - (double)(2 * mdl->m + 2);
+    if (!(t > -2147483000.0)) t = -2147483000.0;        // everything is a candidate
+    if (t >= 2147483000.0) { sp->thr_fix = CGBK_NO_THRESHOLD; sp->thr = thr; sp->revseq = revseq; return; }
+    sp->thr_fix = (int)t;
+    sp->thr = thr;
+    sp->revseq = revseq ? 1 : 0;
+}
+
+cudaError_t launch_fast_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, int L,
+                              int grid, const StatsParams& sp, cudaStream_t st) {
+    return dispatch_stats(mdl->G, mdl->d_precise, g, seqs, w, mdl->m, L, grid, sp, mdl->device, st);
+}

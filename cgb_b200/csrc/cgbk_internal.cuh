@@ -16,6 +16,8 @@ struct cgbk_model {
     int m;
     int G;       // ceil(m / 4): number of 4-mer groups
     int device;
+    int sms;     // multiprocessors of that device
+    int owns_block;   // d_exact was allocated for this model alone (not part of a model batch)
     // host float64 tables, [pos][ACGT]
     double fwd[CGBK_MAXM * 4];
     double rc[CGBK_MAXM * 4];     // rc[j][b] = fwd[m-1-j][3-b]  (pssm_model.py:52-55)
@@ -44,13 +46,16 @@ struct cgbk_seqset {
     // different numbers of resident warps and therefore different best tilings.
     struct Tiling {
         int cached_m, cached_L;
+        int64_t cached_wcap;     // window cap the tiling was built with (-1: none)
         int64_t* d_tile_prefix;  // [n_seq + 1]
         int64_t* h_tile_prefix;  // [n_seq + 1] (staging for the async upload; inline copy source)
         int64_t n_tiles;
-    } tiling[2];
+    } tiling[3];
 };
+#define CGBK_N_TILINGS 3
 #define CGBK_TILING_STATS 0
 #define CGBK_TILING_HITS 1
+#define CGBK_TILING_BATCH 2   // cgbk_scan_batch: many motif lengths in a row; leaves the score plane's tiling alone
 
 #define CGBK_EXACT_DOUBLES (CGBK_MAXM * 4 * 2 + CGBK_MAXM * 2)
 // d_exact holds the plain tables (CGBK_EXACT_DOUBLES doubles) followed by the same numbers in
@@ -85,6 +90,9 @@ struct SeqTable {
 // per-thread error text + status helpers (cgbk_api.cu)
 int cgbk_set_error(int code, const char* fmt, ...);
 int cgbk_check_cuda(cudaError_t e, const char* what);
+// multiprocessor count of a device / of the current device (cached per device)
+int cgbk_device_sms(int device);
+int cgbk_current_sms();
 
 // ---------------------------------------------------------------------------
 // launchers implemented in the kernel translation units
@@ -103,7 +111,19 @@ struct FastWork {      // carved out of the caller's workspace
     long long tile_begin, tile_end;
     int ctr_slot;
     int partial_base;
+    // fused stats scan: compact hit list shared by the models of a batch.  Tiles with
+    // non-ACGT bytes are scored exactly inside the scan and append their hits right there.
+    unsigned long long* hits8;  // cgbk_hit8 records
+    long long hit_cap;
+    long long* hit_cursor;      // append position (one counter for the whole batch)
 };
+
+// compact hit record (include/cgbk.h cgbk_hit8): gpos << 33 | minus << 32 | float32 score bits
+__host__ __device__ inline unsigned long long cgbk_pack_hit8(long long gpos, int minus, unsigned int score_bits) {
+    return ((unsigned long long)gpos << 33) | ((unsigned long long)(minus ? 1u : 0u) << 32) | score_bits;
+}
+
+#define CGBK_NO_THRESHOLD 0x7fffffff   // StatsParams.thr_fix of a scan without hit search
 
 cudaError_t launch_pack(const uint8_t* d_ascii, long long n, long long dst_off, uint32_t* b2,
                         uint32_t* amb, uint32_t* lower, cudaStream_t st);
@@ -132,6 +152,13 @@ cudaError_t launch_rescore(const cgbk_model* mdl, GenomeView g, SeqTable seqs, F
 
 cudaError_t launch_bg_finalize(const double* partials, int n_partials, double* d_stats,
                                int accumulate, cudaStream_t st);
+
+cudaError_t launch_bg_finalize_batch(double* d_stats, int n_records, cudaStream_t st);
+
+cudaError_t launch_region_stats(const cgbk_model* mdl, GenomeView g, const long long* d_start, const int* d_nwin,
+                                int n_regions, double hist_lo, double hist_hi, int n_bins,
+                                unsigned long long* d_hist, double* partials, int partial_cap, double* d_stats,
+                                int accumulate, cudaStream_t st);
 
 cudaError_t launch_fast_filter(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
                                int L, int grid, cudaStream_t st);
@@ -165,13 +192,27 @@ struct StatsParams {
     // stores the finished record (and histogram) there, sparing the caller a D2H copy
     double* host_stats;
     unsigned long long* host_hist;
+    // fused scan: windows whose fixed-point strand score reaches thr_fix are hit candidates
+    // (CGBK_NO_THRESHOLD: none); thr / revseq serve the exactly scored tiles
+    int thr_fix;
+    int revseq;
+    double thr;
 };
 
 StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist_hi, int n_bins,
                               unsigned long long* d_hist, int* plane);
 
+void set_stats_threshold(StatsParams* sp, const cgbk_model* mdl, double thr, int revseq);
+
 cudaError_t launch_fast_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
                               int L, int grid, const StatsParams& sp, cudaStream_t st);
+// the same without the histogram (MODE 2)
+cudaError_t launch_fast_moments(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
+                                int L, int grid, const StatsParams& sp, cudaStream_t st);
+
+// exact re-score of the fused scan's candidates into the compact hit list
+cudaError_t launch_rescore8(const cgbk_model* mdl, GenomeView g, FastWork w, double thr, int flags,
+                            cudaStream_t st);
 
 // score plane addressing shared by the writers (cgbk_fast.cu, dirty tiles) and the reader
 // (posteriors): window wt of a tile with lane segment L = 32 * B and overlap D = 4 * (G - 1)
@@ -200,6 +241,7 @@ struct BgScan {
     FastWork w;
     StatsParams sp;
     int L, sms, threads;
+    int moments_only;      // no histogram asked for: the scan runs without one (MODE 2)
     double* d_stats;
     long long next_tile;
     int n_ranges, partials_used, finalized;

@@ -73,7 +73,7 @@ static PipeLayout pipe_layout(int64_t n_bases, int n_regions, int m, int n_bins)
     int64_t o = 0;
     p.off_ascii = o;  o += align256(n_bases);
     p.off_planes = o; o += align256(padded / 2);                // bases2 (cap/4) + amb + lower (cap/8 each)
-    p.off_table = o;  o += align256(8 * 6);                      // cgbk_seqset_table_ints(1) int64
+    p.off_table = o;  o += align256(8 * cgbk_seqset_table_ints(1));
     p.off_plane = o;  o += align256(4 * p.plane_ints);
     p.off_msm = o;    o += 256;
     p.off_desc = o;   o += align256(12 * (int64_t)n_regions);
@@ -197,7 +197,7 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
         return cgbk_set_error(CGBK_ERR_CUDA, "H2D of the sequence failed");
 
     // promoter slices -> (packed offset, window count): Chromid.subsequence's Python slice
-    // (cgb/chromid.py:94) then len(seq) - m + 1 windows; len(seq) < m raises in the reference
+    // (cgb/chromid.py:94) then len(seq) - m + 1 windows; len(seq) < m - 1 raises in the reference
     int64_t* st_start = (int64_t*)h_staging;
     int32_t* st_nwin = (int32_t*)((unsigned char*)h_staging + 8 * (int64_t)n_regions);
     for (int i = 0; i < n_regions; ++i) {
@@ -206,9 +206,9 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
         e = e < 0 ? (e + n_bases > 0 ? e + n_bases : 0) : (e < n_bases ? e : n_bases);
         if (e < s) e = s;
         const int64_t nw = e - s - m + 1;
-        if (nw < 1) {
+        if (nw < 0) {      // len == m - 1 is an empty score list in the reference (posterior = prior)
             cudaStreamSynchronize(st);              // the upload may be in flight
-            return cgbk_set_error(CGBK_ERR_INVALID, "region %d is shorter than the motif "
+            return cgbk_set_error(CGBK_ERR_INVALID, "region %d is more than one base shorter than the motif "
                                   "(negative dimensions are not allowed)", i);
         }
         st_start[i] = s;           // sequence 0 starts at packed offset 0

@@ -69,6 +69,30 @@ def allreduce_background(bg, group=None):
     return bg
 
 
+def allreduce_batch(stats, hist, group=None):
+    """The same for a motif batch: ``stats`` float64 [K][8] and ``hist`` int64 [K][n_bins] (or
+    None) of ``motif_batch.scan_batch(..., to_host=False)`` are summed over the ranks with ONE
+    collective -- a float64 buffer [K][3 + n_bins] -- and mean / std of all K records recomputed
+    (``cgbk_background_finalize_batch``).  In place; returns the buffer size in bytes."""
+    cols = [stats[:, :3]]
+    if hist is not None:
+        cols.append(hist.to(torch.float64))
+    buf = torch.cat(cols, dim=1).contiguous()
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    stats[:, :3] = buf[:, :3]
+    if hist is not None:
+        hist.copy_(buf[:, 3:].round().to(hist.dtype))
+    if stats.is_cuda:
+        if not stats.is_contiguous():
+            raise ValueError("stats must be contiguous")
+        _cabi.check(_cabi.lib().cgbk_background_finalize_batch(
+            stats.data_ptr(), int(stats.shape[0]), torch.cuda.current_stream(stats.device).cuda_stream))
+    else:
+        for k in range(stats.shape[0]):
+            finalize_stats_host(stats[k])
+    return buf.numel() * 8
+
+
 def finalize_stats_host(stats):
     """mean / std (ddof = 0) from n, sum, sumsq — the host mirror of
     cgbk_background_finalize, used on CPU tensors."""

@@ -81,12 +81,38 @@ class Genome(object):
         return self._TF_binding_model
 
     # -- genome.py:203-227
-    def build_PSSM_model(self, collections, weights):
-        """PSSM model + Bayesian estimator.  The background is the score distribution of ALL
-        windows of every replicon (the reference samples <= 10 000 upstream m-mers with
-        ``random.sample``; the scan makes the full distribution cheaper than the sample)."""
+    def upstream_regions(self, down=50):
+        """Region table of the reference's background population (genome.py:215): every gene's
+        ``upstream_noncoding_region_location(None, down)`` (gene.py:72-104), per replicon."""
+        return [(gt.seq_index,) + tuple(gt.upstream_noncoding_region_location(None, down))
+                for gt in self.gene_tables if len(gt)]
+
+    def build_PSSM_model(self, collections, weights, mode="upstream"):
+        """PSSM model + Bayesian estimator (genome.py:203-227).
+
+        ``mode="upstream"`` (default): the background is the reference's own population -- every
+        m-mer of every gene's upstream non-coding region (to the previous gene, 50 bp into the
+        gene; the last m-mer of each region dropped as ``xrange(len(seq) - m)`` does), each scored
+        by ``score_seq`` as a sequence of its own, regions overlapping or repeated as the gene
+        table has them.  The reference then keeps a ``random.sample`` of <= 10 000 of those
+        m-mers; here ALL of them are scored (deterministic; the sample's mean / std scatter
+        around these values).
+        ``mode="all"``: every window of every replicon, coding sequence included (the genome-wide
+        distribution of the benchmark; a different population: intergenic and coding
+        composition differ on real genomes, so mu_bg / std_bg shift)."""
         model = PSSMModel(collections, weights, device=self._device)
-        model.fit_background(self.packed)
+        if mode == "all":
+            model.fit_background(self.packed)
+        elif mode == "upstream":
+            # the genome-wide scan still runs: its score plane serves the promoter posteriors;
+            # the estimator's moments come from the region table
+            bg = model.background_stats(self.packed, keep_scores=True)
+            reg = model.background_stats(self.packed, regions=self.upstream_regions(), n_bins=bg["n_bins"],
+                                         hist_lo=bg["hist_lo"], hist_hi=bg["hist_hi"])
+            bg = dict(bg, stats=reg["stats"], hist=reg["hist"], work=None, work_key=None)
+            model.fit_background(bg=bg)
+        else:
+            raise ValueError("mode must be 'upstream' or 'all'")
         self._TF_binding_model = model
 
     # -- genome.py:394-455

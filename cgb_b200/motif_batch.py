@@ -1,0 +1,348 @@
+"""Many PSWMs at once: batched model tables and the batched (fused) scan.
+
+The reference builds one ``PSSMModel`` per genome inside its ``go()`` loop
+(cgb/__init__.py:673-686, pssm_model.py:31-35) and scores one motif per call
+(pssm_model.py:103-133).  For a motif set (BASELINE configs[4]: 500 JASPAR-scale motifs over a
+Gbp sequence) or a genome batch with several PSWMs each (configs[2]) that is one device
+allocation, one synchronous upload and a handful of launches *per model*.  Here
+
+* :class:`ModelBatch` puts the device tables of K models into ONE block with ONE upload
+  (``cgbk_model_batch_create``);
+* :func:`scan_batch` runs K models over a packed genome in ONE library call: per model a
+  single pass that yields the background record (moments, optional histogram;
+  genome.py:215-226) AND the thresholded sites of both strands (genome.py:433-445), the
+  latter as compact 8-byte records in one shared buffer.  No allocation and no host
+  synchronisation per model; the host sees one counters block per sub-batch.
+
+A rank's shard of a longer sequence passes ``win_cap`` = the number of windows it owns: the
+shard carries the halo of the longest motif, every motif stops at the shard's own windows
+(SURVEY.md §8e).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+HIT_DTYPE = np.dtype([("gpos", "<i8"), ("strand", "<i4"), ("score", "<f4")])
+
+
+def unpack_hits(rec):
+    """Compact records (uint64 ndarray, ``cgbk_hit8``) -> (gpos int64, strand int32, score float32)."""
+    rec = np.asarray(rec, dtype=np.uint64)
+    gpos = (rec >> np.uint64(33)).astype(np.int64)
+    strand = (1 - 2 * ((rec >> np.uint64(32)) & np.uint64(1)).astype(np.int32)).astype(np.int32)
+    score = (rec & np.uint64(0xffffffff)).astype(np.uint32).view(np.float32)
+    return gpos, strand, score
+
+
+class ModelBatch:
+    """Device tables of many :class:`PSSMModel` in one block.  The models' handles are borrowed
+    from the batch, which they keep alive; models that already have tables are left alone."""
+
+    def __init__(self, models, device=None):
+        models = list(models)
+        todo = [M for M in models if M._handle is None]
+        self.models = models
+        self._batch = C.c_void_p()
+        if not todo:
+            return
+        dev = torch.device(device) if device is not None else todo[0]._dev()
+        rows = []
+        for M in todo:
+            if sorted(M.alphabet) != ["A", "C", "G", "T"]:
+                raise ValueError("PSSM has wrong alphabet: %s - Use only with DNA motifs" % M.alphabet)
+            M._device = dev
+            rows.append(np.asarray(M.pssm.rows(), dtype=np.float64))
+        flat = np.ascontiguousarray(np.concatenate([r.reshape(-1) for r in rows]))
+        ms = np.ascontiguousarray(np.array([len(r) for r in rows], dtype=np.int32))
+        lib = _cabi.lib()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _cabi.check(lib.cgbk_model_batch_create(
+            flat.ctypes.data_as(C.POINTER(C.c_double)), ms.ctypes.data_as(C.POINTER(C.c_int)), len(todo),
+            dev.index or 0, stream, C.byref(self._batch)))
+        for k, M in enumerate(todo):
+            M._handle = C.c_void_p(lib.cgbk_model_batch_get(self._batch, k))
+            M._batch_owner = self          # the tables live as long as any model refers to them
+
+    def __del__(self):
+        try:
+            if getattr(self, "_batch", None) is not None and self._batch.value:
+                _cabi.lib().cgbk_model_batch_destroy(self._batch)
+                self._batch = C.c_void_p()
+        except Exception:
+            pass
+
+
+class _ScanBuffers:
+    """Device and pinned host buffers of :func:`scan_batch`, kept on the genome and reused between
+    calls.  Two hit buffers: while the host receives the sites of one sub-batch, the next is scanned."""
+
+    def __init__(self, dev, n_models, n_bins, hit_cap, cand_cap, host_hits):
+        lib = _cabi.lib()
+        self.n_models, self.n_bins, self.hit_cap, self.cand_cap = n_models, n_bins, hit_cap, cand_cap
+        # stats | histograms | counters back to back: the library clears them with one memset
+        n_rec = n_models * _cabi.BG_COUNT + n_models * n_bins + (n_models + 1) * _cabi.CTR_COUNT
+        self.record = torch.empty(n_rec, dtype=torch.int64, device=dev)
+        self.host_record = torch.empty(n_rec, dtype=torch.int64).pin_memory()
+        n_buf = 2 if host_hits else 1
+        self.hits = [torch.empty(max(hit_cap, 1), dtype=torch.int64, device=dev) for _ in range(n_buf)]
+        self.host_hits = [torch.empty(max(hit_cap, 1), dtype=torch.int64).pin_memory() for _ in range(n_buf)] \
+            if host_hits else []
+        self.copied = [None] * n_buf                  # event: the D2H out of hits[p] has finished
+        self.copy_stream = torch.cuda.Stream(device=dev) if host_hits else None
+        wbytes = int(lib.cgbk_scan_batch_workspace_bytes(cand_cap))
+        self.work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        self.sort_tmp = None
+
+
+# one set of scratch buffers per device, shared by all genomes scanned there (calls on one device
+# are expected to come from one thread at a time; the buffers are stream-ordered on the current
+# stream and host-synchronised before they are handed out again)
+_BUFFER_CACHE = {}
+
+
+def _buffers(genome, n_models, n_bins, hit_cap, cand_cap, host_hits):
+    key = genome.device.index or 0
+    b = _BUFFER_CACHE.get(key)
+    if (b is None or b.n_models < n_models or b.n_bins != n_bins or b.hit_cap < hit_cap or b.cand_cap < cand_cap
+            or (host_hits and not b.host_hits)):
+        _BUFFER_CACHE.pop(key, None)
+        b = None                                          # free the old buffers first
+        b = _ScanBuffers(genome.device, n_models, n_bins, hit_cap, cand_cap, host_hits)
+        _BUFFER_CACHE[key] = b
+    return b
+
+
+def release_buffers(device=None):
+    """Drop the cached scratch buffers (all devices, or one)."""
+    if device is None:
+        _BUFFER_CACHE.clear()
+    else:
+        _BUFFER_CACHE.pop(torch.device(device).index or 0, None)
+
+
+def expected_hits(model, n_windows):
+    """Sites expected at the Patser operating point (FPR = 2^-IC per strand, pssm_model.py:62-70)
+    under the uniform background, both strands."""
+    return 2.0 * n_windows * 2.0 ** (-max(float(model.IC), 0.0))
+
+
+def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, revseq_order=True,
+               hit_cap=None, sort=True, to_host=True, sink=None, recycle=False, kernel_ms=None):
+    """Background record and thresholded sites of every model over ``genome`` (a PackedGenome).
+
+    ``thresholds``: ``"patser"`` (each model's own, pssm_model.py:72-77), a sequence of floats, or
+    ``None`` for background records only.  ``n_bins`` = 0 runs without histograms.
+    Returns a dict:
+
+      stats   float64 [K][8] (n, sum, sumsq, mean, std), hist int64 [K][n_bins] or None
+      hits    list of K compact uint64 arrays (see :func:`unpack_hits`), each sorted by
+              (position, + strand first) when ``sort``; positions are offsets into the packed
+              buffer.  ``None`` without thresholds
+      counters  int64 [K][8];  launches: kernels launched
+
+    ``to_host`` (default): numpy arrays.  The models go through the device in sub-batches sized
+    to the hit buffer; each sub-batch's sites cross PCIe on a copy stream (pinned staging) while
+    the next sub-batch is scanned.  ``sink(k, records)``: called with model k's records as a
+    view of the pinned staging buffer instead of a fresh array (valid until it returns).
+    ``to_host=False``: device tensors; the sites stay in the device hit buffer, so the whole
+    batch must fit ``hit_cap`` (ValueError otherwise) -- unless ``recycle``: then the buffer is
+    reused from sub-batch to sub-batch and ``hits`` holds the per-model COUNTS only (a consumer
+    on the device would take each sub-batch's sorted lists before the next overwrites them; the
+    benchmark's device-resident leg).
+    ``kernel_ms``: float array [K]; with ``_cabi.profile_enable(2)`` every model's scan-kernel time
+    (CUDA events around the launch) is ADDED to it."""
+    from .pssm_model import prepare_thresholds
+    models = list(models)
+    K = len(models)
+    if K == 0:
+        raise ValueError("no models")
+    dev = genome.device
+    ModelBatch(models, dev)                               # tables of the models that have none yet
+    lib = _cabi.lib()
+    want_hits = thresholds is not None
+    if want_hits and isinstance(thresholds, str):
+        if thresholds != "patser":
+            raise ValueError
+        prepare_thresholds(models)
+        thresholds = [M.threshold() for M in models]
+    thr = np.ascontiguousarray(thresholds, dtype=np.float64) if want_hits else None
+    if want_hits and len(thr) != K:
+        raise ValueError("one threshold per model")
+    nwin_all = genome.total_windows(min(M.length for M in models))
+    if win_cap is not None:
+        nwin_all = min(nwin_all, int(win_cap) * genome.n_seq)
+    # expected sites per model; explicit thresholds below the Patser point are only guessed (the
+    # overflow path below re-runs with the real count)
+    exp = np.array([expected_hits(M, nwin_all) * 1.25 + 4096 for M in models]) if want_hits else np.zeros(K)
+    if hit_cap is None:
+        hit_cap = 0
+        if want_hits:
+            free_bytes, _ = torch.cuda.mem_get_info(dev)
+            want = exp.sum() if (not to_host and not recycle) else max(exp.max() * 1.5, 1 << 20)
+            hit_cap = int(min(max(want, 1 << 20), free_bytes // 4 // 16))
+    # candidates are re-scored model by model: the buffer holds ONE model's worth (candidates are
+    # the hits plus the few windows within the fixed-point error of the threshold)
+    cand_cap = int(min(max(exp.max() * 1.5, 1 << 16), max(hit_cap, 1 << 16))) if want_hits else 0
+    handles_all = [M._model() for M in models]
+    stream = torch.cuda.current_stream(dev)
+    flags = _cabi.RC_REVSEQ_ORDER if revseq_order else _cabi.RC_MATRIX_ORDER
+    BG, CT = _cabi.BG_COUNT, _cabi.CTR_COUNT
+    if to_host:
+        stats_out = np.zeros((K, BG))
+        hist_out = np.zeros((K, n_bins), dtype=np.int64) if n_bins else None
+    else:
+        stats_out = torch.empty((K, BG), dtype=torch.float64, device=dev)
+        hist_out = torch.empty((K, n_bins), dtype=torch.int64, device=dev) if n_bins else None
+    ctr_out = np.zeros((K, CT), dtype=np.int64)
+    hits_out = [None] * K if want_hits else None
+    launches = 0
+    host_hits = want_hits and to_host
+    pending = None        # (first model, cum offsets, buffer index) of the sub-batch whose sites are in flight
+
+    def deliver(first, cum, p, buf):
+        buf.copied[p].synchronize()
+        host = buf.host_hits[p].numpy().view(np.uint64)
+        for k in range(len(cum) - 1):
+            seg = host[cum[k]:cum[k + 1]]
+            if sort and 1 < len(seg) < (1 << 15):
+                seg.sort()                                 # small segments: cheaper here than a launch
+            if sink is not None:
+                sink(first + k, seg)
+                hits_out[first + k] = len(seg)
+            else:
+                hits_out[first + k] = seg.copy()
+
+    i = 0
+    n_sub = 0
+    while i < K:
+        # sub-batch [i, j): as many models as the hit buffer is expected to hold
+        j = i + 1
+        acc = exp[i]
+        while j < K and acc + exp[j] <= hit_cap:
+            acc += exp[j]
+            j += 1
+        n = j - i
+        buf = _buffers(genome, K, n_bins, hit_cap, cand_cap, host_hits)
+        p = n_sub & 1 if host_hits else 0
+        if host_hits and buf.copied[p] is not None and pending is not None and pending[2] == p:
+            deliver(*pending, buf)                         # cannot happen with two buffers, kept for safety
+            pending = None
+        hp = (C.c_void_p * n)(*[h.value for h in handles_all[i:j]])
+        # stats | hist | counters of n models, adjacent, at the head of the record buffer
+        a, b = n * BG, n * BG + n * n_bins
+        rec = buf.record[:b + (n + 1) * CT]
+        d_stats, d_hist, d_ctr = rec[:a], (rec[a:b] if n_bins else None), rec[b:]
+        _cabi.check(lib.cgbk_scan_batch(
+            hp, n, genome.struct_ref(), genome.seqset, -1 if win_cap is None else int(win_cap),
+            thr[i:j].ctypes.data if want_hits else None, flags, None, None, int(n_bins),
+            d_hist.data_ptr() if d_hist is not None else None, d_stats.data_ptr(),
+            buf.hits[p].data_ptr() if want_hits else None, int(buf.hit_cap) if want_hits else 0, d_ctr.data_ptr(),
+            buf.work.data_ptr(), buf.work.numel(), int(buf.cand_cap) if want_hits else 0, stream.cuda_stream))
+        launches += int(_cabi.last_launch_info()["launches"])
+        if not to_host and not want_hits:
+            stats_out[i:j] = d_stats.view(torch.float64).view(n, BG)
+            if n_bins:
+                hist_out[i:j] = d_hist.view(n, n_bins)
+            i = j
+            continue
+        # one D2H of the record (pinned), then the host knows the counts; the sites of the previous
+        # sub-batch cross PCIe on the copy stream meanwhile
+        host = buf.host_record[:rec.numel()]
+        host.copy_(rec, non_blocking=True)
+        stream.synchronize()
+        h = host.numpy()
+        ctr = h[b:].reshape(n + 1, CT)
+        n_done = n
+        if want_hits:
+            cand_over = np.nonzero(ctr[:n, _cabi.CTR_CANDIDATES] > buf.cand_cap)[0]
+            cum_all = np.concatenate([[0], np.cumsum(ctr[:n, _cabi.CTR_HITS])])
+            hit_over = np.nonzero(cum_all[1:] > buf.hit_cap)[0]
+            bad = min([int(x[0]) for x in (cand_over, hit_over) if len(x)] or [n])
+            if bad < n:
+                # records were dropped from model `bad` on: keep the models before it and run the
+                # rest again, with buffers grown to what model `bad` needs if it was the first
+                n_done = bad
+                need = float(max(ctr[bad, _cabi.CTR_HITS], ctr[bad, _cabi.CTR_CANDIDATES])) + 4096
+                exp[i + bad] = max(exp[i + bad], need)
+                if bad == 0:
+                    if not to_host and not recycle:
+                        raise ValueError("the sites of the batch do not fit hit_cap=%d (to_host=False keeps "
+                                         "them on the device)" % hit_cap)
+                    free_bytes, _ = torch.cuda.mem_get_info(dev)
+                    if need * 16 * 2 > free_bytes + 16 * buf.hit_cap * 2:
+                        raise MemoryError("model %d needs %d hit records, more than the device can hold"
+                                          % (i, int(need)))
+                    if pending is not None:
+                        deliver(*pending, buf)
+                        pending = None
+                    hit_cap = max(hit_cap, int(need))
+                    cand_cap = max(cand_cap, int(need))
+                    release_buffers(dev)
+                    del buf
+                    continue
+        if to_host:
+            stats_out[i:i + n_done] = h[:a].view(np.float64).reshape(n, BG)[:n_done]
+            if n_bins:
+                hist_out[i:i + n_done] = h[a:b].reshape(n, n_bins)[:n_done]
+        else:
+            stats_out[i:i + n_done] = d_stats.view(torch.float64).view(n, BG)[:n_done]
+            if n_bins:
+                hist_out[i:i + n_done] = d_hist.view(n, n_bins)[:n_done]
+        ctr_out[i:i + n_done] = ctr[:n_done]
+        if kernel_ms is not None and n_done:
+            kernel_ms[i:i + n_done] += np.array(_cabi.profile_batch_ms(n_done))
+        if want_hits and n_done:
+            cum = np.concatenate([[0], np.cumsum(ctr[:n_done, _cabi.CTR_HITS])]).astype(np.int64)
+            used = int(cum[-1])
+            if sort:
+                # large segments on the device (radix sort), small ones on the host after the copy
+                for k in range(n_done):
+                    nk = int(cum[k + 1] - cum[k])
+                    if nk >= (1 << 15) or (not to_host and nk > 1):
+                        need_b = int(lib.cgbk_sort_hits_workspace_bytes(nk))
+                        if buf.sort_tmp is None or buf.sort_tmp.numel() < need_b:
+                            buf.sort_tmp = torch.empty(need_b, dtype=torch.uint8, device=dev)
+                        _cabi.check(lib.cgbk_sort_hits(buf.hits[p].data_ptr() + 8 * int(cum[k]), nk,
+                                                       buf.sort_tmp.data_ptr(), buf.sort_tmp.numel(),
+                                                       stream.cuda_stream))
+            if to_host:
+                # D2H on the copy stream, behind the sorts; delivered while the next sub-batch runs
+                ready = torch.cuda.Event()
+                ready.record(stream)
+                with torch.cuda.stream(buf.copy_stream):
+                    buf.copy_stream.wait_event(ready)
+                    if used:
+                        buf.host_hits[p][:used].copy_(buf.hits[p][:used], non_blocking=True)
+                    buf.copied[p] = torch.cuda.Event()
+                    buf.copied[p].record(buf.copy_stream)
+                if pending is not None:
+                    deliver(*pending, buf)
+                pending = (i, cum, p)
+                # the next scan must not overwrite hits[p ^ 1] before ITS copy is done: deliver()
+                # above has just waited for it
+            elif recycle:
+                for k in range(n_done):
+                    hits_out[i + k] = int(cum[k + 1] - cum[k])
+            else:
+                if i + n_done < K or i > 0:
+                    raise ValueError("the sites of the batch do not fit hit_cap=%d (to_host=False keeps them "
+                                     "on the device)" % hit_cap)
+                for k in range(n_done):
+                    hits_out[i + k] = buf.hits[p][cum[k]:cum[k + 1]]
+            n_sub += 1
+        i += n_done
+    if pending is not None:
+        deliver(*pending, _buffers(genome, K, n_bins, hit_cap, cand_cap, host_hits))
+    return {"stats": stats_out, "hist": hist_out, "hits": hits_out, "counters": ctr_out, "launches": launches}
+
+
+def hits_of(genome, rec):
+    """Compact records of one model -> (seq_index, pos, strand, score) like ``PSSMModel.scan_hits``."""
+    gpos, strand, score = unpack_hits(rec)
+    seq = np.searchsorted(genome.seq_off, gpos, side="right") - 1
+    return seq, gpos - genome.seq_off[seq], strand, score

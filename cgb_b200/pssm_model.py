@@ -155,7 +155,9 @@ class PSSMModel(TFBindingModel):
 
     def __del__(self):
         try:
-            if getattr(self, "_handle", None) is not None and self._handle.value:
+            if getattr(self, "_batch_owner", None) is not None:
+                self._handle = None             # borrowed from a ModelBatch, which frees the tables
+            elif getattr(self, "_handle", None) is not None and self._handle.value:
                 _cabi.lib().cgbk_model_destroy(self._handle)
                 self._handle = None
         except Exception:
@@ -172,9 +174,17 @@ class PSSMModel(TFBindingModel):
         lens = np.array([len(s) for s in seqs], dtype=np.int64)
         if len(seqs) == 0:
             return []
-        if (lens < m).any():
-            # Biopython's C scorer fails on the negative window count
+        if (lens < m - 1).any():
+            # Biopython allocates numpy.empty(len(seq) - m + 1): a negative count raises ...
             raise ValueError("negative dimensions are not allowed")
+        if (lens == m - 1).any():
+            # ... and a count of zero is an empty score array (no window): [] from score_seq
+            full = [k for k in range(len(seqs)) if lens[k] >= m]
+            scored = self.score_seqs([seqs[k] for k in full], both) if full else []
+            out = [[] if both else np.empty(0, dtype=np.float32) for _ in seqs]
+            for k, v in zip(full, scored):
+                out[k] = v
+            return out
         model = self._model()
         dev = self._dev()
         g = PackedGenome.from_sequences(seqs, dev)
@@ -214,8 +224,21 @@ class PSSMModel(TFBindingModel):
         return self.score_seqs([seq], both)[0]
 
     def score_self(self):
-        """pssm_model.py:84-86 (one batched launch instead of one call per site)."""
-        return self.score_seqs(self.sites, True)
+        """pssm_model.py:84-86.  The sites are as long as the motif, one window each: scored by
+        the library on the host in the reference's arithmetic (``cgbk_score_sites_host``; a few
+        thousand table look-ups are not worth a launch).  Ragged site lists take the device path."""
+        sites = self.sites
+        m = self.length
+        if len(sites) == 0:
+            return []
+        if any(len(s) != m for s in sites):
+            return self.score_seqs(sites, True)
+        rows = self.pssm.rows()
+        flat = (C.c_double * (4 * m))(*[x for row in rows for x in row])
+        raw = b"".join(s if isinstance(s, (bytes, bytearray)) else str(s).encode("ascii") for s in sites)
+        out = np.empty(len(sites), dtype=np.float64)
+        _cabi.check(_cabi.lib().cgbk_score_sites_host(flat, m, raw, len(sites), None, None, out.ctypes.data))
+        return [[float(v)] for v in out]
 
     # ------------------------------------------------------------ tiled scans
     def scan_hits(self, genome, threshold=None, revseq_order=True, hit_cap=None):
@@ -291,10 +314,34 @@ class PSSMModel(TFBindingModel):
         pos = gpos - genome.seq_off[seq]
         return seq, pos, rec["strand"].copy(), rec["score"].copy()
 
+    def region_descriptors(self, genome, regions, drop_last=True):
+        """(window start offsets, window counts) device tensors of a region table.
+
+        ``regions``: iterable of ``(seq_index, starts, ends)``: slices ``sequence[start:end]`` of
+        replicon ``seq_index`` (Python slice semantics, chromid.py:94).  Every m-mer start of a
+        slice is a window; ``drop_last`` leaves out the last one, as ``xrange(len(seq) - m)`` does
+        in Genome.build_PSSM_model (genome.py:217-218).  Slices too short for a window add none."""
+        m = self.length
+        all_s, all_n = [], []
+        for seq_index, starts, ends in regions:
+            L = genome.length(seq_index)
+            s, e = python_slice_bounds(np.asarray(starts, dtype=np.int64), np.asarray(ends, dtype=np.int64), L)
+            nwin = e - s - m + (0 if drop_last else 1)
+            keep = nwin > 0
+            all_s.append(s[keep] + int(genome.seq_off[seq_index]))
+            all_n.append(nwin[keep])
+        s = np.concatenate(all_s) if all_s else np.zeros(0, dtype=np.int64)
+        n = np.concatenate(all_n).astype(np.int32) if all_n else np.zeros(0, dtype=np.int32)
+        dev = self._dev()
+        return torch.from_numpy(np.ascontiguousarray(s)).to(dev), torch.from_numpy(np.ascontiguousarray(n)).to(dev)
+
     def background_stats(self, genome, n_bins=256, hist_lo=None, hist_hi=None, accumulate_into=None,
-                         out=None, keep_scores=False):
+                         out=None, keep_scores=False, regions=None, drop_last=True):
         """Soft-max score distribution over ALL windows of ``genome`` (both strands
-        combined as in score_seq): returns a dict with device tensors ``stats``
+        combined as in score_seq), or -- with ``regions`` (see :meth:`region_descriptors`) -- over
+        the m-mers of those regions only, each scored as a sequence of its own: the reference's
+        background population when the regions are the genes' upstream non-coding regions
+        (genome.py:215-218).  Returns a dict with device tensors ``stats``
         (float64[8]: n, sum, sumsq, mean, std) and ``hist`` (int64[n_bins]) plus the
         bin range.  ``accumulate_into``: a previous result to add this genome to;
         ``out``: a previous result whose buffers are overwritten (no allocation).
@@ -309,6 +356,25 @@ class PSSMModel(TFBindingModel):
             hist_lo = self._score_bounds[0]
         if hist_hi is None:
             hist_hi = self._score_bounds[1]
+        if regions is not None:
+            lib = _cabi.lib()
+            d_start, d_nwin = regions if (isinstance(regions, tuple) and len(regions) == 2 and
+                                          isinstance(regions[0], torch.Tensor)) \
+                else self.region_descriptors(genome, regions, drop_last)
+            if accumulate_into is not None:
+                stats, hist, acc = accumulate_into["stats"], accumulate_into["hist"], 1
+                n_bins = int(hist.numel())
+            else:
+                rec = torch.empty(_cabi.BG_COUNT + n_bins, dtype=torch.int64, device=dev)
+                stats, hist, acc = rec[:_cabi.BG_COUNT].view(torch.float64), rec[_cabi.BG_COUNT:], 0
+            work = torch.empty(int(lib.cgbk_region_stats_workspace_bytes()), dtype=torch.uint8, device=dev)
+            _cabi.check(lib.cgbk_background_stats_regions(
+                model, genome.struct_ref(), d_start.data_ptr(), d_nwin.data_ptr(), int(d_start.numel()),
+                float(hist_lo), float(hist_hi), int(n_bins), hist.data_ptr() if n_bins else None,
+                stats.data_ptr(), acc, work.data_ptr(), work.numel(), self._stream()))
+            work.record_stream(torch.cuda.current_stream(dev))
+            return {"stats": stats, "hist": hist, "hist_lo": float(hist_lo), "hist_hi": float(hist_hi),
+                    "n_bins": int(n_bins), "plane": None, "genome": None, "work": None, "work_key": None}
         plane = None
         work = None
         if out is not None:
@@ -346,12 +412,15 @@ class PSSMModel(TFBindingModel):
                 "n_bins": int(n_bins), "plane": plane, "genome": genome if plane is not None else None,
                 "work": work if own_work else None, "work_key": (id(genome), m) if own_work else None}
 
-    def fit_background(self, genome=None, bg=None, sync=True, keep_scores=True):
+    def fit_background(self, genome=None, bg=None, sync=True, keep_scores=True, regions=None):
         """build_bayesian_estimator (binding_model.py:71-92) with the background
-        moments taken from the genome-wide scan (or from a finished
-        ``background_stats`` result, e.g. after a cross-rank all-reduce).  The score
-        plane of the scan (``keep_scores``) is remembered and reused by
+        moments taken from the genome-wide scan, from the m-mers of ``regions`` (the
+        reference's upstream non-coding population, genome.py:215-218), or from a finished
+        ``background_stats`` result, e.g. after a cross-rank all-reduce.  The score
+        plane of the genome-wide scan (``keep_scores``) is remembered and reused by
         ``binding_probabilities`` on the same genome."""
+        if bg is None and regions is not None:
+            bg = self.background_stats(genome, regions=regions)
         if bg is None:
             bg = self.background_stats(genome, keep_scores=keep_scores)
         self._bg_stats_dev = bg["stats"]
@@ -405,11 +474,20 @@ class PSSMModel(TFBindingModel):
             bg = getattr(self, "_last_bg", None)
             if bg is not None and bg.get("genome") is genome and bg.get("plane") is not None:
                 plane = bg["plane"]
-        _cabi.check(_cabi.lib().cgbk_posteriors(
-            model, genome.struct_ref(), genome.seqset, plane.data_ptr() if plane is not None else None,
-            d_start.data_ptr(), d_nwin.data_ptr(), n,
-            self._dev_ms_m.data_ptr(), self._dev_ms_bg.data_ptr(), float(p_motif), float(alpha),
-            out.data_ptr(), self._stream()))
+        def launch(pl):
+            return _cabi.lib().cgbk_posteriors(
+                model, genome.struct_ref(), genome.seqset, pl.data_ptr() if pl is not None else None,
+                d_start.data_ptr(), d_nwin.data_ptr(), n,
+                self._dev_ms_m.data_ptr(), self._dev_ms_bg.data_ptr(), float(p_motif), float(alpha),
+                out.data_ptr(), self._stream())
+        rc = launch(plane)
+        if rc == _cabi.ERR_INVALID and plane is not None:
+            # another model re-tiled the shared sequence set since the plane was written (the
+            # plane's addressing is gone with the tiling): forget it and score the windows again
+            self._last_bg["plane"] = None
+            self._last_bg["genome"] = None
+            rc = launch(None)
+        _cabi.check(rc)
         return out
 
     def promoter_descriptors(self, genome, starts, ends, seq_index=0):
@@ -425,8 +503,8 @@ class PSSMModel(TFBindingModel):
             s, e = python_slice_bounds(starts, ends, L)
         nwin = e - s
         nwin -= m - 1
-        if nwin.min(initial=1) < 1:
-            raise ValueError("negative dimensions are not allowed")   # Biopython, len(seq) < m
+        if nwin.min(initial=0) < 0:
+            raise ValueError("negative dimensions are not allowed")   # Biopython, len(seq) < m - 1
         dev = self._dev()
         # one pinned staging buffer [n x int64 starts | n x int32 counts], one async H2D copy
         n = len(s)
@@ -451,7 +529,7 @@ class PSSMModel(TFBindingModel):
         m = self.length
         seqs = [str(s) if not isinstance(s, (bytes, bytearray)) else s for s in seqs]
         lens = np.array([len(s) for s in seqs], dtype=np.int64)
-        if (lens < m).any():
+        if (lens < m - 1).any():
             raise ValueError("negative dimensions are not allowed")
         dev = self._dev()
         g = PackedGenome.from_sequences(seqs, dev)
@@ -473,7 +551,15 @@ class PSSMModel(TFBindingModel):
         (``stats``: n, sum, sumsq, mean, std of the background) and sets ``_mu_bg`` /
         ``_std_bg`` like ``build_bayesian_estimator``."""
         if isinstance(sequence, torch.Tensor):
-            seq_t = sequence
+            # the library reads these bytes from HOST memory: a device tensor, another dtype or a
+            # strided view would hand it a wrong pointer or length
+            if sequence.device.type != "cpu":
+                raise ValueError("sequence must be a CPU tensor (the pipeline uploads it itself)")
+            if sequence.dtype != torch.uint8:
+                raise ValueError("sequence must be a uint8 tensor of ASCII bytes, got %s" % sequence.dtype)
+            seq_t = sequence if sequence.is_contiguous() else sequence.contiguous()
+            if seq_t.dim() != 1:
+                seq_t = seq_t.reshape(-1)
         elif isinstance(sequence, np.ndarray):
             seq_t = torch.from_numpy(np.ascontiguousarray(sequence, dtype=np.uint8))
         else:

@@ -37,7 +37,7 @@ def identify_sites(model, genome, gene_tables, promoter_up_distance=300, promote
         threshold = model.threshold()
     m = model.length
     seq, pos, strand, score = model.scan_hits(genome, threshold, revseq_order=True)
-    sites = []
+    parts = []
     for gt in gene_tables:
         k = gt.seq_index
         L = genome.length(k)
@@ -46,28 +46,40 @@ def identify_sites(model, genome, gene_tables, promoter_up_distance=300, promote
         else:
             start, end = gt.upstream_noncoding_region_location(None, promoter_dw_distance)
         s, e = python_slice_bounds(start, end, L)
+        if len(s) and int((e - s).min()) < m - 1:
+            # score_seq on a region more than one base shorter than the motif: Biopython's
+            # numpy.empty(len(seq) - m + 1) raises (a region of m - 1 bases has no window, no error)
+            raise ValueError("negative dimensions are not allowed")
         sel = seq == k
-        hp, hs, hv = pos[sel], strand[sel], score[sel]
-        order = np.argsort(hp, kind="stable")
-        hp, hs, hv = hp[order], hs[order], hv[order]
+        hp, hs, hv = pos[sel], strand[sel], score[sel]       # sorted by (pos, + strand first)
         # windows fully inside [s, e): s <= p <= e - m
         lo = np.searchsorted(hp, s, side="left")
-        hi = np.searchsorted(hp, e - m, side="right")
-        for gi in range(len(gt)):
-            if e[gi] - s[gi] < m or hi[gi] <= lo[gi]:
-                continue
-            p = hp[lo[gi]:hi[gi]]
-            st = hs[lo[gi]:hi[gi]]
-            sc = hv[lo[gi]:hi[gi]]
-            # reported coordinate: enumerate(scores, start=start) uses the UNclamped
-            # region start (genome.py:435,442)
-            label = p - s[gi] + start[gi]
-            for strand_value in (1, -1):              # + strand hits first, then - strand
-                idx = np.nonzero(st == strand_value)[0]
-                for j in idx:
-                    sites.append(Site(k, int(label[j]), int(label[j]) + m, strand_value, sc[j], gi))
-    sites.sort(key=lambda site: site.score, reverse=True)
-    return sites
+        hi = np.maximum(np.searchsorted(hp, e - m, side="right"), lo)
+        cnt = hi - lo
+        total = int(cnt.sum())
+        if total == 0:
+            continue
+        # one row per (gene, hit under its region), no per-gene loop: gene ids repeated by their
+        # hit counts, hit indices as a ramp inside each gene's [lo, hi)
+        gene = np.repeat(np.arange(len(cnt)), cnt)
+        first = np.repeat(np.cumsum(cnt) - cnt, cnt)
+        idx = np.repeat(lo, cnt) + (np.arange(total) - first)
+        st = hs[idx]
+        # the reference's order before its sort: genes in order, per gene the + strand hits by
+        # position, then the - strand hits by position (genome.py:435-445)
+        order = np.lexsort((idx, st == -1, gene))
+        gene, idx, st = gene[order], idx[order], st[order]
+        # reported coordinate: enumerate(scores, start=start) uses the UNclamped region start
+        label = hp[idx] - s[gene] + start[gene]
+        parts.append((np.full(total, k, dtype=np.int64), label, st, hv[idx], gene))
+    if not parts:
+        return []
+    chrom, label, st, sc, gene = [np.concatenate(x) for x in zip(*parts)]
+    # sites.sort(key=score, reverse=True) is stable: equal scores keep their order
+    order = np.argsort(-sc.astype(np.float64), kind="stable")
+    chrom, label, st, sc, gene = chrom[order], label[order], st[order], sc[order], gene[order]
+    return [Site(c, a, a + m, t, v, g)
+            for c, a, t, v, g in zip(chrom.tolist(), label.tolist(), st.tolist(), list(sc), gene.tolist())]
 
 
 def calculate_regulation_probabilities(model, genome, gene_table, prior, alpha,

@@ -7,8 +7,12 @@
  * torch.Tensor.data_ptr()); `stream` is a cudaStream_t (NULL = default stream).
  * Every call is asynchronous on `stream` unless stated otherwise and returns a
  * status code; cgbk_last_error() returns the message of the calling thread's last
- * failure.  The library never frees caller memory and keeps no global state
- * besides per-thread error text.
+ * failure.  The library never frees caller memory.  State outside the handles: the
+ * calling thread's error text and launch statistics, a per-device cache of the
+ * multiprocessor count and of the kernels' shared-memory attribute (set once per device
+ * under a lock), and the regulation pipeline's per-thread copy stream.  Entry points that
+ * take a handle run on the handle's device: if another device is current it is selected for
+ * the duration of the call and restored on return.
  *
  * Each entry point names the reference interface (file:line under
  * /root/reference) it replaces.
@@ -22,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CGBK_VERSION 100
+#define CGBK_VERSION 200
 
 /* status codes; the Python layer maps them to the reference's exception types */
 #define CGBK_OK 0
@@ -35,6 +39,7 @@ extern "C" {
 #define CGBK_MAX_HIST_BINS 4096
 
 typedef struct cgbk_model cgbk_model;    /* opaque: one PSSM (log-odds) on one device */
+typedef struct cgbk_model_batch cgbk_model_batch;  /* opaque: K models in one device block */
 typedef struct cgbk_seqset cgbk_seqset;  /* opaque: sequence table of a packed buffer */
 
 /* Packed genome buffer ("Chromid.sequence", cgb/chromid.py:57-60, as HBM planes).
@@ -53,6 +58,14 @@ typedef struct {
     int32_t strand;  /* +1 / -1 (genome.py:438,445) */
     float score;     /* float32 PSSM score of that strand, as Biopython's calculate() stores it */
 } cgbk_hit;
+
+/* Compact site record of the batched scan: (gpos << 33) | (minus strand ? 1 << 32 : 0) |
+ * float32 score bits.  Sorting the integers sorts by (position, + strand first).  Addresses
+ * packed buffers below 2^31 bases (a rank's shard of a longer sequence). */
+typedef uint64_t cgbk_hit8;
+#define CGBK_HIT8_GPOS(h) ((int64_t)((h) >> 33))
+#define CGBK_HIT8_STRAND(h) ((((h) >> 32) & 1u) ? -1 : 1)
+#define CGBK_HIT8_SCORE_BITS(h) ((uint32_t)((h) & 0xffffffffu))
 
 /* Counters written by cgbk_scan_hits (device int64[8]). */
 #define CGBK_CTR_CANDIDATES 0   /* windows passed by the 16-bit filter */
@@ -114,6 +127,26 @@ int cgbk_pack_ascii(const uint8_t* d_ascii, int64_t n, int64_t dst_off,
  * The reverse-complement table (pssm_model.py:52-55) is derived inside.  Synchronous. */
 int cgbk_model_create(const double* logodds, int m, int device, cgbk_model** out);
 void cgbk_model_destroy(cgbk_model* model);
+
+/* n models at once (one PSSMModel per genome in the reference's go() loop,
+ * cgb/__init__.py:673-686, pssm_model.py:31-35; or a JASPAR-scale motif set): logodds holds the
+ * [m_i][4] tables back to back.  ONE device allocation and ONE upload ordered on `stream`
+ * instead of n synchronous allocate + copy pairs.  cgbk_model_batch_get returns a borrowed
+ * handle, valid until the batch is destroyed (cgbk_model_destroy on it is a no-op). */
+int cgbk_model_batch_create(const double* logodds, const int* m, int n, int device, void* stream,
+                            cgbk_model_batch** out);
+cgbk_model* cgbk_model_batch_get(cgbk_model_batch* batch, int k);
+int cgbk_model_batch_size(const cgbk_model_batch* batch);
+void cgbk_model_batch_destroy(cgbk_model_batch* batch);
+
+/* PSSMModel.score_self (cgb/pssm_model.py:84-86): score_seq of n_sites sequences of exactly m
+ * bases each (sites: n_sites * m bytes back to back), on the HOST in the reference's
+ * arithmetic -- the ~10^2 sites of a model are a few thousand table look-ups, not worth a
+ * launch.  Outputs (each may be NULL): forward / minus-strand score as score_seq(both=False)
+ * would return it for a single window (float32-rounded unless the ambiguity repair of
+ * pssm_model.py:88-101 touched it) and the soft-max log2(2**f + 2**r). */
+int cgbk_score_sites_host(const double* logodds, int m, const char* sites, int n_sites,
+                          double* fwd, double* rc, double* both);
 
 /* Sequence table of a packed buffer (host int64 arrays).  d_table: caller-owned device
  * int64[cgbk_seqset_table_ints(n_seq)] that must outlive the set (the library allocates
@@ -186,9 +219,60 @@ int cgbk_background_stats(cgbk_model* model, const cgbk_genome* genome, const cg
                           int32_t* d_plane, int64_t plane_ints,
                           void* d_work, int64_t work_bytes, void* stream);
 
+/* The reference's own background population (cgb/genome.py:215-218): every m-mer of every
+ * gene's upstream non-coding region, each scored as a sequence of its own (score_seq with
+ * len(seq) == m), regions overlapping or repeated as the gene table has them.  Region k is the
+ * windows [d_start[k], d_start[k] + d_nwin[k]) of the packed buffer -- the caller drops the
+ * last window of each region as xrange(len(seq) - m) does.  Exact float64 arithmetic in the
+ * reference's order; moments (and the optional histogram) as cgbk_background_stats.  The
+ * reference then scores a random.sample of <= 10 000 of these m-mers; here all of them count. */
+int64_t cgbk_region_stats_workspace_bytes(void);
+int cgbk_background_stats_regions(const cgbk_model* model, const cgbk_genome* genome,
+                                  const int64_t* d_start, const int32_t* d_nwin, int n_regions,
+                                  double hist_lo, double hist_hi, int n_bins,
+                                  unsigned long long* d_hist, double* d_stats, int accumulate,
+                                  void* d_work, int64_t work_bytes, void* stream);
+
+/* ---- motif batches ------------------------------------------------------------- */
+
+/* n_models PSWMs over one packed buffer in ONE call and one pass per motif: for model k the
+ * background record of all windows (d_stats[k][CGBK_BG_COUNT], and d_hist[k][n_bins] unless
+ * d_hist is NULL: then the scan runs without a histogram) and -- when `thresholds` is given --
+ * every site with float32 score >= thresholds[k] on either strand (Genome.identify_sites' hit
+ * test, cgb/genome.py:433-445), found by the SAME pass: the stats scan's int32 fixed-point
+ * strand scores are compared with the threshold minus their error bound and the candidates are
+ * re-scored in float64 in the reference's order (bit-exact hit lists).
+ *   win_cap      >= 0: only the first win_cap windows of each sequence are scored (sets of up to
+ *                4 sequences).  A rank's shard of a longer sequence carries the halo of the longest
+ *                motif and caps every motif at the shard's own windows; < 0: all windows
+ *   hist_lo/hi   per model, or NULL for [floor(min score), ceil(max score) + 1)
+ *   d_hits8      one compact list for the whole batch; model k's sites are the records
+ *                [sum of CGBK_CTR_HITS of the models before k, + its own count), unordered
+ *                inside the segment (cgbk_sort_hits orders a segment)
+ *   d_counters   int64[n_models + 1][CGBK_CTR_COUNT]: per model candidates / hits / tiles with
+ *                non-ACGT bytes; block n_models: [0] = records appended in total.  A total above
+ *                hit_cap or a candidate count above cand_cap means records were dropped: run the
+ *                models from the first affected one again with larger buffers
+ *   d_work       >= cgbk_scan_batch_workspace_bytes(cand_cap)
+ * flags: CGBK_RC_*.  No allocation, no synchronisation. */
+int64_t cgbk_scan_batch_workspace_bytes(int64_t cand_cap);
+int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cgbk_genome* genome,
+                    const cgbk_seqset* set, int64_t win_cap, const double* thresholds, int flags,
+                    const double* hist_lo, const double* hist_hi, int n_bins,
+                    unsigned long long* d_hist, double* d_stats,
+                    cgbk_hit8* d_hits8, int64_t hit_cap, int64_t* d_counters,
+                    void* d_work, int64_t work_bytes, int64_t cand_cap, void* stream);
+
+/* Sort n compact records in place by (position, + strand first); d_tmp >=
+ * cgbk_sort_hits_workspace_bytes(n) bytes of device scratch. */
+int64_t cgbk_sort_hits_workspace_bytes(int64_t n);
+int cgbk_sort_hits(cgbk_hit8* d_hits8, int64_t n, void* d_tmp, int64_t tmp_bytes, void* stream);
+
 /* Recompute CGBK_BG_MEAN / CGBK_BG_STD from n/sum/sumsq in d_stats (after an
  * all-reduce of the raw sums across ranks). */
 int cgbk_background_finalize(double* d_stats, void* stream);
+/* The same for n_records records laid out back to back (a motif batch after ONE all-reduce). */
+int cgbk_background_finalize_batch(double* d_stats, int n_records, void* stream);
 
 /* ---- host-buffer entry point -------------------------------------------------- */
 
@@ -255,6 +339,10 @@ int cgbk_last_launch_info(int64_t* out3);
  * event and returns the elapsed milliseconds of the calling thread's last scan. */
 int cgbk_profile_enable(int on);
 int cgbk_profile_last_ms(float* ms);
+/* on == 2: cgbk_scan_batch also brackets every model's scan kernel with its own event pair;
+ * cgbk_profile_batch_ms returns the n first models' kernel times of the calling thread's last
+ * cgbk_scan_batch (synchronises on the events). */
+int cgbk_profile_batch_ms(float* ms, int n);
 
 #ifdef __cplusplus
 }

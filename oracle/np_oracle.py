@@ -291,8 +291,10 @@ def calculate(table, seq_bytes):
     m = table.shape[0]
     n = seq.shape[0]
     nwin = n - m + 1
-    if nwin <= 0:
+    if nwin < 0:
         raise ValueError("negative dimensions are not allowed")
+    if nwin == 0:                            # len(seq) == m - 1: numpy.empty(0), no error
+        return np.empty(0, dtype=np.float32)
     codes = _CODE[seq]
     bad = codes < 0
     safe = np.where(bad, 0, codes).astype(np.intp)
@@ -528,6 +530,38 @@ def identify_sites(model, sequence, genes, up=None, down=50, threshold=None, ind
                 sites.append(OSite(i, i + m, -1, score, gi))
     sites.sort(key=lambda s: s.score, reverse=True)
     return sites
+
+
+# a10 background population of Genome.build_PSSM_model (genome.py:215-226)
+def upstream_background_scores(model, sequence, genes, down=50, index=None, softmax="legacy64"):
+    """``bg_scores`` of genome.py:215-223 for one replicon with ``random.sample`` taken as the
+    identity: every m-mer ``seq[start:start + m]``, ``start in xrange(len(seq) - m)`` (the last
+    window is dropped), of every gene's ``upstream_noncoding_region_sequence()``, each scored by
+    ``score_seq`` as a sequence of its own (one window: a repaired score stays float64,
+    pssm_model.py:117-127).  Returns the flat list of soft-max scores in the reference's order."""
+    if isinstance(sequence, str):
+        sequence = sequence.encode("ascii")
+    m = model.length
+    out = []
+    for i in range(len(genes)):
+        a, b = upstream_noncoding_region_location(genes, i, len(sequence), None, down, index)
+        region = subsequence(sequence, a, b)
+        n = len(region) - m
+        if n <= 0:
+            continue
+        if softmax == "legacy64":
+            both, f, r = score_seq_both_vec(model, region[:n + m - 1], softmax)
+            # windows with a non-ACGT byte were repaired: as single-window sequences their strand
+            # scores are Python floats, not float32 -- redo those through score_seq
+            bad = np.nonzero(np.convolve((_CODE[np.frombuffer(region[:n + m - 1], dtype=np.uint8)] < 0).astype(np.int32),
+                                         np.ones(m, dtype=np.int32), "valid") > 0)[0]
+            both = both.tolist()
+            for w in bad:
+                both[w] = score_seq(model, region[w:w + m], True, softmax)[0][0]
+            out.extend(both)
+        else:
+            out.extend(score_seq(model, region[w:w + m], True, softmax)[0][0] for w in range(n))
+    return out
 
 
 def scan_hits_whole(model, seq, threshold):

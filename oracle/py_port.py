@@ -46,8 +46,10 @@ class PortModel:
 
     def _c_calculate(self, table, seq):
         n = len(seq) - self.length + 1
-        if n <= 0:
+        if n < 0:
             raise ValueError("negative dimensions are not allowed")
+        if n == 0:
+            return np.empty(0, np.float32)
         out = np.empty(n, np.float32)
         c_oracle.lib().cgbo_calculate(seq, len(seq), table.ctypes.data_as(C.POINTER(C.c_double)),
                                       self.length, out.ctypes.data_as(C.POINTER(C.c_float)))

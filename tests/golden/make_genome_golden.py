@@ -160,17 +160,38 @@ def main():
                          "promoter_region": g.promoter_region(up, dw)})
         out["genes"].append({"accession": c.accession_number, "length": c.length, "rows": rows})
 
-    # --- model: background over ALL windows of every replicon (the new build's definition of
-    # Genome.build_PSSM_model's background, genome.py:215-226 without the 10 000-window sample)
-    model = ns.PSSMModel(colls, weights)
-    bg_scores = []
-    for c in genome.chromids:
-        bg_scores.extend(model.score_seq(c.sequence))
-    model.build_bayesian_estimator(bg_scores)
-    genome._TF_binding_model = model
+    # --- model: the reference's own Genome.build_PSSM_model (genome.py:203-227) run VERBATIM, with
+    # random.sample made the identity so that the background is the whole population the sample
+    # is drawn from -- every m-mer (last one dropped, genome.py:218) of every gene's upstream
+    # non-coding region, each scored by score_seq as a sequence of its own -- and the result is
+    # reproducible.  (The reference scores a random 10 000 of them.)
+    sampled = {}
+
+    def identity_sample(population, k):
+        sampled["population"], sampled["k"] = len(population), k
+        return list(population)
+
+    real_random = ns.genome.random
+    ns.genome.random = types.SimpleNamespace(sample=identity_sample)
+    try:
+        genome.build_PSSM_model(colls, weights)
+    finally:
+        ns.genome.random = real_random
+    model = genome.TF_binding_model
     out["estimator"] = {"mu_m": float(model._mu_m), "std_m": float(model._std_m),
                         "mu_bg": float(model._mu_bg), "std_bg": float(model._std_bg),
-                        "threshold": float(model.threshold()), "n_bg": len(bg_scores)}
+                        "threshold": float(model.threshold()), "n_bg": sampled["population"],
+                        "population": "upstream non-coding m-mers (genome.py:215-218), random.sample = identity",
+                        "reference_sample_size": sampled["k"]}
+    # the same model with the background over ALL windows of every replicon (the opt-in
+    # mode="all" of the new build; north_star's genome-wide distribution)
+    model_all = ns.PSSMModel(colls, weights)
+    bg_scores = []
+    for c in genome.chromids:
+        bg_scores.extend(model_all.score_seq(c.sequence))
+    model_all.build_bayesian_estimator(bg_scores)
+    out["estimator_all_windows"] = {"mu_bg": float(model_all._mu_bg), "std_bg": float(model_all._std_bg),
+                                    "n_bg": len(bg_scores)}
 
     tmp = tempfile.mkdtemp()
     for scen, use_up in (("scan_to_upstream_gene", False), ("scan_up_distance", True)):

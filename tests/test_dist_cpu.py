@@ -117,3 +117,72 @@ def test_finalize_stats_host():
     st[0], st[1], st[2] = len(x), x.sum(), (x * x).sum()
     cdist.finalize_stats_host(st)
     assert abs(float(st[_cabi.BG_MEAN]) - x.mean()) < 1e-12 and abs(float(st[_cabi.BG_STD]) - x.std()) < 1e-10
+
+
+def _batch_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(100 + rank)
+        K, nb = 5, 16
+        x = [rng.normal(-10 - k, 3 + k, size=200 + 10 * rank) for k in range(K)]
+        stats = torch.zeros(K, _cabi.BG_COUNT, dtype=torch.float64)
+        hist = torch.zeros(K, nb, dtype=torch.int64)
+        for k in range(K):
+            stats[k, 0], stats[k, 1], stats[k, 2] = len(x[k]), x[k].sum(), (x[k] * x[k]).sum()
+            hist[k] = torch.from_numpy(np.histogram(x[k], bins=np.linspace(-40, 20, nb + 1))[0])
+        nbytes = cdist.allreduce_batch(stats, hist)          # ONE collective for the K records
+        if rank == 0:
+            q.put((stats.numpy().copy(), hist.numpy().copy(), nbytes))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_batch_gloo():
+    """The motif-batch collective (bench.py's step): K background records summed over 2 ranks in
+    one all-reduce, mean / std recomputed per record."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_batch_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    stats, hist, nbytes = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    K, nb = 5, 16
+    assert nbytes == K * (3 + nb) * 8
+    for k in range(K):
+        parts = []
+        for r in range(world):
+            rng = np.random.default_rng(100 + r)
+            xs = [rng.normal(-10 - j, 3 + j, size=200 + 10 * r) for j in range(K)]
+            parts.append(xs[k])
+        x = np.concatenate(parts)
+        assert stats[k, _cabi.BG_N] == len(x) and hist[k].sum() == np.histogram(x, bins=np.linspace(-40, 20, nb + 1))[0].sum()
+        assert abs(stats[k, _cabi.BG_MEAN] - x.mean()) < 1e-10 and abs(stats[k, _cabi.BG_STD] - x.std()) < 1e-9
+
+
+def test_bench_shards_cover_every_window_once():
+    """bench.py's sharding: rank r owns the windows that start in its slice; with the cap every
+    motif length counts each window of the sequence exactly once."""
+    import bench
+    for bp, world in ((1000, 3), (10 ** 9, 8), (997, 4), (40, 8)):
+        m_max = 30
+        for m in (8, 19, 30):
+            total = 0
+            prev_end = 0
+            for r in range(world):
+                lo, cap, hi = bench.shard_bounds(bp, m_max, world, r)
+                assert lo == prev_end and hi <= bp and hi - lo <= cap + m_max - 1
+                prev_end = lo + cap
+                total += max(0, min(cap, bp - lo - m + 1))
+            assert prev_end == bp and total == max(0, bp - m + 1)
+    # the benchmark sequence is a function of the position only: any slice of it is the same bases
+    a = bench.generate_bases(0, 3000).numpy()
+    b = bench.generate_bases(1234, 2000).numpy()
+    assert np.array_equal(a[1234:2000], b) and set(np.unique(a)) <= set(b"ACGT")
+    assert bench.motif_site_lists(5) == bench.motif_site_lists(5)
+    assert all(8 <= len(s[0]) <= 30 and len(s) == 20 for s in bench.motif_site_lists(40))

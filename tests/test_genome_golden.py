@@ -263,3 +263,96 @@ ORIGIN
     gt = rec.gene_table()
     assert list(gt.locus_tag) == ["T_0002", "T_0003"] and gt.index.tolist() == [1, 2]   # the join gene is skipped
     assert list(gt.product) == ["two-line product name", ""] and list(gt.protein_id) == ["WP_1.1", ""]
+
+
+def test_oracle_upstream_background_matches_verbatim_build_PSSM_model(gv, lexa):
+    """The background population of Genome.build_PSSM_model (genome.py:215-226): the golden
+    estimator was recorded by the reference's own method with random.sample as the identity;
+    the oracle's restatement gives the same n and bit-equal mean / std (numpy-2 soft-max mode of
+    the recording run) and the pinned-numpy mode within 1e-9."""
+    om = O.OracleModel([mo["sites"] for mo in lexa["motifs"]], gv["weights"])
+    est = gv["estimator"]
+    for mode, tol in (("nep50", 0.0), ("legacy64", 1e-9)):
+        bg = []
+        for rep, gold in zip(gv["replicons"], gv["genes"]):
+            genes = [O.OGene(r["start"], r["end"], r["strand"]) for r in gold["rows"]]
+            bg.extend(O.upstream_background_scores(om, rep["sequence"], genes, gv["promoter_dw_distance"],
+                                                   [r["index"] for r in gold["rows"]], mode))
+        assert len(bg) == est["n_bg"]
+        assert abs(np.mean(bg) - est["mu_bg"]) <= tol and abs(np.std(bg) - est["std_bg"]) <= tol
+    # the region table the product hands to the kernel covers exactly those m-mers
+    m = om.length
+    n = 0
+    for k, gold in enumerate(gv["genes"]):
+        gt = _table(gold, k)
+        s, e = python_slice_bounds(*gt.upstream_noncoding_region_location(None, gv["promoter_dw_distance"]),
+                                   gold["length"])
+        n += int(np.maximum(e - s - m, 0).sum())
+    assert n == est["n_bg"]
+    # a different population from "all windows of every replicon"
+    assert gv["estimator_all_windows"]["n_bg"] != est["n_bg"]
+    assert abs(gv["estimator_all_windows"]["mu_bg"] - est["mu_bg"]) > 1e-3
+
+
+class _OracleScanModel:
+    """Stands in for PSSMModel in site_search.identify_sites: the genome-wide hit list comes from
+    the oracle, so the vectorised join with the gene regions runs without a GPU."""
+
+    def __init__(self, om, sequences):
+        self.om, self.sequences, self.length = om, sequences, om.length
+
+    def threshold(self):
+        return self.om.threshold()
+
+    def scan_hits(self, genome, threshold, revseq_order=True):
+        seq, pos, strand, score = [], [], [], []
+        for k, s in enumerate(self.sequences):
+            p, st, v = O.scan_hits_whole(self.om, s, threshold)
+            seq.append(np.full(len(p), k)); pos.append(p); strand.append(st); score.append(v)
+        return tuple(np.concatenate(x) for x in (seq, pos, strand, score))
+
+
+class _Lengths:
+    def __init__(self, sequences):
+        self._len = [len(s) for s in sequences]
+
+    def length(self, k=0):
+        return self._len[k]
+
+
+@pytest.mark.parametrize("scen,use_up", [("scan_to_upstream_gene", False), ("scan_up_distance", True)])
+def test_vectorised_site_join_matches_reference(gv, lexa, scen, use_up):
+    """site_search.identify_sites (one scan + array join, no per-gene loop) yields the verbatim
+    run's sites in the verbatim run's order (genome.py:419-448)."""
+    from cgb_b200.site_search import identify_sites
+    om = _oracle_model(gv, lexa)
+    seqs = [rep["sequence"] for rep in gv["replicons"]]
+    tables = [_table(gold, k) for k, gold in enumerate(gv["genes"])]
+    sites = identify_sites(_OracleScanModel(om, seqs), _Lengths(seqs), tables, gv["promoter_up_distance"],
+                           gv["promoter_dw_distance"], use_up)
+    want = gv["scenarios"][scen]["sites"]
+    assert len(sites) == len(want)
+    for s, w in zip(sites, want):
+        assert (gv["replicons"][s.chromid]["accession"], s.start, s.end, s.strand, float(s.score),
+                tables[s.chromid].locus_tag[s.gene]) == \
+            (w["chromid"], w["start"], w["end"], w["strand"], w["score"], w["gene"])
+
+
+def test_site_join_raises_like_biopython_on_too_short_region():
+    from cgb_b200.site_search import identify_sites
+
+    class M:
+        length = 22
+        def threshold(self):
+            return 5.0
+        def scan_hits(self, genome, threshold, revseq_order=True):
+            z = np.zeros(0, dtype=np.int64)
+            return z, z, z.astype(np.int32), z.astype(np.float32)
+
+    # forward gene at 5 with down = 10: region [0, 15), 15 < m - 1 = 21 -> numpy.empty(negative)
+    gt = GeneTable([5], [400], [1], 1000)
+    with pytest.raises(ValueError):
+        identify_sites(M(), _Lengths(["A" * 1000]), [gt], 300, 10, False)
+    # a region of exactly m - 1 bases scores no window and raises nothing
+    gt = GeneTable([11], [400], [1], 1000)
+    assert identify_sites(M(), _Lengths(["A" * 1000]), [gt], 300, 10, False) == []

@@ -48,8 +48,29 @@ def _worker(rank, world, port, n, q):
         M.fit_background(bg=bg)
         _, pos, strand, score = M.scan_hits(g, M.threshold() - 3.0)
         gp, gs, gv = cdist.gather_hits(pos, strand, score, starts[rank])
+        # the motif-batch form of the same (bench.py's step): a shard with the halo of the longest
+        # motif, every motif capped at the shard's own windows, ONE all-reduce for all records
+        from cgb_b200 import motif_batch as mb
+        import numpy as np
+        rng = np.random.default_rng(9)
+        site_lists = []
+        for m in (8, 13, 22, 30):
+            cols = rng.dirichlet([0.5] * 4, size=m)
+            site_lists.append(["".join("ACGT"[rng.choice(4, p=cols[j])] for j in range(m)) for _ in range(20)])
+        Ms = [PSSMModel([SiteCollection(s2)], [1.0], device=dev) for s2 in site_lists]
+        m_max = 30
+        own = (n + world - 1) // world
+        lo = rank * own
+        cap = min(own, n - lo)
+        gb = PackedGenome.from_sequences([seq[lo:min(n, lo + cap + m_max - 1)]], dev)
+        thr = [Mk.threshold() for Mk in Ms]
+        res = mb.scan_batch(Ms, gb, thr, n_bins=128, win_cap=cap, to_host=False)
+        counts = torch.tensor([int(h.numel()) for h in res["hits"]], dtype=torch.int64, device=dev)
+        cdist.allreduce_batch(res["stats"], res["hist"])
+        dist.all_reduce(counts)
         if rank == 0:
-            q.put((bg["stats"].cpu().numpy(), bg["hist"].cpu().numpy(), gp, gs, gv))
+            q.put((bg["stats"].cpu().numpy(), bg["hist"].cpu().numpy(), gp, gs, gv,
+                   res["stats"].cpu().numpy(), res["hist"].cpu().numpy(), counts.cpu().numpy(), site_lists, thr))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -69,7 +90,7 @@ def test_chunk_sharded_two_gpus():
     procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
     for p in procs:
         p.start()
-    stats, hist, gp, gs, gv = q.get()
+    stats, hist, gp, gs, gv, bstats, bhist, bcounts, site_lists, bthr = q.get()
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
@@ -85,3 +106,9 @@ def test_chunk_sharded_two_gpus():
     assert abs(stats[_cabi.BG_MEAN] - b.mean()) < 1e-6 and abs(stats[_cabi.BG_STD] - b.std()) < 1e-6
     p, s, v = c_oracle.scan_hits(om, seq, om.threshold() - 3.0)
     assert np.array_equal(gp, p) and np.array_equal(gs, s) and np.array_equal(gv, v)
+    for k, sites in enumerate(site_lists):
+        omk = O.OracleModel([sites], [1.0])
+        _, _, bk = c_oracle.score_seq(omk, seq)
+        assert bstats[k, _cabi.BG_N] == len(bk) == bhist[k].sum()
+        assert abs(bstats[k, _cabi.BG_MEAN] - bk.mean()) < 1e-6 and abs(bstats[k, _cabi.BG_STD] - bk.std()) < 1e-6
+        assert bcounts[k] == len(c_oracle.scan_hits(omk, seq, bthr[k])[0])

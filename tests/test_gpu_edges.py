@@ -73,8 +73,22 @@ def test_slice_bounds_and_short_regions(pair, lexa):
         assert len(sub) >= m
         exp = c_oracle.binding_probability(om, sub, om._mu_m, om._std_m, om._mu_bg, om._std_bg, prior, alpha)
         assert abs(p - exp) < 1e-6, (s, e)
-    with pytest.raises(ValueError):                                  # shorter than the motif
-        M.binding_probabilities(g, [10], [10 + m - 1], prior, alpha)
+    # one base short of the motif: Biopython's calculate() returns an EMPTY score array
+    # (numpy.empty(0)), so the likelihood ratio is exp(0) and the posterior is the prior ...
+    got = M.binding_probabilities(g, [10, 0], [10 + m - 1, 350], prior, alpha).cpu().numpy()
+    assert abs(got[0] - prior) < 1e-15
+    assert M.binding_probability(seq[10:10 + m - 1].decode(), prior, alpha) == pytest.approx(prior, abs=1e-15)
+    assert M.score_seq(seq[10:10 + m - 1].decode()) == []
+    assert len(M.score_seq(seq[10:10 + m - 1].decode(), both=False)) == 0
+    assert M.score_seqs([seq[:m - 1], seq[:m + 3]], True)[0] == [] and len(M.score_seqs([seq[:m - 1], seq[:m + 3]], True)[1]) == 4
+    p2, _, _ = M.regulation_pipeline(seq, [10], [10 + m - 1], prior, alpha)
+    assert abs(p2[0] - prior) < 1e-15
+    with pytest.raises(ValueError):                                  # two bases short: numpy.empty(-1)
+        M.binding_probabilities(g, [10], [10 + m - 2], prior, alpha)
+    with pytest.raises(ValueError):
+        M.score_seq(seq[10:10 + m - 2].decode())
+    with pytest.raises(ValueError):
+        M.regulation_pipeline(seq, [10], [10 + m - 2], prior, alpha)
     # no promoters at all: the pipeline still returns the background record
     post, stats, hist = M.regulation_pipeline(seq, [], [], prior, alpha)
     assert len(post) == 0 and stats[_cabi.BG_N] == len(b) and hist.sum() == len(b)

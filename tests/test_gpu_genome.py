@@ -41,8 +41,16 @@ def _read(path):
 def test_genome_pipeline_matches_reference(gv, lexa, tmp_path):
     colls = [SiteCollection(mo["sites"], None, mo["name"]) for mo in lexa["motifs"]]
     genome = _genome(gv)
+    # mode="all": every window of every replicon (the benchmark's genome-wide distribution)
+    genome.build_PSSM_model(colls, gv["weights"], mode="all")
+    alw = gv["estimator_all_windows"]
+    assert abs(genome.TF_binding_model._mu_bg - alw["mu_bg"]) < 1e-6
+    assert abs(genome.TF_binding_model._std_bg - alw["std_bg"]) < 1e-6
+    # default: the reference's own population (upstream non-coding m-mers, genome.py:215-218);
+    # the golden estimator is the verbatim build_PSSM_model with random.sample = identity
     genome.build_PSSM_model(colls, gv["weights"])
     M, est = genome.TF_binding_model, gv["estimator"]
+    assert int(M._bg_stats_dev[0].item()) == est["n_bg"]
     assert M.threshold() == est["threshold"]
     assert abs(M._mu_m - est["mu_m"]) < 1e-6 and abs(M._std_m - est["std_m"]) < 1e-6
     # the fixture's soft-max ran with float32 pow (numpy 2); the pinned numpy 1.x, which the

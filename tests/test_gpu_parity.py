@@ -106,8 +106,9 @@ def test_score_seq_kat_and_errors(golden):
     k = golden["kat_acgt"]
     assert float(M.score_seq("ACGT", both=False)[0]) == k["fwd"]
     assert abs(M.score_seq("ACGT")[0] - 3.7122876) < 1e-6
+    assert M.score_seq("ACG") == []        # one base short: Biopython returns an empty array
     with pytest.raises(ValueError):
-        M.score_seq("ACG")                 # shorter than the motif: Biopython raises
+        M.score_seq("AC")                  # numpy.empty(len - m + 1) with a negative count raises
     assert M.score_seqs([]) == []
 
 
@@ -273,7 +274,7 @@ def test_posteriors_golden(golden, models, wname):
     p = rec["posteriors"][-1]
     assert abs(M.binding_probability(p["seq"], 0.01) - p["posterior"]) < POST_TOL   # default alpha 1/350
     with pytest.raises(ValueError):
-        M.binding_probability("ACGT", 0.03)
+        M.binding_probability("ACGT", 0.03)        # 4 < m - 1
     fresh = PSSMModel(M.site_collections, [1.0 / 6] * 6)
     with pytest.raises(AttributeError):
         fresh.binding_probability(seq[:350], 0.03)       # estimator not built, as in the reference

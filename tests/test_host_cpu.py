@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(_cabi.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _cabi.lib().cgbk_version() == 100
+    assert _cabi.lib().cgbk_version() == 200
 
 
 def test_site_collection_pwm(golden, lexa):
@@ -168,3 +168,27 @@ def test_identified_sites_rows_match_reference_format(tmp_path):
     rows = list(csv.reader(open(path)))
     assert rows[0] == CSV_HEADER and len(rows) == 41
     assert rows[1][1] == got[0][1] and rows[1][7] in ("operator", "intergenic")
+
+
+@pytest.mark.parametrize("wname", ["equal", "site_count"])
+def test_score_self_on_the_host_matches_verbatim_reference(golden, lexa, lexa_weights, wname):
+    """PSSMModel.score_self goes through cgbk_score_sites_host (float64 on the host, no GPU): the
+    164 LexA self scores against the verbatim reference run, and mu_m / std_m from them."""
+    rec = golden["models"][wname]
+    M = PSSMModel(_collections(lexa), lexa_weights[wname])
+    got = M.score_self()
+    assert len(got) == len(rec["score_self"]) and all(len(x) == 1 for x in got)
+    # the fixture's soft-max ran with numpy 2's float32 pow; the pinned numpy 1.x (what the
+    # library follows) differs by < 5e-7 per score
+    assert np.max(np.abs(np.array([x[0] for x in got]) - np.array(rec["score_self"]))) < 5e-7
+    om = O.OracleModel([mo["sites"] for mo in lexa["motifs"]], lexa_weights[wname])
+    exp = O.score_self(om)                                    # legacy64 mode: the same arithmetic
+    assert np.max(np.abs(np.array([x[0] for x in got]) - np.array([x[0] for x in exp]))) < 1e-13
+    # non-ACGT and lower-case bytes: _calculate's repair (pssm_model.py:88-101), float64 kept
+    m = M.length
+    site = M.sites[0]
+    for edited in (site[:4] + "N" + site[5:], site.lower(), site[:2] + "n" + site[3:8].lower() + site[8:]):
+        M2 = PSSMModel(_collections(lexa), lexa_weights[wname])
+        M2.__dict__["sites"] = [edited]
+        assert abs(M2.score_self()[0][0] - O.score_seq(om, edited, True)[0][0]) < 1e-13
+    assert m == 22

@@ -17,7 +17,8 @@ class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap"}
 
-    def __init__(self, torch_device):
+    def __init__(self, torch_device, period_s=0.0005):
+        self.period_s = period_s
         self.samples = []
         self.reason_bits = 0
         self.max_mhz = None
@@ -52,7 +53,7 @@ class ClockSampler:
                     self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
             except Exception:
                 pass
-            time.sleep(0.0005)
+            time.sleep(self.period_s)
 
     def start(self):
         if self._h is None:
@@ -62,7 +63,7 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0,
-               "how": "NVML polled every ~0.5 ms from a thread during the timed loops"}
+               "how": "NVML polled every ~%g ms from a thread during the timed loops" % (self.period_s * 1e3)}
         if self._thread is not None:
             self._stop.set()
             self._thread.join(timeout=2)
