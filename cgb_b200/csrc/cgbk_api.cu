@@ -385,9 +385,10 @@ static void build_model_host(const double* lo, int m, int device, cgbk_model* M,
     memcpy(ex.data() + CGBK_MAXM * 8, M->mean_f, sizeof(M->mean_f));
     memcpy(ex.data() + CGBK_MAXM * 8 + CGBK_MAXM, M->mean_r, sizeof(M->mean_r));
     // int32 fixed-point tables: scale 2^kexp (at most 2^28) with |any window sum| < 2^30
+    // (a little below 2^30, so that threshold - score of the fused scan cannot overflow either)
     int kexp = 28;
     if (R > 0) {
-        const int k2 = (int)floor(log2(1073741824.0 / R));
+        const int k2 = (int)floor(log2((1073741824.0 - 8192.0) / R));
         if (k2 < kexp) kexp = k2;
     }
     M->kexp = kexp;
@@ -812,7 +813,7 @@ static int carve(const cgbk_seqset* S, int m, void* d_work, int64_t work_bytes, 
     w->cand_cap = cand_cap;
     w->tile_begin = 0; w->tile_end = 0;          // set by the caller once the tiling is known
     w->ctr_slot = CGBK_CTR_INTERNAL_TILE; w->partial_base = 0;
-    w->hits8 = nullptr; w->hit_cap = 0; w->hit_cursor = nullptr;
+    w->hits8 = nullptr; w->hit_cap = 0; w->hit_cursor = nullptr; w->fplane = nullptr;
     return CGBK_OK;
 }
 
@@ -1125,16 +1126,26 @@ extern "C" int cgbk_background_finalize_batch(double* d_stats, int n_records, vo
 // ---------------------------------------------------------------------------
 // motif batches: K models over one packed buffer in one call
 // ---------------------------------------------------------------------------
-extern "C" int64_t cgbk_scan_batch_workspace_bytes(int64_t cand_cap) {
-    return (3 * 8 * PARTIAL_CAP + 8 * (cand_cap > 0 ? cand_cap : 0) + 255) / 256 * 256;
+// flag plane of the fused scan for any motif length and tiling: tiles x (B + 1) rows x 128 bytes
+static int64_t flag_plane_bytes(const cgbk_seqset* S, int64_t wcap) {
+    int64_t best = 0;
+    for (int L = 32; L <= 128; L += 32) {
+        const int64_t need = count_tiles(S, 1, L, wcap) * (int64_t)((L / 32 + 1) * 128);
+        if (need > best) best = need;
+    }
+    return best;
+}
+
+extern "C" int64_t cgbk_scan_batch_workspace_bytes(const cgbk_seqset* set, int64_t win_cap, int with_hits) {
+    if (!set) return 0;
+    return (3 * 8 * PARTIAL_CAP + (with_hits ? flag_plane_bytes(set, win_cap) : 0) + 255) / 256 * 256;
 }
 
 extern "C" int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cgbk_genome* genome,
                                const cgbk_seqset* set, int64_t win_cap, const double* thresholds, int flags,
                                const double* hist_lo, const double* hist_hi, int n_bins,
                                unsigned long long* d_hist, double* d_stats, uint64_t* d_hits8, int64_t hit_cap,
-                               int64_t* d_counters, void* d_work, int64_t work_bytes, int64_t cand_cap,
-                               void* stream) {
+                               int64_t* d_counters, void* d_work, int64_t work_bytes, void* stream) {
     if (!models || n_models < 1 || !set || !d_stats || !d_counters)
         return cgbk_set_error(CGBK_ERR_INVALID, "NULL or empty argument");
     int rc = check_genome(genome);
@@ -1146,19 +1157,18 @@ extern "C" int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cg
         if (thresholds && isnan(thresholds[k])) return cgbk_set_error(CGBK_ERR_INVALID, "threshold %d is NaN", k);
     }
     if (thresholds) {
-        if (hit_cap < 0 || cand_cap < 1 || (hit_cap > 0 && !d_hits8))
+        if (hit_cap < 0 || (hit_cap > 0 && !d_hits8))
             return cgbk_set_error(CGBK_ERR_INVALID, "bad hit capacity");
         if (genome->cap_bases >= (1ll << 31))
             return cgbk_set_error(CGBK_ERR_UNSUPPORTED, "compact hit records address buffers below 2^31 bases "
                                   "(shard the sequence, or use cgbk_scan_hits)");
-    } else {
-        cand_cap = 0;
     }
     if (d_hist && (n_bins < 1 || n_bins > CGBK_MAX_HIST_BINS))
         return cgbk_set_error(CGBK_ERR_INVALID, "histogram needs 1..%d bins", CGBK_MAX_HIST_BINS);
-    if (!d_work || work_bytes < cgbk_scan_batch_workspace_bytes(cand_cap))
+    const int64_t work_need = cgbk_scan_batch_workspace_bytes(set, win_cap, thresholds ? 1 : 0);
+    if (!d_work || work_bytes < work_need)
         return cgbk_set_error(CGBK_ERR_INVALID, "workspace of %lld bytes is smaller than the %lld required",
-                              (long long)work_bytes, (long long)cgbk_scan_batch_workspace_bytes(cand_cap));
+                              (long long)work_bytes, (long long)work_need);
     ON_DEVICE(models[0]->device);
     cudaStream_t st = (cudaStream_t)stream;
     cgbk_seqset* S = const_cast<cgbk_seqset*>(set);
@@ -1206,8 +1216,9 @@ extern "C" int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cg
         w.partials = (double*)d_work;
         w.partial_cap = PARTIAL_CAP;
         w.dirty_tiles = nullptr;
-        w.cands = (unsigned long long*)((unsigned char*)d_work + 3 * 8 * PARTIAL_CAP);
-        w.cand_cap = cand_cap;
+        w.cands = nullptr;
+        w.cand_cap = 0;
+        w.fplane = thresholds ? (unsigned int*)((unsigned char*)d_work + 3 * 8 * PARTIAL_CAP) : nullptr;
         w.tile_begin = 0; w.tile_end = n_tiles;
         w.ctr_slot = CGBK_CTR_INTERNAL_TILE; w.partial_base = 0;
         w.hits8 = thresholds ? (unsigned long long*)d_hits8 : nullptr;
@@ -1224,7 +1235,7 @@ extern "C" int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cg
             if (g_prof_on == 2) CUDA_TRY(prof_pair_event(k, 1, st));
             ++launches;
             if (thresholds) {
-                CUDA_TRY(launch_rescore8(M, gv, w, thresholds[k], flags, st));
+                CUDA_TRY(launch_rescore_flags(M, gv, tab, w, L, thresholds[k], flags, st));
                 ++launches;
             }
         } else {

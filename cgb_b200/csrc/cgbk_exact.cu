@@ -411,38 +411,65 @@ cudaError_t launch_rescore(const cgbk_model* mdl, GenomeView g, SeqTable seqs, F
     return cudaGetLastError();
 }
 
-// Candidates of the fused stats scan -> compact hit list shared by a batch of models
-// (cgbk_scan_batch): same exact arithmetic and comparison as rescore_kernel.
-__global__ void __launch_bounds__(128) rescore8_kernel(const double* __restrict__ d_exact, int m,
-                                                       GenomeView g, FastWork w, double thr, int flags) {
+// Flag plane of the fused stats scan -> compact hit list shared by a batch of models
+// (cgbk_scan_batch): every flagged window is scored with the exact arithmetic and compared like
+// rescore_kernel does.  One thread per flag word (coalesced), the warp pops one flagged window
+// per lane and round so that the hits of a round are appended with one atomic.
+__global__ void __launch_bounds__(128) rescore_flags_kernel(const double* __restrict__ d_exact, int m,
+                                                            GenomeView g, SeqTable seqs, FastWork w, int L,
+                                                            int D, double thr, int flags) {
     __shared__ ExactTables tab;
     stage_exact(&tab, d_exact);
     __syncthreads();
     const bool revseq = (flags & CGBK_RC_REVSEQ_ORDER) != 0;
-    long long n = w.counters[CGBK_CTR_CANDIDATES];
-    if (n > w.cand_cap) n = w.cand_cap;
-    for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < n;
-         i0 += (long long)gridDim.x * blockDim.x) {
-        const long long i = i0 + (threadIdx.x & 31);
-        bool hf = false, hr = false;
-        long long gpos = 0;
-        float ff = 0.f, rf = 0.f;
-        if (i < n) {
-            const unsigned long long rec = w.cands[i];
-            gpos = (long long)(rec & 0x3fffffffffffffffull);
-            double f, r;
-            exact_window(g, &tab, m, gpos, revseq, f, r);
-            ff = (float)f; rf = (float)r;
-            hf = (rec >> 63) && (double)ff >= thr;
-            hr = ((rec >> 62) & 1ull) && (double)rf >= thr;
+    const int B = L >> 5;
+    const long long rows = (w.tile_end - w.tile_begin) * (long long)(B + 1);     // 32-word rows
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    unsigned long long n_flagged = 0;
+    for (long long row = warp0; row < rows; row += nwarps) {
+        uint32_t word = __ldg(w.fplane + row * 32 + lane);
+        if (!__any_sync(0xffffffffu, word != 0u)) continue;
+        const long long tile = w.tile_begin + row / (B + 1);
+        const int r = (int)(row % (B + 1));
+        long long gbase, w_lo, w_hi;
+        tile_range(seqs, (unsigned int)tile, L, m, gbase, w_lo, w_hi);
+        const int own_n = (int)(w_hi - w_lo);
+        const int S = lane * L;
+        while (__any_sync(0xffffffffu, word != 0u)) {
+            bool hf = false, hr = false;
+            float ff = 0.f, rf = 0.f;
+            long long gpos = 0;
+            if (word) {
+                const int p = 31 - __clz(word);
+                word &= ~(1u << p);
+                // body row r: bit 31 - t <-> window S + 32 r + t - D;  tail row: bit D - 1 - j <-> S + L - D + j
+                const int wt = r < B ? S + 32 * r + (31 - p) - D : S + L - D + (D - 1 - p);
+                if (wt >= S && wt < own_n) {          // (junk bits of the unified first body sit below S)
+                    ++n_flagged;
+                    gpos = gbase + w_lo + wt;
+                    double f, rr;
+                    exact_window(g, &tab, m, gpos, revseq, f, rr);
+                    ff = (float)f; rf = (float)rr;
+                    hf = (double)ff >= thr;
+                    hr = (double)rf >= thr;
+                }
+            }
+            emit_hits8_warp(w.hits8, w.hit_cap, w.hit_cursor, w.counters, gpos, hf, ff, hr, rf);
         }
-        emit_hits8_warp(w.hits8, w.hit_cap, w.hit_cursor, w.counters, gpos, hf, ff, hr, rf);
     }
+    // candidates examined (diagnostics: CGBK_CTR_CANDIDATES)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_flagged += __shfl_down_sync(0xffffffffu, n_flagged, o);
+    if (lane == 0 && n_flagged)
+        atomicAdd(reinterpret_cast<unsigned long long*>(w.counters + CGBK_CTR_CANDIDATES), n_flagged);
 }
 
-cudaError_t launch_rescore8(const cgbk_model* mdl, GenomeView g, FastWork w, double thr, int flags,
-                            cudaStream_t st) {
-    rescore8_kernel<<<mdl->sms * 4, 128, 0, st>>>(mdl->d_exact, mdl->m, g, w, thr, flags);
+cudaError_t launch_rescore_flags(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, int L,
+                                 double thr, int flags, cudaStream_t st) {
+    rescore_flags_kernel<<<mdl->sms * 8, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, w, L, 4 * (mdl->G - 1), thr,
+                                                      flags);
     return cudaGetLastError();
 }
 

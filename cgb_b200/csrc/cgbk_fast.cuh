@@ -43,9 +43,13 @@
 //    uses mean and std, binding_model.py:85-87);
 //  * MODE 1 / 2 with a threshold ("fused" scan): the fixed-point strand scores are exact to a
 //    few units of 2^-kexp, so the same pass also finds the site-search candidates
-//    (genome.py:433-445): one compare per window against the fixed-point threshold minus
-//    its error bound, the rare candidates parked and flushed like the filter's.  One pass
-//    over the sequence then yields the background record AND the hit candidates;
+//    (genome.py:433-445).  Per window TWO instructions: the sign of (threshold - 1 - max(f, r))
+//    is shifted into a flag register (no branch, no atomic, the same cost whether one window
+//    in a million or one in twenty is a candidate -- low-information motifs reach the latter);
+//    the register goes to a "flag plane" [tile][row][lane] once per 32-position body, one
+//    coalesced 128-byte store like the score plane's.  cgbk_exact.cu walks the plane and
+//    re-scores the flagged windows exactly.  One pass over the sequence then yields the
+//    background record AND the hit candidates;
 //  * VAR 2 ("peeled"): the first 32-position body of a lane segment is its own code copy
 //    without the epilogues of the D windows that belong to the previous lane (they are
 //    only parked), the following bodies a second copy without the parking: no work is
@@ -216,30 +220,6 @@ static __device__ __noinline__ void emit_candidates4(uint32_t a0, uint32_t a1, u
     }
 }
 
-// The same for the fused stats scan: the four windows' fixed-point strand scores against the
-// fixed-point candidate threshold.  The staging buffer is found from the shared-memory window
-// (no pointer is kept live in the hot loop).
-static __device__ __noinline__ void emit_candidates4_fix(int f0, int f1, int f2, int f3, int r0, int r1, int r2, int r3,
-                                                  int thr_fix, int wt0, int lane_first, int own_n,
-                                                  long long gpos0, unsigned char* cand_base,
-                                                  long long* counters, unsigned long long* cands,
-                                                  long long cand_cap) {
-    unsigned long long* stage = reinterpret_cast<unsigned long long*>(cand_base);
-    unsigned int* stage_cnt = reinterpret_cast<unsigned int*>(cand_base + CGBK_CAND_STAGE * 8);
-    const int f[4] = {f0, f1, f2, f3}, r[4] = {r0, r1, r2, r3};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int wt = wt0 + k;
-        const bool cf = f[k] >= thr_fix, cr = r[k] >= thr_fix;
-        if ((cf || cr) && wt >= lane_first && wt < own_n) {
-            const unsigned long long rec = (unsigned long long)(gpos0 + wt) |
-                                           ((unsigned long long)(cf ? 1u : 0u) << 63) |
-                                           ((unsigned long long)(cr ? 1u : 0u) << 62);
-            park_candidate(rec, stage, stage_cnt, counters, cands, cand_cap);
-        }
-    }
-}
-
 // warp-convergent: move this warp's parked candidates to the global list
 static __device__ __noinline__ void flush_candidates(unsigned long long* stage, unsigned int* stage_cnt, int lane,
                                                  long long* counters, unsigned long long* cands,
@@ -337,8 +317,8 @@ struct FastCfg {
     static constexpr int NW = MODE == 0 ? G : 2 * G;
     static constexpr int D = 4 * (G - 1);
     static constexpr int STASH_BYTES = ((THREADS / 32) * D * 33 * (MODE == 0 ? 4 : 8) + 15) / 16 * 16;
-    // per-warp candidate staging [CGBK_CAND_STAGE] u64 + one counter word (padded to 16 B)
-    static constexpr int CAND_BYTES = (THREADS / 32) * (CGBK_CAND_STAGE * 8 + 16);
+    // MODE 0: per-warp candidate staging [CGBK_CAND_STAGE] u64 + one counter word (padded to 16 B)
+    static constexpr int CAND_BYTES = MODE == 0 ? (THREADS / 32) * (CGBK_CAND_STAGE * 8 + 16) : 0;
 };
 
 #define CGBK_VAR_UNIFIED 0   // one 32-position body for every part of a lane segment
@@ -421,7 +401,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     fill_tables<NW, Cfg::THREADS>(smem, gtab);
     if (HIST)
         for (int i = threadIdx.x; i < sp.n_bins * sp.hist_words; i += blockDim.x) hist[i] = 0u;
-    if ((threadIdx.x & 31) == 0) *reinterpret_cast<unsigned int*>(cand_ptr() + CGBK_CAND_STAGE * 8) = 0u;
+    if (MODE == 0 && (threadIdx.x & 31) == 0) *reinterpret_cast<unsigned int*>(cand_ptr() + CGBK_CAND_STAGE * 8) = 0u;
     if (MODE != 0 && threadIdx.x < 3) exact_acc[threadIdx.x] = 0.0;
     __syncthreads();
 
@@ -487,6 +467,8 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                                  g.cap_bases, gbase, A, A + (own_n > 0 ? own_n : 0), m, tile, L, D, sp.d_hist,
                                  sp.n_bins, sp.hist_lo_d, sp.inv_binw_d, sp.plane, (double)sp.scale, exact_acc,
                                  &sink);
+                if (work.fplane)       // its sites are final already: no flags for the re-score pass
+                    for (int r = 0; r <= B; ++r) work.fplane[(tile * (B + 1) + r) * 32 + lane] = 0u;
             }
             tile = advance();
             preload(tile);
@@ -501,6 +483,10 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         // score plane rows of this tile: [(B + 1) * 32][32] ints, row = body*32 + t (last: the tail)
         int* prow = (MODE != 0 && sp.plane) ? sp.plane + tile * (long long)((B + 1) * 1024) + lane : nullptr;
 
+        // fused scan: candidate flags of the current body's completed windows (shifted in one by
+        // one, newest at bit 0) and this lane's column of the tile's flag rows
+        uint32_t cflags = 0u;
+        unsigned int* fprow = (MODE != 0 && work.fplane) ? work.fplane + tile * (long long)((B + 1) * 32) + lane : nullptr;
         uint32_t flag_or = 0u, pend[EW], pendb[EW];            // the last (up to) EW completed windows
 #pragma unroll
         for (int i = 0; i < EW; ++i) { pend[i] = 0u; pendb[i] = 0u; }
@@ -539,22 +525,14 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 if (q == EW - 1) {
                     int mx[EW], sfix[EW];
                     float u[EW];
-                    bool any_cand = false;
 #pragma unroll
                     for (int k = 0; k < EW; ++k) {
                         const int fq = (int)pend[k], rq = (int)pendb[k];
                         mx[k] = max(fq, rq);
                         u[k] = (float)(mx[k] - min(fq, rq)) * sp.neg_inv_scale;
-                        any_cand |= mx[k] >= sp.thr_fix;
-                    }
-                    if (any_cand) {
-                        // rare: some window of the four may reach the hit threshold (examined out of
-                        // line; the strand scores are not needed past this point)
-                        emit_candidates4_fix((int)pend[0], (int)pend[1], (int)pend[2], (int)pend[3], (int)pendb[0],
-                                             (int)pendb[1], (int)pendb[2], (int)pendb[3], sp.thr_fix, wt - 3, S,
-                                             own_n, (wbase << 4) - S, cand_ptr(), work.counters, work.cands,
-                                             work.cand_cap);
-                        staged = true;
+                        // candidate <=> max(f, r) >= thr_fix <=> (thr_fix - 1 - max) < 0: its sign bit
+                        // is shifted into the flag register (|both terms| < 2^30: no overflow)
+                        cflags = __funnelshift_l((uint32_t)(sp.thr_m1 - mx[k]), cflags, 1);
                     }
 #pragma unroll
                     for (int k = 0; k < EW; ++k) u[k] = ex2_approx(u[k]);                 // 2^-|f-r|
@@ -631,9 +609,13 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
               }
             }
         };
-        auto after_body = [&]() {
-            if (MODE != 0) { sum_d += acc_d; acc_d = 0; }
-            if (__any_sync(0xffffffffu, staged)) {     // a vote, no memory access, when idle
+        auto after_body = [&](int b) {
+            if (MODE != 0) {
+                sum_d += acc_d; acc_d = 0;
+                if (fprow) fprow[b * 32] = cflags;     // one coalesced 128-byte row per body
+                cflags = 0u;
+            }
+            if (MODE == 0 && __any_sync(0xffffffffu, staged)) {     // a vote, no memory access, when idle
                 flush_staged();
                 staged = false;
             }
@@ -643,19 +625,19 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
             uint2 nxt = ld_stream2(g.bases2, wbase + 2, nwords);
             body(std::integral_constant<int, 1>(), 0, cur.x, cur.y, nxt.x);
             cur = nxt;
-            after_body();
+            after_body(0);
             for (int b = 1; b < B; ++b) {
                 nxt = ld_stream2(g.bases2, wbase + 2 * (b + 1), nwords);
                 body(std::integral_constant<int, 2>(), b, cur.x, cur.y, nxt.x);
                 cur = nxt;
-                after_body();
+                after_body(b);
             }
         } else {
             for (int b = 0; b < B; ++b) {
                 const uint2 nxt = ld_stream2(g.bases2, wbase + 2 * (b + 1), nwords);
                 body(std::integral_constant<int, 0>(), b, cur.x, cur.y, nxt.x);
                 cur = nxt;
-                after_body();
+                after_body(b);
             }
         }
         const long long next_tile = advance();
@@ -676,12 +658,13 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 complete(sa[si] + ia, sb[si] + ib, S + L, j - D, own_n - (S + L), true, B * 32 + j, (32 - D + j) & (EW - 1));
             }
             __syncwarp();
-            if (__any_sync(0xffffffffu, staged)) {
+            if (MODE == 0 && __any_sync(0xffffffffu, staged)) {
                 flush_staged();
                 staged = false;
             }
         }
         if (MODE != 0) {
+            if (fprow) fprow[B * 32] = cflags;         // the D straddling windows (zero when D == 0)
             sum_d += acc_d;
             sum_d2 += (double)acc_d2;
             const int mine = own_n - S;

@@ -77,6 +77,7 @@ StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist
     sp.d_hist = d_hist;
     sp.plane = plane;
     sp.thr_fix = CGBK_NO_THRESHOLD;
+    sp.thr_m1 = 1 << 30;                 // above every score: no flag is ever set
     sp.thr = 0.0;
     sp.revseq = 0;
     return sp;
@@ -92,11 +93,19 @@ void set_stats_threshold(StatsParams* sp, const cgbk_model* mdl, double thr, int
     const double scale = ldexp(1.0, mdl->kexp);
     const double slack = 1e-5 + fabs(thr) * 1.2e-7;
     double t = floor((thr - slack) * scale) - (double)(2 * mdl->m + 2);
-    if (!(t > -2147483000.0)) t = -2147483000.0;        // everything is a candidate
-    if (t >= 2147483000.0) { sp->thr_fix = CGBK_NO_THRESHOLD; sp->thr = thr; sp->revseq = revseq; return; }
-    sp->thr_fix = (int)t;
+    // every window sum is below 2^30 - 4000 in magnitude (cgbk_api.cu picks kexp that way), so a
+    // threshold clamped to that range decides the same and thr - 1 - score stays inside int32
+    const double lim = 1073741824.0 - 4000.0;
     sp->thr = thr;
     sp->revseq = revseq ? 1 : 0;
+    if (t > lim) {                       // above every score: no candidates
+        sp->thr_fix = CGBK_NO_THRESHOLD;
+        sp->thr_m1 = 1 << 30;
+        return;
+    }
+    if (!(t > -lim)) t = -lim;           // at or below every score: everything is a candidate
+    sp->thr_fix = (int)t;
+    sp->thr_m1 = (int)t - 1;
 }
 
 cudaError_t launch_fast_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, int L,

@@ -116,6 +116,10 @@ struct FastWork {      // carved out of the caller's workspace
     unsigned long long* hits8;  // cgbk_hit8 records
     long long hit_cap;
     long long* hit_cursor;      // append position (one counter for the whole batch)
+    // candidate flags of the fused scan: [tile][B + 1 rows][32 lanes] words, one bit per completed
+    // window (row b < B: bit 31 - t is the window completed at body position t, i.e. tile-local
+    // window lane * L + 32 b + t - D; row B: bit D - 1 - j is window lane * L + L - D + j)
+    unsigned int* fplane;
 };
 
 // compact hit record (include/cgbk.h cgbk_hit8): gpos << 33 | minus << 32 | float32 score bits
@@ -193,8 +197,10 @@ struct StatsParams {
     double* host_stats;
     unsigned long long* host_hist;
     // fused scan: windows whose fixed-point strand score reaches thr_fix are hit candidates
-    // (CGBK_NO_THRESHOLD: none); thr / revseq serve the exactly scored tiles
+    // (CGBK_NO_THRESHOLD: none; thr_m1 = thr_fix - 1 clamped so that thr_m1 - score cannot
+    // overflow); thr / revseq serve the exactly scored tiles
     int thr_fix;
+    int thr_m1;
     int revseq;
     double thr;
 };
@@ -210,9 +216,9 @@ cudaError_t launch_fast_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs
 cudaError_t launch_fast_moments(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
                                 int L, int grid, const StatsParams& sp, cudaStream_t st);
 
-// exact re-score of the fused scan's candidates into the compact hit list
-cudaError_t launch_rescore8(const cgbk_model* mdl, GenomeView g, FastWork w, double thr, int flags,
-                            cudaStream_t st);
+// exact re-score of the windows flagged in the fused scan's flag plane into the compact hit list
+cudaError_t launch_rescore_flags(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, int L,
+                                 double thr, int flags, cudaStream_t st);
 
 // score plane addressing shared by the writers (cgbk_fast.cu, dirty tiles) and the reader
 // (posteriors): window wt of a tile with lane segment L = 32 * B and overlap D = 4 * (G - 1)

@@ -81,9 +81,8 @@ class _ScanBuffers:
     """Device and pinned host buffers of :func:`scan_batch`, kept on the genome and reused between
     calls.  Two hit buffers: while the host receives the sites of one sub-batch, the next is scanned."""
 
-    def __init__(self, dev, n_models, n_bins, hit_cap, cand_cap, host_hits):
-        lib = _cabi.lib()
-        self.n_models, self.n_bins, self.hit_cap, self.cand_cap = n_models, n_bins, hit_cap, cand_cap
+    def __init__(self, dev, n_models, n_bins, hit_cap, work_bytes, host_hits):
+        self.n_models, self.n_bins, self.hit_cap, self.work_bytes = n_models, n_bins, hit_cap, work_bytes
         # stats | histograms | counters back to back: the library clears them with one memset
         n_rec = n_models * _cabi.BG_COUNT + n_models * n_bins + (n_models + 1) * _cabi.CTR_COUNT
         self.record = torch.empty(n_rec, dtype=torch.int64, device=dev)
@@ -94,8 +93,7 @@ class _ScanBuffers:
             if host_hits else []
         self.copied = [None] * n_buf                  # event: the D2H out of hits[p] has finished
         self.copy_stream = torch.cuda.Stream(device=dev) if host_hits else None
-        wbytes = int(lib.cgbk_scan_batch_workspace_bytes(cand_cap))
-        self.work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        self.work = torch.empty(work_bytes, dtype=torch.uint8, device=dev)
         self.sort_tmp = None
 
 
@@ -105,14 +103,14 @@ class _ScanBuffers:
 _BUFFER_CACHE = {}
 
 
-def _buffers(genome, n_models, n_bins, hit_cap, cand_cap, host_hits):
+def _buffers(genome, n_models, n_bins, hit_cap, work_bytes, host_hits):
     key = genome.device.index or 0
     b = _BUFFER_CACHE.get(key)
-    if (b is None or b.n_models < n_models or b.n_bins != n_bins or b.hit_cap < hit_cap or b.cand_cap < cand_cap
+    if (b is None or b.n_models < n_models or b.n_bins != n_bins or b.hit_cap < hit_cap or b.work_bytes < work_bytes
             or (host_hits and not b.host_hits)):
         _BUFFER_CACHE.pop(key, None)
         b = None                                          # free the old buffers first
-        b = _ScanBuffers(genome.device, n_models, n_bins, hit_cap, cand_cap, host_hits)
+        b = _ScanBuffers(genome.device, n_models, n_bins, hit_cap, work_bytes, host_hits)
         _BUFFER_CACHE[key] = b
     return b
 
@@ -185,9 +183,9 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
             free_bytes, _ = torch.cuda.mem_get_info(dev)
             want = exp.sum() if (not to_host and not recycle) else max(exp.max() * 1.5, 1 << 20)
             hit_cap = int(min(max(want, 1 << 20), free_bytes // 4 // 16))
-    # candidates are re-scored model by model: the buffer holds ONE model's worth (candidates are
-    # the hits plus the few windows within the fixed-point error of the threshold)
-    cand_cap = int(min(max(exp.max() * 1.5, 1 << 16), max(hit_cap, 1 << 16))) if want_hits else 0
+    # scratch of the scan: moment partials + the candidate flag plane (one bit per window)
+    work_bytes = int(lib.cgbk_scan_batch_workspace_bytes(genome.seqset, -1 if win_cap is None else int(win_cap),
+                                                         1 if want_hits else 0))
     handles_all = [M._model() for M in models]
     stream = torch.cuda.current_stream(dev)
     flags = _cabi.RC_REVSEQ_ORDER if revseq_order else _cabi.RC_MATRIX_ORDER
@@ -227,7 +225,7 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
             acc += exp[j]
             j += 1
         n = j - i
-        buf = _buffers(genome, K, n_bins, hit_cap, cand_cap, host_hits)
+        buf = _buffers(genome, K, n_bins, hit_cap, work_bytes, host_hits)
         p = n_sub & 1 if host_hits else 0
         if host_hits and buf.copied[p] is not None and pending is not None and pending[2] == p:
             deliver(*pending, buf)                         # cannot happen with two buffers, kept for safety
@@ -242,7 +240,7 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
             thr[i:j].ctypes.data if want_hits else None, flags, None, None, int(n_bins),
             d_hist.data_ptr() if d_hist is not None else None, d_stats.data_ptr(),
             buf.hits[p].data_ptr() if want_hits else None, int(buf.hit_cap) if want_hits else 0, d_ctr.data_ptr(),
-            buf.work.data_ptr(), buf.work.numel(), int(buf.cand_cap) if want_hits else 0, stream.cuda_stream))
+            buf.work.data_ptr(), buf.work.numel(), stream.cuda_stream))
         launches += int(_cabi.last_launch_info()["launches"])
         if not to_host and not want_hits:
             stats_out[i:j] = d_stats.view(torch.float64).view(n, BG)
@@ -259,15 +257,14 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
         ctr = h[b:].reshape(n + 1, CT)
         n_done = n
         if want_hits:
-            cand_over = np.nonzero(ctr[:n, _cabi.CTR_CANDIDATES] > buf.cand_cap)[0]
             cum_all = np.concatenate([[0], np.cumsum(ctr[:n, _cabi.CTR_HITS])])
             hit_over = np.nonzero(cum_all[1:] > buf.hit_cap)[0]
-            bad = min([int(x[0]) for x in (cand_over, hit_over) if len(x)] or [n])
+            bad = int(hit_over[0]) if len(hit_over) else n
             if bad < n:
                 # records were dropped from model `bad` on: keep the models before it and run the
                 # rest again, with buffers grown to what model `bad` needs if it was the first
                 n_done = bad
-                need = float(max(ctr[bad, _cabi.CTR_HITS], ctr[bad, _cabi.CTR_CANDIDATES])) + 4096
+                need = float(ctr[bad, _cabi.CTR_HITS]) + 4096
                 exp[i + bad] = max(exp[i + bad], need)
                 if bad == 0:
                     if not to_host and not recycle:
@@ -281,7 +278,6 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
                         deliver(*pending, buf)
                         pending = None
                     hit_cap = max(hit_cap, int(need))
-                    cand_cap = max(cand_cap, int(need))
                     release_buffers(dev)
                     del buf
                     continue
@@ -337,7 +333,7 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
             n_sub += 1
         i += n_done
     if pending is not None:
-        deliver(*pending, _buffers(genome, K, n_bins, hit_cap, cand_cap, host_hits))
+        deliver(*pending, _buffers(genome, K, n_bins, hit_cap, work_bytes, host_hits))
     return {"stats": stats_out, "hist": hist_out, "hits": hits_out, "counters": ctr_out, "launches": launches}
 
 

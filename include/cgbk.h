@@ -240,8 +240,9 @@ int cgbk_background_stats_regions(const cgbk_model* model, const cgbk_genome* ge
  * d_hist is NULL: then the scan runs without a histogram) and -- when `thresholds` is given --
  * every site with float32 score >= thresholds[k] on either strand (Genome.identify_sites' hit
  * test, cgb/genome.py:433-445), found by the SAME pass: the stats scan's int32 fixed-point
- * strand scores are compared with the threshold minus their error bound and the candidates are
- * re-scored in float64 in the reference's order (bit-exact hit lists).
+ * strand scores are compared with the threshold minus their error bound (one flag bit per
+ * window) and the flagged windows are re-scored in float64 in the reference's order (bit-exact
+ * hit lists).
  *   win_cap      >= 0: only the first win_cap windows of each sequence are scored (sets of up to
  *                4 sequences).  A rank's shard of a longer sequence carries the halo of the longest
  *                motif and caps every motif at the shard's own windows; < 0: all windows
@@ -251,17 +252,18 @@ int cgbk_background_stats_regions(const cgbk_model* model, const cgbk_genome* ge
  *                inside the segment (cgbk_sort_hits orders a segment)
  *   d_counters   int64[n_models + 1][CGBK_CTR_COUNT]: per model candidates / hits / tiles with
  *                non-ACGT bytes; block n_models: [0] = records appended in total.  A total above
- *                hit_cap or a candidate count above cand_cap means records were dropped: run the
- *                models from the first affected one again with larger buffers
- *   d_work       >= cgbk_scan_batch_workspace_bytes(cand_cap)
+ *                hit_cap means records were dropped: run the models from the first affected one
+ *                again with a larger buffer
+ *   d_work       >= cgbk_scan_batch_workspace_bytes(set, win_cap, thresholds != NULL): the
+ *                moment partials and the scan's candidate flag plane (one bit per window)
  * flags: CGBK_RC_*.  No allocation, no synchronisation. */
-int64_t cgbk_scan_batch_workspace_bytes(int64_t cand_cap);
+int64_t cgbk_scan_batch_workspace_bytes(const cgbk_seqset* set, int64_t win_cap, int with_hits);
 int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cgbk_genome* genome,
                     const cgbk_seqset* set, int64_t win_cap, const double* thresholds, int flags,
                     const double* hist_lo, const double* hist_hi, int n_bins,
                     unsigned long long* d_hist, double* d_stats,
                     cgbk_hit8* d_hits8, int64_t hit_cap, int64_t* d_counters,
-                    void* d_work, int64_t work_bytes, int64_t cand_cap, void* stream);
+                    void* d_work, int64_t work_bytes, void* stream);
 
 /* Sort n compact records in place by (position, + strand first); d_tmp >=
  * cgbk_sort_hits_workspace_bytes(n) bytes of device scratch. */

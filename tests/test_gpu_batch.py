@@ -191,7 +191,7 @@ def test_scan_batch_many_sequences_and_large_segments(lexa, lexa_weights):
     seqs = [O.synthetic_genome(int(n), 60 + i, n_frac=0.002 if i % 2 else 0.0)
             for i, n in enumerate([50_000, 21, 22, 23, 0, 140_001, 3_000, 700_000])]
     g = PackedGenome.from_sequences(seqs)
-    thr = M.threshold() - 9.0                       # a few percent of the windows: > 2^15 sites
+    thr = M.threshold() - 10.5                      # a few percent of the windows: > 2^15 sites
     res = mb.scan_batch([M], g, [thr], n_bins=256)
     seq_i, pos, strand, score = mb.hits_of(g, res["hits"][0])
     assert len(pos) > (1 << 15)
