@@ -88,10 +88,10 @@ SYMBOLS = {
     "cgbk_background_stats_regions": (C.c_int, [C.c_void_p, C.POINTER(Genome), C.c_void_p, C.c_void_p, C.c_int,
                                                  C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                                  C.c_void_p, C.c_int64, C.c_void_p]),
-    "cgbk_scan_batch_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int]),
+    "cgbk_scan_batch_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64]),
     "cgbk_scan_batch": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Genome), C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
-                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "cgbk_sort_hits_workspace_bytes": (C.c_int64, [C.c_int64]),
     "cgbk_sort_hits": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "cgbk_pipeline_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int, C.c_int]),

@@ -1126,26 +1126,43 @@ extern "C" int cgbk_background_finalize_batch(double* d_stats, int n_records, vo
 // ---------------------------------------------------------------------------
 // motif batches: K models over one packed buffer in one call
 // ---------------------------------------------------------------------------
-// flag plane of the fused scan for any motif length and tiling: tiles x (B + 1) rows x 128 bytes
-static int64_t flag_plane_bytes(const cgbk_seqset* S, int64_t wcap) {
-    int64_t best = 0;
-    for (int L = 32; L <= 128; L += 32) {
-        const int64_t need = count_tiles(S, 1, L, wcap) * (int64_t)((L / 32 + 1) * 128);
-        if (need > best) best = need;
+// Workspace of a batched scan: moment partials | 4 per-tile int arrays | prefix-sum scratch |
+// flag plane (one bit per window) | candidate record pairs.  Sized for any motif length and tiling
+// of the set (the L = 32 tiling has the most tiles, the largest rows-per-window ratio).
+struct BatchLayout {
+    int64_t max_tiles, off_tiles, off_scan, scan_bytes, off_flags, flag_bytes, off_pairs, total;
+};
+
+static BatchLayout batch_layout(const cgbk_seqset* S, int64_t wcap, int with_hits, int64_t cand_cap) {
+    BatchLayout b = {};
+    int64_t o = 3 * 8 * PARTIAL_CAP;
+    if (with_hits) {
+        b.max_tiles = count_tiles(S, 1, 32, wcap);
+        for (int L = 32; L <= 128; L += 32) {
+            const int64_t need = count_tiles(S, 1, L, wcap) * (int64_t)((L / 32 + 1) * 128);
+            if (need > b.flag_bytes) b.flag_bytes = need;
+        }
+        b.off_tiles = o;  o += (4 * 4 * (b.max_tiles + 1) + 255) / 256 * 256;
+        b.scan_bytes = cgbk_scan_tmp_bytes(b.max_tiles + 1);
+        b.off_scan = o;   o += (b.scan_bytes + 255) / 256 * 256;
+        b.off_flags = o;  o += (b.flag_bytes + 255) / 256 * 256;
+        b.off_pairs = o;  o += 16 * (cand_cap > 0 ? cand_cap : 0);
     }
-    return best;
+    b.total = (o + 255) / 256 * 256;
+    return b;
 }
 
-extern "C" int64_t cgbk_scan_batch_workspace_bytes(const cgbk_seqset* set, int64_t win_cap, int with_hits) {
+extern "C" int64_t cgbk_scan_batch_workspace_bytes(const cgbk_seqset* set, int64_t win_cap, int64_t cand_cap) {
     if (!set) return 0;
-    return (3 * 8 * PARTIAL_CAP + (with_hits ? flag_plane_bytes(set, win_cap) : 0) + 255) / 256 * 256;
+    return batch_layout(set, win_cap, cand_cap > 0 ? 1 : 0, cand_cap).total;
 }
 
 extern "C" int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cgbk_genome* genome,
                                const cgbk_seqset* set, int64_t win_cap, const double* thresholds, int flags,
                                const double* hist_lo, const double* hist_hi, int n_bins,
                                unsigned long long* d_hist, double* d_stats, uint64_t* d_hits8, int64_t hit_cap,
-                               int64_t* d_counters, void* d_work, int64_t work_bytes, void* stream) {
+                               int64_t* d_counters, void* d_work, int64_t work_bytes, int64_t cand_cap,
+                               void* stream) {
     if (!models || n_models < 1 || !set || !d_stats || !d_counters)
         return cgbk_set_error(CGBK_ERR_INVALID, "NULL or empty argument");
     int rc = check_genome(genome);
@@ -1156,16 +1173,18 @@ extern "C" int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cg
             return cgbk_set_error(CGBK_ERR_INVALID, "model %d lives on another device", k);
         if (thresholds && isnan(thresholds[k])) return cgbk_set_error(CGBK_ERR_INVALID, "threshold %d is NaN", k);
     }
+    if (!thresholds) cand_cap = 0;
     if (thresholds) {
-        if (hit_cap < 0 || (hit_cap > 0 && !d_hits8))
-            return cgbk_set_error(CGBK_ERR_INVALID, "bad hit capacity");
+        if (hit_cap < 0 || cand_cap < 1 || cand_cap >= (1ll << 30) || (hit_cap > 0 && !d_hits8))
+            return cgbk_set_error(CGBK_ERR_INVALID, "bad hit / candidate capacity");
         if (genome->cap_bases >= (1ll << 31))
             return cgbk_set_error(CGBK_ERR_UNSUPPORTED, "compact hit records address buffers below 2^31 bases "
                                   "(shard the sequence, or use cgbk_scan_hits)");
     }
     if (d_hist && (n_bins < 1 || n_bins > CGBK_MAX_HIST_BINS))
         return cgbk_set_error(CGBK_ERR_INVALID, "histogram needs 1..%d bins", CGBK_MAX_HIST_BINS);
-    const int64_t work_need = cgbk_scan_batch_workspace_bytes(set, win_cap, thresholds ? 1 : 0);
+    const BatchLayout lay = batch_layout(set, win_cap, thresholds ? 1 : 0, cand_cap);
+    const int64_t work_need = lay.total;
     if (!d_work || work_bytes < work_need)
         return cgbk_set_error(CGBK_ERR_INVALID, "workspace of %lld bytes is smaller than the %lld required",
                               (long long)work_bytes, (long long)work_need);
@@ -1218,7 +1237,9 @@ extern "C" int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cg
         w.dirty_tiles = nullptr;
         w.cands = nullptr;
         w.cand_cap = 0;
-        w.fplane = thresholds ? (unsigned int*)((unsigned char*)d_work + 3 * 8 * PARTIAL_CAP) : nullptr;
+        w.fplane = thresholds ? (unsigned int*)((unsigned char*)d_work + lay.off_flags) : nullptr;
+        int* tile_ints = (int*)((unsigned char*)d_work + lay.off_tiles);
+        w.tile_cand = thresholds ? tile_ints : nullptr;
         w.tile_begin = 0; w.tile_end = n_tiles;
         w.ctr_slot = CGBK_CTR_INTERNAL_TILE; w.partial_base = 0;
         w.hits8 = thresholds ? (unsigned long long*)d_hits8 : nullptr;
@@ -1235,8 +1256,17 @@ extern "C" int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cg
             if (g_prof_on == 2) CUDA_TRY(prof_pair_event(k, 1, st));
             ++launches;
             if (thresholds) {
-                CUDA_TRY(launch_rescore_flags(M, gv, tab, w, L, thresholds[k], flags, st));
-                ++launches;
+                SitePass sp2;
+                sp2.tile_cand = tile_ints;
+                sp2.tile_cand_off = tile_ints + (lay.max_tiles + 1);
+                sp2.tile_hits = tile_ints + 2 * (lay.max_tiles + 1);
+                sp2.tile_hit_off = tile_ints + 3 * (lay.max_tiles + 1);
+                sp2.pairs = (unsigned long long*)((unsigned char*)d_work + lay.off_pairs);
+                sp2.cand_cap = cand_cap;
+                sp2.scan_tmp = (unsigned char*)d_work + lay.off_scan;
+                sp2.scan_tmp_bytes = lay.scan_bytes;
+                CUDA_TRY(launch_site_pass(M, gv, tab, w, sp2, L, thresholds[k], flags, st));
+                launches += 3;          // score, emit, finish (+ two library prefix sums)
             }
         } else {
             if (g_prof_on == 2) { CUDA_TRY(prof_pair_event(k, 0, st)); CUDA_TRY(prof_pair_event(k, 1, st)); }

@@ -411,65 +411,151 @@ cudaError_t launch_rescore(const cgbk_model* mdl, GenomeView g, SeqTable seqs, F
     return cudaGetLastError();
 }
 
-// Flag plane of the fused stats scan -> compact hit list shared by a batch of models
-// (cgbk_scan_batch): every flagged window is scored with the exact arithmetic and compared like
-// rescore_kernel does.  One thread per flag word (coalesced), the warp pops one flagged window
-// per lane and round so that the hits of a round are appended with one atomic.
-__global__ void __launch_bounds__(128) rescore_flags_kernel(const double* __restrict__ d_exact, int m,
-                                                            GenomeView g, SeqTable seqs, FastWork w, int L,
-                                                            int D, double thr, int flags) {
+// Fused scan, site pass (cgbk_scan_batch): the windows flagged in the scan's flag plane are
+// scored with the exact arithmetic and compared like rescore_kernel does (genome.py:436,443), and
+// the sites come out ORDERED by (position, + strand first) without a sort:
+//   1. exclusive prefix sum of the scan's per-tile flag counts        -> where a tile's candidates go
+//   2. site_score_kernel, one warp per tile: the tile's flagged windows are listed in position
+//      order (lanes own consecutive segments, rows and bits ascend inside a lane), dealt out to the
+//      lanes 32 at a time (balanced however unevenly the flags fall) and scored; each candidate
+//      leaves a (+ strand record, - strand record) pair, ~0 where that strand is no site
+//   3. exclusive prefix sum of the per-tile site counts               -> where a tile's sites go
+//   4. site_emit_kernel, one warp per tile: the pairs are compacted into the batch's hit list
+//   5. site_finish_kernel: counters and the batch's append position
+#define CGBK_SITE_QUEUE 256     // candidates listed per warp and round
+#define CGBK_NO_SITE 0xffffffffffffffffull
+
+__global__ void __launch_bounds__(128) site_score_kernel(const double* __restrict__ d_exact, int m, GenomeView g,
+                                                         SeqTable seqs, FastWork w, SitePass sp, int L, int D,
+                                                         double thr, int flags) {
     __shared__ ExactTables tab;
+    __shared__ unsigned short queue[4][CGBK_SITE_QUEUE];
     stage_exact(&tab, d_exact);
     __syncthreads();
     const bool revseq = (flags & CGBK_RC_REVSEQ_ORDER) != 0;
-    const int B = L >> 5;
-    const long long rows = (w.tile_end - w.tile_begin) * (long long)(B + 1);     // 32-word rows
-    const int lane = threadIdx.x & 31;
+    const int B = L >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long n_tiles = w.tile_end - w.tile_begin;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    unsigned long long n_flagged = 0;
-    for (long long row = warp0; row < rows; row += nwarps) {
-        uint32_t word = __ldg(w.fplane + row * 32 + lane);
-        if (!__any_sync(0xffffffffu, word != 0u)) continue;
-        const long long tile = w.tile_begin + row / (B + 1);
-        const int r = (int)(row % (B + 1));
+    unsigned short* q = queue[wib];
+    for (long long ti = warp0; ti < n_tiles; ti += nwarps) {
+        const long long tile = w.tile_begin + ti;
+        const int total = __ldg(sp.tile_cand + tile);
+        if (total == 0) {                                   // warp-uniform
+            if (lane == 0) sp.tile_hits[tile] = 0;
+            continue;
+        }
+        uint32_t words[5];
+        int c = 0;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            words[r] = r <= B ? __ldg(w.fplane + (tile * (B + 1) + r) * 32 + lane) : 0u;
+            c += __popc(words[r]);
+        }
+        int off = c;                                        // inclusive scan over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, off, o);
+            if (lane >= o) off += v;
+        }
+        off -= c;
         long long gbase, w_lo, w_hi;
         tile_range(seqs, (unsigned int)tile, L, m, gbase, w_lo, w_hi);
-        const int own_n = (int)(w_hi - w_lo);
+        const long long base = __ldg(sp.tile_cand_off + tile);
         const int S = lane * L;
-        while (__any_sync(0xffffffffu, word != 0u)) {
-            bool hf = false, hr = false;
-            float ff = 0.f, rf = 0.f;
-            long long gpos = 0;
-            if (word) {
-                const int p = 31 - __clz(word);
-                word &= ~(1u << p);
-                // body row r: bit 31 - t <-> window S + 32 r + t - D;  tail row: bit D - 1 - j <-> S + L - D + j
-                const int wt = r < B ? S + 32 * r + (31 - p) - D : S + L - D + (D - 1 - p);
-                if (wt >= S && wt < own_n) {          // (junk bits of the unified first body sit below S)
-                    ++n_flagged;
-                    gpos = gbase + w_lo + wt;
-                    double f, rr;
-                    exact_window(g, &tab, m, gpos, revseq, f, rr);
-                    ff = (float)f; rf = (float)rr;
-                    hf = (double)ff >= thr;
-                    hr = (double)rf >= thr;
+        int n_hits = 0;
+        for (int chunk0 = 0; chunk0 < total; chunk0 += CGBK_SITE_QUEUE) {
+            // this lane's flagged windows, in position order, that fall into the round
+            int idx = off;
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                uint32_t word = words[r];
+                while (word) {
+                    const int p = 31 - __clz(word);
+                    word &= ~(1u << p);
+                    if (idx >= chunk0 && idx < chunk0 + CGBK_SITE_QUEUE)
+                        q[idx - chunk0] = (unsigned short)(r < B ? S + 32 * r + (31 - p) - D : S + L - D + (D - 1 - p));
+                    ++idx;
                 }
             }
-            emit_hits8_warp(w.hits8, w.hit_cap, w.hit_cursor, w.counters, gpos, hf, ff, hr, rf);
+            __syncwarp();
+            const int n = total - chunk0 < CGBK_SITE_QUEUE ? total - chunk0 : CGBK_SITE_QUEUE;
+            for (int i = lane; i < n; i += 32) {
+                const long long gpos = gbase + w_lo + q[i];
+                double f, r;
+                exact_window(g, &tab, m, gpos, revseq, f, r);
+                const float ff = (float)f, rf = (float)r;
+                const bool hf = (double)ff >= thr, hr = (double)rf >= thr;
+                const long long k = base + chunk0 + i;
+                if (k < sp.cand_cap) {
+                    sp.pairs[2 * k] = hf ? cgbk_pack_hit8(gpos, 0, __float_as_uint(ff)) : CGBK_NO_SITE;
+                    sp.pairs[2 * k + 1] = hr ? cgbk_pack_hit8(gpos, 1, __float_as_uint(rf)) : CGBK_NO_SITE;
+                }
+                n_hits += (hf ? 1 : 0) + (hr ? 1 : 0);
+            }
+            __syncwarp();
         }
-    }
-    // candidates examined (diagnostics: CGBK_CTR_CANDIDATES)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n_flagged += __shfl_down_sync(0xffffffffu, n_flagged, o);
-    if (lane == 0 && n_flagged)
-        atomicAdd(reinterpret_cast<unsigned long long*>(w.counters + CGBK_CTR_CANDIDATES), n_flagged);
+        for (int o = 16; o > 0; o >>= 1) n_hits += __shfl_down_sync(0xffffffffu, n_hits, o);
+        if (lane == 0) sp.tile_hits[tile] = n_hits;
+    }
 }
 
-cudaError_t launch_rescore_flags(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, int L,
-                                 double thr, int flags, cudaStream_t st) {
-    rescore_flags_kernel<<<mdl->sms * 8, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, w, L, 4 * (mdl->G - 1), thr,
-                                                      flags);
+__global__ void __launch_bounds__(128) site_emit_kernel(FastWork w, SitePass sp) {
+    const int lane = threadIdx.x & 31;
+    const long long n_tiles = w.tile_end - w.tile_begin;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long cursor = *w.hit_cursor;
+    for (long long ti = warp0; ti < n_tiles; ti += nwarps) {
+        const long long tile = w.tile_begin + ti;
+        const long long n_rec = 2ll * __ldg(sp.tile_cand + tile);
+        if (n_rec == 0) continue;
+        const long long in0 = 2ll * __ldg(sp.tile_cand_off + tile);
+        long long out = cursor + __ldg(sp.tile_hit_off + tile);
+        for (long long i0 = 0; i0 < n_rec; i0 += 32) {
+            const long long i = i0 + lane;
+            unsigned long long rec = CGBK_NO_SITE;
+            if (i < n_rec && in0 + i < 2 * sp.cand_cap) rec = sp.pairs[in0 + i];
+            const bool keep = rec != CGBK_NO_SITE;
+            const unsigned int mask = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const long long k = out + __popc(mask & ((1u << lane) - 1u));
+                if (k < w.hit_cap) w.hits8[k] = rec;
+            }
+            out += __popc(mask);
+        }
+    }
+}
+
+__global__ void site_finish_kernel(FastWork w, SitePass sp) {
+    if (threadIdx.x == 0) {
+        const long long last = w.tile_end - 1;
+        const long long n_cand = (long long)sp.tile_cand_off[last] + sp.tile_cand[last];
+        const long long n_hits = (long long)sp.tile_hit_off[last] + sp.tile_hits[last];
+        w.counters[CGBK_CTR_CANDIDATES] = n_cand;
+        w.counters[CGBK_CTR_HITS] = n_hits;
+        *w.hit_cursor += n_hits;
+    }
+}
+
+cudaError_t launch_site_pass(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, const SitePass& sp,
+                             int L, double thr, int flags, cudaStream_t st) {
+    const long long n_tiles = w.tile_end - w.tile_begin;
+    if (n_tiles <= 0) return cudaSuccess;
+    cudaError_t e = cgbk_exclusive_sum(sp.tile_cand + w.tile_begin, sp.tile_cand_off + w.tile_begin, n_tiles,
+                                       sp.scan_tmp, sp.scan_tmp_bytes, st);
+    if (e != cudaSuccess) return e;
+    long long blocks = (n_tiles + 3) / 4;
+    if (blocks > mdl->sms * 16) blocks = mdl->sms * 16;
+    site_score_kernel<<<(int)blocks, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, w, sp, L, 4 * (mdl->G - 1), thr, flags);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    e = cgbk_exclusive_sum(sp.tile_hits + w.tile_begin, sp.tile_hit_off + w.tile_begin, n_tiles, sp.scan_tmp,
+                           sp.scan_tmp_bytes, st);
+    if (e != cudaSuccess) return e;
+    site_emit_kernel<<<(int)blocks, 128, 0, st>>>(w, sp);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    site_finish_kernel<<<1, 32, 0, st>>>(w, sp);
     return cudaGetLastError();
 }
 

@@ -47,9 +47,10 @@
 //    is shifted into a flag register (no branch, no atomic, the same cost whether one window
 //    in a million or one in twenty is a candidate -- low-information motifs reach the latter);
 //    the register goes to a "flag plane" [tile][row][lane] once per 32-position body, one
-//    coalesced 128-byte store like the score plane's.  cgbk_exact.cu walks the plane and
-//    re-scores the flagged windows exactly.  One pass over the sequence then yields the
-//    background record AND the hit candidates;
+//    coalesced 128-byte store like the score plane's, and the tile's flag count to a per-tile
+//    array.  cgbk_exact.cu walks the plane tile by tile, re-scores the flagged windows exactly
+//    and writes the sites out IN ORDER (prefix sums over the tile counts: no sort).  One pass
+//    over the sequence then yields the background record AND the hit candidates;
 //  * VAR 2 ("peeled"): the first 32-position body of a lane segment is its own code copy
 //    without the epilogues of the D windows that belong to the previous lane (they are
 //    only parked), the following bodies a second copy without the parking: no work is
@@ -244,66 +245,62 @@ static __device__ __noinline__ void flush_candidates(unsigned long long* stage, 
 // it with the reference's exact arithmetic (PSSMModel._calculate repair included), straight from
 // the device ExactTables (L1 resident, 5 KB).  Deliberately NOT inlined: the hot loop keeps its
 // registers.  Moments go to three per-block doubles in shared memory, the histogram to global.
-// In a fused scan (thr finite) the tile's hits are final right here and go to the compact hit
-// list (one atomic per warp step); the minus strand is then scored a second time in the
-// site-search order when that order is asked for (genome.py:440-445).
-struct ExactHitSink {
-    unsigned long long* hits8;      // compact records (NULL: no hit search)
-    long long hit_cap;
-    long long* hit_cursor;          // shared append position of the batch
-    long long* counters;            // this model's counters (CGBK_CTR_HITS)
+// In a fused scan the windows that may be sites are flagged in the tile's rows of the flag plane
+// like the table path does (conservatively: either strand within 1e-9 of the threshold; the
+// re-score pass decides), and the tile's flag count is returned.
+struct ExactFlagSink {
+    unsigned int* frows;            // this tile's (B + 1) x 32 flag words (NULL: no hit search)
     double thr;
-    int revseq;
 };
 
-static __device__ __noinline__ void exact_tile_stats(const ExactTables* tab, const uint32_t* bases2, const uint32_t* amb,
+static __device__ __noinline__ int exact_tile_stats(const ExactTables* tab, const uint32_t* bases2, const uint32_t* amb,
                                               const uint32_t* lower, long long cap_bases, long long gbase,
                                               long long w_lo, long long w_hi, int m, long long tile, int L, int D,
                                               unsigned long long* d_hist, int n_bins, double hist_lo,
                                               double inv_binw, int* plane, double scale, double* acc3,
-                                              const ExactHitSink* sink) {
+                                              const ExactFlagSink* sink) {
     GenomeView g;
     g.bases2 = bases2; g.amb = amb; g.lower = lower; g.cap_bases = cap_bases;
     double s1 = 0.0, s2 = 0.0, cnt = 0.0;
-    const int lane = threadIdx.x & 31;
-    for (long long x0 = w_lo; x0 < w_hi; x0 += 32) {        // warp-uniform trip count
-        const long long x = x0 + lane;
-        bool hf = false, hr = false;
-        float ff = 0.f, rf = 0.f;
-        if (x < w_hi) {
-            double f, r;
-            exact_window(g, tab, m, gbase + x, false, f, r);
-            ff = (float)f; rf = (float)r;
-            const double s = softmax2_f64((double)ff, (double)rf);
-            s1 += s; s2 += s * s; cnt += 1.0;
-            if (d_hist) {
-                int bin = (int)floor((s - hist_lo) * inv_binw);
-                bin = bin < 0 ? 0 : (bin >= n_bins ? n_bins - 1 : bin);
-                atomicAdd(d_hist + bin, 1ull);
-            }
-            if (plane) plane[plane_index(tile, (int)(x - w_lo), L, D)] = (int)llrint(s * scale);
-            if (sink->hits8) {
-                if (sink->revseq) {
-                    double f2, r2;
-                    exact_window(g, tab, m, gbase + x, true, f2, r2);
-                    rf = (float)r2;
-                }
-                hf = (double)ff >= sink->thr;
-                hr = (double)rf >= sink->thr;
-            }
+    const int lane = threadIdx.x & 31, B = L >> 5;
+    int n_flag = 0;
+    if (sink->frows) {
+        for (int r = 0; r <= B; ++r) sink->frows[r * 32 + lane] = 0u;
+        __syncwarp();
+    }
+    for (long long x = w_lo + lane; x < w_hi; x += 32) {
+        double f, r;
+        exact_window(g, tab, m, gbase + x, false, f, r);
+        const double s = softmax2_f64((double)(float)f, (double)(float)r);
+        s1 += s; s2 += s * s; cnt += 1.0;
+        if (d_hist) {
+            int bin = (int)floor((s - hist_lo) * inv_binw);
+            bin = bin < 0 ? 0 : (bin >= n_bins ? n_bins - 1 : bin);
+            atomicAdd(d_hist + bin, 1ull);
         }
-        if (sink->hits8)
-            emit_hits8_warp(sink->hits8, sink->hit_cap, sink->hit_cursor, sink->counters, gbase + x, hf, ff, hr, rf);
+        if (plane) plane[plane_index(tile, (int)(x - w_lo), L, D)] = (int)llrint(s * scale);
+        if (sink->frows && ((double)(float)f >= sink->thr - 1e-9 || (double)(float)r >= sink->thr - 1e-9)) {
+            // the flag plane's addressing: row b < B holds bit 31 - t of the window completed at body
+            // position t (within + D = 32 b + t), the tail row bit D - 1 - j
+            const int wt = (int)(x - w_lo), ln = wt / L, within = wt - ln * L;
+            int row, bit;
+            if (within < L - D) { const int c = within + D; row = c >> 5; bit = 31 - (c & 31); }
+            else { row = B; bit = D - 1 - (within - (L - D)); }
+            atomicOr(sink->frows + row * 32 + ln, 1u << bit);
+            ++n_flag;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         s1 += __shfl_down_sync(0xffffffffu, s1, o);
         s2 += __shfl_down_sync(0xffffffffu, s2, o);
         cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        n_flag += __shfl_down_sync(0xffffffffu, n_flag, o);
     }
     if (lane == 0) {
         atomicAdd(acc3, s1); atomicAdd(acc3 + 1, s2); atomicAdd(acc3 + 2, cnt);
     }
+    return n_flag;          // valid in lane 0
 }
 
 __host__ __device__ constexpr int fast_threads_of(int G, int MODE) {
@@ -459,16 +456,14 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
             } else {
                 if (lane == 0)
                     atomicAdd(reinterpret_cast<unsigned long long*>(work.counters + CGBK_CTR_DIRTY_TILES), 1ull);
-                ExactHitSink sink;
-                sink.hits8 = sp.thr_fix != CGBK_NO_THRESHOLD ? work.hits8 : nullptr;
-                sink.hit_cap = work.hit_cap; sink.hit_cursor = work.hit_cursor; sink.counters = work.counters;
-                sink.thr = sp.thr; sink.revseq = sp.revseq;
-                exact_tile_stats(static_cast<const ExactTables*>(sp.exact_tab), g.bases2, g.amb, g.lower,
-                                 g.cap_bases, gbase, A, A + (own_n > 0 ? own_n : 0), m, tile, L, D, sp.d_hist,
-                                 sp.n_bins, sp.hist_lo_d, sp.inv_binw_d, sp.plane, (double)sp.scale, exact_acc,
-                                 &sink);
-                if (work.fplane)       // its sites are final already: no flags for the re-score pass
-                    for (int r = 0; r <= B; ++r) work.fplane[(tile * (B + 1) + r) * 32 + lane] = 0u;
+                ExactFlagSink sink;
+                sink.frows = work.fplane ? work.fplane + tile * (long long)((B + 1) * 32) : nullptr;
+                sink.thr = sp.thr;
+                const int nf = exact_tile_stats(static_cast<const ExactTables*>(sp.exact_tab), g.bases2, g.amb, g.lower,
+                                                g.cap_bases, gbase, A, A + (own_n > 0 ? own_n : 0), m, tile, L, D,
+                                                sp.d_hist, sp.n_bins, sp.hist_lo_d, sp.inv_binw_d, sp.plane,
+                                                (double)sp.scale, exact_acc, &sink);
+                if (work.fplane && lane == 0) work.tile_cand[tile] = nf;
             }
             tile = advance();
             preload(tile);
@@ -486,7 +481,10 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         // fused scan: candidate flags of the current body's completed windows (shifted in one by
         // one, newest at bit 0) and this lane's column of the tile's flag rows
         uint32_t cflags = 0u;
+        int n_flag = 0;            // flagged windows of this lane in this tile
         unsigned int* fprow = (MODE != 0 && work.fplane) ? work.fplane + tile * (long long)((B + 1) * 32) + lane : nullptr;
+        // bits [0, n) of a word, n in 0..32
+        auto lowmask = [](int n) -> uint32_t { return (uint32_t)((1ull << n) - 1ull); };
         uint32_t flag_or = 0u, pend[EW], pendb[EW];            // the last (up to) EW completed windows
 #pragma unroll
         for (int i = 0; i < EW; ++i) { pend[i] = 0u; pendb[i] = 0u; }
@@ -612,7 +610,17 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         auto after_body = [&](int b) {
             if (MODE != 0) {
                 sum_d += acc_d; acc_d = 0;
-                if (fprow) fprow[b * 32] = cflags;     // one coalesced 128-byte row per body
+                if (fprow) {
+                    // bit 31 - t <-> the window completed at body position t; keep the lane's own
+                    // valid windows: t >= D in the first body (before: the previous lane's tail), and
+                    // S + 32 b + t - D < own_n
+                    const int t_lo = b == 0 ? D : 0;
+                    int t_hi = own_n - (S + 32 * b) + D;
+                    t_hi = t_hi < t_lo ? t_lo : (t_hi > 32 ? 32 : t_hi);
+                    const uint32_t word = cflags & lowmask(32 - t_lo) & ~lowmask(32 - t_hi);
+                    n_flag += __popc(word);
+                    fprow[b * 32] = word;              // one coalesced 128-byte row per body
+                }
                 cflags = 0u;
             }
             if (MODE == 0 && __any_sync(0xffffffffu, staged)) {     // a vote, no memory access, when idle
@@ -664,7 +672,17 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
             }
         }
         if (MODE != 0) {
-            if (fprow) fprow[B * 32] = cflags;         // the D straddling windows (zero when D == 0)
+            if (fprow) {
+                // the D straddling windows: bit D - 1 - j <-> window S + L - D + j (no bit when D == 0)
+                int j_hi = own_n - (S + L - D);
+                j_hi = j_hi < 0 ? 0 : (j_hi > D ? D : j_hi);
+                const uint32_t word = cflags & lowmask(D) & ~lowmask(D - j_hi);
+                n_flag += __popc(word);
+                fprow[B * 32] = word;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) n_flag += __shfl_down_sync(0xffffffffu, n_flag, o);
+                if (lane == 0) work.tile_cand[tile] = n_flag;
+            }
             sum_d += acc_d;
             sum_d2 += (double)acc_d2;
             const int mine = own_n - S;

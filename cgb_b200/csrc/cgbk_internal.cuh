@@ -120,6 +120,7 @@ struct FastWork {      // carved out of the caller's workspace
     // window (row b < B: bit 31 - t is the window completed at body position t, i.e. tile-local
     // window lane * L + 32 b + t - D; row B: bit D - 1 - j is window lane * L + L - D + j)
     unsigned int* fplane;
+    int* tile_cand;             // [n_tiles] flagged windows per tile (written with the flag plane)
 };
 
 // compact hit record (include/cgbk.h cgbk_hit8): gpos << 33 | minus << 32 | float32 score bits
@@ -216,9 +217,24 @@ cudaError_t launch_fast_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs
 cudaError_t launch_fast_moments(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
                                 int L, int grid, const StatsParams& sp, cudaStream_t st);
 
-// exact re-score of the windows flagged in the fused scan's flag plane into the compact hit list
-cudaError_t launch_rescore_flags(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, int L,
-                                 double thr, int flags, cudaStream_t st);
+// Fused scan, site pass: the flagged windows of the flag plane are re-scored exactly and written
+// to the compact hit list in (position, + strand first) order.  Scratch arrays of n_tiles ints
+// and cand_cap record pairs come carved out of the caller's workspace.
+struct SitePass {
+    const int* tile_cand;       // [n_tiles] from the scan
+    int* tile_cand_off;         // [n_tiles] exclusive prefix of tile_cand
+    int* tile_hits;             // [n_tiles] sites per tile
+    int* tile_hit_off;          // [n_tiles] exclusive prefix of tile_hits
+    unsigned long long* pairs;  // [2 * cand_cap] per flagged window: + strand record, - strand record (or ~0)
+    long long cand_cap;
+    void* scan_tmp;             // prefix-sum scratch
+    long long scan_tmp_bytes;
+};
+cudaError_t launch_site_pass(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, const SitePass& sp,
+                             int L, double thr, int flags, cudaStream_t st);
+// exclusive prefix sum of n ints (cgbk_sort.cu, CUB)
+long long cgbk_scan_tmp_bytes(long long n);
+cudaError_t cgbk_exclusive_sum(const int* in, int* out, long long n, void* tmp, long long tmp_bytes, cudaStream_t st);
 
 // score plane addressing shared by the writers (cgbk_fast.cu, dirty tiles) and the reader
 // (posteriors): window wt of a tile with lane segment L = 32 * B and overlap D = 4 * (G - 1)

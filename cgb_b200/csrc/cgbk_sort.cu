@@ -5,6 +5,7 @@
 // positions, cgb_b200/site_search.py) wants it sorted.  Library code on purpose: sorting is not
 // the path's hot operation.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "cgbk_internal.cuh"
 
@@ -40,4 +41,17 @@ extern "C" int cgbk_sort_hits(uint64_t* d_hits8, int64_t n, void* d_tmp, int64_t
         if (e != cudaSuccess) return cgbk_check_cuda(e, "copy of the sorted hit list");
     }
     return CGBK_OK;
+}
+
+// Exclusive prefix sum over the per-tile counts of the fused scan's site pass (n = tiles of one
+// scan, at most a few hundred thousand).
+long long cgbk_scan_tmp_bytes(long long n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int*)nullptr, (int*)nullptr, n, (cudaStream_t)0);
+    return (long long)align256((int64_t)bytes) + 256;
+}
+
+cudaError_t cgbk_exclusive_sum(const int* in, int* out, long long n, void* tmp, long long tmp_bytes, cudaStream_t st) {
+    size_t bytes = (size_t)tmp_bytes;
+    return cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, n, st);
 }

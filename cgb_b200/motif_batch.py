@@ -94,7 +94,6 @@ class _ScanBuffers:
         self.copied = [None] * n_buf                  # event: the D2H out of hits[p] has finished
         self.copy_stream = torch.cuda.Stream(device=dev) if host_hits else None
         self.work = torch.empty(work_bytes, dtype=torch.uint8, device=dev)
-        self.sort_tmp = None
 
 
 # one set of scratch buffers per device, shared by all genomes scanned there (calls on one device
@@ -130,7 +129,7 @@ def expected_hits(model, n_windows):
 
 
 def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, revseq_order=True,
-               hit_cap=None, sort=True, to_host=True, sink=None, recycle=False, kernel_ms=None):
+               hit_cap=None, to_host=True, sink=None, recycle=False, kernel_ms=None):
     """Background record and thresholded sites of every model over ``genome`` (a PackedGenome).
 
     ``thresholds``: ``"patser"`` (each model's own, pssm_model.py:72-77), a sequence of floats, or
@@ -138,9 +137,9 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
     Returns a dict:
 
       stats   float64 [K][8] (n, sum, sumsq, mean, std), hist int64 [K][n_bins] or None
-      hits    list of K compact uint64 arrays (see :func:`unpack_hits`), each sorted by
-              (position, + strand first) when ``sort``; positions are offsets into the packed
-              buffer.  ``None`` without thresholds
+      hits    list of K compact uint64 arrays (see :func:`unpack_hits`), each ordered by
+              (position, + strand first) -- the scan delivers them in that order; positions are
+              offsets into the packed buffer.  ``None`` without thresholds
       counters  int64 [K][8];  launches: kernels launched
 
     ``to_host`` (default): numpy arrays.  The models go through the device in sub-batches sized
@@ -183,9 +182,12 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
             free_bytes, _ = torch.cuda.mem_get_info(dev)
             want = exp.sum() if (not to_host and not recycle) else max(exp.max() * 1.5, 1 << 20)
             hit_cap = int(min(max(want, 1 << 20), free_bytes // 4 // 16))
-    # scratch of the scan: moment partials + the candidate flag plane (one bit per window)
+    # candidates are re-scored model by model: room for ONE model's worth (its sites plus the few
+    # windows within the fixed-point error of the threshold)
+    cand_cap = int(min(max(exp.max() * 1.25, 1 << 16), (1 << 30) - 1)) if want_hits else 0
+    # scratch of the scan: moment partials, candidate flag plane, per-tile counts, candidate records
     work_bytes = int(lib.cgbk_scan_batch_workspace_bytes(genome.seqset, -1 if win_cap is None else int(win_cap),
-                                                         1 if want_hits else 0))
+                                                         cand_cap))
     handles_all = [M._model() for M in models]
     stream = torch.cuda.current_stream(dev)
     flags = _cabi.RC_REVSEQ_ORDER if revseq_order else _cabi.RC_MATRIX_ORDER
@@ -207,8 +209,6 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
         host = buf.host_hits[p].numpy().view(np.uint64)
         for k in range(len(cum) - 1):
             seg = host[cum[k]:cum[k + 1]]
-            if sort and 1 < len(seg) < (1 << 15):
-                seg.sort()                                 # small segments: cheaper here than a launch
             if sink is not None:
                 sink(first + k, seg)
                 hits_out[first + k] = len(seg)
@@ -240,7 +240,7 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
             thr[i:j].ctypes.data if want_hits else None, flags, None, None, int(n_bins),
             d_hist.data_ptr() if d_hist is not None else None, d_stats.data_ptr(),
             buf.hits[p].data_ptr() if want_hits else None, int(buf.hit_cap) if want_hits else 0, d_ctr.data_ptr(),
-            buf.work.data_ptr(), buf.work.numel(), stream.cuda_stream))
+            buf.work.data_ptr(), buf.work.numel(), cand_cap, stream.cuda_stream))
         launches += int(_cabi.last_launch_info()["launches"])
         if not to_host and not want_hits:
             stats_out[i:j] = d_stats.view(torch.float64).view(n, BG)
@@ -257,15 +257,23 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
         ctr = h[b:].reshape(n + 1, CT)
         n_done = n
         if want_hits:
+            cand_over = np.nonzero(ctr[:n, _cabi.CTR_CANDIDATES] > cand_cap)[0]
             cum_all = np.concatenate([[0], np.cumsum(ctr[:n, _cabi.CTR_HITS])])
             hit_over = np.nonzero(cum_all[1:] > buf.hit_cap)[0]
-            bad = int(hit_over[0]) if len(hit_over) else n
+            bad = min([int(x[0]) for x in (cand_over, hit_over) if len(x)] or [n])
             if bad < n:
                 # records were dropped from model `bad` on: keep the models before it and run the
                 # rest again, with buffers grown to what model `bad` needs if it was the first
                 n_done = bad
-                need = float(ctr[bad, _cabi.CTR_HITS]) + 4096
+                need = float(max(ctr[bad, _cabi.CTR_HITS], ctr[bad, _cabi.CTR_CANDIDATES])) + 4096
                 exp[i + bad] = max(exp[i + bad], need)
+                if need > cand_cap:
+                    if pending is not None:            # the buffers are about to be re-allocated
+                        deliver(*pending, buf)
+                        pending = None
+                    cand_cap = int(need)
+                    work_bytes = int(lib.cgbk_scan_batch_workspace_bytes(
+                        genome.seqset, -1 if win_cap is None else int(win_cap), cand_cap))
                 if bad == 0:
                     if not to_host and not recycle:
                         raise ValueError("the sites of the batch do not fit hit_cap=%d (to_host=False keeps "
@@ -278,6 +286,9 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
                         deliver(*pending, buf)
                         pending = None
                     hit_cap = max(hit_cap, int(need))
+                    cand_cap = max(cand_cap, int(need))
+                    work_bytes = int(lib.cgbk_scan_batch_workspace_bytes(
+                        genome.seqset, -1 if win_cap is None else int(win_cap), cand_cap))
                     release_buffers(dev)
                     del buf
                     continue
@@ -295,19 +306,8 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
         if want_hits and n_done:
             cum = np.concatenate([[0], np.cumsum(ctr[:n_done, _cabi.CTR_HITS])]).astype(np.int64)
             used = int(cum[-1])
-            if sort:
-                # large segments on the device (radix sort), small ones on the host after the copy
-                for k in range(n_done):
-                    nk = int(cum[k + 1] - cum[k])
-                    if nk >= (1 << 15) or (not to_host and nk > 1):
-                        need_b = int(lib.cgbk_sort_hits_workspace_bytes(nk))
-                        if buf.sort_tmp is None or buf.sort_tmp.numel() < need_b:
-                            buf.sort_tmp = torch.empty(need_b, dtype=torch.uint8, device=dev)
-                        _cabi.check(lib.cgbk_sort_hits(buf.hits[p].data_ptr() + 8 * int(cum[k]), nk,
-                                                       buf.sort_tmp.data_ptr(), buf.sort_tmp.numel(),
-                                                       stream.cuda_stream))
             if to_host:
-                # D2H on the copy stream, behind the sorts; delivered while the next sub-batch runs
+                # D2H on the copy stream, behind the scan; delivered while the next sub-batch runs
                 ready = torch.cuda.Event()
                 ready.record(stream)
                 with torch.cuda.stream(buf.copy_stream):

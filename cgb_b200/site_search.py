@@ -27,12 +27,15 @@ Site = namedtuple('Site', 'chromid start end strand score gene')
 
 
 def identify_sites(model, genome, gene_tables, promoter_up_distance=300, promoter_dw_distance=50,
-                   use_up_dist_site_scan=False, threshold=None):
+                   use_up_dist_site_scan=False, threshold=None, strict=True):
     """genome.py:394-448: sites with score >= threshold in the upstream region of
     every gene, both strands, sorted by score (stable, descending).
 
     ``gene_tables``: one GeneTable per replicon that has genes.  Returns the list
-    of :class:`Site` in the reference's order."""
+    of :class:`Site` in the reference's order.  ``strict``: a region more than one base shorter
+    than the motif raises ValueError, as the reference does inside Biopython (e.g. a
+    reverse-strand gene within ``promoter_dw_distance`` of the replicon start, whose region
+    start goes negative and wraps); ``strict=False`` leaves such regions out."""
     if threshold is None:
         threshold = model.threshold()
     m = model.length
@@ -46,7 +49,7 @@ def identify_sites(model, genome, gene_tables, promoter_up_distance=300, promote
         else:
             start, end = gt.upstream_noncoding_region_location(None, promoter_dw_distance)
         s, e = python_slice_bounds(start, end, L)
-        if len(s) and int((e - s).min()) < m - 1:
+        if strict and len(s) and int((e - s).min()) < m - 1:
             # score_seq on a region more than one base shorter than the motif: Biopython's
             # numpy.empty(len(seq) - m + 1) raises (a region of m - 1 bases has no window, no error)
             raise ValueError("negative dimensions are not allowed")

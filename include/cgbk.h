@@ -248,25 +248,31 @@ int cgbk_background_stats_regions(const cgbk_model* model, const cgbk_genome* ge
  *                motif and caps every motif at the shard's own windows; < 0: all windows
  *   hist_lo/hi   per model, or NULL for [floor(min score), ceil(max score) + 1)
  *   d_hits8      one compact list for the whole batch; model k's sites are the records
- *                [sum of CGBK_CTR_HITS of the models before k, + its own count), unordered
- *                inside the segment (cgbk_sort_hits orders a segment)
+ *                [sum of CGBK_CTR_HITS of the models before k, + its own count), ordered by
+ *                (position, + strand first) -- the order comes from prefix sums over the scan
+ *                tiles, not from a sort, and is the same on every run
  *   d_counters   int64[n_models + 1][CGBK_CTR_COUNT]: per model candidates / hits / tiles with
  *                non-ACGT bytes; block n_models: [0] = records appended in total.  A total above
- *                hit_cap means records were dropped: run the models from the first affected one
- *                again with a larger buffer
- *   d_work       >= cgbk_scan_batch_workspace_bytes(set, win_cap, thresholds != NULL): the
- *                moment partials and the scan's candidate flag plane (one bit per window)
+ *                hit_cap, or a model's candidate count above cand_cap, means records were
+ *                dropped: run the models from the first affected one again with larger buffers
+ *   cand_cap     windows of ONE model that may be flagged for the exact re-score (its sites plus
+ *                the few windows within the fixed-point error of the threshold); 0 with
+ *                thresholds == NULL
+ *   d_work       >= cgbk_scan_batch_workspace_bytes(set, win_cap, cand_cap): moment partials,
+ *                the scan's candidate flag plane (one bit per window), per-tile counts and
+ *                16 bytes per candidate
  * flags: CGBK_RC_*.  No allocation, no synchronisation. */
-int64_t cgbk_scan_batch_workspace_bytes(const cgbk_seqset* set, int64_t win_cap, int with_hits);
+int64_t cgbk_scan_batch_workspace_bytes(const cgbk_seqset* set, int64_t win_cap, int64_t cand_cap);
 int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cgbk_genome* genome,
                     const cgbk_seqset* set, int64_t win_cap, const double* thresholds, int flags,
                     const double* hist_lo, const double* hist_hi, int n_bins,
                     unsigned long long* d_hist, double* d_stats,
                     cgbk_hit8* d_hits8, int64_t hit_cap, int64_t* d_counters,
-                    void* d_work, int64_t work_bytes, void* stream);
+                    void* d_work, int64_t work_bytes, int64_t cand_cap, void* stream);
 
 /* Sort n compact records in place by (position, + strand first); d_tmp >=
- * cgbk_sort_hits_workspace_bytes(n) bytes of device scratch. */
+ * cgbk_sort_hits_workspace_bytes(n) bytes of device scratch.  (cgbk_scan_batch already delivers
+ * ordered lists; this is for lists merged from several shards or scans.) */
 int64_t cgbk_sort_hits_workspace_bytes(int64_t n);
 int cgbk_sort_hits(cgbk_hit8* d_hits8, int64_t n, void* d_tmp, int64_t tmp_bytes, void* stream);
 

@@ -506,9 +506,11 @@ def reverse_complement(seq):
 OSite = namedtuple("OSite", "start end strand score gene")
 
 
-def identify_sites(model, sequence, genes, up=None, down=50, threshold=None, index=None):
+def identify_sites(model, sequence, genes, up=None, down=50, threshold=None, index=None, skip_short=False):
     """Hit loop of genome.py:419-448 over one chromid.  ``gene`` in the result
-    is the gene index.  float32 score vs float64 threshold (pinned numpy)."""
+    is the gene index.  float32 score vs float64 threshold (pinned numpy).  A region more than
+    one base shorter than the motif raises inside Biopython's calculate() in the reference
+    (ValueError, numpy.empty of a negative count); ``skip_short`` leaves such regions out instead."""
     if threshold is None:
         threshold = model.threshold()
     m = model.length
@@ -517,8 +519,8 @@ def identify_sites(model, sequence, genes, up=None, down=50, threshold=None, ind
     for gi in range(len(genes)):
         start, end = upstream_noncoding_region_location(genes, gi, L, up, down, index)
         seq = subsequence(sequence, start, end)
-        if len(seq) < m:
-            continue   # the reference would raise inside Biopython here
+        if len(seq) < m - 1 and skip_short:
+            continue
         scores = score_seq(model, seq, both=False)[0]
         for i, score in enumerate(scores, start=start):
             if float(score) >= threshold:
