@@ -644,6 +644,24 @@ def posteriors_leg(args, dev, rank, world, barrier, max_over_ranks):
         M.regulation_pipeline(pinned, ps, pe, prior, alpha, n_bins=256)
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
     barrier()
+    # the same from the host-PACKED form of the genome (cgbk_pack_host once, outside the loop: the
+    # form a replicon is kept / stored in): bases2 plane only for this upper-case ACGT genome
+    from cgb_b200 import HostPackedGenome
+    t0 = time.perf_counter()
+    hp = HostPackedGenome.from_ascii(pinned)
+    pack_host_ms = (time.perf_counter() - t0) * 1e3
+    for _ in range(5):
+        pp, _, _ = M.regulation_pipeline(hp, ps, pe, prior, alpha, n_bins=256)
+    torch.cuda.synchronize()
+    e2e_packed_ms = []
+    for _ in range(args.post_steps):
+        t0 = time.perf_counter()
+        pp, sp_, hp_ = M.regulation_pipeline(hp, ps, pe, prior, alpha, n_bins=256)
+        e2e_packed_ms.append((time.perf_counter() - t0) * 1e3)
+    pa, sa_, ha_ = M.regulation_pipeline(pinned, ps, pe, prior, alpha, n_bins=256)
+    assert np.array_equal(pp, pa) and np.array_equal(hp_, ha_), "packed and ASCII pipelines disagree"
+    barrier()
+    e2e_packed_med = float(max_over_ranks([float(np.median(e2e_packed_ms))])[0])
     cold_med = float(max_over_ranks([float(np.median(cold))])[0])
     warm_med = float(max_over_ranks([float(np.median(warm))])[0])
     e2e_med = float(max_over_ranks([float(np.median(e2e_ms))])[0])
@@ -667,6 +685,15 @@ def posteriors_leg(args, dev, rank, world, barrier, max_over_ranks):
                     "h2d_bytes_per_step": int(pinned.numel()) + 12 * N_GENES + 16,
                     "d2h_bytes_per_step": N_GENES * 8 + 64 + 256 * 8,
                     "call": "PSSMModel.regulation_pipeline -> cgbk_regulation_pipeline (host buffers)"},
+            "e2e_packed": {"ms_per_step": e2e_packed_med, "step_ms": spread(e2e_packed_ms),
+                           "promoter_posteriors_per_s": world * N_GENES / (e2e_packed_med * 1e-3),
+                           "bp_motif_per_s": world * n_windows / (e2e_packed_med * 1e-3),
+                           "h2d_bytes_per_step": int(hp.upload_bytes) + 12 * N_GENES + 16,
+                           "d2h_bytes_per_step": N_GENES * 8 + 64 + 256 * 8,
+                           "host_pack_ms_once": pack_host_ms,
+                           "call": "PSSMModel.regulation_pipeline(HostPackedGenome) -> cgbk_regulation_pipeline_packed "
+                                   "(genome kept packed on the host: 0.25 B/base uploaded, no pack kernel); "
+                                   "results identical to the ASCII call (asserted)"},
         }
         if world == 1 and not args.no_cpu:
             from oracle import c_oracle

@@ -6,7 +6,7 @@ Importing the package does not need a GPU; any scoring call does (no CPU fallbac
 """
 from .binding_model import TFBindingModel
 from .gene_regions import GeneTable, python_slice_bounds
-from .genome_buffer import PackedGenome
+from .genome_buffer import HostPackedGenome, PackedGenome
 from .pssm_model import PSSMModel, prepare_thresholds, scan_hits_many
 from .site_collection import SiteCollection
 from .site_search import Site, calculate_regulation_probabilities, identify_sites
@@ -14,5 +14,5 @@ from .genome import Chromid, Genome, get_prior
 from . import genbank, operons, motif_batch
 from .motif_batch import ModelBatch, scan_batch, unpack_hits
 
-__all__ = ["TFBindingModel", "PSSMModel", "SiteCollection", "PackedGenome", "GeneTable",
+__all__ = ["TFBindingModel", "PSSMModel", "SiteCollection", "PackedGenome", "HostPackedGenome", "GeneTable",
            "Site", "Genome", "ModelBatch", "scan_batch", "unpack_hits", "motif_batch", "Chromid", "get_prior", "prepare_thresholds", "genbank", "operons", "identify_sites", "scan_hits_many", "calculate_regulation_probabilities", "python_slice_bounds"]

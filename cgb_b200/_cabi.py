@@ -35,7 +35,8 @@ class PipelineArgs(C.Structure):
                 ("hist_lo", C.c_double), ("hist_hi", C.c_double),
                 ("d_scratch", C.c_void_p), ("scratch_bytes", C.c_int64),
                 ("h_staging", C.c_void_p), ("staging_bytes", C.c_int64),
-                ("h_post", C.c_void_p), ("h_stats", C.c_void_p), ("h_hist", C.c_void_p), ("stream", C.c_void_p)]
+                ("h_post", C.c_void_p), ("h_stats", C.c_void_p), ("h_hist", C.c_void_p), ("stream", C.c_void_p),
+                ("h_bases2", C.c_void_p), ("h_amb", C.c_void_p), ("h_lower", C.c_void_p)]
 
 
 class CgbkError(RuntimeError):
@@ -101,7 +102,16 @@ SYMBOLS = {
                                             C.c_double, C.c_double, C.c_int,
                                             C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cgbk_regulation_pipeline_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                                   C.c_void_p, C.c_void_p, C.c_int,
+                                                   C.c_double, C.c_double, C.c_double, C.c_double,
+                                                   C.c_double, C.c_double, C.c_int,
+                                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cgbk_regulation_pipeline_args": (C.c_int, [C.c_void_p]),
+    "cgbk_packed_capacity": (C.c_int64, [C.c_int64]),
+    "cgbk_pack_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                  C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cgbk_last_launch_info": (C.c_int, [C.POINTER(C.c_int64)]),
     "cgbk_profile_enable": (C.c_int, [C.c_int]),
     "cgbk_profile_last_ms": (C.c_int, [C.POINTER(C.c_float)]),
@@ -121,7 +131,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.cgbk_version() != 200:
+        if L.cgbk_version() != 210:
             raise CgbkError("libcgbk.so version %d does not match the Python layer" % L.cgbk_version())
         _lib = L
     return _lib

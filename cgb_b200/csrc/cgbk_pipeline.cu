@@ -131,10 +131,10 @@ static bool device_alias(const void* h, void** d) {
 // cost of a launch.  At 5 MB that cancels the overlap exactly (202 us either way); at 50 MB the
 // chunked form wins ~5 % (1.17 vs 1.23 ms).  So small replicons go up in one piece and only
 // large ones are pipelined, the last (exposed) chunk being the smallest.
-static int plan_chunks(int64_t n, int64_t* cut) {
+static int plan_chunks(int64_t n, int64_t* cut, int bases_per_byte) {
     static const double frac3[3] = {0.50, 0.30, 0.20};
     static const double frac4[4] = {0.35, 0.30, 0.20, 0.15};
-    int k = n >= (16ll << 20) ? 4 : 1;
+    int k = n >= (16ll << 20) * bases_per_byte ? 4 : 1;
     if (const char* e = getenv("CGBK_PIPE_CHUNKS")) {          // tuning knob: 1, 3 or 4
         const int want = atoi(e);
         if (want == 1 || ((want == 3 || want == 4) && n >= 4 * CGBK_SEQ_ALIGN)) k = want;
@@ -157,15 +157,25 @@ extern "C" int64_t cgbk_pipeline_scratch_bytes(int64_t n_bases, int n_regions, i
 
 extern "C" int64_t cgbk_pipeline_staging_bytes(int n_regions) { return align256(12 * (int64_t)n_regions) + 256; }
 
-extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, int64_t n_bases,
-                                        const int64_t* h_start, const int64_t* h_end, int n_regions,
-                                        double mu_m, double std_m, double p_motif, double alpha,
-                                        double hist_lo, double hist_hi, int n_bins,
-                                        void* d_scratch, int64_t scratch_bytes,
-                                        void* h_staging, int64_t staging_bytes,
-                                        double* h_post, double* h_stats, unsigned long long* h_hist,
-                                        void* stream) {
-    if (!M || !h_ascii || n_bases < 1 || n_regions < 0 || !d_scratch || !h_stats ||
+// Where the sequence comes from: ASCII bytes (packed on the device), or the three planes already
+// in the kernels' layout (cgbk_pack_host / a packed genome file): a quarter to a half of the bytes
+// cross PCIe and no pack kernel runs.  A NULL amb / lower plane stands for "all zero".
+struct PipeSource {
+    const uint8_t* h_ascii;
+    const uint32_t *h_bases2, *h_amb, *h_lower;
+};
+
+static int pipeline_impl(cgbk_model* M, const PipeSource& src, int64_t n_bases,
+                         const int64_t* h_start, const int64_t* h_end, int n_regions,
+                         double mu_m, double std_m, double p_motif, double alpha,
+                         double hist_lo, double hist_hi, int n_bins,
+                         void* d_scratch, int64_t scratch_bytes,
+                         void* h_staging, int64_t staging_bytes,
+                         double* h_post, double* h_stats, unsigned long long* h_hist,
+                         void* stream) {
+    const uint8_t* h_ascii = src.h_ascii;
+    const bool packed = h_ascii == nullptr;
+    if (!M || (!h_ascii && !src.h_bases2) || n_bases < 1 || n_regions < 0 || !d_scratch || !h_stats ||
         (n_regions > 0 && (!h_start || !h_end || !h_post)))
         return cgbk_set_error(CGBK_ERR_INVALID, "NULL or empty argument");
     if (n_bins < 0 || n_bins > CGBK_MAX_HIST_BINS) return cgbk_set_error(CGBK_ERR_INVALID, "bad n_bins");
@@ -185,7 +195,25 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
     cudaStream_t cs = ps->copy;
     uint8_t* d_ascii = base + P.off_ascii;
     int64_t cut[PIPE_MAX_CHUNKS + 1];
-    const int n_chunks = plan_chunks(n_bases, cut);
+    // the chunking threshold is about bytes on the wire: packed input is 2-4x denser
+    const int n_chunks = plan_chunks(n_bases, cut, packed ? 4 : 1);
+    cgbk_genome G;
+    uint32_t* planes = (uint32_t*)(base + P.off_planes);
+    G.d_bases2 = planes;
+    G.d_amb = planes + P.cap_bases / 16;
+    G.d_lower = planes + P.cap_bases / 16 + P.cap_bases / 32;
+    G.cap_bases = P.cap_bases;
+    // bases [a, b) of the packed source -> device planes (b rounded up to the padded capacity for
+    // the last piece: the host planes cover it, zero filled)
+    auto upload_planes = [&](int64_t a, int64_t b, cudaStream_t s) -> cudaError_t {
+        if (b >= n_bases) b = P.cap_bases;
+        cudaError_t e = cudaMemcpyAsync(planes + a / 16, src.h_bases2 + a / 16, (b - a) / 4, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && src.h_amb)
+            e = cudaMemcpyAsync((uint32_t*)G.d_amb + a / 32, src.h_amb + a / 32, (b - a) / 8, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && src.h_lower)
+            e = cudaMemcpyAsync((uint32_t*)G.d_lower + a / 32, src.h_lower + a / 32, (b - a) / 8, cudaMemcpyHostToDevice, s);
+        return e;
+    };
     // whatever the caller's stream still has queued may use the scratch: the side stream starts
     // behind it
     if (cudaEventRecord(ps->ev[PIPE_MAX_CHUNKS], st) != cudaSuccess ||
@@ -193,8 +221,17 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
         return cgbk_set_error(CGBK_ERR_CUDA, "stream hand-over failed");
     // one-piece upload: start the DMA now, prepare the promoter table while it runs
     const bool early = n_chunks == 1;
-    if (early && cudaMemcpyAsync(d_ascii, h_ascii, n_bases, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    if (early && !packed && cudaMemcpyAsync(d_ascii, h_ascii, n_bases, cudaMemcpyHostToDevice, st) != cudaSuccess)
         return cgbk_set_error(CGBK_ERR_CUDA, "H2D of the sequence failed");
+    if (early && packed && upload_planes(0, n_bases, st) != cudaSuccess)
+        return cgbk_set_error(CGBK_ERR_CUDA, "H2D of the packed sequence failed");
+    if (packed) {
+        // absent planes are all zero (a replicon of upper-case ACGT only)
+        cudaError_t e = cudaSuccess;
+        if (!src.h_amb) e = cudaMemsetAsync((void*)G.d_amb, 0, P.cap_bases / 8, st);
+        if (e == cudaSuccess && !src.h_lower) e = cudaMemsetAsync((void*)G.d_lower, 0, P.cap_bases / 8, st);
+        if (e != cudaSuccess) { cudaStreamSynchronize(st); return cgbk_check_cuda(e, "clearing the absent planes"); }
+    }
 
     // promoter slices -> (packed offset, window count): Chromid.subsequence's Python slice
     // (cgb/chromid.py:94) then len(seq) - m + 1 windows; len(seq) < m - 1 raises in the reference
@@ -225,7 +262,8 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
     TRACE("host prep");
     cudaError_t ce = cudaSuccess;
     for (int c = 0; c < n_chunks && !early && ce == cudaSuccess; ++c) {
-        ce = cudaMemcpyAsync(d_ascii + cut[c], h_ascii + cut[c], cut[c + 1] - cut[c], cudaMemcpyHostToDevice, cs);
+        if (packed) ce = upload_planes(cut[c], cut[c + 1], cs);
+        else ce = cudaMemcpyAsync(d_ascii + cut[c], h_ascii + cut[c], cut[c + 1] - cut[c], cudaMemcpyHostToDevice, cs);
         if (ce == cudaSuccess) ce = cudaEventRecord(ps->ev[c], cs);
         TRACE_ON("chunk copied", cs);
     }
@@ -240,12 +278,6 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
         return cgbk_check_cuda(ce, "H2D of the sequence");
     }
     TRACE("h2d issued");
-    cgbk_genome G;
-    uint32_t* planes = (uint32_t*)(base + P.off_planes);
-    G.d_bases2 = planes;
-    G.d_amb = planes + P.cap_bases / 16;
-    G.d_lower = planes + P.cap_bases / 16 + P.cap_bases / 32;
-    G.cap_bases = P.cap_bases;
 
     // 2. background: stats scan (+ score plane) over all windows, chunk by chunk
     cgbk_seqset* S = nullptr;
@@ -274,7 +306,7 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
     for (int c = 0; c < n_chunks && !rc; ++c) {
         if (!early && cudaStreamWaitEvent(st, ps->ev[c], 0) != cudaSuccess)
             rc = cgbk_set_error(CGBK_ERR_CUDA, "stream wait failed");
-        if (!rc)
+        if (!rc && !packed)
             rc = cgbk_pack_ascii(d_ascii + cut[c], cut[c + 1] - cut[c], cut[c], planes, planes + P.cap_bases / 16,
                                  planes + P.cap_bases / 16 + P.cap_bases / 32,
                                  P.cap_bases, st);
@@ -317,26 +349,58 @@ extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, i
         // nothing to copy
     } else if (n_regions > 0 && (unsigned char*)h_stats == (unsigned char*)h_post + post_bytes &&
                (!want_hist || (unsigned char*)h_hist == (unsigned char*)h_stats + stats_bytes)) {
-        cudaMemcpyAsync(h_post, base + P.off_post, post_bytes + stats_bytes + (want_hist ? 8 * (int64_t)n_bins : 0),
-                        cudaMemcpyDeviceToHost, st);
+        ce = cudaMemcpyAsync(h_post, base + P.off_post, post_bytes + stats_bytes + (want_hist ? 8 * (int64_t)n_bins : 0),
+                             cudaMemcpyDeviceToHost, st);
     } else {
-        if (n_regions > 0) cudaMemcpyAsync(h_post, base + P.off_post, post_bytes, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(h_stats, d_stats, stats_bytes, cudaMemcpyDeviceToHost, st);
-        if (want_hist)
-            cudaMemcpyAsync(h_hist, d_hist, sizeof(unsigned long long) * n_bins, cudaMemcpyDeviceToHost, st);
+        if (n_regions > 0) ce = cudaMemcpyAsync(h_post, base + P.off_post, post_bytes, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_stats, d_stats, stats_bytes, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess && want_hist)
+            ce = cudaMemcpyAsync(h_hist, d_hist, sizeof(unsigned long long) * n_bins, cudaMemcpyDeviceToHost, st);
     }
     TRACE("d2h");
     cudaError_t e = cudaStreamSynchronize(st);
     TRACE_DUMP();
     cgbk_seqset_destroy(S);
+    if (ce != cudaSuccess) return cgbk_check_cuda(ce, "D2H of the results");
     if (e != cudaSuccess) return cgbk_check_cuda(e, "regulation pipeline");
     return CGBK_OK;
 }
 
+extern "C" int cgbk_regulation_pipeline(cgbk_model* M, const uint8_t* h_ascii, int64_t n_bases,
+                                        const int64_t* h_start, const int64_t* h_end, int n_regions,
+                                        double mu_m, double std_m, double p_motif, double alpha,
+                                        double hist_lo, double hist_hi, int n_bins,
+                                        void* d_scratch, int64_t scratch_bytes,
+                                        void* h_staging, int64_t staging_bytes,
+                                        double* h_post, double* h_stats, unsigned long long* h_hist,
+                                        void* stream) {
+    if (!h_ascii) return cgbk_set_error(CGBK_ERR_INVALID, "NULL or empty argument");
+    const PipeSource src = {h_ascii, nullptr, nullptr, nullptr};
+    return pipeline_impl(M, src, n_bases, h_start, h_end, n_regions, mu_m, std_m, p_motif, alpha, hist_lo, hist_hi,
+                         n_bins, d_scratch, scratch_bytes, h_staging, staging_bytes, h_post, h_stats, h_hist, stream);
+}
+
+extern "C" int cgbk_regulation_pipeline_packed(cgbk_model* M, const uint32_t* h_bases2, const uint32_t* h_amb,
+                                               const uint32_t* h_lower, int64_t n_bases,
+                                               const int64_t* h_start, const int64_t* h_end, int n_regions,
+                                               double mu_m, double std_m, double p_motif, double alpha,
+                                               double hist_lo, double hist_hi, int n_bins,
+                                               void* d_scratch, int64_t scratch_bytes,
+                                               void* h_staging, int64_t staging_bytes,
+                                               double* h_post, double* h_stats, unsigned long long* h_hist,
+                                               void* stream) {
+    if (!h_bases2) return cgbk_set_error(CGBK_ERR_INVALID, "NULL or empty argument");
+    const PipeSource src = {nullptr, h_bases2, h_amb, h_lower};
+    return pipeline_impl(M, src, n_bases, h_start, h_end, n_regions, mu_m, std_m, p_motif, alpha, hist_lo, hist_hi,
+                         n_bins, d_scratch, scratch_bytes, h_staging, staging_bytes, h_post, h_stats, h_hist, stream);
+}
+
 extern "C" int cgbk_regulation_pipeline_args(const cgbk_pipeline_args* a) {
     if (!a) return cgbk_set_error(CGBK_ERR_INVALID, "NULL argument struct");
-    return cgbk_regulation_pipeline(a->model, a->h_ascii, a->n_bases, a->h_start, a->h_end, a->n_regions, a->mu_m,
-                                    a->std_m, a->p_motif, a->alpha, a->hist_lo, a->hist_hi, a->n_bins,
-                                    a->d_scratch, a->scratch_bytes, a->h_staging, a->staging_bytes, a->h_post,
-                                    a->h_stats, a->h_hist, a->stream);
+    const PipeSource src = {a->h_ascii, a->h_ascii ? nullptr : a->h_bases2, a->h_ascii ? nullptr : a->h_amb,
+                            a->h_ascii ? nullptr : a->h_lower};
+    return pipeline_impl(a->model, src, a->n_bases, a->h_start, a->h_end, a->n_regions, a->mu_m,
+                         a->std_m, a->p_motif, a->alpha, a->hist_lo, a->hist_hi, a->n_bins,
+                         a->d_scratch, a->scratch_bytes, a->h_staging, a->staging_bytes, a->h_post,
+                         a->h_stats, a->h_hist, a->stream);
 }

@@ -31,6 +31,81 @@ def _as_bytes(seq):
     return str(seq).encode("ascii")
 
 
+class HostPackedGenome:
+    """One replicon packed ON THE HOST into the kernels' three planes (``cgbk_pack_host``: AVX2,
+    host threads; no GPU involved), held in pinned memory when a CUDA runtime is there.
+
+    This is the form a sequence is kept in between runs (and stored in, :meth:`save`): it crosses
+    PCIe as 0.25 byte per base (upper-case ACGT only) to 0.5 byte per base instead of 1, and
+    ``PSSMModel.regulation_pipeline`` / ``PackedGenome.from_host_packed`` take it without running
+    the pack kernel.  Replaces ``Chromid.sequence`` (cgb/chromid.py:57-60) as the sequence store."""
+
+    FILE_MAGIC = "cgbk-packed-genome-1"
+
+    def __init__(self, n_bases, planes, n_amb, n_lower):
+        self.n_bases = int(n_bases)
+        self.cap_bases = int(_cabi.lib().cgbk_packed_capacity(self.n_bases))
+        c16, c32 = self.cap_bases // 16, self.cap_bases // 32
+        if planes.dtype != torch.int32 or planes.numel() != c16 + 2 * c32:
+            raise ValueError("planes do not match the sequence length")
+        self.planes = planes                          # bases2 | amb | lower, one (pinned) int32 tensor
+        self.bases2, self.amb, self.lower = planes[:c16], planes[c16:c16 + c32], planes[c16 + c32:]
+        self.n_amb, self.n_lower = int(n_amb), int(n_lower)
+
+    @classmethod
+    def from_ascii(cls, seq, pin=True, n_threads=0):
+        """Pack ``seq`` (str / bytes / uint8 array / uint8 CPU tensor)."""
+        if isinstance(seq, torch.Tensor):
+            if seq.device.type != "cpu" or seq.dtype != torch.uint8:
+                raise ValueError("sequence must be a uint8 CPU tensor")
+            src = seq.contiguous().reshape(-1)
+        elif isinstance(seq, np.ndarray):
+            src = torch.from_numpy(np.ascontiguousarray(seq, dtype=np.uint8).reshape(-1))
+        else:
+            raw = seq if isinstance(seq, (bytes, bytearray)) else str(seq).encode("ascii")
+            src = torch.frombuffer(bytearray(raw), dtype=torch.uint8) if len(raw) else torch.empty(0, dtype=torch.uint8)
+        n = int(src.numel())
+        lib = _cabi.lib()
+        cap = int(lib.cgbk_packed_capacity(n))
+        planes = torch.empty(cap // 16 + 2 * (cap // 32), dtype=torch.int32)
+        if pin and torch.cuda.is_available():
+            planes = planes.pin_memory()
+        p = planes.data_ptr()
+        na, nl = C.c_int64(), C.c_int64()
+        _cabi.check(lib.cgbk_pack_host(src.data_ptr() if n else None, n, p, p + cap // 4, p + cap // 4 + cap // 8, cap,
+                                       int(n_threads), C.byref(na), C.byref(nl)))
+        return cls(n, planes, na.value, nl.value)
+
+    @property
+    def upload_bytes(self):
+        """Bytes that cross PCIe for this replicon (absent planes are cleared on the device)."""
+        return self.cap_bases // 4 + (self.cap_bases // 8 if self.n_amb else 0) + (self.cap_bases // 8 if self.n_lower else 0)
+
+    def save(self, path, name=""):
+        """The packed genome file (same container as ``PackedGenome.save``)."""
+        with open(path, "wb") as f:
+            np.savez(f, magic=np.array(self.FILE_MAGIC), seq_len=np.array([self.n_bases], dtype=np.int64),
+                     planes=self.planes.numpy(), names=np.array([name]))
+
+    @classmethod
+    def load(cls, path, pin=True):
+        """Returns ``(host_packed_genome, name)``; single-replicon files only."""
+        with np.load(path, allow_pickle=False) as z:
+            if str(z["magic"]) != cls.FILE_MAGIC:
+                raise ValueError("%s is not a packed genome file" % path)
+            seq_len, planes, names = z["seq_len"], z["planes"], [str(x) for x in z["names"]]
+        if len(seq_len) != 1:
+            raise ValueError("%s holds %d replicons; load it with PackedGenome.load" % (path, len(seq_len)))
+        t = torch.from_numpy(np.ascontiguousarray(planes, dtype=np.int32))
+        if pin and torch.cuda.is_available():
+            t = t.pin_memory()
+        cap = int(_cabi.lib().cgbk_packed_capacity(int(seq_len[0])))
+        c16, c32 = cap // 16, cap // 32
+        n_amb = int(np.unpackbits(planes[c16:c16 + c32].view(np.uint8)).sum())
+        n_lower = int(np.unpackbits(planes[c16 + c32:].view(np.uint8)).sum())
+        return cls(int(seq_len[0]), t, n_amb, n_lower), names[0]
+
+
 class PackedGenome:
     def __init__(self, seq_lens, device=None):
         if device is None:
@@ -106,6 +181,24 @@ class PackedGenome:
             dev = host.to(g.device, non_blocking=True) if lens[k] else torch.empty(0, dtype=torch.uint8,
                                                                                    device=g.device)
             g.pack_into(k, dev, stream)
+        return g
+
+    @classmethod
+    def from_host_packed(cls, hp, device=None):
+        """Device genome of one host-packed replicon: the planes are copied as they are (no pack
+        kernel); a plane without a set bit is cleared on the device instead of uploaded."""
+        g = cls([hp.n_bases], device)
+        c16, c32 = g.cap_bases // 16, g.cap_bases // 32
+        g.bases2.copy_(hp.bases2, non_blocking=True)
+        if hp.n_amb:
+            g.amb.copy_(hp.amb, non_blocking=True)
+        else:
+            g.amb.zero_()
+        if hp.n_lower:
+            g.lower.copy_(hp.lower, non_blocking=True)
+        else:
+            g.lower.zero_()
+        g._packed[:] = True
         return g
 
     def pack_into(self, k, dev_ascii, stream=None):

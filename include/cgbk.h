@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CGBK_VERSION 200
+#define CGBK_VERSION 210
 
 /* status codes; the Python layer maps them to the reference's exception types */
 #define CGBK_OK 0
@@ -120,6 +120,19 @@ int64_t cgbk_bases2_words(int64_t cap_bases);
 int cgbk_pack_ascii(const uint8_t* d_ascii, int64_t n, int64_t dst_off,
                     uint32_t* d_bases2, uint32_t* d_amb, uint32_t* d_lower,
                     int64_t cap_bases, void* stream);
+
+/* The same packing on the HOST (AVX2 when the CPU has it, host threads for large inputs;
+ * n_threads 0 = as many as the machine has, at most 16): ascii[0..n_bases) -> three host planes
+ * of cgbk_packed_capacity(n_bases) bases (n_bases rounded up to CGBK_SEQ_ALIGN, at least one
+ * block; the tail is zero), bit for bit what cgbk_pack_ascii writes on the device.  n_amb /
+ * n_lower (optional) receive the number of set bits of the two flag planes: a replicon with
+ * none of either can travel as its bases2 plane alone (0.25 byte per base).  A sequence kept or
+ * stored in this form (the "packed genome file" of PackedGenome.save) is what
+ * cgbk_regulation_pipeline_packed takes.  No GPU is involved. */
+int64_t cgbk_packed_capacity(int64_t n_bases);
+int cgbk_pack_host(const uint8_t* ascii, int64_t n_bases, uint32_t* bases2, uint32_t* amb,
+                   uint32_t* lower, int64_t cap_bases, int n_threads, int64_t* n_amb,
+                   int64_t* n_lower);
 
 /* ---- handles ---------------------------------------------------------------- */
 
@@ -314,9 +327,26 @@ int cgbk_regulation_pipeline(cgbk_model* model, const uint8_t* h_ascii, int64_t 
                              double* h_post, double* h_stats, unsigned long long* h_hist,
                              void* stream);
 
-/* The same call with its arguments in one struct: a binding keeps the struct alive and only
+/* The same with the sequence already PACKED on the host (cgbk_pack_host, or a packed genome
+ * file): h_bases2[cap / 16], h_amb[cap / 32], h_lower[cap / 32] with cap =
+ * cgbk_packed_capacity(n_bases); h_amb and / or h_lower may be NULL, meaning "no such byte in
+ * this replicon" (the plane is cleared on the device instead of uploaded).  0.25 - 0.5 byte per
+ * base crosses PCIe instead of 1 and no pack kernel runs; from 64 Mbp on the planes go up in
+ * four chunks beside the scan like the ASCII form does.  Scratch as for the ASCII call. */
+int cgbk_regulation_pipeline_packed(cgbk_model* model, const uint32_t* h_bases2,
+                                    const uint32_t* h_amb, const uint32_t* h_lower, int64_t n_bases,
+                                    const int64_t* h_start, const int64_t* h_end, int n_regions,
+                                    double mu_m, double std_m, double p_motif, double alpha,
+                                    double hist_lo, double hist_hi, int n_bins,
+                                    void* d_scratch, int64_t scratch_bytes,
+                                    void* h_staging, int64_t staging_bytes,
+                                    double* h_post, double* h_stats, unsigned long long* h_hist,
+                                    void* stream);
+
+/* Either call with its arguments in one struct: a binding keeps the struct alive and only
  * rewrites the fields that change between calls (a ctypes call with 21 scalar arguments costs
- * several microseconds of marshalling; with one pointer it costs one). */
+ * several microseconds of marshalling; with one pointer it costs one).  h_ascii != NULL selects
+ * the ASCII form, otherwise h_bases2 (+ optional h_amb / h_lower) the packed one. */
 typedef struct {
     cgbk_model* model;
     const uint8_t* h_ascii;
@@ -334,6 +364,9 @@ typedef struct {
     double* h_stats;
     unsigned long long* h_hist;
     void* stream;
+    const uint32_t* h_bases2;      /* packed form (used when h_ascii is NULL) */
+    const uint32_t* h_amb;
+    const uint32_t* h_lower;
 } cgbk_pipeline_args;
 int cgbk_regulation_pipeline_args(const cgbk_pipeline_args* args);
 
