@@ -117,25 +117,6 @@ int cgbk_current_sms() {
     return cgbk_device_sms(dev);
 }
 
-// Every entry point that takes a handle runs on the handle's device: if another device is
-// current it is switched for the duration of the call and restored on return.
-struct DeviceGuard {
-    int prev = -1;
-    bool changed = false;
-    cudaError_t err = cudaSuccess;
-    explicit DeviceGuard(int device) {
-        err = cudaGetDevice(&prev);
-        if (err == cudaSuccess && prev != device) {
-            err = cudaSetDevice(device);
-            changed = err == cudaSuccess;
-        }
-    }
-    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
-};
-#define ON_DEVICE(dev)                                                    \
-    DeviceGuard _guard(dev);                                              \
-    if (_guard.err != cudaSuccess) return cgbk_check_cuda(_guard.err, "selecting the handle's device")
-
 extern "C" int cgbk_version(void) { return CGBK_VERSION; }
 extern "C" const char* cgbk_last_error(void) { return g_err; }
 
@@ -391,6 +372,9 @@ static void build_model_host(const double* lo, int m, int device, cgbk_model* M,
         const int k2 = (int)floor(log2((1073741824.0 - 8192.0) / R));
         if (k2 < kexp) kexp = k2;
     }
+    // ... and with the whole score range (soft-max <= max + 1, default histogram edges at the
+    // integers around it) below 2^31 units, so that (score - histogram edge) fits an int32
+    while (kexp > 0 && (M->max_score - M->min_score + 4.0) * ldexp(1.0, kexp) >= 2147483648.0 - 1048576.0) --kexp;
     M->kexp = kexp;
     const double scale = ldexp(1.0, kexp);
     std::vector<long long> qf(4 * m), qr(4 * m);
@@ -409,6 +393,26 @@ static void build_model_host(const double* lo, int m, int device, cgbk_model* M,
         }
         const long long shift_f = llrint(bias_f), shift_r = llrint(bias_r);
         for (int b = 0; b < 4; ++b) { qf[b] -= shift_f; qr[b] -= shift_r; }
+    }
+    // Moment centre and unit (see make_stats_params): the centre is the middle of the score range,
+    // the unit 2^-(kexp - sh) the finest the integer accumulators allow.  A body adds 32 re-centred
+    // scores in an int32 (|d| < 2^26) and a tile up to 128 squares in an int64 (|d| < 2^28).  For
+    // LexA (score range 70 bits, kexp 24) that is 2^-20; a motif with a narrow range gets an exact
+    // sum.  (With a fixed 2^-18 a degenerate 2-bp motif -- 14 distinct scores, so the rounding does
+    // not average out -- was off by 9e-7 in the mean, which its 3 000-window posteriors amplify
+    // past 1e-6; found by tools/fuzz_parity.py.)
+    {
+        const double centre = 0.5 * (M->min_score + M->max_score);
+        M->c_fix = (int)llrint(centre * scale);
+        const double half_range_fix = (0.5 * (M->max_score - M->min_score) + 1.0) * scale + 1.0;  // soft-max <= max + 1
+        int need = 0;
+        while (need < 30 && ldexp(1.0, 26 + need) <= half_range_fix) ++need;
+        M->sh = need;
+        // The tables carry -(c_fix - half) at position 0 of each strand: the scan's strand sums are
+        // then centred on c_fix and already hold the rounding half-unit, so a window's moment
+        // term is one shift.  |sum - bias| <= range / 2 + half: further inside int32 than before.
+        M->tab_bias = M->c_fix - (need > 0 ? (1 << (need - 1)) : 0);
+        for (int b = 0; b < 4; ++b) { qf[b] -= M->tab_bias; qr[b] -= M->tab_bias; }
     }
     const int G = M->G;
     std::vector<uint32_t> precise((size_t)256 * 2 * G);
@@ -962,8 +966,7 @@ int cgbk_bg_scan_begin(cgbk_model* M, const cgbk_genome* genome, const cgbk_seqs
     if (d_hist) {
         if (n_bins < 1 || n_bins > CGBK_MAX_HIST_BINS || !(hist_hi > hist_lo))
             return cgbk_set_error(CGBK_ERR_INVALID, "histogram needs 1..%d bins and hi > lo", CGBK_MAX_HIST_BINS);
-        if ((hist_hi - hist_lo) * ldexp(1.0, M->kexp) >= 4294967296.0 ||
-            fabs(hist_lo) * ldexp(1.0, M->kexp) >= 2147483648.0)
+        if (!cgbk_hist_range_ok(M, hist_lo, hist_hi))
             return cgbk_set_error(CGBK_ERR_INVALID, "histogram range too wide for the fixed-point scores");
     } else {
         n_bins = 1; hist_lo = M->min_score - 1.0; hist_hi = M->max_score + 2.0;
@@ -1220,8 +1223,7 @@ extern "C" int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cg
         double lo = hist_lo ? hist_lo[k] : floor(M->min_score), hi = hist_hi ? hist_hi[k] : ceil(M->max_score) + 1.0;
         unsigned long long* hist_k = d_hist ? d_hist + (size_t)k * n_bins : nullptr;
         if (hist_k) {
-            if (!(hi > lo) || (hi - lo) * ldexp(1.0, M->kexp) >= 4294967296.0 ||
-                fabs(lo) * ldexp(1.0, M->kexp) >= 2147483648.0)
+            if (!(hi > lo) || !cgbk_hist_range_ok(M, lo, hi))
                 return cgbk_set_error(CGBK_ERR_INVALID, "model %d: bad histogram range", k);
         } else {
             lo = M->min_score - 1.0; hi = M->max_score + 2.0;

@@ -51,12 +51,11 @@ __device__ __forceinline__ void stage_exact(ExactTables* s, const double* __rest
 //   windows holding a byte outside ACGTacgt: PSSMModel._calculate (pssm_model.py:88-101),
 //   where lower-case letters are KeyErrors too and add the column mean.
 // Returns true when the window went through the ambiguity repair.
-__device__ __forceinline__ bool exact_window(const GenomeView& g, const ExactTables* t, int m,
-                                             long long p, bool revseq, double& f, double& r) {
-    const uint64_t x = load_bases32(g, p);
+// x = the window's bases (2 bits each from bit 0), amb = its ambiguity bits (already masked to m).
+__device__ __forceinline__ bool exact_window_bits(const GenomeView& g, const ExactTables* t, int m, long long p,
+                                                  uint64_t x, uint32_t amb, bool revseq, double& f, double& r) {
     const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
     const uint32_t maskm = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);
-    const uint32_t amb = load_bits32(g.amb, g.cap_bases, p) & maskm;
     double fs = 0.0, rs = 0.0;
     const int m_lo = m < 16 ? m : 16;
     if (amb == 0) {
@@ -72,11 +71,23 @@ __device__ __forceinline__ bool exact_window(const GenomeView& g, const ExactTab
                 fs += v.x; rs += v.y;
             }
         } else {
-            for (int j = 0; j < m; ++j) {
-                const int b = (int)((x >> (2 * j)) & 3);
-                const int bq = (int)((x >> (2 * (m - 1 - j))) & 3);
-                fs += t->fr[j * 4 + b].x;
-                rs += t->fr[j * 4 + (3 - bq)].x;
+            // y_j = 3 - x_{m-1-j}: the reverse complement as a base string of its own (bit reversal
+            // mirrors the positions and swaps the two bits of every base; swap them back, complement,
+            // right-align), so that both strands walk j upwards with one shift-and-mask per look-up.
+            // Same addends in the same order as fs += fr[j][x_j].x; rs += fr[j][3 - x_{m-1-j}].x.
+            uint64_t y = __brevll(x);
+            y = ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
+            y = (~y) >> (64 - 2 * m);
+            const uint32_t yl = (uint32_t)y, yh = (uint32_t)(y >> 32);
+#pragma unroll 4
+            for (int j = 0; j < m_lo; ++j) {
+                fs += t->fr[j * 4 + ((xl >> (2 * j)) & 3)].x;
+                rs += t->fr[j * 4 + ((yl >> (2 * j)) & 3)].x;
+            }
+#pragma unroll 4
+            for (int j = 16; j < m; ++j) {
+                fs += t->fr[j * 4 + ((xh >> (2 * (j - 16))) & 3)].x;
+                rs += t->fr[j * 4 + ((yh >> (2 * (j - 16))) & 3)].x;
             }
         }
         f = fs; r = rs;
@@ -97,6 +108,14 @@ __device__ __forceinline__ bool exact_window(const GenomeView& g, const ExactTab
     }
     f = fs; r = rs;
     return true;
+}
+
+__device__ __forceinline__ bool exact_window(const GenomeView& g, const ExactTables* t, int m,
+                                             long long p, bool revseq, double& f, double& r) {
+    const uint64_t x = load_bases32(g, p);
+    const uint32_t maskm = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);
+    const uint32_t amb = load_bits32(g.amb, g.cap_bases, p) & maskm;
+    return exact_window_bits(g, t, m, p, x, amb, revseq, f, r);
 }
 
 // pssm_model.py:129-131 with the pinned numpy 1.x: pow(2, s) in double, math.log(x, 2)

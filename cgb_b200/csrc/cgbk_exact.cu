@@ -425,79 +425,173 @@ cudaError_t launch_rescore(const cgbk_model* mdl, GenomeView g, SeqTable seqs, F
 #define CGBK_SITE_QUEUE 256     // candidates listed per warp and round
 #define CGBK_NO_SITE 0xffffffffffffffffull
 
+// words of a warp's staged tile: 32 L + 32 bases (the last window's far end) rounded up, + 1 for
+// the funnel shift's look-ahead
+#define CGBK_SITE_B2_WORDS (2 * 128 + 4)
+#define CGBK_SITE_AMB_WORDS (128 + 3)
+#define CGBK_SITE_GROUP 8        // consecutive tiles a warp takes together
+#define CGBK_SITE_DENSE 32       // a tile with at least this many candidates is scored on its own
+
+// Per-warp scratch of the site pass.
+struct SiteWarp {
+    unsigned short queue[CGBK_SITE_QUEUE];
+    uint32_t b2[CGBK_SITE_B2_WORDS];
+    uint32_t amb[CGBK_SITE_AMB_WORDS];
+    long long p0[CGBK_SITE_GROUP];       // first base of the group's tiles
+    long long cand_off[CGBK_SITE_GROUP]; // where a tile's candidate pairs start
+    int qstart[CGBK_SITE_GROUP];         // where a sparse tile's entries start in the queue
+    int hits[CGBK_SITE_GROUP];
+};
+
+// A warp takes CGBK_SITE_GROUP consecutive tiles at a time.  Motif sets are mostly SPARSE in
+// candidates (two thirds of the JASPAR-scale benchmark set have fewer than 32 per 4 096-window
+// tile, 40 % fewer than 4): scoring tile by tile would run the 32-lane exact scorer for three or
+// four candidates.  So the group's sparse tiles pool their candidates in one queue (entry = tile
+// within the group << 12 | window within the tile; 8 x 31 entries at most) that is scored with
+// all lanes busy, straight from the packed genome; a dense tile is scored on its own from a
+// shared-memory copy of its bases (one coalesced load per tile instead of five scattered loads
+// per candidate).  A candidate's place in the pair list depends only on its tile and its rank in
+// the tile, so the order of the output is the same either way.
 __global__ void __launch_bounds__(128) site_score_kernel(const double* __restrict__ d_exact, int m, GenomeView g,
                                                          SeqTable seqs, FastWork w, SitePass sp, int L, int D,
                                                          double thr, int flags) {
     __shared__ ExactTables tab;
-    __shared__ unsigned short queue[4][CGBK_SITE_QUEUE];
+    __shared__ SiteWarp scratch[4];
     stage_exact(&tab, d_exact);
     __syncthreads();
     const bool revseq = (flags & CGBK_RC_REVSEQ_ORDER) != 0;
     const int B = L >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long n_tiles = w.tile_end - w.tile_begin;
+    const long long n_groups = (n_tiles + CGBK_SITE_GROUP - 1) / CGBK_SITE_GROUP;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    unsigned short* q = queue[wib];
-    for (long long ti = warp0; ti < n_tiles; ti += nwarps) {
-        const long long tile = w.tile_begin + ti;
-        const int total = __ldg(sp.tile_cand + tile);
-        if (total == 0) {                                   // warp-uniform
-            if (lane == 0) sp.tile_hits[tile] = 0;
+    SiteWarp& sw = scratch[wib];
+    unsigned short* q = sw.queue;
+    const long long nw2 = g.cap_bases >> 4, nwa = g.cap_bases >> 5;
+    const uint32_t maskm = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);
+    const int n_b2 = 2 * L + 4, n_amb = L + 3;
+    const int S = lane * L;
+
+    // one scored candidate -> its pair of records; returns the number of sites (0..2)
+    auto emit = [&](long long k, long long gpos, double f, double r) -> int {
+        const float ff = (float)f, rf = (float)r;
+        const bool hf = (double)ff >= thr, hr = (double)rf >= thr;
+        if (k < sp.cand_cap) {
+            sp.pairs[2 * k] = hf ? cgbk_pack_hit8(gpos, 0, __float_as_uint(ff)) : CGBK_NO_SITE;
+            sp.pairs[2 * k + 1] = hr ? cgbk_pack_hit8(gpos, 1, __float_as_uint(rf)) : CGBK_NO_SITE;
+        }
+        return (hf ? 1 : 0) + (hr ? 1 : 0);
+    };
+
+    for (long long grp = warp0; grp < n_groups; grp += nwarps) {
+        const long long tile0 = w.tile_begin + grp * CGBK_SITE_GROUP;
+        const int nt = (int)(w.tile_end - tile0 < CGBK_SITE_GROUP ? w.tile_end - tile0 : CGBK_SITE_GROUP);
+        const int my_total = lane < nt ? __ldg(sp.tile_cand + tile0 + lane) : 0;
+        if (!__any_sync(0xffffffffu, my_total > 0)) {
+            if (lane < nt) sp.tile_hits[tile0 + lane] = 0;
             continue;
         }
-        uint32_t words[5];
-        int c = 0;
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-            words[r] = r <= B ? __ldg(w.fplane + (tile * (B + 1) + r) * 32 + lane) : 0u;
-            c += __popc(words[r]);
+        if (lane < CGBK_SITE_GROUP) {
+            sw.hits[lane] = 0;
+            sw.cand_off[lane] = lane < nt ? (long long)__ldg(sp.tile_cand_off + tile0 + lane) : 0;
         }
-        int off = c;                                        // inclusive scan over the lanes
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, off, o);
-            if (lane >= o) off += v;
-        }
-        off -= c;
-        long long gbase, w_lo, w_hi;
-        tile_range(seqs, (unsigned int)tile, L, m, gbase, w_lo, w_hi);
-        const long long base = __ldg(sp.tile_cand_off + tile);
-        const int S = lane * L;
-        int n_hits = 0;
-        for (int chunk0 = 0; chunk0 < total; chunk0 += CGBK_SITE_QUEUE) {
-            // this lane's flagged windows, in position order, that fall into the round
-            int idx = off;
+        __syncwarp();
+        int qn = 0;                                         // pooled (sparse) queue entries, warp-uniform
+        for (int t = 0; t < nt; ++t) {
+            const int total = __shfl_sync(0xffffffffu, my_total, t);
+            if (total == 0) continue;                       // warp-uniform
+            const long long tile = tile0 + t;
+            uint32_t words[5];
+            int c = 0;
 #pragma unroll
             for (int r = 0; r < 5; ++r) {
-                uint32_t word = words[r];
-                while (word) {
-                    const int p = 31 - __clz(word);
-                    word &= ~(1u << p);
-                    if (idx >= chunk0 && idx < chunk0 + CGBK_SITE_QUEUE)
-                        q[idx - chunk0] = (unsigned short)(r < B ? S + 32 * r + (31 - p) - D : S + L - D + (D - 1 - p));
-                    ++idx;
-                }
+                words[r] = r <= B ? __ldg(w.fplane + (tile * (B + 1) + r) * 32 + lane) : 0u;
+                c += __popc(words[r]);
             }
-            __syncwarp();
-            const int n = total - chunk0 < CGBK_SITE_QUEUE ? total - chunk0 : CGBK_SITE_QUEUE;
-            for (int i = lane; i < n; i += 32) {
-                const long long gpos = gbase + w_lo + q[i];
-                double f, r;
-                exact_window(g, &tab, m, gpos, revseq, f, r);
-                const float ff = (float)f, rf = (float)r;
-                const bool hf = (double)ff >= thr, hr = (double)rf >= thr;
-                const long long k = base + chunk0 + i;
-                if (k < sp.cand_cap) {
-                    sp.pairs[2 * k] = hf ? cgbk_pack_hit8(gpos, 0, __float_as_uint(ff)) : CGBK_NO_SITE;
-                    sp.pairs[2 * k + 1] = hr ? cgbk_pack_hit8(gpos, 1, __float_as_uint(rf)) : CGBK_NO_SITE;
-                }
-                n_hits += (hf ? 1 : 0) + (hr ? 1 : 0);
-            }
-            __syncwarp();
-        }
+            int off = c;                                    // inclusive scan over the lanes
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) n_hits += __shfl_down_sync(0xffffffffu, n_hits, o);
-        if (lane == 0) sp.tile_hits[tile] = n_hits;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, off, o);
+                if (lane >= o) off += v;
+            }
+            off -= c;
+            long long gbase, w_lo, w_hi;
+            tile_range(seqs, (unsigned int)tile, L, m, gbase, w_lo, w_hi);
+            const long long p0 = gbase + w_lo;              // a multiple of 32
+            // tile-local window of flag bit p in row r of this lane
+            auto window_of = [&](int r, int p) -> int {
+                return r < B ? S + 32 * r + (31 - p) - D : S + L - D + (D - 1 - p);
+            };
+            if (total < CGBK_SITE_DENSE) {
+                // sparse tile: pool its candidates
+                int idx = qn + off;
+#pragma unroll
+                for (int r = 0; r < 5; ++r) {
+                    uint32_t word = words[r];
+                    while (word) {
+                        const int p = 31 - __clz(word);
+                        word &= ~(1u << p);
+                        q[idx++] = (unsigned short)((t << 12) | window_of(r, p));
+                    }
+                }
+                if (lane == 0) { sw.qstart[t] = qn; sw.p0[t] = p0; }
+                qn += total;
+                continue;
+            }
+            // dense tile: bases and ambiguity bits staged once (coalesced), candidates in rounds
+            __syncwarp();
+            for (int i = lane; i < n_b2; i += 32) sw.b2[i] = ldw(g.bases2, (p0 >> 4) + i, nw2);
+            for (int i = lane; i < n_amb; i += 32) sw.amb[i] = ldw(g.amb, (p0 >> 5) + i, nwa);
+            // the pooled entries share the queue: dense rounds use its upper part
+            unsigned short* dq = q + qn;
+            const int room = CGBK_SITE_QUEUE - qn;          // >= 256 - 7 * 31
+            const long long base = sw.cand_off[t];
+            int n_hits = 0;
+            for (int chunk0 = 0; chunk0 < total; chunk0 += room) {
+                int idx = off;
+#pragma unroll
+                for (int r = 0; r < 5; ++r) {
+                    uint32_t word = words[r];
+                    while (word) {
+                        const int p = 31 - __clz(word);
+                        word &= ~(1u << p);
+                        if (idx >= chunk0 && idx < chunk0 + room) dq[idx - chunk0] = (unsigned short)window_of(r, p);
+                        ++idx;
+                    }
+                }
+                __syncwarp();
+                const int n = total - chunk0 < room ? total - chunk0 : room;
+                for (int i = lane; i < n; i += 32) {
+                    const int wt = dq[i];
+                    const long long gpos = p0 + wt;
+                    const int wi = wt >> 4, sh = (wt & 15) * 2;
+                    const uint32_t w0 = sw.b2[wi], w1 = sw.b2[wi + 1], w2 = sw.b2[wi + 2];
+                    const uint64_t x = (uint64_t)__funnelshift_r(w0, w1, sh) |
+                                       ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+                    const uint32_t amb = __funnelshift_r(sw.amb[wt >> 5], sw.amb[(wt >> 5) + 1], (uint32_t)(wt & 31)) & maskm;
+                    double f, r;
+                    exact_window_bits(g, &tab, m, gpos, x, amb, revseq, f, r);
+                    n_hits += emit(base + chunk0 + i, gpos, f, r);
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) n_hits += __shfl_down_sync(0xffffffffu, n_hits, o);
+            if (lane == 0) sw.hits[t] = n_hits;
+        }
+        __syncwarp();
+        // the pooled candidates of the group's sparse tiles, all lanes busy
+        for (int i = lane; i < qn; i += 32) {
+            const int e = q[i], t = e >> 12, wt = e & 4095;
+            const long long gpos = sw.p0[t] + wt;
+            double f, r;
+            exact_window(g, &tab, m, gpos, revseq, f, r);
+            const int nh = emit(sw.cand_off[t] + (i - sw.qstart[t]), gpos, f, r);
+            if (nh) atomicAdd(&sw.hits[t], nh);
+        }
+        __syncwarp();
+        if (lane < nt) sp.tile_hits[tile0 + lane] = sw.hits[lane];
+        __syncwarp();
     }
 }
 
@@ -548,7 +642,10 @@ cudaError_t launch_site_pass(const cgbk_model* mdl, GenomeView g, SeqTable seqs,
     if (e != cudaSuccess) return e;
     long long blocks = (n_tiles + 3) / 4;
     if (blocks > mdl->sms * 16) blocks = mdl->sms * 16;
-    site_score_kernel<<<(int)blocks, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, w, sp, L, 4 * (mdl->G - 1), thr, flags);
+    // the score kernel's warps take CGBK_SITE_GROUP tiles at a time
+    long long sblocks = ((n_tiles + CGBK_SITE_GROUP - 1) / CGBK_SITE_GROUP + 3) / 4;
+    if (sblocks > mdl->sms * 16) sblocks = mdl->sms * 16;
+    site_score_kernel<<<(int)sblocks, 128, 0, st>>>(mdl->d_exact, mdl->m, g, seqs, w, sp, L, 4 * (mdl->G - 1), thr, flags);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     e = cgbk_exclusive_sum(sp.tile_hits + w.tile_begin, sp.tile_hit_off + w.tile_begin, n_tiles, sp.scan_tmp,
                            sp.scan_tmp_bytes, st);

@@ -41,6 +41,11 @@
 //    the promoters;
 //  * MODE 2 ("moments"): MODE 1 without the histogram (the reference's estimator only ever
 //    uses mean and std, binding_model.py:85-87);
+//  * MODE 3 / 4 ("lean" stats / moments): MODE 1 / 2 for callers that keep no score plane and
+//    whose histogram range covers every possible score (the batched scan's default): no plane
+//    store and no clamping of the bin index in the per-window epilogue -- a score that rounding
+//    pushes a hair outside the range lands in a guard row on either side of the shared-memory
+//    histogram, folded into the first / last bin at the flush (3 of ~38 instructions per window);
 //  * MODE 1 / 2 with a threshold ("fused" scan): the fixed-point strand scores are exact to a
 //    few units of 2^-kexp, so the same pass also finds the site-search candidates
 //    (genome.py:433-445).  Per window TWO instructions: the sign of (threshold - 1 - max(f, r))
@@ -74,6 +79,34 @@
 #endif
 #ifndef CGBK_STATS_THREADS_SMALLG      // G <= 2 (motifs of up to 8 bases): fewer registers, more warps
 #define CGBK_STATS_THREADS_SMALLG 384
+#endif
+// per group count (tuning builds: -DCGBK_STATS_THREADS_G3=384 ...).  Up to G = 5 the kernel fits 128
+// registers (no or a few bytes of spills): 512 threads measured 5-6 % faster than 384 on B200
+// (250 Mbp, fused scan: G3 0.418 -> 0.394 ms, G4 0.420 -> 0.398, G5 0.474 -> 0.449); G = 6 needs
+// its 168 registers (448 threads: 0.503 -> 0.550 ms)
+#ifndef CGBK_STATS_THREADS_G1
+#define CGBK_STATS_THREADS_G1 512
+#endif
+#ifndef CGBK_STATS_THREADS_G2
+#define CGBK_STATS_THREADS_G2 512
+#endif
+#ifndef CGBK_STATS_THREADS_G3
+#define CGBK_STATS_THREADS_G3 512
+#endif
+#ifndef CGBK_STATS_THREADS_G4
+#define CGBK_STATS_THREADS_G4 512
+#endif
+#ifndef CGBK_STATS_THREADS_G5
+#define CGBK_STATS_THREADS_G5 512
+#endif
+#ifndef CGBK_STATS_THREADS_G6
+#define CGBK_STATS_THREADS_G6 CGBK_STATS_THREADS
+#endif
+#ifndef CGBK_STATS_THREADS_G7
+#define CGBK_STATS_THREADS_G7 256
+#endif
+#ifndef CGBK_STATS_THREADS_G8
+#define CGBK_STATS_THREADS_G8 256
 #endif
 #ifndef CGBK_STATS_EW
 #define CGBK_STATS_EW 4
@@ -134,33 +167,45 @@ __device__ __forceinline__ void fill_tables(unsigned char* smem, const uint32_t*
     }
 }
 
-// all NW words of table entry E (= 4-mer << 7); o16/o8/o4 = this lane's replica offsets
+// (x & 0x7f80) | o in ONE LOP3 (ptxas otherwise keeps the masked index as a common subexpression
+// and spends a second instruction on every replica offset)
+__device__ __forceinline__ uint32_t entry_addr(uint32_t x, uint32_t o) {
+    uint32_t a;
+    asm("lop3.b32 %0, %1, 0x7f80, %2, 0xEA;" : "=r"(a) : "r"(x), "r"(o));
+    return a;
+}
+
+// all NW words of the table entry of stream word x (4-mer index at bits 7..14, anything around it);
+// o16/o8/o4 = this lane's replica offsets
 template <int NW>
-__device__ __forceinline__ void lookup(const unsigned char* sb, uint32_t E, uint32_t o16, uint32_t o8,
+__device__ __forceinline__ void lookup(const unsigned char* sb, uint32_t x, uint32_t o16, uint32_t o8,
                                        uint32_t o4, uint32_t (&v)[NW]) {
     using TL = TableLayout<NW>;
+    if (TL::N16 > 0) {
+        const uint32_t a = entry_addr(x, o16);
 #pragma unroll
-    for (int c = 0; c < TL::N16; ++c) {
-        const uint4 q = *reinterpret_cast<const uint4*>(sb + c * 32768 + (E | o16));
-        v[4 * c] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+        for (int c = 0; c < TL::N16; ++c) {
+            const uint4 q = *reinterpret_cast<const uint4*>(sb + c * 32768 + a);
+            v[4 * c] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+        }
     }
     if (TL::HAS8) {
-        const uint2 q = *reinterpret_cast<const uint2*>(sb + TL::N16 * 32768 + (E | o8));
+        const uint2 q = *reinterpret_cast<const uint2*>(sb + TL::N16 * 32768 + entry_addr(x, o8));
         v[4 * TL::N16] = q.x; v[4 * TL::N16 + 1] = q.y;
     }
     if (TL::HAS4) {
-        v[NW - 1] = *reinterpret_cast<const uint32_t*>(sb + (TL::N16 + TL::HAS8) * 32768 + (E | o4));
+        v[NW - 1] = *reinterpret_cast<const uint32_t*>(sb + (TL::N16 + TL::HAS8) * 32768 + entry_addr(x, o4));
     }
 }
 
-// (4-mer at body position t) << 7, from the body's two stream words + one lookahead word
+// the stream shifted so that the 4-mer at body position t sits at bits 7..14 (NOT masked: lookup()
+// masks and adds the replica offset in one instruction), from the body's two stream words + one
+// lookahead word
 __device__ __forceinline__ uint32_t kmer_addr(int t, uint32_t w0, uint32_t w1, uint32_t w2) {
     const uint32_t lo = t < 16 ? w0 : w1, hi = t < 16 ? w1 : w2;
     const int sh = t < 16 ? 2 * t : 2 * t - 32;
-    uint32_t x;
-    if (sh >= 7) x = __funnelshift_r(lo, hi, sh - 7);
-    else x = lo << (7 - sh);
-    return x & 0x7f80u;
+    if (sh >= 7) return __funnelshift_r(lo, hi, sh - 7);
+    return lo << (7 - sh);
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -305,7 +350,9 @@ static __device__ __noinline__ int exact_tile_stats(const ExactTables* tab, cons
 
 __host__ __device__ constexpr int fast_threads_of(int G, int MODE) {
     return MODE == 0 ? CGBK_FILTER_THREADS
-                     : (G <= 2 ? CGBK_STATS_THREADS_SMALLG : (G <= 6 ? CGBK_STATS_THREADS : 256));
+         : G == 1 ? CGBK_STATS_THREADS_G1 : G == 2 ? CGBK_STATS_THREADS_G2 : G == 3 ? CGBK_STATS_THREADS_G3
+         : G == 4 ? CGBK_STATS_THREADS_G4 : G == 5 ? CGBK_STATS_THREADS_G5 : G == 6 ? CGBK_STATS_THREADS_G6
+         : G == 7 ? CGBK_STATS_THREADS_G7 : CGBK_STATS_THREADS_G8;
 }
 
 template <int G, int MODE>
@@ -331,7 +378,8 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     constexpr int D = Cfg::D;
     constexpr bool ONE = VAR == CGBK_VAR_ONE;
     constexpr bool PEEL = VAR == CGBK_VAR_PEEL;
-    constexpr bool HIST = MODE == 1;
+    constexpr bool HIST = MODE == 1 || MODE == 3;
+    constexpr bool LEAN = MODE >= 3;       // no score plane, histogram guard rows instead of clamps
     // completed windows are handled in groups: 4 for the filter's deferred flag test, CGBK_STATS_EW
     // for the stats epilogue (its dependent chains run side by side)
     constexpr int EW = MODE == 0 ? 4 : CGBK_STATS_EW;
@@ -346,7 +394,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     auto cand_ptr = [&]() -> unsigned char* {
         return smem + TL::BYTES + Cfg::STASH_BYTES + (threadIdx.x >> 5) * (CGBK_CAND_STAGE * 8 + 16);
     };
-    unsigned int* hist = reinterpret_cast<unsigned int*>(smem + TL::BYTES + Cfg::STASH_BYTES + Cfg::CAND_BYTES);
+    unsigned int* hist_rows = reinterpret_cast<unsigned int*>(smem + TL::BYTES + Cfg::STASH_BYTES + Cfg::CAND_BYTES);
     __shared__ double red_scratch[96];
     __shared__ double exact_acc[3];     // stats modes: moments of the exactly scored (non-ACGT) tiles
     __shared__ int is_last_block;
@@ -396,8 +444,10 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     preload(tile);
 
     fill_tables<NW, Cfg::THREADS>(smem, gtab);
+    // LEAN: one guard row before bin 0 and one after the last bin
+    unsigned int* hist = hist_rows + (LEAN ? sp.hist_words : 0);
     if (HIST)
-        for (int i = threadIdx.x; i < sp.n_bins * sp.hist_words; i += blockDim.x) hist[i] = 0u;
+        for (int i = threadIdx.x; i < (sp.n_bins + (LEAN ? 2 : 0)) * sp.hist_words; i += blockDim.x) hist_rows[i] = 0u;
     if (MODE == 0 && (threadIdx.x & 31) == 0) *reinterpret_cast<unsigned int*>(cand_ptr() + CGBK_CAND_STAGE * 8) = 0u;
     if (MODE != 0 && threadIdx.x < 3) exact_acc[threadIdx.x] = 0.0;
     __syncthreads();
@@ -407,10 +457,10 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     uint2* stash64 = reinterpret_cast<uint2*>(stash_base) + warp * (D * 33) + lane;
     const int last_bin = sp.n_bins - 1;
 
+    int filler = 0;               // completions counted into the centre bin that are no real windows
     long long sum_d = 0;          // exact integer sum of re-centred scores (moment units)
     double sum_d2 = 0.0;          // sum of their squares
     long long cnt = 0;
-    int filler = 0;               // completions counted into the centre bin that are no real windows
 
     // histogram row of bin b starts at b * hist_words words; with 32 words per row every lane
     // counts into its own bank (conflict free), with 1 word per row lanes share the counters
@@ -461,7 +511,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 sink.thr = sp.thr;
                 const int nf = exact_tile_stats(static_cast<const ExactTables*>(sp.exact_tab), g.bases2, g.amb, g.lower,
                                                 g.cap_bases, gbase, A, A + (own_n > 0 ? own_n : 0), m, tile, L, D,
-                                                sp.d_hist, sp.n_bins, sp.hist_lo_d, sp.inv_binw_d, sp.plane,
+                                                sp.d_hist, sp.n_bins, sp.hist_lo_d, sp.inv_binw_d, LEAN ? nullptr : sp.plane,
                                                 (double)sp.scale, exact_acc, &sink);
                 if (work.fplane && lane == 0) work.tile_cand[tile] = nf;
             }
@@ -476,7 +526,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         int acc_d = 0;                 // per-body integer sum (stats modes)
         long long acc_d2 = 0;          // per-tile integer sum of squares (stats modes)
         // score plane rows of this tile: [(B + 1) * 32][32] ints, row = body*32 + t (last: the tail)
-        int* prow = (MODE != 0 && sp.plane) ? sp.plane + tile * (long long)((B + 1) * 1024) + lane : nullptr;
+        int* prow = (MODE != 0 && !LEAN && sp.plane) ? sp.plane + tile * (long long)((B + 1) * 1024) + lane : nullptr;
 
         // fused scan: candidate flags of the current body's completed windows (shifted in one by
         // one, newest at bit 0) and this lane's column of the tile's flag rows
@@ -540,22 +590,27 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                     for (int k = 0; k < EW; ++k) sfix[k] = mx[k] + __float2int_rn(u[k] * sp.scale);   // fixed point
 #pragma unroll
                     for (int k = 0; k < EW; ++k) {
-                        if (prow) prow[(row - (EW - 1) + k) * 32] = sfix[k];
+                        // (the table path's scores are off by -tab_bias; the plane holds true scores)
+                        if (!LEAN && prow) prow[(row - (EW - 1) + k) * 32] = sfix[k] + sp.tab_bias;
                         // Validity is ONE select, not a branch: a window that is not the tile's own
                         // takes the moment centre as its score.  It then adds nothing to the
                         // moments and lands in the centre's histogram bin, from which the block's
-                        // count of such windows is taken out again before the flush.
+                        // count of such windows is taken out again before the flush.  (Predicating
+                        // the three side effects instead was tried: ptxas wraps a predicated
+                        // shared-memory reduction in a convergence region, +4 instructions per window.)
                         const bool valid = live && (wrel - (EW - 1) + k < lim);
-                        const int sv = valid ? sfix[k] : sp.c_fix;
+                        const int sv = valid ? sfix[k] : sp.half;        // = c_fix - tab_bias
                         if (HIST) {
-                            const int bin = min((int)(__umulhi((unsigned)max(sv - sp.lo_fix, 0), sp.bin_mul) >> sp.bin_shift),
-                                                last_bin);
+                            // bin = floor((sv - lo) * n_bins / range) as a signed high multiply (a value a
+                            // hair below lo gives -1); LEAN: no clamps, -1 and n_bins are the guard rows
+                            int bin = __mulhi(sv - sp.lo_fix, (int)sp.bin_mul) >> sp.bin_shift;
+                            if (!LEAN) bin = min(max(bin, 0), last_bin);
                             // plain shared-memory reduction (atomicAdd(.., 1) would be wrapped in a
                             // warp-collective region by ptxas)
                             asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_saddr + hist_row_bytes * (unsigned)bin),
                                          "r"(1u));
                         }
-                        const int dq = (sv - sp.c_fix + sp.half) >> sp.sh;
+                        const int dq = sv >> sp.sh;       // the tables hold -c_fix + half already
                         acc_d += dq;
                         acc_d2 += (long long)dq * dq;
                     }
@@ -700,8 +755,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         if (HIST) {
             // the filler completions leave the centre's bin again (every lane's own bank word when
             // the rows are 32 words wide, one shared word otherwise)
-            const int cbin = min((int)(__umulhi((unsigned)max(sp.c_fix - sp.lo_fix, 0), sp.bin_mul) >> sp.bin_shift),
-                                 last_bin);
+            const int cbin = min(max(__mulhi(sp.half - sp.lo_fix, (int)sp.bin_mul) >> sp.bin_shift, 0), last_bin);
             if (filler) atomicSub(hist + cbin * sp.hist_words + (sp.hist_words == 32 ? lane : 0), (unsigned)filler);
         }
         __syncthreads();
@@ -710,6 +764,12 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 unsigned int v = 0;
                 for (int l = 0; l < sp.hist_words; ++l)       // rotate the start: no bank conflict
                     v += hist[i * sp.hist_words + ((l + i) & (sp.hist_words - 1))];
+                if (LEAN && (i == 0 || i == last_bin)) {       // the guard rows (both when n_bins == 1)
+                    for (int l = 0; l < sp.hist_words; ++l) {
+                        if (i == 0) v += hist_rows[l];
+                        if (i == last_bin) v += hist[sp.n_bins * sp.hist_words + l];
+                    }
+                }
                 if (v) atomicAdd(sp.d_hist + i, (unsigned long long)v);
             }
         // block totals: n, sum d (exact in double up to 2^53), sum d^2
@@ -785,8 +845,9 @@ static cudaError_t launch_one(const uint32_t* gtab, GenomeView g, SeqTable seqs,
     using Cfg = FastCfg<G, MODE>;
     const size_t fixed = TableLayout<Cfg::NW>::BYTES + Cfg::STASH_BYTES + Cfg::CAND_BYTES;
     // histogram: (n_bins + 1) rows of 1 word (<= 4096 bins) or of 32 words (<= 256 bins, conflict free)
-    const size_t smem_max = fixed + (MODE == 1 ? (size_t)(256 + 1) * 128 : 0);
-    const size_t smem = fixed + (MODE == 1 ? ((size_t)sp.n_bins + 1) * 4 * sp.hist_words : 0);
+    constexpr bool HIST = MODE == 1 || MODE == 3;
+    const size_t smem_max = fixed + (HIST ? (size_t)(256 + 2) * 128 : 0);
+    const size_t smem = fixed + (HIST ? ((size_t)sp.n_bins + 2) * 4 * sp.hist_words : 0);
     static std::mutex mu;
     static bool configured[CGBK_MAX_DEVICES] = {};   // per template instance
     auto kern = fast_scan_kernel<G, MODE, VAR>;

@@ -21,5 +21,6 @@ static cudaError_t dispatch_moments(int G, const uint32_t* gtab, GenomeView g, S
 
 cudaError_t launch_fast_moments(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, int L,
                                 int grid, const StatsParams& sp, cudaStream_t st) {
+    if (!sp.plane) return launch_fast_moments_lean(mdl, g, seqs, w, L, grid, sp, st);
     return dispatch_moments(mdl->G, mdl->d_precise, g, seqs, w, mdl->m, L, grid, sp, mdl->device, st);
 }

@@ -33,6 +33,15 @@ static cudaError_t dispatch_stats(int G, const uint32_t* gtab, GenomeView g, Seq
 #undef CGBK_CASE
 }
 
+bool cgbk_hist_range_ok(const cgbk_model* mdl, double hist_lo, double hist_hi) {
+    const double scale = ldexp(1.0, mdl->kexp), lim = 2147483648.0 - 65536.0;
+    if (!(hist_hi > hist_lo) || (hist_hi - hist_lo) * scale >= lim) return false;
+    const double lo_rel = hist_lo * scale - (double)mdl->tab_bias;            // lower edge as the kernel sees it
+    const double s_min = mdl->min_score * scale - (double)mdl->tab_bias - 65536.0;
+    const double s_max = (mdl->max_score + 1.0) * scale - (double)mdl->tab_bias + 65536.0;
+    return fabs(lo_rel) < lim && s_max - lo_rel < lim && s_min - lo_rel > -lim;
+}
+
 StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist_hi, int n_bins,
                               unsigned long long* d_hist, int* plane) {
     StatsParams sp;
@@ -40,16 +49,26 @@ StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist
     sp.neg_inv_scale = (float)(-1.0 / scale);
     sp.scale = (float)scale;
     sp.inv_scale_d = 1.0 / scale;
-    sp.lo_fix = (int)llrint(hist_lo * scale);
+    // histogram lower edge as the table path sees it (its scores are off by -tab_bias)
+    sp.lo_fix = (int)(llrint(hist_lo * scale) - (long long)mdl->tab_bias);
     const double range_fix = (hist_hi - hist_lo) * scale;
-    // bin = (u * n_bins / range_fix) as umulhi(u, M) >> k with M = floor(2^(32+k) n_bins / range_fix)
-    // scaled up to just below 2^32, i.e. bin edges exact to a relative 2^-31
+    // bin = floor(u * n_bins / range_fix) as mulhi(u, M) >> k (signed: a u a hair below zero gives
+    // -1) with M = ceil(2^(32+k) n_bins / range_fix) scaled up to just below 2^31.  M overstates
+    // the ratio by less than a relative 2^-30, i.e. by less than 2^-22 of a bin over 256 bins,
+    // while two distinct integers u lie n_bins / range_fix >= 2^-19 of a bin apart for every
+    // admissible range: rounded UP, every integer u gets exactly floor(u * n_bins / range_fix)
+    // (rounded down, a u that sits exactly on a bin edge would fall into the bin below).
     double mul = 4294967296.0 * (double)n_bins / range_fix;
     int k = 0;
-    while (k < 24 && mul * 2.0 < 4294967295.0) { mul *= 2.0; ++k; }
-    if (mul > 4294967295.0) mul = 4294967295.0;
+    while (k < 24 && mul * 2.0 < 2147483647.0) { mul *= 2.0; ++k; }
+    mul = ceil(mul);
+    if (mul > 2147483647.0) mul = 2147483647.0;
     sp.bin_mul = (unsigned int)mul;
     sp.bin_shift = k;
+    // the lean kernel drops the clamps of the bin index: allowed when the range covers every score
+    // a window can take (soft-max <= max + 1) with a margin for the fixed-point rounding
+    sp.lean_ok = (d_hist == nullptr) ||
+                 (hist_lo <= mdl->min_score - 1e-3 && hist_hi >= mdl->max_score + 1.0 + 1e-3) ? 1 : 0;
     sp.n_bins = n_bins;
     sp.hist_words = n_bins <= 256 ? 32 : 1;
     sp.exact_tab = mdl->d_exact + CGBK_EXACT_TAB_OFFSET;
@@ -59,20 +78,12 @@ StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist
     sp.finalize = 0;
     sp.host_stats = nullptr;
     sp.host_hist = nullptr;
-    const double centre = 0.5 * (mdl->min_score + mdl->max_score);
-    sp.c_fix = (int)llrint(centre * scale);
+    // moment centre / unit / table bias: fixed per model (build_model_host in cgbk_api.cu)
+    sp.c_fix = mdl->c_fix;
     sp.c = (double)sp.c_fix / scale;
-    // Moment unit 2^-(kexp - sh): the finest the integer accumulators allow.  A body adds 32
-    // re-centred scores in an int32 (|d| < 2^26) and a tile up to 128 squares in an int64
-    // (|d| < 2^28).  For LexA (score range 70 bits, kexp 24) that is 2^-20; a motif with a
-    // narrow range gets an exact sum.  (With a fixed 2^-18 a degenerate 2-bp motif -- 14
-    // distinct scores, so the rounding does not average out -- was off by 9e-7 in the mean,
-    // which its 3 000-window posteriors amplify past 1e-6; found by tools/fuzz_parity.py.)
-    const double half_range_fix = (0.5 * (mdl->max_score - mdl->min_score) + 1.0) * scale + 1.0;  // soft-max <= max + 1
-    int need = 0;
-    while (need < 30 && ldexp(1.0, 26 + need) <= half_range_fix) ++need;
-    sp.sh = need;
+    sp.sh = mdl->sh;
     sp.half = sp.sh > 0 ? (1 << (sp.sh - 1)) : 0;
+    sp.tab_bias = mdl->tab_bias;
     sp.q = ldexp(1.0, -(mdl->kexp - sp.sh));
     sp.d_hist = d_hist;
     sp.plane = plane;
@@ -105,10 +116,13 @@ void set_stats_threshold(StatsParams* sp, const cgbk_model* mdl, double thr, int
     }
     if (!(t > -lim)) t = -lim;           // at or below every score: everything is a candidate
     sp->thr_fix = (int)t;
-    sp->thr_m1 = (int)t - 1;
+    // compared against table-path sums, which are off by -tab_bias (|t - bias| < 2^31: t is within
+    // +-2^30, the bias within half the score range)
+    sp->thr_m1 = (int)((long long)t - 1 - (long long)mdl->tab_bias);
 }
 
 cudaError_t launch_fast_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w, int L,
                               int grid, const StatsParams& sp, cudaStream_t st) {
+    if (!sp.plane && sp.lean_ok) return launch_fast_stats_lean(mdl, g, seqs, w, L, grid, sp, st);
     return dispatch_stats(mdl->G, mdl->d_precise, g, seqs, w, mdl->m, L, grid, sp, mdl->device, st);
 }

@@ -29,6 +29,10 @@ struct cgbk_model {
     uint32_t* d_precise;          // [256][2G] int32 fixed point (f, r interleaved per group)
     uint32_t* d_coarse;           // [256][G]  packed (f16 << 16 | r16), threshold dependent
     int kexp;                     // precise scale = 2^kexp
+    // moment centre (fixed point), moment rounding shift, and the constant tab_bias = c_fix - half
+    // that the int32 group tables carry: every fixed-point strand sum comes out of the scan already
+    // re-centred (and pre-rounded) for the moment sums, one addition per window less
+    int c_fix, sh, tab_bias;
     // coarse-table cache key
     int coarse_valid;
     double coarse_thr;
@@ -93,6 +97,26 @@ int cgbk_check_cuda(cudaError_t e, const char* what);
 // multiprocessor count of a device / of the current device (cached per device)
 int cgbk_device_sms(int device);
 int cgbk_current_sms();
+
+// Every entry point that takes a handle runs on the handle's device: if another device is
+// current it is switched for the duration of the call and restored on return.
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) {
+            err = cudaSetDevice(device);
+            changed = err == cudaSuccess;
+        }
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(dev)                                                    \
+    DeviceGuard _guard(dev);                                              \
+    if (_guard.err != cudaSuccess) return cgbk_check_cuda(_guard.err, "selecting the handle's device")
+
 
 // ---------------------------------------------------------------------------
 // launchers implemented in the kernel translation units
@@ -174,10 +198,12 @@ struct StatsParams {
     float scale;           // 2^kexp
     double inv_scale_d;    // 2^-kexp
     int lo_fix;            // histogram lower edge, fixed point
-    unsigned int bin_mul;  // floor(2^(32 + bin_shift) * n_bins / range_fix)
+    unsigned int bin_mul;  // ceil(2^(32 + bin_shift) * n_bins / range_fix), below 2^31 (signed high multiply)
     int bin_shift;
+    int lean_ok;           // the histogram range covers every possible score: no clamping needed
     int n_bins;
     int hist_words;        // shared-memory words per histogram bin: 32 (one per lane, <= 256 bins) or 1
+    int tab_bias;          // the strand sums of the table path are (true sum - tab_bias): c_fix - half
     int c_fix;             // moment centre, fixed point
     int sh;                // kexp - 18: moment rounding shift
     int half;              // 1 << (sh - 1) (0 when sh == 0)
@@ -206,6 +232,10 @@ struct StatsParams {
     double thr;
 };
 
+// the histogram edges are usable with this model's fixed-point scores: (score - lower edge) of
+// every score the table path can produce fits an int32, and so does the range
+bool cgbk_hist_range_ok(const cgbk_model* mdl, double hist_lo, double hist_hi);
+
 StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist_hi, int n_bins,
                               unsigned long long* d_hist, int* plane);
 
@@ -213,6 +243,11 @@ void set_stats_threshold(StatsParams* sp, const cgbk_model* mdl, double thr, int
 
 cudaError_t launch_fast_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
                               int L, int grid, const StatsParams& sp, cudaStream_t st);
+// MODE 3 / 4: no score plane, no bin clamps (chosen by the two launchers above when they apply)
+cudaError_t launch_fast_stats_lean(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
+                                   int L, int grid, const StatsParams& sp, cudaStream_t st);
+cudaError_t launch_fast_moments_lean(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
+                                     int L, int grid, const StatsParams& sp, cudaStream_t st);
 // the same without the histogram (MODE 2)
 cudaError_t launch_fast_moments(const cgbk_model* mdl, GenomeView g, SeqTable seqs, FastWork w,
                                 int L, int grid, const StatsParams& sp, cudaStream_t st);

@@ -90,26 +90,39 @@ static PipeLayout pipe_layout(int64_t n_bases, int n_regions, int m, int n_bins)
     return p;
 }
 
-// side stream + events of the chunked upload, one set per device, created on first use and
-// kept for the life of the process
+// side stream + events of the chunked upload: one set per (host thread, device), created on first
+// use and released when the thread ends.  Per thread, not per process: two host threads that drive
+// the same device through their own streams must not share the "scratch free" / "chunk arrived"
+// events (a record by one would replace what the other is about to wait on).
 #define PIPE_MAX_CHUNKS CGBK_MAX_TILE_RANGES
 struct PipeStreams {
     cudaStream_t copy = nullptr;
     cudaEvent_t ev[PIPE_MAX_CHUNKS + 2] = {};   // chunk c arrived | scratch free | promoter table arrived
 };
-static std::mutex g_pipe_mu;
-static PipeStreams* g_pipe[64] = {};
+struct PipeStreamSet {
+    PipeStreams* dev[64] = {};
+    ~PipeStreamSet() {
+        for (PipeStreams* p : dev) {
+            if (!p) continue;
+            // best effort: at process exit the context may already be gone
+            for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
+            if (p->copy) cudaStreamDestroy(p->copy);
+            delete p;
+        }
+        cudaGetLastError();
+    }
+};
+static thread_local PipeStreamSet g_pipe;
 
 static PipeStreams* pipe_streams(int device) {
-    if (device < 0 || device >= 64) return nullptr;
-    std::lock_guard<std::mutex> lock(g_pipe_mu);
-    if (g_pipe[device]) return g_pipe[device];
+    if (device < 0 || device >= 64) return nullptr;     // the caller has made `device` current
+    if (g_pipe.dev[device]) return g_pipe.dev[device];
     PipeStreams* p = new PipeStreams;
     bool ok = cudaStreamCreateWithFlags(&p->copy, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < PIPE_MAX_CHUNKS + 2; ++i)
         ok = cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { delete p; return nullptr; }
-    g_pipe[device] = p;
+    g_pipe.dev[device] = p;
     return p;
 }
 
@@ -186,6 +199,7 @@ static int pipeline_impl(cgbk_model* M, const PipeSource& src, int64_t n_bases,
                               (long long)scratch_bytes, (long long)P.total);
     if (!h_staging || staging_bytes < cgbk_pipeline_staging_bytes(n_regions))
         return cgbk_set_error(CGBK_ERR_INVALID, "staging buffer too small");
+    ON_DEVICE(M->device);
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* base = (unsigned char*)d_scratch;
     TRACE_DECL;

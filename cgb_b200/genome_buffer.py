@@ -236,13 +236,20 @@ class PackedGenome:
         return self._seqset
 
     def workspace(self, m, cand_cap):
-        """Device scratch for the tiled scans, cached per (m, cand_cap)."""
-        key = (int(m), int(cand_cap))
+        """Device scratch for the tiled scans of motif length ``m``: one buffer per length, grown to
+        the largest candidate capacity asked for so far and handed out whole for smaller requests
+        (the library only needs "at least" the size it reports).  A buffer that is replaced may
+        still be read by queued kernels: it is kept until the next replacement, by which time the
+        stream has moved past them (everything runs on the allocating stream)."""
+        key = int(m)
+        nbytes = int(_cabi.lib().cgbk_scan_workspace_bytes(self._seqset, int(m), int(cand_cap)))
         w = self._work.get(key)
-        if w is None:
-            nbytes = int(_cabi.lib().cgbk_scan_workspace_bytes(self._seqset, int(m), int(cand_cap)))
+        if w is None or w.numel() < nbytes:
+            self._retired = w
             w = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self._work = {key: w}
+            if len(self._work) >= 8:                       # many motif lengths over one genome: bound the cache
+                self._work.pop(next(iter(self._work)))
+            self._work[key] = w
         return w
 
     # --------------------------------------------------- packed on-disk form
