@@ -547,15 +547,17 @@ __global__ void __launch_bounds__(128) site_score_kernel(const double* __restric
             const int room = CGBK_SITE_QUEUE - qn;          // >= 256 - 7 * 31
             const long long base = sw.cand_off[t];
             int n_hits = 0;
+            int idx = off;                                  // rank (in the tile) of this lane's next candidate
             for (int chunk0 = 0; chunk0 < total; chunk0 += room) {
-                int idx = off;
+                // every flag bit is popped once: a lane resumes where the previous round stopped it
+                // (its candidates are consecutive ranks, rows and bits in position order)
+                const int limit = chunk0 + room;
 #pragma unroll
                 for (int r = 0; r < 5; ++r) {
-                    uint32_t word = words[r];
-                    while (word) {
-                        const int p = 31 - __clz(word);
-                        word &= ~(1u << p);
-                        if (idx >= chunk0 && idx < chunk0 + room) dq[idx - chunk0] = (unsigned short)window_of(r, p);
+                    while (words[r] && idx < limit) {
+                        const int p = 31 - __clz(words[r]);
+                        words[r] &= ~(1u << p);
+                        dq[idx - chunk0] = (unsigned short)window_of(r, p);
                         ++idx;
                     }
                 }

@@ -112,3 +112,41 @@ def test_chunk_sharded_two_gpus():
         assert bstats[k, _cabi.BG_N] == len(bk) == bhist[k].sum()
         assert abs(bstats[k, _cabi.BG_MEAN] - bk.mean()) < 1e-6 and abs(bstats[k, _cabi.BG_STD] - bk.std()) < 1e-6
         assert bcounts[k] == len(c_oracle.scan_hits(omk, seq, bthr[k])[0])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_devices_from_one_process(lexa, lexa_weights):
+    """One host process driving two GPUs through the C ABI (the per-device kernel attributes,
+    multiprocessor counts and pipeline streams are keyed by device; every entry point runs on its
+    handle's device whatever device is current): same numbers on both, equal to the oracle."""
+    from cgb_b200 import PackedGenome, PSSMModel, SiteCollection, _cabi
+    from cgb_b200 import motif_batch as mb
+    from oracle import c_oracle, np_oracle as O
+    sites = [mo["sites"] for mo in lexa["motifs"]]
+    w = lexa_weights["site_count"]
+    om = O.OracleModel(sites, w)
+    seq = O.synthetic_genome(300_000, 5, n_frac=0.001)
+    thr = om.threshold() - 2.0
+    ep, es, ev = c_oracle.scan_hits(om, seq, thr)
+    _, _, b = c_oracle.score_seq(om, seq)
+    starts = np.arange(200, 290000, 9000)
+    results = []
+    torch.cuda.set_device(0)                      # stays current: device 1 is reached through its handles
+    for d in (1, 0, 1):
+        dev = torch.device("cuda", d)
+        M = PSSMModel([SiteCollection(s) for s in sites], w, device=dev)
+        g = PackedGenome.from_sequences([seq], dev)
+        _, pos, strand, score = M.scan_hits(g, thr)
+        M.fit_background(g)
+        post = M.binding_probabilities(g, starts, starts + 350, 0.03, 1 / 350.0).cpu().numpy()
+        p2, st2, h2 = M.regulation_pipeline(seq, starts, starts + 350, 0.03, 1 / 350.0)
+        res = mb.scan_batch([M], g, [thr], n_bins=64)
+        assert torch.cuda.current_device() == 0
+        assert np.array_equal(pos, ep) and np.array_equal(strand, es) and np.array_equal(score, ev)
+        assert abs(M._mu_bg - b.mean()) < 1e-6 and abs(M._std_bg - b.std()) < 1e-6
+        assert int(h2.sum()) == len(b) and np.max(np.abs(p2 - post)) < 1e-9
+        gp, gs, gv = mb.unpack_hits(res["hits"][0])
+        assert len(gp) == len(ep)
+        results.append((post, M._mu_bg, M._std_bg))
+    for post, mu, sd in results[1:]:
+        assert np.array_equal(post, results[0][0]) and mu == results[0][1] and sd == results[0][2]
