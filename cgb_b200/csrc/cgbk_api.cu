@@ -291,6 +291,7 @@ extern "C" int cgbk_pack_ascii(const uint8_t* d_ascii, int64_t n, int64_t dst_of
                               (long long)n, (long long)dst_off, (long long)cap_bases);
     if ((n > 0 && !d_ascii) || !d_bases2 || !d_amb || !d_lower)
         return cgbk_set_error(CGBK_ERR_INVALID, "NULL device pointer");
+    ON_DEVICE(cgbk_device_of(d_bases2));        // no handle: run where the planes live
     CUDA_TRY(launch_pack(d_ascii, n, dst_off, d_bases2, d_amb, d_lower, (cudaStream_t)stream));
     return CGBK_OK;
 }
@@ -677,7 +678,7 @@ extern "C" int cgbk_seqset_create(const int64_t* seq_off, const int64_t* seq_len
         if (i > 0 && seq_off[i] < seq_off[i - 1] + seq_len[i - 1])
             return cgbk_set_error(CGBK_ERR_INVALID, "sequence %d overlaps its predecessor", i);
     }
-    CUDA_TRY(cudaSetDevice(device));
+    ON_DEVICE(device);
     cgbk_seqset* S = (cgbk_seqset*)calloc(1, sizeof(cgbk_seqset));
     S->n_seq = n_seq; S->device = device;
     S->h_off = (int64_t*)malloc(sizeof(int64_t) * n_seq);
@@ -1116,12 +1117,14 @@ extern "C" int cgbk_background_stats_regions(const cgbk_model* M, const cgbk_gen
 
 extern "C" int cgbk_background_finalize(double* d_stats, void* stream) {
     if (!d_stats) return cgbk_set_error(CGBK_ERR_INVALID, "NULL stats");
+    ON_DEVICE(cgbk_device_of(d_stats));
     CUDA_TRY(launch_bg_finalize(nullptr, 0, d_stats, 1, (cudaStream_t)stream));
     return CGBK_OK;
 }
 
 extern "C" int cgbk_background_finalize_batch(double* d_stats, int n_records, void* stream) {
     if (!d_stats || n_records < 0) return cgbk_set_error(CGBK_ERR_INVALID, "bad argument");
+    ON_DEVICE(cgbk_device_of(d_stats));
     if (n_records > 0) CUDA_TRY(launch_bg_finalize_batch(d_stats, n_records, (cudaStream_t)stream));
     return CGBK_OK;
 }
@@ -1267,17 +1270,23 @@ extern "C" int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cg
                 sp2.cand_cap = cand_cap;
                 sp2.scan_tmp = (unsigned char*)d_work + lay.off_scan;
                 sp2.scan_tmp_bytes = lay.scan_bytes;
+                // (profiling: pair n_models + k brackets model k's site pass)
+                if (g_prof_on == 2) CUDA_TRY(prof_pair_event(n_models + k, 0, st));
                 CUDA_TRY(launch_site_pass(M, gv, tab, w, sp2, L, thresholds[k], flags, st));
+                if (g_prof_on == 2) CUDA_TRY(prof_pair_event(n_models + k, 1, st));
                 launches += 3;          // score, emit, finish (+ two library prefix sums)
             }
         } else {
-            if (g_prof_on == 2) { CUDA_TRY(prof_pair_event(k, 0, st)); CUDA_TRY(prof_pair_event(k, 1, st)); }
+            if (g_prof_on == 2) {
+                CUDA_TRY(prof_pair_event(k, 0, st)); CUDA_TRY(prof_pair_event(k, 1, st));
+                if (thresholds) { CUDA_TRY(prof_pair_event(n_models + k, 0, st)); CUDA_TRY(prof_pair_event(n_models + k, 1, st)); }
+            }
             CUDA_TRY(launch_bg_finalize(nullptr, 0, sp.d_stats, 1, st));    // n = 0, mean = std = NaN
             ++launches;
         }
         tiles_total += n_tiles;
     }
-    g_prof_pairs = g_prof_on == 2 ? n_models : 0;
+    g_prof_pairs = g_prof_on == 2 ? (thresholds ? 2 * n_models : n_models) : 0;
     PROF_STOP(st);
     g_launch_info[0] = launches; g_launch_info[1] = tiles_total; g_launch_info[2] = 0;
     return CGBK_OK;

@@ -113,6 +113,15 @@ struct DeviceGuard {
     }
     ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
 };
+// device that owns a device pointer (entry points without a handle run where their buffers live);
+// the current device when the pointer is unknown to the runtime
+static inline int cgbk_device_of(const void* d_ptr) {
+    cudaPointerAttributes at;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (!d_ptr || cudaPointerGetAttributes(&at, d_ptr) != cudaSuccess) { cudaGetLastError(); return cur; }
+    return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? at.device : cur;
+}
 #define ON_DEVICE(dev)                                                    \
     DeviceGuard _guard(dev);                                              \
     if (_guard.err != cudaSuccess) return cgbk_check_cuda(_guard.err, "selecting the handle's device")

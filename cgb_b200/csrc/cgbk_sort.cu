@@ -29,6 +29,7 @@ extern "C" int cgbk_sort_hits(uint64_t* d_hits8, int64_t n, void* d_tmp, int64_t
     if (!d_hits8 || !d_tmp || tmp_bytes < cgbk_sort_hits_workspace_bytes(n))
         return cgbk_set_error(CGBK_ERR_INVALID, "sort workspace of %lld bytes is smaller than the %lld required",
                               (long long)tmp_bytes, (long long)cgbk_sort_hits_workspace_bytes(n));
+    ON_DEVICE(cgbk_device_of(d_hits8));
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* alt = (unsigned long long*)d_tmp;
     void* cub_tmp = (unsigned char*)d_tmp + align256(8 * n);

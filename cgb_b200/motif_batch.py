@@ -129,7 +129,7 @@ def expected_hits(model, n_windows):
 
 
 def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, revseq_order=True,
-               hit_cap=None, to_host=True, sink=None, recycle=False, kernel_ms=None):
+               hit_cap=None, to_host=True, sink=None, recycle=False, kernel_ms=None, site_ms=None):
     """Background record and thresholded sites of every model over ``genome`` (a PackedGenome).
 
     ``thresholds``: ``"patser"`` (each model's own, pssm_model.py:72-77), a sequence of floats, or
@@ -152,7 +152,8 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
     on the device would take each sub-batch's sorted lists before the next overwrites them; the
     benchmark's device-resident leg).
     ``kernel_ms``: float array [K]; with ``_cabi.profile_enable(2)`` every model's scan-kernel time
-    (CUDA events around the launch) is ADDED to it."""
+    (CUDA events around the launch) is ADDED to it; ``site_ms`` likewise the time of every model's
+    site pass (candidate re-score + ordered emission)."""
     from .pssm_model import prepare_thresholds
     models = list(models)
     K = len(models)
@@ -303,6 +304,8 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
         ctr_out[i:i + n_done] = ctr[:n_done]
         if kernel_ms is not None and n_done:
             kernel_ms[i:i + n_done] += np.array(_cabi.profile_batch_ms(n_done))
+        if site_ms is not None and n_done and want_hits:
+            site_ms[i:i + n_done] += np.array(_cabi.profile_batch_ms(2 * n))[n:n + n_done]
         if want_hits and n_done:
             cum = np.concatenate([[0], np.cumsum(ctr[:n_done, _cabi.CTR_HITS])]).astype(np.int64)
             used = int(cum[-1])

@@ -380,9 +380,10 @@ int cgbk_last_launch_info(int64_t* out3);
  * event and returns the elapsed milliseconds of the calling thread's last scan. */
 int cgbk_profile_enable(int on);
 int cgbk_profile_last_ms(float* ms);
-/* on == 2: cgbk_scan_batch also brackets every model's scan kernel with its own event pair;
- * cgbk_profile_batch_ms returns the n first models' kernel times of the calling thread's last
- * cgbk_scan_batch (synchronises on the events). */
+/* on == 2: cgbk_scan_batch also brackets every model's scan kernel with its own event pair and,
+ * when sites are searched, every model's site pass with another; cgbk_profile_batch_ms returns the
+ * n first times of the calling thread's last cgbk_scan_batch (synchronises on the events): the
+ * scan kernels of models 0 .. n_models - 1, then their site passes. */
 int cgbk_profile_batch_ms(float* ms, int n);
 
 #ifdef __cplusplus

@@ -24,7 +24,6 @@ def main():
     from cgb_b200 import motif_batch as mb
     ap = argparse.ArgumentParser()
     ap.add_argument("--bp", type=int, default=1_000_000_000)
-    ap.add_argument("--pick", type=int, default=14)
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -32,35 +31,35 @@ def main():
     Ms = [PSSMModel([SiteCollection(s)], [1.0], device=dev) for s in sl]
     prepare_thresholds(Ms)
     e = np.array([mb.expected_hits(M, a.bp) for M in Ms])
-    order = np.argsort(e)
-    picks = [order[int(round(x))] for x in np.linspace(0, len(order) - 1, a.pick)]
     g = PackedGenome([a.bp], dev)
     g.pack_into(0, bench.generate_bases(0, a.bp, dev))
     torch.cuda.synchronize()
+    batch = mb.ModelBatch(Ms, dev)
+    thr = [M.threshold() for M in Ms]
+    cap = int(min(e.sum() * 1.3, 1.5e9))
     _cabi.profile_enable(2)
-    rows = []
-    for k in picks:
-        M = Ms[k]
-        batch = mb.ModelBatch([M], dev)
-        cap = int(e[k] * 1.3 + 1e6)
-        acc = np.zeros(1)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        reps = 4
-        for it in range(2 + reps):
-            if it == 2:
-                acc[:] = 0
-                ev[0].record()
-            res = mb.scan_batch([M], g, [M.threshold()], n_bins=256, to_host=False, recycle=True, hit_cap=cap,
-                                kernel_ms=acc)
-        ev[1].record()
-        torch.cuda.synchronize()
-        step = ev[0].elapsed_time(ev[1]) / reps
-        kern = float(acc[0]) / reps
-        rows.append({"m": M.length, "hits": int(res["hits"][0]), "cands_per_tile": round(float(e[k]) / a.bp * 4064, 2),
-                     "scan_ms": round(kern, 3), "site_pass_ms": round(step - kern, 3)})
-        print(json.dumps(rows[-1]))
-        del batch
-        mb.release_buffers(dev)
+    kern, site = np.zeros(len(Ms)), np.zeros(len(Ms))
+    reps = 2
+    for it in range(1 + reps):
+        if it == 1:
+            kern[:] = 0
+            site[:] = 0
+        res = mb.scan_batch(Ms, g, thr, n_bins=256, to_host=False, recycle=True, hit_cap=cap, kernel_ms=kern,
+                            site_ms=site)
+    kern /= reps
+    site /= reps
+    hits = np.array(res["hits"], dtype=np.float64)
+    dens = hits / a.bp * 4064
+    print(json.dumps({"motifs": len(Ms), "scan_ms_total": round(float(kern.sum()), 1),
+                      "site_pass_ms_total": round(float(site.sum()), 1), "hits": float(hits.sum())}))
+    edges = [0, 1, 4, 16, 32, 64, 256, 1024, 4097]
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        sel = (dens >= lo) & (dens < hi)
+        if sel.any():
+            print(json.dumps({"sites_per_tile": "[%d, %d)" % (lo, hi), "motifs": int(sel.sum()),
+                              "hits": float(hits[sel].sum()), "site_pass_ms_sum": round(float(site[sel].sum()), 2),
+                              "site_pass_ms_mean": round(float(site[sel].mean()), 4),
+                              "ns_per_hit": round(float(site[sel].sum() * 1e6 / max(hits[sel].sum(), 1)), 4)}))
 
 
 if __name__ == "__main__":
