@@ -149,7 +149,7 @@ def ncu_traffic(kernel_key):
     e = d.get(kernel_key)
     if not e:
         return None, None
-    return e.get("dram_bytes_per_launch"), {k: e.get(k) for k in ("captured_at_commit", "workload", "source")}
+    return e.get("dram_bytes_per_base"), {k: e.get(k) for k in ("captured_at_commit", "workload", "source", "note")}
 
 
 def spread(ms):
@@ -511,7 +511,10 @@ def run_ours(args):
                 by_g["G%d" % G] = {"motifs": int(sel.sum()), "kernel_ms_mean": float(kern_ms[sel].mean()),
                                    "bp_motif_per_s": float(win_rank[sel].sum() / t),
                                    "issue_frac": float((2.0 * m_len[sel] * win_rank[sel]).sum() / t / issue_peak)}
-        traffic, traffic_src = ncu_traffic("fused_scan_1gbp_m22")
+        # DRAM bytes of one scan launch: measured per base under ncu (1 Gbp launches), times this
+        # rank's shard (the kernel streams the shard once, whatever its size)
+        per_base, traffic_src = ncu_traffic("fused_scan_1gbp")
+        traffic = per_base * float(hi - lo) if per_base is not None else None
         roofline = {
             "bound": "issue", "kernel": "fast_scan_kernel<G, hist+moments+candidates> (fused scan), all %d motifs" % K,
             "achieved": la_rank / (kern_rank * 1e-3), "peak": issue_peak, "unit": "lookup-add/s",
@@ -525,6 +528,7 @@ def run_ours(args):
             "site_pass": "per motif: prefix sums of the scan's per-tile candidate counts, exact float64 re-score of "
                          "the flagged windows, ordered compaction into the site list (CUDA events around the pass)",
             "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": 0.25 * float(hi - lo),
             "hbm": {"achieved": float(np.nansum(0.25 * win_rank * (~np.isnan(kern_ms)))) / (kern_rank * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s",
                     "frac": float(np.nansum(0.25 * win_rank * (~np.isnan(kern_ms)))) / (kern_rank * 1e-3) / 1e9 / hbm_peak,
