@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libcgbk.so")
 SOURCES = ["cgbk_fast_stats.cu", "cgbk_fast_lean.cu", "cgbk_fast_moments.cu", "cgbk_fast_lean_moments.cu", "cgbk_fast_filter.cu", "cgbk_api.cu", "cgbk_exact.cu",
-           "cgbk_pipeline.cu", "cgbk_sort.cu", "cgbk_hostpack.cu"]
+           "cgbk_pipeline.cu", "cgbk_sort.cu", "cgbk_hostpack.cu", "cgbk_genbank.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # exact kernels must not contract a*b+c into FMA: they restate CPU double arithmetic
 EXTRA = {"cgbk_exact.cu": ["-fmad=false"], "cgbk_fast_stats.cu": ["-fmad=false"],

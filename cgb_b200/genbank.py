@@ -34,14 +34,81 @@ _SPAN = re.compile(r"^(?:[A-Za-z0-9_.]+:)?[<>]?(\d+)(?:\.\.[<>]?(\d+)|\.[<>]?(\d
 _UPPER = bytes.maketrans(b"abcdefghijklmnopqrstuvwxyz", b"ABCDEFGHIJKLMNOPQRSTUVWXYZ")
 
 
+class FeatureIndex(object):
+    """Structural index of a feature table built by the library's host code
+    (``cgbk_genbank_index``: one C pass instead of a Python walk over every line): per feature the
+    key, the parsed location and its qualifier range; per qualifier the key and the RAW value span.
+    Values are decoded on demand -- the gene table needs five qualifiers out of dozens."""
+
+    def __init__(self, block):
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _cabi
+        self.block = block                                   # bytes of the table (no FEATURES header line)
+        lines = block.count(b"\n") + 2
+        feat = np.empty((lines, 10), dtype=np.int32)
+        qual = np.empty((lines, 5), dtype=np.int32)
+        nf, nq = C.c_int32(), C.c_int32()
+        _cabi.check(_cabi.lib().cgbk_genbank_index(block, len(block), feat.ctypes.data, lines, qual.ctypes.data,
+                                                   lines, C.byref(nf), C.byref(nq)))
+        self.feat = feat[:nf.value]
+        self.qual = qual[:nq.value]
+        self._types = None
+
+    def __len__(self):
+        return len(self.feat)
+
+    @property
+    def types(self):
+        if self._types is None:
+            b = self.block
+            self._types = [b[o:o + n].decode("ascii", "replace") for o, n in self.feat[:, :2].tolist()]
+        return self._types
+
+    def qualifier_values(self, k, key):
+        """Decoded values of qualifier ``key`` (bytes) of feature ``k``, in file order; ``None`` when
+        the feature has no such qualifier."""
+        b = self.block
+        q0, qn = int(self.feat[k, 4]), int(self.feat[k, 5])
+        out = None
+        for ko, kn, vo, vn, _ in self.qual[q0:q0 + qn].tolist():
+            if kn == len(key) and b[ko:ko + kn] == key:
+                if out is None:
+                    out = []
+                out.append("" if vn < 0 else _clean_value(key.decode("ascii"), b[vo:vo + vn].decode("ascii", "replace")))
+        return out
+
+    def feature(self, k):
+        b = self.block
+        f = self.feat[k].tolist()
+        quals = {}
+        for ko, kn, vo, vn, _ in self.qual[f[4]:f[4] + f[5]].tolist():
+            key = b[ko:ko + kn].decode("ascii", "replace")
+            if vn < 0:
+                quals.setdefault(key.strip(), []).append("")
+            else:
+                quals.setdefault(key, []).append(_clean_value(key, b[vo:vo + vn].decode("ascii", "replace")))
+        return Feature(self.types[k], f[6], f[7], f[8], bool(f[9]), quals)
+
+
 class GenBankRecord(object):
-    """One LOCUS ... // entry."""
+    """One LOCUS ... // entry.  ``features`` may be given as a list of :class:`Feature` or as a
+    :class:`FeatureIndex` (then the Feature tuples are only built when somebody asks for them)."""
 
     def __init__(self, accession, description, sequence, features):
         self.id = accession
         self.description = description
         self.sequence = sequence            # bytes, upper case
-        self.features = features            # [Feature]
+        self._index = features if isinstance(features, FeatureIndex) else None
+        self._features = None if self._index is not None else features
+
+    @property
+    def features(self):
+        if self._features is None:
+            self._features = [self._index.feature(k) for k in range(len(self._index))]
+        return self._features
 
     @property
     def length(self):
@@ -50,6 +117,8 @@ class GenBankRecord(object):
     def gene_table(self, seq_index=0):
         """``Chromid.genes`` (cgb/chromid.py:99-122) as a GeneTable with the annotation columns
         the reports use (locus_tag, gene name, product type, product, protein_id)."""
+        if self._index is not None and self._features is None:
+            return self._gene_table_from_index(seq_index)
         start, end, strand, index = [], [], [], []
         locus, name, ptype, product, protein = [], [], [], [], []
         k = 0
@@ -76,6 +145,164 @@ class GenBankRecord(object):
             k += 1
         return GeneTable(start, end, strand, self.length, seq_index=seq_index, locus_tag=locus,
                          protein_id=protein, product=product, index=index, name=name, product_type=ptype)
+
+
+    def _gene_table_from_index(self, seq_index):
+        """The same selection over the feature index: the qualifier keys are matched with numpy
+        over the whole table, and only the values of ``gene`` features and of the feature after
+        each are decoded."""
+        import numpy as np
+        ix = self._index
+        feat, qual, b = ix.feat, ix.qual, ix.block
+        nf = len(feat)
+        raw = np.frombuffer(b, dtype=np.uint8)
+
+        def spans_equal(off, length, word):
+            """mask over spans: the span text equals ``word`` (bytes)."""
+            m = length == len(word)
+            idx = np.nonzero(m)[0]
+            if len(idx):
+                cols = off[idx][:, None].astype(np.int64) + np.arange(len(word))
+                m[idx] = (raw[cols] == np.frombuffer(word, dtype=np.uint8)).all(axis=1)
+            return m
+
+        is_gene = spans_equal(feat[:, 0], feat[:, 1], b"gene")
+        feature_of_qual = np.repeat(np.arange(nf), feat[:, 5])
+
+        class ByFeature(object):
+            """feature -> [qualifier rows] of one key, file order (first row and count per feature as
+            arrays; the rare repeated key is collected on demand)."""
+
+            def __init__(self, word):
+                rows = np.nonzero(spans_equal(qual[:, 0], qual[:, 1], word))[0]
+                f = feature_of_qual[rows]
+                self.count = np.bincount(f, minlength=nf)
+                self.first = np.full(nf, -1, dtype=np.int64)
+                self.first[f[::-1]] = rows[::-1]                 # the earliest row wins
+                self.rows, self.f = rows, f
+
+            def get(self, i):
+                c = self.count[i]
+                if c == 0:
+                    return None
+                if c == 1:
+                    return [int(self.first[i])]
+                return self.rows[self.f == i].tolist()
+
+        q_locus, q_gene, q_product, q_protein = (ByFeature(w) for w in (b"locus_tag", b"gene", b"product",
+                                                                       b"protein_id"))
+        qv = qual[:, 2:4].tolist()
+        simple = qual[:, 4].tolist()
+
+        def value(q, key):
+            vo, vn = qv[q]
+            if vn < 0:
+                return ""
+            r = b[vo:vo + vn]
+            if simple[q]:                               # one line, quoted, no doubled quote: nothing to clean
+                return r[1:-1].decode("ascii", "replace")
+            return _clean_value(key, r.decode("ascii", "replace"))
+
+        genes = np.nonzero(is_gene[:nf - 1])[0]                    # the last feature is never looked at
+        fast = self._gene_table_simple(seq_index, genes, feat, qual, raw, b, q_locus, q_gene, q_product, q_protein)
+        if fast is not None:
+            return fast
+        start, end, strand, index = [], [], [], []
+        locus, name, ptype, product, protein = [], [], [], [], []
+        k = 0
+        loc = feat[:, 6:10].tolist()
+        for i in genes.tolist():
+            qs = q_locus.get(i)
+            if qs is None:
+                raise KeyError("locus_tag")                       # as in the reference
+            tags = [value(q, "locus_tag") for q in qs]
+            nq = q_locus.get(i + 1)
+            follows = nq is not None and tags == [value(q, "locus_tag") for q in nq]
+            st, en, sd, compound = loc[i]
+            if compound:
+                k += 1
+                continue
+            assert len(tags) == 1                                 # Gene.locus_tag, gene.py:178
+            start.append(st); end.append(en); strand.append(sd); index.append(k)
+            locus.append(tags[0])
+            g = q_gene.get(i)
+            name.append(value(g[0], "gene") if g is not None else tags[0])
+            if follows:
+                o, n = feat[i + 1, 0], feat[i + 1, 1]
+                pt = b[o:o + n].decode("ascii", "replace")
+                pr = q_product.get(i + 1)
+                product.append(value(pr[0], "product") if pr is not None else "")
+                pid = q_protein.get(i + 1) if pt == "CDS" else None
+                protein.append(value(pid[0], "protein_id") if pid is not None else "")
+            else:
+                pt = ""
+                product.append("")
+                protein.append("")
+            ptype.append(pt)
+            k += 1
+        return GeneTable(start, end, strand, self.length, seq_index=seq_index, locus_tag=locus,
+                         protein_id=protein, product=product, index=index, name=name, product_type=ptype)
+
+
+    def _gene_table_simple(self, seq_index, genes, feat, qual, raw, b, q_locus, q_gene, q_product, q_protein):
+        """The whole table with array operations, for the layout every annotation pipeline writes:
+        each needed qualifier at most once per feature, its value quoted on one line with no
+        doubled quote.  Returns None when any needed value is not that simple (the caller then
+        walks the genes one by one)."""
+        import numpy as np
+        if len(genes) == 0:
+            return None
+        nxt = genes + 1
+        cl = q_locus.count
+        if (cl[genes] != 1).any() or (cl[nxt] > 1).any():
+            return None
+        first = {"l": q_locus.first, "g": q_gene.first, "p": q_product.first, "i": q_protein.first}
+        for cnt, idx in ((q_gene.count, genes), (q_product.count, nxt), (q_protein.count, nxt)):
+            if (cnt[idx] > 1).any():
+                return None
+        rows = np.concatenate([first["l"][genes], first["l"][nxt], first["g"][genes], first["p"][nxt], first["i"][nxt]])
+        rows = rows[rows >= 0]
+        if not qual[rows, 4].all():                   # the indexer marks one-line quoted values without inner quotes
+            return None
+
+        def strings(q):
+            """decoded values of qualifier rows ``q`` (-1: no such qualifier -> None)"""
+            off = (qual[q, 2].astype(np.int64) + 1).tolist()
+            ln = (qual[q, 3].astype(np.int64) - 2).tolist()
+            out = b"\x00".join([b[o:o + n] for o, n in zip(off, ln)]).decode("ascii", "replace").split("\x00")
+            return [v if r >= 0 else None for v, r in zip(out, q.tolist())]
+
+        tags = strings(first["l"][genes])
+        tags_n = strings(first["l"][nxt])
+        follows = np.array([a == c for a, c in zip(tags, tags_n)], dtype=bool)
+        keep = feat[genes, 9] == 0                                    # one contiguous span
+        types_n = [b[o:o + n].decode("ascii", "replace") for o, n in feat[nxt, :2].tolist()]
+        gname = strings(first["g"][genes])
+        prod = strings(first["p"][nxt])
+        pid = strings(first["i"][nxt])
+        sel = np.nonzero(keep)[0].tolist()
+        fl = follows.tolist()
+        ptype = [types_n[j] if fl[j] else "" for j in sel]
+        return GeneTable(feat[genes, 6][keep].tolist(), feat[genes, 7][keep].tolist(), feat[genes, 8][keep].tolist(),
+                         self.length, seq_index=seq_index, locus_tag=[tags[j] for j in sel],
+                         protein_id=[(pid[j] or "") if fl[j] and types_n[j] == "CDS" else "" for j in sel],
+                         product=[(prod[j] or "") if fl[j] else "" for j in sel], index=sel,
+                         name=[gname[j] if gname[j] is not None else tags[j] for j in sel], product_type=ptype)
+
+
+def _clean_value(key, value):
+    """Raw qualifier value (continuation lines and quotes still in it) -> the string Biopython
+    reports: lines joined (with a blank; /translation without), outer quotes off, "" -> "."""
+    if "\n" in value:
+        value = _CONTINUATION.sub("" if key == "translation" else " ", value)
+    value = value.rstrip()
+    if value.startswith('"'):
+        value = value[1:-1] if value.endswith('"') and len(value) >= 2 else value[1:]
+        if '""' in value:
+            value = value.replace('""', '"')
+    if key == "translation" and " " in value:
+        value = value.replace(" ", "")
+    return value
 
 
 def parse_location(text):
@@ -156,6 +383,18 @@ def _parse_features(block):
     return feats
 
 
+def _index_or_parse(feat_block):
+    """The C index of the table (libcgbk host code, no GPU needed); the pure-Python walk only when
+    the library has not been built (the parser is host logic and must stay importable then)."""
+    try:
+        return FeatureIndex(feat_block)
+    except Exception as exc:                                  # library missing / too old
+        from . import _cabi
+        if isinstance(exc, _cabi.CgbkError) or isinstance(exc, (OSError, AttributeError)):
+            return _parse_features(feat_block.decode("ascii", "replace"))
+        raise
+
+
 def parse(text):
     """All records of a GenBank flat file (``str`` or ``bytes``).  The three big blocks of a
     record (header, feature table, ORIGIN) are cut out with ``find`` and the sequence is
@@ -195,15 +434,15 @@ def parse(text):
                     version = rest.split()[0]
             elif section == "DEFINITION":
                 definition.append(line.strip())
-        feat_block = ""
+        feat_block = b""
         if f0 >= 0:
-            block = rec[f0 + 1:o0 if o0 > f0 else len(rec)].decode("ascii", "replace")
-            nl = block.find("\n")
-            feat_block = block[nl + 1:] if nl >= 0 else ""       # drop the FEATURES header line
+            block = rec[f0 + 1:o0 if o0 > f0 else len(rec)]
+            nl = block.find(b"\n")
+            feat_block = block[nl + 1:] if nl >= 0 else b""      # drop the FEATURES header line
             # anything after the table that starts in column 1 (CONTIG, BASE COUNT, ...) is not a
             # feature: feature lines are indented, so the table ends at the first such line
             cut = len(feat_block)
-            for word in ("\nCONTIG", "\nBASE COUNT", "\nWGS", "\nCOMMENT"):
+            for word in (b"\nCONTIG", b"\nBASE COUNT", b"\nWGS", b"\nCOMMENT"):
                 k = feat_block.find(word)
                 if 0 <= k < cut:
                     cut = k + 1
@@ -217,7 +456,7 @@ def parse(text):
         if description.endswith("."):
             description = description[:-1]
         records.append(GenBankRecord(version or accession or locus_name, description, sequence,
-                                     _parse_features(feat_block)))
+                                     _index_or_parse(feat_block)))
     return records
 
 

@@ -134,6 +134,23 @@ int cgbk_pack_host(const uint8_t* ascii, int64_t n_bases, uint32_t* bases2, uint
                    uint32_t* lower, int64_t cap_bases, int n_threads, int64_t* n_amb,
                    int64_t* n_lower);
 
+/* ---- GenBank feature table (host only) ---------------------------------------- */
+
+/* Structural index of a GenBank feature table (the text between the FEATURES header line and
+ * ORIGIN): what Biopython's SeqIO.read hands the reference as record.features
+ * (cgb/chromid.py:32-35,99-122), found in one C pass so that the host never walks the table line
+ * by line.  Offsets are relative to `block`.
+ *   feat[k][10] = key_off, key_len, loc_off, loc_len, q_first, q_count, start, end, strand, compound
+ *                 (start/end 0-based half-open, fuzzy ends dropped; compound = join/order/bond or
+ *                 unparsable: not one contiguous span)
+ *   qual[j][5]  = key_off, key_len, val_off, val_len, simple  (raw value, right-stripped:
+ *                 continuation lines and quotes still inside; val_len = -1 for a flag qualifier
+ *                 such as /pseudo; simple = 1 when the value is one line, quoted, with no quote
+ *                 inside: its text is then raw[1 .. val_len - 1))
+ * Nothing is written beyond the capacities; n_feat / n_qual always return the full counts. */
+int cgbk_genbank_index(const char* block, int64_t n, int32_t* feat, int32_t feat_cap, int32_t* qual,
+                       int32_t qual_cap, int32_t* n_feat, int32_t* n_qual);
+
 /* ---- handles ---------------------------------------------------------------- */
 
 /* logodds: host [m][4] float64, columns A,C,G,T (PSSMModel.pssm, pssm_model.py:47-50).
