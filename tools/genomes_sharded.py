@@ -30,6 +30,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--genomes", type=int, default=100)
     ap.add_argument("--bp", type=int, default=4_000_000)
+    ap.add_argument("--profile", action="store_true", help="cProfile of the timed loop on rank 0 (stderr)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
@@ -56,6 +57,11 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    prof = None
+    if args.profile and rank == 0:
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     t0 = time.perf_counter()
     n_hits = 0
     post_sum = 0.0
@@ -68,6 +74,10 @@ def main():
             post_sum += float(post.sum())
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(18)
     t = torch.tensor([dt, float(n_hits), float(len(mine))], dtype=torch.float64, device=dev)
     tmax = t.clone()
     if world > 1:
