@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import threading
 from functools import cached_property
 
 import numpy as np
@@ -590,21 +591,26 @@ class PSSMModel(TFBindingModel):
         # buffers, pointers and result views for this problem size are set up once and reused:
         # the per-call host work is argument marshalling + three small copies
         key = (n_bases, n, int(n_bins))
-        if plan is None or plan["key"] != key:
+        shared = _pipeline_buffers(self._dev())
+        if plan is None or plan["key"] != key or plan["scratch"] is not shared.get("scratch") or \
+                plan["host"] is not shared.get("host"):
             reuse_ptrs = False
             lib = _cabi.lib()
             dev = self._dev()
+            # device scratch and pinned result buffers are shared by all models of this thread on
+            # the device (a pipeline call returns synchronised, so nothing of the previous call is
+            # in flight): a run over many (genome, PSWM) pairs allocates them once, not per model
             need = int(lib.cgbk_pipeline_scratch_bytes(n_bases, n, self.length, n_bins))
-            scratch = getattr(self, "_pipe_scratch", None)
-            if scratch is None or scratch.numel() < need or scratch.device != dev:
-                scratch = torch.empty(need, dtype=torch.uint8, device=dev)
-                self._pipe_scratch = scratch
+            scratch = shared.get("scratch")
+            if scratch is None or scratch.numel() < need:
+                scratch = torch.empty(need + need // 8, dtype=torch.uint8, device=dev)
+                shared["scratch"] = scratch
             stage_bytes = int(lib.cgbk_pipeline_staging_bytes(n))
             host_need = stage_bytes + 8 * n + 64 + 8 * n_bins
-            host = getattr(self, "_pipe_host", None)
+            host = shared.get("host")
             if host is None or host.numel() < host_need:
-                host = torch.empty(host_need, dtype=torch.uint8).pin_memory()
-                self._pipe_host = host
+                host = torch.empty(host_need + host_need // 8, dtype=torch.uint8).pin_memory()
+                shared["host"] = host
             arr = host.numpy()
             hp = host.data_ptr()
             args = _cabi.PipelineArgs()
@@ -615,6 +621,7 @@ class PSSMModel(TFBindingModel):
             args.h_post, args.h_stats = hp + stage_bytes, hp + stage_bytes + 8 * n
             args.h_hist = (hp + stage_bytes + 8 * n + 64) if n_bins > 0 else None
             plan = {"key": key, "fn": lib.cgbk_regulation_pipeline_args, "args": args, "ref": C.addressof(args),
+                    "scratch": scratch, "host": host,
                     "post": arr[stage_bytes:stage_bytes + 8 * n].view(np.float64),
                     "stats": arr[stage_bytes + 8 * n:stage_bytes + 8 * n + 64].view(np.float64),
                     "hist": arr[stage_bytes + 8 * n + 64:stage_bytes + 8 * n + 64 + 8 * n_bins].view(np.uint64)}
@@ -641,6 +648,17 @@ class PSSMModel(TFBindingModel):
         self._dev_ms_bg = None                         # re-uploaded lazily by _require_estimator
         self._last_bg = None
         return post, stats, hist
+
+
+_PIPE_SHARED = threading.local()
+
+
+def _pipeline_buffers(dev):
+    """Per (host thread, device): the regulation pipeline's device scratch and pinned host block."""
+    d = getattr(_PIPE_SHARED, "by_device", None)
+    if d is None:
+        d = _PIPE_SHARED.by_device = {}
+    return d.setdefault(dev.index or 0, {})
 
 
 def prepare_thresholds(models, n_threads=0):

@@ -51,7 +51,12 @@ def main():
         rng = np.random.default_rng(gi)
         ws = [[1.0 / len(colls)] * len(colls), weights, rng.dirichlet([1.0] * len(colls)).tolist()]
         models.append([PSSMModel(colls, w, device=dev) for w in ws])
-    prepare_thresholds([M for ms in models for M in ms])
+    # tables of all models in ONE device block / one upload (cgbk_model_batch_create), thresholds by
+    # the threaded host DP
+    from cgb_b200 import motif_batch as mb
+    all_models = [M for ms in models for M in ms]
+    batch = mb.ModelBatch(all_models, dev)
+    prepare_thresholds(all_models)
     for M in models[0]:                                   # warm-up: context, allocator, tables
         M.regulation_pipeline(genomes[0], ps, pe, prior, alpha)
     torch.cuda.synchronize()
