@@ -57,18 +57,28 @@ __device__ __forceinline__ bool exact_window_bits(const GenomeView& g, const Exa
     const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
     const uint32_t maskm = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);
     double fs = 0.0, rs = 0.0;
-    const int m_lo = m < 16 ? m : 16;
     if (amb == 0) {
+        // Four positions per iteration, the window's 2-bit word shifted along by one byte: the
+        // look-up offsets come from immediate shifts of that byte ((code << 4) & 0x30 into the
+        // 64-byte row of a position).  The last block may run past the motif: rows j >= m hold
+        // +0.0 (the model block is zero filled), and s + 0.0 == s exactly, so the sums are the
+        // reference's left-to-right sums over j < m, bit for bit.
+        const char* tb = reinterpret_cast<const char*>(t->fr);
+        const int nblk = (m + 3) >> 2;
         if (!revseq) {
-#pragma unroll 4
-            for (int j = 0; j < m_lo; ++j) {
-                const double2 v = t->fr[j * 4 + ((xl >> (2 * j)) & 3)];
-                fs += v.x; rs += v.y;
-            }
-#pragma unroll 4
-            for (int j = 16; j < m; ++j) {
-                const double2 v = t->fr[j * 4 + ((xh >> (2 * (j - 16))) & 3)];
-                fs += v.x; rs += v.y;
+            uint32_t xw = xl;
+            for (int b = 0; b < nblk; ++b) {
+                if (b == 4) xw = xh;
+                const char* q = tb + b * 256;
+                const double2 v0 = *reinterpret_cast<const double2*>(q + ((xw << 4) & 0x30));
+                const double2 v1 = *reinterpret_cast<const double2*>(q + 64 + ((xw << 2) & 0x30));
+                const double2 v2 = *reinterpret_cast<const double2*>(q + 128 + (xw & 0x30));
+                const double2 v3 = *reinterpret_cast<const double2*>(q + 192 + ((xw >> 2) & 0x30));
+                fs += v0.x; rs += v0.y;
+                fs += v1.x; rs += v1.y;
+                fs += v2.x; rs += v2.y;
+                fs += v3.x; rs += v3.y;
+                xw >>= 8;
             }
         } else {
             // y_j = 3 - x_{m-1-j}: the reverse complement as a base string of its own (bit reversal
@@ -78,16 +88,19 @@ __device__ __forceinline__ bool exact_window_bits(const GenomeView& g, const Exa
             uint64_t y = __brevll(x);
             y = ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
             y = (~y) >> (64 - 2 * m);
-            const uint32_t yl = (uint32_t)y, yh = (uint32_t)(y >> 32);
-#pragma unroll 4
-            for (int j = 0; j < m_lo; ++j) {
-                fs += t->fr[j * 4 + ((xl >> (2 * j)) & 3)].x;
-                rs += t->fr[j * 4 + ((yl >> (2 * j)) & 3)].x;
-            }
-#pragma unroll 4
-            for (int j = 16; j < m; ++j) {
-                fs += t->fr[j * 4 + ((xh >> (2 * (j - 16))) & 3)].x;
-                rs += t->fr[j * 4 + ((yh >> (2 * (j - 16))) & 3)].x;
+            uint32_t xw = xl, yw = (uint32_t)y;
+            for (int b = 0; b < nblk; ++b) {
+                if (b == 4) { xw = xh; yw = (uint32_t)(y >> 32); }
+                const char* q = tb + b * 256;
+                fs += *reinterpret_cast<const double*>(q + ((xw << 4) & 0x30));
+                rs += *reinterpret_cast<const double*>(q + ((yw << 4) & 0x30));
+                fs += *reinterpret_cast<const double*>(q + 64 + ((xw << 2) & 0x30));
+                rs += *reinterpret_cast<const double*>(q + 64 + ((yw << 2) & 0x30));
+                fs += *reinterpret_cast<const double*>(q + 128 + (xw & 0x30));
+                rs += *reinterpret_cast<const double*>(q + 128 + (yw & 0x30));
+                fs += *reinterpret_cast<const double*>(q + 192 + ((xw >> 2) & 0x30));
+                rs += *reinterpret_cast<const double*>(q + 192 + ((yw >> 2) & 0x30));
+                xw >>= 8; yw >>= 8;
             }
         }
         f = fs; r = rs;

@@ -476,10 +476,10 @@ __global__ void __launch_bounds__(128) site_score_kernel(const double* __restric
     auto emit = [&](long long k, long long gpos, double f, double r) -> int {
         const float ff = (float)f, rf = (float)r;
         const bool hf = (double)ff >= thr, hr = (double)rf >= thr;
-        if (k < sp.cand_cap) {
-            sp.pairs[2 * k] = hf ? cgbk_pack_hit8(gpos, 0, __float_as_uint(ff)) : CGBK_NO_SITE;
-            sp.pairs[2 * k + 1] = hr ? cgbk_pack_hit8(gpos, 1, __float_as_uint(rf)) : CGBK_NO_SITE;
-        }
+        if (k < sp.cand_cap)                  // both records in one 16-byte store
+            *reinterpret_cast<ulonglong2*>(sp.pairs + 2 * k) =
+                make_ulonglong2(hf ? cgbk_pack_hit8(gpos, 0, __float_as_uint(ff)) : CGBK_NO_SITE,
+                                hr ? cgbk_pack_hit8(gpos, 1, __float_as_uint(rf)) : CGBK_NO_SITE);
         return (hf ? 1 : 0) + (hr ? 1 : 0);
     };
 
