@@ -591,15 +591,16 @@ class PSSMModel(TFBindingModel):
         # buffers, pointers and result views for this problem size are set up once and reused:
         # the per-call host work is argument marshalling + three small copies
         key = (n_bases, n, int(n_bins))
-        shared = _pipeline_buffers(self._dev())
-        if plan is None or plan["key"] != key or plan["scratch"] is not shared.get("scratch") or \
-                plan["host"] is not shared.get("host"):
+        if plan is None or plan["key"] != key:
             reuse_ptrs = False
             lib = _cabi.lib()
             dev = self._dev()
+            shared = _pipeline_buffers(dev)
             # device scratch and pinned result buffers are shared by all models of this thread on
             # the device (a pipeline call returns synchronised, so nothing of the previous call is
-            # in flight): a run over many (genome, PSWM) pairs allocates them once, not per model
+            # in flight): a run over many (genome, PSWM) pairs allocates them once, not per model.
+            # A plan keeps the buffers it was made with alive, so a later, larger request of another
+            # model (which replaces the shared ones) leaves this plan valid.
             need = int(lib.cgbk_pipeline_scratch_bytes(n_bases, n, self.length, n_bins))
             scratch = shared.get("scratch")
             if scratch is None or scratch.numel() < need:

@@ -33,9 +33,16 @@ def main():
     gs, ge, gstrand = bench.gene_layout(bp, bench.N_GENES)
     gt = GeneTable(gs, ge, gstrand, bp)
     ps, pe = gt.promoter_region_location(bench.UP, bench.DOWN)
+    src = pinned
+    if "--packed" in sys.argv:
+        from cgb_b200 import HostPackedGenome
+        src = HostPackedGenome.from_ascii(pinned)
+    import time
     for i in range(6):
         sys.stderr.write("--- call %d\n" % i)
-        M.regulation_pipeline(pinned, ps, pe, prior, alpha)
+        t0 = time.perf_counter()
+        M.regulation_pipeline(src, ps, pe, prior, alpha)
+        sys.stderr.write("python call %.1f us\n" % ((time.perf_counter() - t0) * 1e6))
 
 
 if __name__ == "__main__":
