@@ -304,3 +304,33 @@ def test_models_on_two_devices_from_one_process(lexa, lexa_weights):
         assert np.array_equal(pos, ep) and np.array_equal(strand, es) and np.array_equal(score, ev)
         gp, st, sc = mb.unpack_hits(res["hits"][0])
         assert np.array_equal(gp, ep) and np.array_equal(sc, ev)
+
+
+def test_histogram_modes_agree_and_narrow_range_clamps(lexa, lexa_weights):
+    """The lean scan (no score plane, default range: guard rows instead of clamps) and the generic
+    one (score plane kept) must fill identical histograms and moments; a caller-chosen range
+    narrower than the scores clamps: everything below the lower edge lands in the first bin,
+    everything at or above the upper edge in the last (np.histogram of the clipped scores)."""
+    site_lists = [mo["sites"] for mo in lexa["motifs"]]
+    M = PSSMModel([SiteCollection(s) for s in site_lists], lexa_weights["site_count"])
+    om = O.OracleModel(site_lists, lexa_weights["site_count"])
+    seq = O.synthetic_genome(700_000, 65, n_frac=0.0008)
+    g = PackedGenome.from_sequences([seq])
+    lean = M.background_stats(g, n_bins=256)                        # no plane: lean kernel
+    full = M.background_stats(g, n_bins=256, keep_scores=True)      # plane: generic kernel
+    assert torch.equal(lean["hist"], full["hist"])
+    assert np.array_equal(lean["stats"].cpu().numpy()[:5], full["stats"].cpu().numpy()[:5])
+    one = mb.scan_batch([M], g, None, n_bins=256)                   # the batched entry point, lean as well
+    assert np.array_equal(one["hist"][0], lean["hist"].cpu().numpy())
+    _, _, b = c_oracle.score_seq(om, seq)
+    mu = float(b.mean())
+    lo, hi, nb = mu - 2.0, mu + 3.0, 37
+    narrow = M.background_stats(g, n_bins=nb, hist_lo=lo, hist_hi=hi)
+    h = narrow["hist"].cpu().numpy()
+    assert h.sum() == len(b)
+    edges = np.linspace(lo, hi, nb + 1)
+    eh, _ = np.histogram(np.clip(b, lo, np.nextafter(hi, lo)), bins=edges)
+    near = int((np.abs(b[:, None] - edges[None, 1:-1]).min(axis=1) < 1e-5).sum()) if len(b) < 2_000_000 else 8
+    assert np.abs(np.cumsum(h) - np.cumsum(eh)).max() <= max(2, near)
+    assert h[0] > 0.1 * len(b) and h[-1] > 0.001 * len(b)          # the clamped tails are really there
+    assert abs(narrow["stats"][_cabi.BG_MEAN].item() - mu) < 1e-6  # moments do not depend on the range
