@@ -37,22 +37,23 @@ def directons(gt):
     if len(gt) == 0:
         return []
     order = np.argsort(gt.start, kind="stable")
-    runs, cur = [], [int(order[0])]
-    for g in order[1:]:
-        g = int(g)
-        if gt.strand[cur[-1]] == gt.strand[g]:
-            cur.append(g)
-        else:
-            runs.append(cur)
-            cur = [g]
-    runs.append(cur)
-    return [r if gt.strand[r[0]] == 1 else r[::-1] for r in runs]
+    # run boundaries where the strand changes along the start order (array operations; the runs
+    # themselves are short Python lists of GeneTable rows)
+    strand = np.asarray(gt.strand)[order]
+    cuts = (np.nonzero(strand[1:] != strand[:-1])[0] + 1).tolist()
+    rows = order.tolist()
+    first = strand[[0] + cuts].tolist()
+    runs = [rows[a:b] for a, b in zip([0] + cuts, cuts + [len(rows)])]
+    return [r if s == 1 else r[::-1] for r, s in zip(runs, first)]
 
 
 def intergenic_distance_threshold(gene_tables, sigma=1.0):
     """Genome.intergenic_distance_threshold: sigma * mean distance between the first two genes
     of every directon with more than one gene, over all replicons."""
-    dists = [gene_distance(gt, d[0], d[1]) for gt in gene_tables for d in directons(gt) if len(d) > 1]
+    dists = []
+    for gt in gene_tables:
+        st, en = np.asarray(gt.start).tolist(), np.asarray(gt.end).tolist()
+        dists.extend(max(st[d[0]], st[d[1]]) - min(en[d[0]], en[d[1]]) for d in directons(gt) if len(d) > 1)
     total = 0
     for x in dists:                      # misc.mean: left-to-right sum / float(len)
         total = total + x
@@ -69,13 +70,17 @@ def predict_operons(gt, distance_th, probability_th, regulation_probability, sta
         split = np.zeros(len(gt), dtype=bool)
     groups, splits = [], 0
     rest = directons(gt)
+    # plain lists: the loops below index single elements, which numpy arrays are slow at
+    split = split.tolist()
+    st, en, sd = np.asarray(gt.start).tolist(), np.asarray(gt.end).tolist(), np.asarray(gt.strand).tolist()
     while rest:
         processing, rest = rest, []
         for d in processing:
             operon = [d[0]]
             i = 1
             while i < len(d):
-                if gene_distance(gt, d[i - 1], d[i]) >= distance_th:
+                a, b = d[i - 1], d[i]
+                if max(st[a], st[b]) - min(en[a], en[b]) >= distance_th:       # Gene.distance, gene.py:283-288
                     break
                 if split[d[i]]:
                     splits += 1
@@ -86,14 +91,15 @@ def predict_operons(gt, distance_th, probability_th, regulation_probability, sta
             if i < len(d):
                 rest.append(d[i:])
     out = []
+    prob = np.asarray(regulation_probability, dtype=np.float64).tolist() if regulation_probability is not None else None
+    chrom = accession if accession is not None else gt.seq_index
     for oid, genes in enumerate(groups, start=start_id):
-        genes = sorted(genes, key=lambda g: gt.start[g])                # operon.py:26 (stable)
-        strand = int(gt.strand[genes[0]])
+        if len(genes) > 1:
+            genes = sorted(genes, key=st.__getitem__)                  # operon.py:26 (stable)
+        strand = sd[genes[0]]
         first = genes[0] if strand == 1 else genes[-1]                 # operon.py:68-73
-        out.append(Operon(oid, gt.seq_index, accession if accession is not None else gt.seq_index, genes,
-                          int(min(gt.start[g] for g in genes)), int(max(gt.end[g] for g in genes)), strand,
-                          first, float(regulation_probability[first]) if regulation_probability is not None
-                          else float("nan")))
+        out.append(Operon(oid, gt.seq_index, chrom, genes, min(st[g] for g in genes), max(en[g] for g in genes),
+                          strand, first, prob[first] if prob is not None else float("nan")))
     return out, splits
 
 
