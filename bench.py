@@ -320,21 +320,34 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t.cpu().numpy()
 
-    # ---- the motif set: tables of all models in one device block, thresholds by the host DP
+    # ---- the motif set; thresholds by the host DP
     site_lists = motif_site_lists(args.motifs)
-    models = [PSSMModel([SiteCollection(s)], [1.0], device=dev) for s in site_lists]
+    all_models = [PSSMModel([SiteCollection(s)], [1.0], device=dev) for s in site_lists]
     t0 = time.perf_counter()
-    batch = mb.ModelBatch(models, dev)
-    prepare_thresholds(models)
-    thr = [M.threshold() for M in models]
-    setup_s = time.perf_counter() - t0
-    m_len = np.array([M.length for M in models])
+    prepare_thresholds(all_models)
+    all_thr = [M.threshold() for M in all_models]
+    m_len = np.array([M.length for M in all_models])
     m_max = int(m_len.max())
-    K = len(models)
+    K = len(all_models)
+    bp = args.bp
+
+    # ---- the grid: S sequence shards x G motif groups over the ranks (cgb_b200/dist.py).  The
+    # sequence is cut while the shards stay >= --min-shard-bp, the remaining ranks split the motif
+    # set by estimated cost; rank r scans shard r % S for group r // S
+    S, G_m = cdist.plan_grid(world, bp, args.min_shard_bp)
+    seq_rank, grp_rank = rank % S, rank // S
+    costs = [mb.estimated_cost_ms(M, bp // S) for M in all_models]
+    groups = cdist.plan_motif_shards(costs, G_m)
+    mine = groups[grp_rank]
+    mine_t = torch.tensor(mine, dtype=torch.int64, device=dev)
+    models = [all_models[i] for i in mine]
+    thr = [all_thr[i] for i in mine]
+    batch = mb.ModelBatch(models, dev)          # this rank's tables in one device block
+    setup_s = time.perf_counter() - t0
+    group_cost = [float(sum(costs[i] for i in gset)) for gset in groups]
 
     # ---- this rank's shard of THE sequence, packed and resident
-    bp = args.bp
-    lo, cap, hi = shard_bounds(bp, m_max, world, rank)
+    lo, cap, hi = shard_bounds(bp, m_max, S, seq_rank)
     ascii_dev = generate_bases(lo, hi, dev)
     g = PackedGenome([hi - lo], dev)
     g.pack_into(0, ascii_dev)
@@ -345,23 +358,40 @@ def run_ours(args):
         pinned.copy_(ascii_dev)
     del ascii_dev
     torch.cuda.empty_cache()
-    win_rank = np.array([max(0, min(cap, bp - lo - m + 1)) for m in m_len], dtype=np.float64)   # windows this rank scores
+    # windows this rank scores (zero for the motifs of other groups)
+    owned = np.zeros(K, dtype=bool)
+    owned[mine] = True
+    win_rank = np.array([max(0, min(cap, bp - lo - m + 1)) for m in m_len], dtype=np.float64) * owned
     win_total = np.array([bp - m + 1 for m in m_len], dtype=np.float64)
     units_total = float(win_total.sum())
     exp_hits = np.array([mb.expected_hits(M, cap) * 1.25 + 4096 for M in models])
     hit_cap = int(min(exp_hits.sum() * 1.05, 1.5e9))
 
-    kern_acc = np.zeros(K)
-    site_acc = np.zeros(K)
+    kern_own = np.zeros(len(models))
+    site_own = np.zeros(len(models))
+    full_stats = torch.zeros((K, _cabi.BG_COUNT), dtype=torch.float64, device=dev)
+    full_hist = torch.zeros((K, args.bins), dtype=torch.int64, device=dev) if args.bins else None
 
     def step():
+        """One step: this rank's motifs over this rank's shard, then ONE all-reduce of the record
+        table of ALL motifs (rows this rank did not scan are zero): afterwards every rank holds the
+        complete background record of every motif."""
         res = mb.scan_batch(models, g, thr, n_bins=args.bins, win_cap=cap, to_host=False, recycle=True,
-                            hit_cap=hit_cap, kernel_ms=kern_acc if timing_kernels[0] else None,
-                            site_ms=site_acc if timing_kernels[0] else None)
+                            hit_cap=hit_cap, kernel_ms=kern_own if timing_kernels[0] else None,
+                            site_ms=site_own if timing_kernels[0] else None)
         nbytes = 0
         if world > 1:
-            nbytes = cdist.allreduce_batch(res["stats"], res["hist"])
-        return res, nbytes
+            full_stats.zero_()
+            full_stats[mine_t] = res["stats"]
+            if full_hist is not None:
+                full_hist.zero_()
+                full_hist[mine_t] = res["hist"]
+            nbytes = cdist.allreduce_batch(full_stats, full_hist)
+            out = {"stats": full_stats, "hist": full_hist}
+        else:
+            out = {"stats": res["stats"], "hist": res["hist"]}
+        out["hits"], out["launches"] = res["hits"], res["launches"]
+        return out, nbytes
 
     timing_kernels = [False]
     # ---- warm-up + the in-run checks (outside the timed region)
@@ -370,7 +400,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     stats = res["stats"].cpu().numpy()
     hist = res["hist"].cpu().numpy() if res["hist"] is not None else None
-    hits_rank = np.array(res["hits"], dtype=np.float64)
+    hits_rank = np.zeros(K)
+    hits_rank[mine] = np.array(res["hits"], dtype=np.float64)
     hits_all = sum_over_ranks(hits_rank)
     checks = {"n_equals_bp_minus_m_plus_1": bool(np.array_equal(stats[:, _cabi.BG_N], win_total)),
               "hist_sums_to_n": bool(hist is None or np.array_equal(hist.sum(axis=1), stats[:, _cabi.BG_N])),
@@ -385,8 +416,8 @@ def run_ours(args):
         if rank == 0:
             whole = PackedGenome([bp], dev)
             whole.pack_into(0, generate_bases(0, bp, dev))
-            one = mb.scan_batch(models[:P], whole, thr[:P], n_bins=args.bins, to_host=False, recycle=True,
-                                hit_cap=int(min(exp_hits[:P].sum() * world * 1.1 + 1e6, 1.5e9)))
+            one = mb.scan_batch(all_models[:P], whole, all_thr[:P], n_bins=args.bins, to_host=False, recycle=True,
+                                hit_cap=int(min(sum(mb.expected_hits(M, bp) for M in all_models[:P]) * 1.3 + 1e6, 1.5e9)))
             s1 = one["stats"].cpu().numpy()
             same_n = np.array_equal(s1[:, _cabi.BG_N], stats[:P, _cabi.BG_N])
             same_hist = hist is None or np.array_equal(one["hist"].cpu().numpy(), hist[:P])
@@ -425,8 +456,10 @@ def run_ours(args):
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     _cabi.profile_enable(False)
     timing_kernels[0] = False
-    kern_ms = kern_acc / args.steps
-    site_ms = site_acc / args.steps
+    kern_ms = np.full(K, np.nan)
+    site_ms = np.full(K, np.nan)
+    kern_ms[mine] = kern_own / args.steps
+    site_ms[mine] = site_own / args.steps
 
     # all-reduce alone (the collective of the step, same buffer)
     ar_us = None
@@ -455,8 +488,10 @@ def run_ours(args):
             gg = PackedGenome.from_sequences(None, dev, pinned=[pinned])        # H2D + pack
             r = mb.scan_batch(models, gg, thr, n_bins=args.bins, win_cap=cap, to_host=True, sink=sink)
             if world > 1:
-                rec = np.concatenate([r["stats"][:, :3], r["hist"].astype(np.float64)], axis=1) \
+                own = np.concatenate([r["stats"][:, :3], r["hist"].astype(np.float64)], axis=1) \
                     if r["hist"] is not None else r["stats"][:, :3].copy()
+                rec = np.zeros((K, own.shape[1]))
+                rec[mine] = own
                 t = torch.from_numpy(rec).to(dev)
                 dist.all_reduce(t)
                 rec = t.cpu().numpy()
@@ -473,7 +508,7 @@ def run_ours(args):
         barrier()
         e2e_s = time.perf_counter() - t0
         e2e_ms = float(max_over_ranks([e2e_s * 1e3 / e2e_steps])[0])
-        d2h = sink_count[0] / e2e_steps * 8 + K * (8 * _cabi.BG_COUNT + 8 * args.bins + 8 * _cabi.CTR_COUNT)
+        d2h = sink_count[0] / e2e_steps * 8 + len(models) * (8 * _cabi.BG_COUNT + 8 * args.bins + 8 * _cabi.CTR_COUNT)
         d2h_all = float(sum_over_ranks([d2h])[0])
         h2d_all = float(sum_over_ranks([float(hi - lo)])[0])
         e2e = {"value": units_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),
@@ -557,7 +592,14 @@ def run_ours(args):
                        "motif_lengths": "8-30 (mean %.1f)" % float(m_len.mean()), "hist_bins": args.bins,
                        "windows_x_motifs_per_step": units_total, "shard_bp_per_rank": int(hi - lo),
                        "halo_bases": m_max - 1,
-                       "collective": "one all-reduce(SUM) of float64 [%d][3 + %d] per step (%d bytes)"
+                       "grid": {"sequence_shards": S, "motif_groups": G_m, "min_shard_bp": args.min_shard_bp,
+                                "motifs_per_group": [len(x) for x in groups],
+                                "estimated_ms_per_group": [round(c, 1) for c in group_cost],
+                                "rule": "the sequence is cut while shards stay >= min_shard_bp; the ranks left over "
+                                        "split the motif set by estimated cost (longest first); rank r scans shard "
+                                        "r % S for group r // S"},
+                       "collective": "one all-reduce(SUM) of float64 [%d][3 + %d] per step (%d bytes): the record table "
+                                     "of all motifs, rows a rank did not scan are zero"
                                      % (K, args.bins, int(ar_bytes)) if world > 1 else "none (one rank)",
                        "allreduce_us": ar_us,
                        "l2": "inputs larger than L2 (packed shard %.0f MB per pass, %d passes per step)"
@@ -731,6 +773,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3, help="end-to-end steps (each moves every site record to the host)")
     ap.add_argument("--post-steps", type=int, default=30, help="timed steps of the posteriors leg")
     ap.add_argument("--check-motifs", type=int, default=8, help="motifs of the sharded-vs-one-GPU check (N > 1)")
+    ap.add_argument("--min-shard-bp", type=int, default=500_000_000,
+                    help="smallest sequence shard; ranks beyond bp / this split the motif set instead")
     ap.add_argument("--cpu-sample-bp", type=int, default=20_000)
     ap.add_argument("--ref-sample-bp", type=int, default=100_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")

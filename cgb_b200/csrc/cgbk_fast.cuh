@@ -289,7 +289,7 @@ static __device__ __noinline__ void flush_candidates(unsigned long long* stage, 
 // Stats scan, rare path: a tile that holds a byte outside ACGT is scored by the warp that drew
 // it with the reference's exact arithmetic (PSSMModel._calculate repair included), straight from
 // the device ExactTables (L1 resident, 5 KB).  Deliberately NOT inlined: the hot loop keeps its
-// registers.  Moments go to three per-block doubles in shared memory, the histogram to global.
+// registers.  Moments go to the warp's three doubles in shared memory, the histogram to global.
 // In a fused scan the windows that may be sites are flagged in the tile's rows of the flag plane
 // like the table path does (conservatively: either strand within 1e-9 of the threshold; the
 // re-score pass decides), and the tile's flag count is returned.
@@ -343,7 +343,9 @@ static __device__ __noinline__ int exact_tile_stats(const ExactTables* tab, cons
         n_flag += __shfl_down_sync(0xffffffffu, n_flag, o);
     }
     if (lane == 0) {
-        atomicAdd(acc3, s1); atomicAdd(acc3 + 1, s2); atomicAdd(acc3 + 2, cnt);
+        // this warp's own slot, plain adds in the order the warp draws its tiles: no atomics, so the
+        // totals do not depend on how the warps of a block interleave
+        acc3[0] += s1; acc3[1] += s2; acc3[2] += cnt;
     }
     return n_flag;          // valid in lane 0
 }
@@ -396,7 +398,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     };
     unsigned int* hist_rows = reinterpret_cast<unsigned int*>(smem + TL::BYTES + Cfg::STASH_BYTES + Cfg::CAND_BYTES);
     __shared__ double red_scratch[96];
-    __shared__ double exact_acc[3];     // stats modes: moments of the exactly scored (non-ACGT) tiles
+    __shared__ double exact_acc[32 * 3];   // stats modes: per warp, moments of the exactly scored (non-ACGT) tiles
     __shared__ int is_last_block;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -449,7 +451,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     if (HIST)
         for (int i = threadIdx.x; i < (sp.n_bins + (LEAN ? 2 : 0)) * sp.hist_words; i += blockDim.x) hist_rows[i] = 0u;
     if (MODE == 0 && (threadIdx.x & 31) == 0) *reinterpret_cast<unsigned int*>(cand_ptr() + CGBK_CAND_STAGE * 8) = 0u;
-    if (MODE != 0 && threadIdx.x < 3) exact_acc[threadIdx.x] = 0.0;
+    if (MODE != 0 && threadIdx.x < 96) exact_acc[threadIdx.x] = 0.0;
     __syncthreads();
 
     // per-warp strip for the partial sums handed to the previous lane: [D][33]
@@ -512,7 +514,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 const int nf = exact_tile_stats(static_cast<const ExactTables*>(sp.exact_tab), g.bases2, g.amb, g.lower,
                                                 g.cap_bases, gbase, A, A + (own_n > 0 ? own_n : 0), m, tile, L, D,
                                                 sp.d_hist, sp.n_bins, sp.hist_lo_d, sp.inv_binw_d, LEAN ? nullptr : sp.plane,
-                                                (double)sp.scale, exact_acc, &sink);
+                                                (double)sp.scale, exact_acc + 3 * warp, &sink);
                 if (work.fplane && lane == 0) work.tile_cand[tile] = nf;
             }
             tile = advance();
@@ -779,9 +781,11 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
             // s_i = centre + d_i * q  ->  raw moments; plus the exactly scored tiles
             const double q = sp.q;
             double* p = work.partials + 3ll * (work.partial_base + blockIdx.x);
-            p[0] = c * sp.c + a * q + exact_acc[0];
-            p[1] = c * sp.c * sp.c + 2.0 * sp.c * q * a + q * q * b2 + exact_acc[1];
-            p[2] = c + exact_acc[2];
+            double e0 = 0.0, e1 = 0.0, e2 = 0.0;                 // warps in index order
+            for (int w = 0; w < wpb; ++w) { e0 += exact_acc[3 * w]; e1 += exact_acc[3 * w + 1]; e2 += exact_acc[3 * w + 2]; }
+            p[0] = c * sp.c + a * q + e0;
+            p[1] = c * sp.c * sp.c + 2.0 * sp.c * q * a + q * q * b2 + e1;
+            p[2] = c + e2;
             __threadfence();
             const unsigned long long done =
                 atomicAdd(reinterpret_cast<unsigned long long*>(work.counters + CGBK_CTR_INTERNAL_DONE), 1ull);

@@ -50,6 +50,34 @@ def chunk_bounds(n_bases, m, world_size):
     return starts, ends, counts
 
 
+def plan_motif_shards(costs, n_groups):
+    """Motif indices for each of ``n_groups`` ranks: longest-processing-time-first over the
+    estimated costs (deterministic), every motif exactly once, each list ascending."""
+    order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+    load = [0.0] * n_groups
+    out = [[] for _ in range(n_groups)]
+    for i in order:
+        r = min(range(n_groups), key=lambda k: (load[k], k))
+        out[r].append(i)
+        load[r] += float(costs[i])
+    return [sorted(x) for x in out]
+
+
+def plan_grid(world_size, n_bases, min_shard_bases=500_000_000):
+    """How a motif set x one long sequence (BASELINE configs[4]) is laid over ``world_size`` ranks:
+    ``S`` sequence shards x ``M`` motif groups, S * M = world_size.  The sequence is cut as far as
+    the shards stay at or above ``min_shard_bases`` (a scan launch has a fixed cost of tens of
+    microseconds: shards much smaller than that stop scaling), the ranks left over split the motif
+    set (SURVEY 8e names both partitions).  Rank r scans sequence shard r % S for motif group
+    r // S; ONE all-reduce over [all motifs][record] -- rows a rank did not scan stay zero --
+    assembles every motif's record on every rank.  Returns (S, M)."""
+    S = 1
+    for d in range(1, world_size + 1):
+        if world_size % d == 0 and (n_bases + d - 1) // d >= min_shard_bases:
+            S = d
+    return S, world_size // S
+
+
 def allreduce_background(bg, group=None):
     """Sum the raw background record of every rank in place and recompute mean / std.
 

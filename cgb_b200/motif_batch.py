@@ -128,6 +128,20 @@ def expected_hits(model, n_windows):
     return 2.0 * n_windows * 2.0 ** (-max(float(model.IC), 0.0))
 
 
+# measured on B200, 1 Gbp, fused scan (profiles/r2_bench_line_n1.json, r2_site_pass_times.log):
+# scan kernel ms per Gbp by group count G = ceil(m / 4), site pass ms = fixed + per site
+_SCAN_MS_PER_GBP = {1: 1.1, 2: 1.2, 3: 1.32, 4: 1.40, 5: 1.61, 6: 1.79, 7: 2.18, 8: 2.42}
+_SITE_MS_FIXED, _SITE_MS_PER_SITE = 0.095, 1.7e-8
+
+
+def estimated_cost_ms(model, n_windows):
+    """Device time of one motif's fused scan + site pass over ``n_windows`` windows (for balancing
+    motif groups over ranks; a model of the measurements above, not a promise)."""
+    g = (int(model.length) + 3) // 4
+    return _SCAN_MS_PER_GBP[min(max(g, 1), 8)] * n_windows * 1e-9 + _SITE_MS_FIXED + \
+        _SITE_MS_PER_SITE * expected_hits(model, n_windows)
+
+
 def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, revseq_order=True,
                hit_cap=None, to_host=True, sink=None, recycle=False, kernel_ms=None, site_ms=None):
     """Background record and thresholded sites of every model over ``genome`` (a PackedGenome).

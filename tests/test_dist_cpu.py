@@ -186,3 +186,39 @@ def test_bench_shards_cover_every_window_once():
     assert np.array_equal(a[1234:2000], b) and set(np.unique(a)) <= set(b"ACGT")
     assert bench.motif_site_lists(5) == bench.motif_site_lists(5)
     assert all(8 <= len(s[0]) <= 30 and len(s) == 20 for s in bench.motif_site_lists(40))
+
+
+def test_plan_grid_and_motif_groups():
+    """bench.py's grid for a motif set x one long sequence: S sequence shards x M motif groups with
+    S * M = world; every (window, motif) pair belongs to exactly one rank; the groups are balanced
+    by estimated cost and deterministic."""
+    import bench
+    assert cdist.plan_grid(1, 10 ** 9) == (1, 1)
+    assert cdist.plan_grid(2, 10 ** 9) == (2, 1)
+    assert cdist.plan_grid(4, 10 ** 9) == (2, 2)
+    assert cdist.plan_grid(8, 10 ** 9) == (2, 4)
+    assert cdist.plan_grid(8, 10 ** 10) == (8, 1)
+    assert cdist.plan_grid(8, 10 ** 9, min_shard_bases=1) == (8, 1)
+    assert cdist.plan_grid(6, 10 ** 9, min_shard_bases=4 * 10 ** 8) == (2, 3)
+    assert cdist.plan_grid(8, 1000) == (1, 8)
+    rng = np.random.default_rng(3)
+    costs = rng.uniform(0.5, 4.0, size=137)
+    for n_groups in (1, 2, 3, 4, 8):
+        groups = cdist.plan_motif_shards(costs, n_groups)
+        assert groups == cdist.plan_motif_shards(list(costs), n_groups)
+        assert sorted(i for g in groups for i in g) == list(range(137))
+        assert all(g == sorted(g) for g in groups)
+        load = [costs[g].sum() for g in groups]
+        assert max(load) - min(load) <= costs.max()          # LPT: within one job of each other
+    # coverage of the (window, motif) grid: rank r scans shard r % S for group r // S
+    bp, world, m_max = 10 ** 6, 8, 30
+    m_len = rng.integers(8, 31, size=40)
+    S, M = cdist.plan_grid(world, bp, min_shard_bases=250_000)
+    assert (S, M) == (4, 2)
+    groups = cdist.plan_motif_shards([float(m) for m in m_len], M)
+    seen = np.zeros(len(m_len))
+    for r in range(world):
+        lo, cap, hi = bench.shard_bounds(bp, m_max, S, r % S)
+        for k in groups[r // S]:
+            seen[k] += max(0, min(cap, bp - lo - int(m_len[k]) + 1))
+    assert np.array_equal(seen, bp - m_len + 1)
