@@ -579,7 +579,13 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                     for (int k = 0; k < EW; ++k) {
                         const int fq = (int)pend[k], rq = (int)pendb[k];
                         mx[k] = max(fq, rq);
+#ifdef CGBK_MINMAX_DIFF
                         u[k] = (float)(mx[k] - min(fq, rq)) * sp.neg_inv_scale;
+#else
+                        // |f - r| as the absolute value of the converted difference: the |.| is a source
+                        // modifier of the multiply (|f|, |r| < 2^30: the difference fits an int32)
+                        u[k] = fabsf((float)(fq - rq)) * sp.neg_inv_scale;
+#endif
                         // candidate <=> max(f, r) >= thr_fix <=> (thr_fix - 1 - max) < 0: its sign bit
                         // is shifted into the flag register (|both terms| < 2^30: no overflow)
                         cflags = __funnelshift_l((uint32_t)(sp.thr_m1 - mx[k]), cflags, 1);
