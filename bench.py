@@ -380,6 +380,8 @@ def run_ours(args):
                             hit_cap=hit_cap, kernel_ms=kern_own if timing_kernels[0] else None,
                             site_ms=site_own if timing_kernels[0] else None)
         nbytes = 0
+        if compute_done[0] is not None:
+            compute_done[0].record()                 # this rank's own work of the step ends here
         if world > 1:
             full_stats.zero_()
             full_stats[mine_t] = res["stats"]
@@ -394,6 +396,7 @@ def run_ours(args):
         return out, nbytes
 
     timing_kernels = [False]
+    compute_done = [None]
     # ---- warm-up + the in-run checks (outside the timed region)
     for _ in range(args.warmup):
         res, ar_bytes = step()
@@ -446,14 +449,23 @@ def run_ours(args):
     launches = 0
     barrier()
     t_wall0 = time.perf_counter()
+    ev_own = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     for i in range(args.steps):
         ev[i][0].record()
+        compute_done[0] = ev_own[i]
         res, ar_bytes = step()
         ev[i][1].record()
         launches += res["launches"] + (1 if world > 1 else 0)
+    compute_done[0] = None
     barrier()
     wall = time.perf_counter() - t_wall0
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    # per rank: its own work of each step (start of the step -> before the all-reduce); the rest of a
+    # step is the collective and the wait for the slowest rank
+    own_ms = np.array([a.elapsed_time(b) for (a, _), b in zip(ev, ev_own)])
+    own_by_rank = np.zeros((world, args.steps))
+    own_by_rank[rank] = own_ms
+    own_by_rank = sum_over_ranks(own_by_rank.ravel().tolist()).reshape(world, args.steps)
     _cabi.profile_enable(False)
     timing_kernels[0] = False
     kern_ms = np.full(K, np.nan)
@@ -585,6 +597,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "step_ms": spread(step_ms_max),
+            "own_work_ms_by_rank": [round(float(x), 2) for x in own_by_rank.mean(axis=1)],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32 fixed point (2^-21..2^-28 per motif) scan, f64 exact re-score of site candidates, f64 moments",
             "data": "synthetic",

@@ -795,7 +795,7 @@ static int choose_L_stats(const cgbk_seqset* S, int m, int sms, int64_t wcap = -
 static int choose_L_hits(const cgbk_seqset* S, int m, int sms) { return choose_L(S, m, sms * 20, kHitsRoundUs); }
 
 #define PARTIAL_CAP 1024
-#define WORK_HEADER (64 + 3 * 8 * PARTIAL_CAP)
+#define WORK_HEADER (64 + 4 * 8 * PARTIAL_CAP)
 
 extern "C" int64_t cgbk_scan_workspace_bytes(const cgbk_seqset* S, int m, int64_t cand_cap) {
     if (!S) return 0;
@@ -810,7 +810,7 @@ static int carve(const cgbk_seqset* S, int m, void* d_work, int64_t work_bytes, 
                               (long long)work_bytes, (long long)need);
     unsigned char* p = (unsigned char*)d_work;
     w->counters = (long long*)p;
-    w->partials = (double*)(p + 64);
+    w->partials = (unsigned long long*)(p + 64);
     w->partial_cap = PARTIAL_CAP;
     const int64_t dirty_bytes = (4 * count_tiles(S, m, 32) + 63) / 64 * 64;
     w->dirty_tiles = (unsigned int*)(p + WORK_HEADER);
@@ -1029,7 +1029,7 @@ int cgbk_bg_scan_range(BgScan* run, long long bases_ready, int last, cudaStream_
     if (t_end <= run->next_tile) {
         // nothing new to scan; a last call still owes the reduction of the earlier ranges
         if (last && run->n_ranges > 0 && !run->finalized) {
-            CUDA_TRY(launch_bg_finalize(run->w.partials, run->partials_used, run->d_stats, 1, st));
+            CUDA_TRY(launch_bg_finalize_int(run->w.partials, run->partials_used, run->sp.c, run->sp.q, run->d_stats, 1, st));
             run->finalized = 1;
             g_launch_info[0] += 1;
         }
@@ -1063,7 +1063,7 @@ int cgbk_bg_scan_range(BgScan* run, long long bases_ready, int last, cudaStream_
 int cgbk_bg_scan_end(BgScan* run, cudaStream_t st) {
     if (!run->finalized) {
         // an empty scan (no tiles at all), or the caller never flagged a last range
-        CUDA_TRY(launch_bg_finalize(run->w.partials, run->partials_used, run->d_stats, 1, st));
+        CUDA_TRY(launch_bg_finalize_int(run->w.partials, run->partials_used, run->sp.c, run->sp.q, run->d_stats, 1, st));
         run->finalized = 1;
         g_launch_info[0] += 1;
     }
@@ -1141,7 +1141,7 @@ struct BatchLayout {
 
 static BatchLayout batch_layout(const cgbk_seqset* S, int64_t wcap, int with_hits, int64_t cand_cap) {
     BatchLayout b = {};
-    int64_t o = 3 * 8 * PARTIAL_CAP;
+    int64_t o = 4 * 8 * PARTIAL_CAP;
     if (with_hits) {
         b.max_tiles = count_tiles(S, 1, 32, wcap);
         for (int L = 32; L <= 128; L += 32) {
@@ -1237,7 +1237,7 @@ extern "C" int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cg
         if (thresholds) set_stats_threshold(&sp, M, thresholds[k], (flags & CGBK_RC_REVSEQ_ORDER) ? 1 : 0);
         FastWork w;
         w.counters = (long long*)d_counters + (size_t)k * CGBK_CTR_COUNT;
-        w.partials = (double*)d_work;
+        w.partials = (unsigned long long*)d_work;
         w.partial_cap = PARTIAL_CAP;
         w.dirty_tiles = nullptr;
         w.cands = nullptr;

@@ -302,11 +302,14 @@ static __device__ __noinline__ int exact_tile_stats(const ExactTables* tab, cons
                                               const uint32_t* lower, long long cap_bases, long long gbase,
                                               long long w_lo, long long w_hi, int m, long long tile, int L, int D,
                                               unsigned long long* d_hist, int n_bins, double hist_lo,
-                                              double inv_binw, int* plane, double scale, double* acc3,
-                                              const ExactFlagSink* sink) {
+                                              double inv_binw, int* plane, double scale, double centre, double inv_q,
+                                              unsigned long long* acc4, const ExactFlagSink* sink) {
     GenomeView g;
     g.bases2 = bases2; g.amb = amb; g.lower = lower; g.cap_bases = cap_bases;
-    double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+    // moments in the scan's own integer units (score = centre + d * q, d rounded to nearest): exact
+    // integer sums, so the totals do not depend on which warp or block scored the tile
+    long long sd = 0, cnt = 0;
+    unsigned long long sd2 = 0;               // |d| < 2^27 and at most 128 windows per lane: below 2^61
     const int lane = threadIdx.x & 31, B = L >> 5;
     int n_flag = 0;
     if (sink->frows) {
@@ -317,7 +320,8 @@ static __device__ __noinline__ int exact_tile_stats(const ExactTables* tab, cons
         double f, r;
         exact_window(g, tab, m, gbase + x, false, f, r);
         const double s = softmax2_f64((double)(float)f, (double)(float)r);
-        s1 += s; s2 += s * s; cnt += 1.0;
+        const long long d = llrint((s - centre) * inv_q);
+        sd += d; sd2 += (unsigned long long)(d * d); cnt += 1;
         if (d_hist) {
             int bin = (int)floor((s - hist_lo) * inv_binw);
             bin = bin < 0 ? 0 : (bin >= n_bins ? n_bins - 1 : bin);
@@ -335,19 +339,58 @@ static __device__ __noinline__ int exact_tile_stats(const ExactTables* tab, cons
             ++n_flag;
         }
     }
+    unsigned long long hi2 = 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_down_sync(0xffffffffu, s1, o);
-        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+        sd += __shfl_down_sync(0xffffffffu, sd, o);
         cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        const unsigned long long lo_o = __shfl_down_sync(0xffffffffu, sd2, o), hi_o = __shfl_down_sync(0xffffffffu, hi2, o);
+        sd2 += lo_o; hi2 += hi_o + (sd2 < lo_o ? 1ull : 0ull);
         n_flag += __shfl_down_sync(0xffffffffu, n_flag, o);
     }
     if (lane == 0) {
-        // this warp's own slot, plain adds in the order the warp draws its tiles: no atomics, so the
-        // totals do not depend on how the warps of a block interleave
-        acc3[0] += s1; acc3[1] += s2; acc3[2] += cnt;
+        // this warp's own slot: (n, sum d, sum d^2 low, sum d^2 high)
+        acc4[0] += (unsigned long long)cnt; acc4[1] += (unsigned long long)sd;
+        const unsigned long long before = acc4[2];
+        acc4[2] = before + sd2; acc4[3] += hi2 + (acc4[2] < before ? 1ull : 0ull);
     }
     return n_flag;          // valid in lane 0
+}
+
+// block-wide sum of (n, sum d, 128-bit sum d^2) in integers: exact, hence the same whatever the
+// order; result valid in thread 0.  scratch: 4 * 32 words of 8 bytes
+__device__ __forceinline__ void block_reduce_moments(unsigned long long& n, unsigned long long& sd,
+                                                     unsigned long long& lo, unsigned long long& hi,
+                                                     unsigned long long* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    auto warp_sum = [&]() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n += __shfl_down_sync(0xffffffffu, n, o);
+            sd += __shfl_down_sync(0xffffffffu, sd, o);
+            const unsigned long long lo_o = __shfl_down_sync(0xffffffffu, lo, o), hi_o = __shfl_down_sync(0xffffffffu, hi, o);
+            lo += lo_o; hi += hi_o + (lo < lo_o ? 1ull : 0ull);
+        }
+    };
+    warp_sum();
+    if (lane == 0) { scratch[warp] = n; scratch[32 + warp] = sd; scratch[64 + warp] = lo; scratch[96 + warp] = hi; }
+    __syncthreads();
+    if (warp == 0) {
+        n = lane < nw ? scratch[lane] : 0ull; sd = lane < nw ? scratch[32 + lane] : 0ull;
+        lo = lane < nw ? scratch[64 + lane] : 0ull; hi = lane < nw ? scratch[96 + lane] : 0ull;
+        warp_sum();
+    }
+    __syncthreads();
+}
+
+// raw moments (sum s, sum s^2) of n scores s_i = centre + d_i * q from the exact integer sums
+__device__ __forceinline__ void moments_from_integers(unsigned long long n, unsigned long long sd, unsigned long long lo,
+                                                      unsigned long long hi, double centre, double q, double& cn,
+                                                      double& s1, double& s2) {
+    const double a = (double)(long long)sd, b2 = (double)hi * 18446744073709551616.0 + (double)lo;
+    cn = (double)n;
+    s1 = cn * centre + a * q;
+    s2 = cn * centre * centre + 2.0 * centre * q * a + q * q * b2;
 }
 
 __host__ __device__ constexpr int fast_threads_of(int G, int MODE) {
@@ -397,8 +440,9 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         return smem + TL::BYTES + Cfg::STASH_BYTES + (threadIdx.x >> 5) * (CGBK_CAND_STAGE * 8 + 16);
     };
     unsigned int* hist_rows = reinterpret_cast<unsigned int*>(smem + TL::BYTES + Cfg::STASH_BYTES + Cfg::CAND_BYTES);
-    __shared__ double red_scratch[96];
-    __shared__ double exact_acc[32 * 3];   // stats modes: per warp, moments of the exactly scored (non-ACGT) tiles
+    __shared__ unsigned long long red_scratch[128];
+    // stats modes: per warp, integer moments (n, sum d, sum d^2 as 128 bits) of the exactly scored tiles
+    __shared__ unsigned long long exact_acc[32 * 4];
     __shared__ int is_last_block;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -451,7 +495,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     if (HIST)
         for (int i = threadIdx.x; i < (sp.n_bins + (LEAN ? 2 : 0)) * sp.hist_words; i += blockDim.x) hist_rows[i] = 0u;
     if (MODE == 0 && (threadIdx.x & 31) == 0) *reinterpret_cast<unsigned int*>(cand_ptr() + CGBK_CAND_STAGE * 8) = 0u;
-    if (MODE != 0 && threadIdx.x < 96) exact_acc[threadIdx.x] = 0.0;
+    if (MODE != 0 && threadIdx.x < 128) exact_acc[threadIdx.x] = 0ull;
     __syncthreads();
 
     // per-warp strip for the partial sums handed to the previous lane: [D][33]
@@ -461,7 +505,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
 
     int filler = 0;               // completions counted into the centre bin that are no real windows
     long long sum_d = 0;          // exact integer sum of re-centred scores (moment units)
-    double sum_d2 = 0.0;          // sum of their squares
+    unsigned long long sum_d2 = 0ull, sum_d2_hi = 0ull;   // sum of their squares, 128 bits
     long long cnt = 0;
 
     // histogram row of bin b starts at b * hist_words words; with 32 words per row every lane
@@ -493,6 +537,15 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         const long long A = (tile - tile0) * stride;
         const long long rem = seq_len - m + 1 - A;            // valid windows from A on
         const int own_n = rem < stride ? (int)rem : stride;   // this tile owns windows [A, A + own_n)
+#ifdef CGBK_VALID_PER_WINDOW
+        const int own_v = own_n;
+#else
+        // The histogram / moment epilogue tests validity once per group of EW windows, so the table
+        // path counts the tile's windows up to a multiple of EW; the up to EW - 1 windows beyond it
+        // (only ever at the end of a sequence: a full tile's count is a multiple of EW) are scored
+        // exactly after the tile.  The candidate flags keep the exact count own_n.
+        const int own_v = MODE == 0 ? own_n : (own_n & ~(EW - 1));
+#endif
         const long long wbase = (gbase + A + S) >> 4;
 
         uint2 cur = pre_cur;
@@ -514,7 +567,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 const int nf = exact_tile_stats(static_cast<const ExactTables*>(sp.exact_tab), g.bases2, g.amb, g.lower,
                                                 g.cap_bases, gbase, A, A + (own_n > 0 ? own_n : 0), m, tile, L, D,
                                                 sp.d_hist, sp.n_bins, sp.hist_lo_d, sp.inv_binw_d, LEAN ? nullptr : sp.plane,
-                                                (double)sp.scale, exact_acc + 3 * warp, &sink);
+                                                (double)sp.scale, sp.c, sp.inv_q, exact_acc + 4 * warp, &sink);
                 if (work.fplane && lane == 0) work.tile_cand[tile] = nf;
             }
             tile = advance();
@@ -606,12 +659,24 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                         // count of such windows is taken out again before the flush.  (Predicating
                         // the three side effects instead was tried: ptxas wraps a predicated
                         // shared-memory reduction in a convergence region, +4 instructions per window.)
+#ifdef CGBK_VALID_PER_WINDOW
                         const bool valid = live && (wrel - (EW - 1) + k < lim);
+#else
+                        // one test per group of EW windows: groups are aligned to multiples of EW in the
+                        // tile and `lim` is too (own_v below), so a group is valid or invalid as a whole
+                        const bool valid = live && (wrel < lim);
+#endif
                         const int sv = valid ? sfix[k] : sp.half;        // = c_fix - tab_bias
                         if (HIST) {
                             // bin = floor((sv - lo) * n_bins / range) as a signed high multiply (a value a
                             // hair below lo gives -1); LEAN: no clamps, -1 and n_bins are the guard rows
+#ifdef CGBK_BIN_MULHI
                             int bin = __mulhi(sv - sp.lo_fix, (int)sp.bin_mul) >> sp.bin_shift;
+#else
+                            // (sv - lo) * M as ONE 64-bit multiply-add sv * M + (-lo * M): same 64-bit product,
+                            // same high word, without the subtraction
+                            int bin = (int)(((long long)sv * (int)sp.bin_mul + sp.bin_c) >> 32) >> sp.bin_shift;
+#endif
                             if (!LEAN) bin = min(max(bin, 0), last_bin);
                             // plain shared-memory reduction (atomicAdd(.., 1) would be wrapped in a
                             // warp-collective region by ptxas)
@@ -631,7 +696,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         auto body = [&](auto fm_tag, int b, uint32_t w0, uint32_t w1, uint32_t w2) {
             constexpr int FM = decltype(fm_tag)::value;
             const int Sb = S + 32 * b;
-            const int lim = own_n - Sb;
+            const int lim = own_v - Sb;
             const bool first = FM == 0 ? (ONE || b == 0) : (FM == 1);
 #pragma unroll
             for (int t0 = 0; t0 < 32; t0 += SB) {
@@ -726,7 +791,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                     const uint2 q = stash64[j * 33 + 1];
                     ia = q.x; ib = q.y;
                 }
-                complete(sa[si] + ia, sb[si] + ib, S + L, j - D, own_n - (S + L), true, B * 32 + j, (32 - D + j) & (EW - 1));
+                complete(sa[si] + ia, sb[si] + ib, S + L, j - D, own_v - (S + L), true, B * 32 + j, (32 - D + j) & (EW - 1));
             }
             __syncwarp();
             if (MODE == 0 && __any_sync(0xffffffffu, staged)) {
@@ -747,14 +812,25 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 if (lane == 0) work.tile_cand[tile] = n_flag;
             }
             sum_d += acc_d;
-            sum_d2 += (double)acc_d2;
-            const int mine = own_n - S;
+            sum_d2 += (unsigned long long)acc_d2;
+            sum_d2_hi += sum_d2 < (unsigned long long)acc_d2 ? 1ull : 0ull;
+            const int mine = own_v - S;
             const int mine_c = mine < 0 ? 0 : (mine > L ? L : mine);
             cnt += mine_c;
             // completions of this tile that were not the lane's own windows (they sit in the
             // centre's histogram bin): L per table-scored tile, plus the D junk completions of
             // the unified first body
             filler += L + (PEEL ? 0 : D) - mine_c;
+            if (own_v != own_n) {
+                // the last windows of the sequence, [own_v, own_n): exact arithmetic, histogram and
+                // moments only (their flags are set above, the score plane holds them already)
+                ExactFlagSink none;
+                none.frows = nullptr;
+                none.thr = 0.0;
+                exact_tile_stats(static_cast<const ExactTables*>(sp.exact_tab), g.bases2, g.amb, g.lower, g.cap_bases,
+                                 gbase, A + own_v, A + own_n, m, tile, L, D, sp.d_hist, sp.n_bins, sp.hist_lo_d,
+                                 sp.inv_binw_d, nullptr, (double)sp.scale, sp.c, sp.inv_q, exact_acc + 4 * warp, &none);
+            }
         }
         tile = next_tile;
     }
@@ -780,18 +856,19 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                 }
                 if (v) atomicAdd(sp.d_hist + i, (unsigned long long)v);
             }
-        // block totals: n, sum d (exact in double up to 2^53), sum d^2
-        double a = (double)sum_d, b2 = sum_d2, c = (double)cnt;
-        block_reduce3(a, b2, c, red_scratch);
+        // block totals in integers: n, sum d, sum d^2 (128 bits) -- the table path's lanes plus the
+        // exactly scored tiles of every warp.  Exact sums: the record does not depend on how the
+        // tiles fell to the warps and blocks.
+        unsigned long long bn = (unsigned long long)cnt, bsd = (unsigned long long)sum_d, blo = sum_d2, bhi = sum_d2_hi;
+        if (lane == 0) {
+            const unsigned long long* e = exact_acc + 4 * warp;
+            bn += e[0]; bsd += e[1];
+            blo += e[2]; bhi += e[3] + (blo < e[2] ? 1ull : 0ull);
+        }
+        block_reduce_moments(bn, bsd, blo, bhi, red_scratch);
         if (threadIdx.x == 0) {
-            // s_i = centre + d_i * q  ->  raw moments; plus the exactly scored tiles
-            const double q = sp.q;
-            double* p = work.partials + 3ll * (work.partial_base + blockIdx.x);
-            double e0 = 0.0, e1 = 0.0, e2 = 0.0;                 // warps in index order
-            for (int w = 0; w < wpb; ++w) { e0 += exact_acc[3 * w]; e1 += exact_acc[3 * w + 1]; e2 += exact_acc[3 * w + 2]; }
-            p[0] = c * sp.c + a * q + e0;
-            p[1] = c * sp.c * sp.c + 2.0 * sp.c * q * a + q * q * b2 + e1;
-            p[2] = c + e2;
+            unsigned long long* p = work.partials + 4ll * (work.partial_base + blockIdx.x);
+            p[0] = bn; p[1] = bsd; p[2] = blo; p[3] = bhi;
             __threadfence();
             const unsigned long long done =
                 atomicAdd(reinterpret_cast<unsigned long long*>(work.counters + CGBK_CTR_INTERNAL_DONE), 1ull);
@@ -805,17 +882,21 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
             // one L2 round trip instead of three dependent ones.
             __threadfence();
             const int n_part = work.partial_base + (int)gridDim.x;
-            double s1 = 0.0, s2 = 0.0, cn = 0.0;
+            unsigned long long tn = 0ull, tsd = 0ull, tlo = 0ull, thi = 0ull;
             for (int i = threadIdx.x; i < n_part; i += blockDim.x) {
-                s1 += __ldcg(work.partials + 3 * i); s2 += __ldcg(work.partials + 3 * i + 1);
-                cn += __ldcg(work.partials + 3 * i + 2);
+                const unsigned long long* p = work.partials + 4ll * i;
+                const unsigned long long l = __ldcg(p + 2);
+                tn += __ldcg(p); tsd += __ldcg(p + 1);
+                tlo += l; thi += __ldcg(p + 3) + (tlo < l ? 1ull : 0ull);
             }
             double prev = 0.0;                                   // n, sum, sumsq accumulated so far
             if (threadIdx.x < 3) prev = __ldcg(sp.d_stats + threadIdx.x);
             unsigned long long hcopy = 0ull;                     // n_bins <= blockDim.x in the common case
             const bool copy_hist = HIST && sp.host_stats && sp.host_hist && sp.d_hist;
             if (copy_hist && (int)threadIdx.x < sp.n_bins) hcopy = __ldcg(sp.d_hist + threadIdx.x);
-            block_reduce3(s1, s2, cn, red_scratch);
+            block_reduce_moments(tn, tsd, tlo, thi, red_scratch);
+            double s1 = 0.0, s2 = 0.0, cn = 0.0;
+            if (threadIdx.x == 0) moments_from_integers(tn, tsd, tlo, thi, sp.c, sp.q, cn, s1, s2);
             // thread 0 holds the totals; threads 0..2 hold the previous n / sum / sumsq
             const double prev_n = __shfl_sync(0xffffffffu, prev, 0), prev_s1 = __shfl_sync(0xffffffffu, prev, 1),
                          prev_s2 = __shfl_sync(0xffffffffu, prev, 2);

@@ -65,6 +65,7 @@ StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist
     if (mul > 2147483647.0) mul = 2147483647.0;
     sp.bin_mul = (unsigned int)mul;
     sp.bin_shift = k;
+    sp.bin_c = -(long long)sp.lo_fix * (long long)sp.bin_mul;
     // the lean kernel drops the clamps of the bin index: allowed when the range covers every score
     // a window can take (soft-max <= max + 1) with a margin for the fixed-point rounding
     sp.lean_ok = (d_hist == nullptr) ||
@@ -85,6 +86,7 @@ StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist
     sp.half = sp.sh > 0 ? (1 << (sp.sh - 1)) : 0;
     sp.tab_bias = mdl->tab_bias;
     sp.q = ldexp(1.0, -(mdl->kexp - sp.sh));
+    sp.inv_q = ldexp(1.0, mdl->kexp - sp.sh);
     sp.d_hist = d_hist;
     sp.plane = plane;
     sp.thr_fix = CGBK_NO_THRESHOLD;
@@ -125,4 +127,37 @@ cudaError_t launch_fast_stats(const cgbk_model* mdl, GenomeView g, SeqTable seqs
                               int grid, const StatsParams& sp, cudaStream_t st) {
     if (!sp.plane && sp.lean_ok) return launch_fast_stats_lean(mdl, g, seqs, w, L, grid, sp, st);
     return dispatch_stats(mdl->G, mdl->d_precise, g, seqs, w, mdl->m, L, grid, sp, mdl->device, st);
+}
+
+// Reduction of the integer partials outside the scan (a chunked scan whose last range was empty,
+// or a scan without tiles): one block.
+__global__ void __launch_bounds__(256) bg_finalize_int_kernel(const unsigned long long* __restrict__ partials,
+                                                              int n_partials, double centre, double q, double* stats,
+                                                              int accumulate) {
+    __shared__ unsigned long long scratch[128];
+    unsigned long long tn = 0ull, tsd = 0ull, tlo = 0ull, thi = 0ull;
+    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) {
+        const unsigned long long* p = partials + 4ll * i;
+        const unsigned long long l = p[2];
+        tn += p[0]; tsd += p[1];
+        tlo += l; thi += p[3] + (tlo < l ? 1ull : 0ull);
+    }
+    block_reduce_moments(tn, tsd, tlo, thi, scratch);
+    if (threadIdx.x == 0) {
+        double cn, s1, s2;
+        moments_from_integers(tn, tsd, tlo, thi, centre, q, cn, s1, s2);
+        if (accumulate) { cn += stats[CGBK_BG_N]; s1 += stats[CGBK_BG_SUM]; s2 += stats[CGBK_BG_SUMSQ]; }
+        stats[CGBK_BG_N] = cn; stats[CGBK_BG_SUM] = s1; stats[CGBK_BG_SUMSQ] = s2;
+        const double mean = cn > 0 ? s1 / cn : nan("");
+        double var = cn > 0 ? s2 / cn - mean * mean : nan("");
+        if (var < 0) var = 0;
+        stats[CGBK_BG_MEAN] = mean;
+        stats[CGBK_BG_STD] = sqrt(var);
+    }
+}
+
+cudaError_t launch_bg_finalize_int(const unsigned long long* partials, int n_partials, double centre, double q,
+                                   double* d_stats, int accumulate, cudaStream_t st) {
+    bg_finalize_int_kernel<<<1, 256, 0, st>>>(partials, n_partials, centre, q, d_stats, accumulate);
+    return cudaGetLastError();
 }

@@ -137,8 +137,8 @@ struct FastWork {      // carved out of the caller's workspace
     unsigned int* dirty_tiles;  // n_tiles entries
     unsigned long long* cands;  // cand_cap entries
     long long cand_cap;
-    double* partials;           // per-block (sum, sumsq, n) triples
-    int partial_cap;            // triples available
+    unsigned long long* partials;   // per-block integer moments (n, sum d, sum d^2 low, sum d^2 high)
+    int partial_cap;            // quadruples available
     // one launch of the tiled scan covers tiles [tile_begin, tile_end) and hands them out
     // through counters[ctr_slot]; its blocks write moment partials from partial_base on
     long long tile_begin, tile_end;
@@ -191,6 +191,10 @@ cudaError_t launch_rescore(const cgbk_model* mdl, GenomeView g, SeqTable seqs, F
 cudaError_t launch_bg_finalize(const double* partials, int n_partials, double* d_stats,
                                int accumulate, cudaStream_t st);
 
+// the same for the tiled scan's integer partials (n, sum d, sum d^2 as 128 bits; score = centre + d * q)
+cudaError_t launch_bg_finalize_int(const unsigned long long* partials, int n_partials, double centre, double q,
+                                   double* d_stats, int accumulate, cudaStream_t st);
+
 cudaError_t launch_bg_finalize_batch(double* d_stats, int n_records, cudaStream_t st);
 
 cudaError_t launch_region_stats(const cgbk_model* mdl, GenomeView g, const long long* d_start, const int* d_nwin,
@@ -209,6 +213,7 @@ struct StatsParams {
     int lo_fix;            // histogram lower edge, fixed point
     unsigned int bin_mul;  // ceil(2^(32 + bin_shift) * n_bins / range_fix), below 2^31 (signed high multiply)
     int bin_shift;
+    long long bin_c;       // -lo_fix * bin_mul: bin = ((score * bin_mul + bin_c) >> 32) >> bin_shift
     int lean_ok;           // the histogram range covers every possible score: no clamping needed
     int n_bins;
     int hist_words;        // shared-memory words per histogram bin: 32 (one per lane, <= 256 bins) or 1
@@ -218,6 +223,7 @@ struct StatsParams {
     int half;              // 1 << (sh - 1) (0 when sh == 0)
     double c;              // centre in score units
     double q;              // moment unit in score units: 2^-(kexp - sh)
+    double inv_q;          // 2^(kexp - sh)
     unsigned long long* d_hist;
     int* plane;            // optional score plane [tile][(B + 1) * 32 rows][32 lanes]
     // tiles with non-ACGT bytes are scored exactly inside the scan (device ExactTables)

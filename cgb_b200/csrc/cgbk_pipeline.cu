@@ -68,7 +68,7 @@ static PipeLayout pipe_layout(int64_t n_bases, int n_regions, int m, int n_bins)
     p.cap_bases = padded;
     const int64_t nwin = n_bases - m + 1 > 0 ? n_bases - m + 1 : 0;
     const int64_t tiles32 = (nwin + 991) / 992;                 // most tiles: lane segment 32
-    p.work_bytes = align256(64 + 3 * 8 * 1024 + 4 * tiles32 + 64 + 64);
+    p.work_bytes = align256(64 + 4 * 8 * 1024 + 4 * tiles32 + 64 + 64);   // = cgbk_scan_workspace_bytes(.., cand_cap 0)
     p.plane_ints = tiles32 * 2048;                              // (B + 1) * 1024 at B = 1 is the largest
     int64_t o = 0;
     p.off_ascii = o;  o += align256(n_bases);

@@ -281,6 +281,24 @@ def test_moments_only_background_equals_histogram_scan(lexa, lexa_weights):
     assert np.array_equal(res["stats"][0][:5], a[:5])          # integer moments: identical
 
 
+def test_background_record_is_repeatable_under_dynamic_tile_assignment(lexa, lexa_weights):
+    """12 Mbp with non-ACGT runs: more tiles than resident warps, so the tiles fall to the warps in a
+    different order every launch.  The moments are exact integer sums (table path and exactly scored
+    tiles alike), so n / sum / sumsq / mean / std come out bit-identical launch after launch and
+    between the histogram scan and the moments-only scan."""
+    site_lists = [mo["sites"] for mo in lexa["motifs"]]
+    M = PSSMModel([SiteCollection(s) for s in site_lists], lexa_weights["site_count"])
+    seq = O.synthetic_genome(12_000_003, 66, n_frac=0.0005)
+    g = PackedGenome.from_sequences([seq])
+    first = M.background_stats(g, n_bins=256)
+    a = first["stats"].cpu().numpy()[:5]
+    for _ in range(3):
+        again = M.background_stats(g, n_bins=256)
+        assert np.array_equal(again["stats"].cpu().numpy()[:5], a) and torch.equal(again["hist"], first["hist"])
+        assert np.array_equal(mb.scan_batch([M], g, None, n_bins=0)["stats"][0][:5], a)
+        assert np.array_equal(mb.scan_batch([M], g, "patser", n_bins=256)["stats"][0][:5], a)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_models_on_two_devices_from_one_process(lexa, lexa_weights):
     """The shared-memory attribute of the scan kernels and the SM count are per device: models
