@@ -648,7 +648,16 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
 #pragma unroll
                     for (int k = 0; k < EW; ++k) u[k] = lg2_approx(1.0f + u[k]);
 #pragma unroll
+#ifdef CGBK_F2I_CORR
                     for (int k = 0; k < EW; ++k) sfix[k] = mx[k] + __float2int_rn(u[k] * sp.scale);   // fixed point
+#else
+                    // fixed point WITHOUT a conversion instruction (F2I shares the quarter-rate unit of
+                    // EX2 / LG2, the most contended one here): u in [0, 1] plus a power of two `magic`
+                    // whose ulp is the fixed-point unit (2^-kexp, at most 2^-23) rounds u to that unit in
+                    // the mantissa; the bits above `magic`, scaled to 2^-kexp, are the correction
+                    for (int k = 0; k < EW; ++k)
+                        sfix[k] = mx[k] + (__float_as_int(u[k] + sp.magic) - sp.magic_bits) * sp.magic_mul;
+#endif
 #pragma unroll
                     for (int k = 0; k < EW; ++k) {
                         // (the table path's scores are off by -tab_bias; the plane holds true scores)
@@ -675,6 +684,8 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
 #else
                             // (sv - lo) * M as ONE 64-bit multiply-add sv * M + (-lo * M): same 64-bit product,
                             // same high word, without the subtraction
+                            // (tried: the shift as a high multiply by 2^(32 - shift) -- the multiply-add pipe is the
+                            // busier one here, +3 %)
                             int bin = (int)(((long long)sv * (int)sp.bin_mul + sp.bin_c) >> 32) >> sp.bin_shift;
 #endif
                             if (!LEAN) bin = min(max(bin, 0), last_bin);

@@ -49,6 +49,12 @@ StatsParams make_stats_params(const cgbk_model* mdl, double hist_lo, double hist
     sp.neg_inv_scale = (float)(-1.0 / scale);
     sp.scale = (float)scale;
     sp.inv_scale_d = 1.0 / scale;
+    {
+        const int j = mdl->kexp < 23 ? 23 - mdl->kexp : 0;
+        sp.magic = (float)ldexp(1.0, j);
+        sp.magic_bits = (127 + j) << 23;
+        sp.magic_mul = mdl->kexp > 23 ? (1 << (mdl->kexp - 23)) : 1;
+    }
     // histogram lower edge as the table path sees it (its scores are off by -tab_bias)
     sp.lo_fix = (int)(llrint(hist_lo * scale) - (long long)mdl->tab_bias);
     const double range_fix = (hist_hi - hist_lo) * scale;

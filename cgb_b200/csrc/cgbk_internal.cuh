@@ -209,6 +209,10 @@ cudaError_t launch_fast_filter(const cgbk_model* mdl, GenomeView g, SeqTable seq
 struct StatsParams {
     float neg_inv_scale;   // -2^-kexp
     float scale;           // 2^kexp
+    // soft-max correction to fixed point through a float add: magic = 2^max(0, 23 - kexp), its bit
+    // pattern, and 2^max(0, kexp - 23) (see the stats epilogue of cgbk_fast.cuh)
+    float magic;
+    int magic_bits, magic_mul;
     double inv_scale_d;    // 2^-kexp
     int lo_fix;            // histogram lower edge, fixed point
     unsigned int bin_mul;  // ceil(2^(32 + bin_shift) * n_bins / range_fix), below 2^31 (signed high multiply)
