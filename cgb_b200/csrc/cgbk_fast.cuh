@@ -425,6 +425,7 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
     constexpr bool PEEL = VAR == CGBK_VAR_PEEL;
     constexpr bool HIST = MODE == 1 || MODE == 3;
     constexpr bool LEAN = MODE >= 3;       // no score plane, histogram guard rows instead of clamps
+    constexpr bool GROUP_VALID = PEEL && MODE != 0;
     // completed windows are handled in groups: 4 for the filter's deferred flag test, CGBK_STATS_EW
     // for the stats epilogue (its dependent chains run side by side)
     constexpr int EW = MODE == 0 ? 4 : CGBK_STATS_EW;
@@ -537,15 +538,13 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
         const long long A = (tile - tile0) * stride;
         const long long rem = seq_len - m + 1 - A;            // valid windows from A on
         const int own_n = rem < stride ? (int)rem : stride;   // this tile owns windows [A, A + own_n)
-#ifdef CGBK_VALID_PER_WINDOW
-        const int own_v = own_n;
-#else
-        // The histogram / moment epilogue tests validity once per group of EW windows, so the table
-        // path counts the tile's windows up to a multiple of EW; the up to EW - 1 windows beyond it
-        // (only ever at the end of a sequence: a full tile's count is a multiple of EW) are scored
-        // exactly after the tile.  The candidate flags keep the exact count own_n.
-        const int own_v = MODE == 0 ? own_n : (own_n & ~(EW - 1));
-#endif
+        // GROUP_VALID (the peeled code of large inputs): the histogram / moment epilogue tests validity
+        // once per group of EW windows, so the table path counts the tile's windows up to a multiple of
+        // EW; the up to EW - 1 windows beyond it (only ever at the end of a sequence: a full tile's count
+        // is a multiple of EW) are scored exactly after the tile.  The candidate flags keep the exact
+        // count own_n.  The unified code (a warp runs a single small tile, launch-latency bound) tests
+        // every window instead and never takes the exact detour.
+        const int own_v = GROUP_VALID ? (own_n & ~(EW - 1)) : own_n;
         const long long wbase = (gbase + A + S) >> 4;
 
         uint2 cur = pre_cur;
@@ -668,13 +667,10 @@ fast_scan_kernel(const uint32_t* __restrict__ gtab, GenomeView g, SeqTable seqs,
                         // count of such windows is taken out again before the flush.  (Predicating
                         // the three side effects instead was tried: ptxas wraps a predicated
                         // shared-memory reduction in a convergence region, +4 instructions per window.)
-#ifdef CGBK_VALID_PER_WINDOW
-                        const bool valid = live && (wrel - (EW - 1) + k < lim);
-#else
-                        // one test per group of EW windows: groups are aligned to multiples of EW in the
-                        // tile and `lim` is too (own_v below), so a group is valid or invalid as a whole
-                        const bool valid = live && (wrel < lim);
-#endif
+                        // GROUP_VALID: one test per group of EW windows -- groups are aligned to multiples
+                        // of EW in the tile and `lim` is too (own_v below), so a group is valid or invalid as
+                        // a whole
+                        const bool valid = live && (GROUP_VALID ? wrel < lim : wrel - (EW - 1) + k < lim);
                         const int sv = valid ? sfix[k] : sp.half;        // = c_fix - tab_bias
                         if (HIST) {
                             // bin = floor((sv - lo) * n_bins / range) as a signed high multiply (a value a
