@@ -545,8 +545,13 @@ __global__ void __launch_bounds__(128) site_score_kernel(const double* __restric
             // the pooled entries share the queue: dense rounds use its upper part
             unsigned short* dq = q + qn;
             const int room = CGBK_SITE_QUEUE - qn;          // >= 256 - 7 * 31
-            const long long base = sw.cand_off[t];
-            int n_hits = 0;
+            // a dense tile's sites are compacted right here: the candidates of a round are in position
+            // order across the lanes, so a ballot gives every record its place; they go, packed, to the
+            // head of the tile's stretch of the pair buffer (8 bytes per SITE instead of 16 per
+            // candidate written here and read back by site_emit_kernel, which then only copies)
+            const long long base = 2 * sw.cand_off[t];
+            const unsigned int lt = (1u << lane) - 1u;
+            int n_hits = 0;                                 // warp-uniform
             int idx = off;                                  // rank (in the tile) of this lane's next candidate
             for (int chunk0 = 0; chunk0 < total; chunk0 += room) {
                 // every flag bit is popped once: a lane resumes where the previous round stopped it
@@ -563,22 +568,34 @@ __global__ void __launch_bounds__(128) site_score_kernel(const double* __restric
                 }
                 __syncwarp();
                 const int n = total - chunk0 < room ? total - chunk0 : room;
-                for (int i = lane; i < n; i += 32) {
-                    const int wt = dq[i];
-                    const long long gpos = p0 + wt;
-                    const int wi = wt >> 4, sh = (wt & 15) * 2;
-                    const uint32_t w0 = sw.b2[wi], w1 = sw.b2[wi + 1], w2 = sw.b2[wi + 2];
-                    const uint64_t x = (uint64_t)__funnelshift_r(w0, w1, sh) |
-                                       ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
-                    const uint32_t amb = __funnelshift_r(sw.amb[wt >> 5], sw.amb[(wt >> 5) + 1], (uint32_t)(wt & 31)) & maskm;
-                    double f, r;
-                    exact_window_bits(g, &tab, m, gpos, x, amb, revseq, f, r);
-                    n_hits += emit(base + chunk0 + i, gpos, f, r);
+                for (int i0 = 0; i0 < n; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool hf = false, hr = false;
+                    float ff = 0.0f, rf = 0.0f;
+                    long long gpos = 0;
+                    if (i < n) {
+                        const int wt = dq[i];
+                        gpos = p0 + wt;
+                        const int wi = wt >> 4, sh = (wt & 15) * 2;
+                        const uint32_t w0 = sw.b2[wi], w1 = sw.b2[wi + 1], w2 = sw.b2[wi + 2];
+                        const uint64_t x = (uint64_t)__funnelshift_r(w0, w1, sh) |
+                                           ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+                        const uint32_t amb = __funnelshift_r(sw.amb[wt >> 5], sw.amb[(wt >> 5) + 1], (uint32_t)(wt & 31)) & maskm;
+                        double f, r;
+                        exact_window_bits(g, &tab, m, gpos, x, amb, revseq, f, r);
+                        ff = (float)f; rf = (float)r;
+                        hf = (double)ff >= thr; hr = (double)rf >= thr;
+                    }
+                    const unsigned int mf = __ballot_sync(0xffffffffu, hf), mr = __ballot_sync(0xffffffffu, hr);
+                    // records of the lanes before this one, then its own + strand, then its - strand
+                    const long long k = base + n_hits + __popc(mf & lt) + __popc(mr & lt);
+                    if (hf && k < 2 * sp.cand_cap) sp.pairs[k] = cgbk_pack_hit8(gpos, 0, __float_as_uint(ff));
+                    if (hr && k + (hf ? 1 : 0) < 2 * sp.cand_cap)
+                        sp.pairs[k + (hf ? 1 : 0)] = cgbk_pack_hit8(gpos, 1, __float_as_uint(rf));
+                    n_hits += __popc(mf) + __popc(mr);
                 }
                 __syncwarp();
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) n_hits += __shfl_down_sync(0xffffffffu, n_hits, o);
             if (lane == 0) sw.hits[t] = n_hits;
         }
         __syncwarp();
@@ -605,10 +622,29 @@ __global__ void __launch_bounds__(128) site_emit_kernel(FastWork w, SitePass sp)
     const long long cursor = *w.hit_cursor;
     for (long long ti = warp0; ti < n_tiles; ti += nwarps) {
         const long long tile = w.tile_begin + ti;
-        const long long n_rec = 2ll * __ldg(sp.tile_cand + tile);
-        if (n_rec == 0) continue;
+        const int n_cand = __ldg(sp.tile_cand + tile);
+        if (n_cand == 0) continue;
         const long long in0 = 2ll * __ldg(sp.tile_cand_off + tile);
         long long out = cursor + __ldg(sp.tile_hit_off + tile);
+        if (n_cand >= CGBK_SITE_DENSE) {
+            // a dense tile's sites were compacted by the scoring warp: a straight copy
+            // (eight independent loads in flight per lane, then the stores)
+            long long n_site = __ldg(sp.tile_hits + tile);
+            if (n_site > 2 * sp.cand_cap - in0) n_site = 2 * sp.cand_cap - in0;
+            if (n_site > w.hit_cap - out) n_site = w.hit_cap - out;
+            const unsigned long long* src = sp.pairs + in0;
+            unsigned long long* dst = w.hits8 + out;
+            for (long long i0 = lane; i0 < n_site; i0 += 256) {
+                unsigned long long v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = i0 + 32 * u < n_site ? __ldcs(src + i0 + 32 * u) : 0ull;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (i0 + 32 * u < n_site) dst[i0 + 32 * u] = v[u];
+            }
+            continue;
+        }
+        const long long n_rec = 2ll * n_cand;
         for (long long i0 = 0; i0 < n_rec; i0 += 32) {
             const long long i = i0 + lane;
             unsigned long long rec = CGBK_NO_SITE;

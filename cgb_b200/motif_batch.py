@@ -194,9 +194,12 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
     if hit_cap is None:
         hit_cap = 0
         if want_hits:
-            free_bytes, _ = torch.cuda.mem_get_info(dev)
             want = exp.sum() if (not to_host and not recycle) else max(exp.max() * 1.5, 1 << 20)
-            hit_cap = int(min(max(want, 1 << 20), free_bytes // 4 // 16))
+            hit_cap = int(max(want, 1 << 20))
+            if hit_cap * 16 > (1 << 30):
+                # (cudaMemGetInfo costs 0.1 - 2 ms: asked only when the request is large)
+                free_bytes, _ = torch.cuda.mem_get_info(dev)
+                hit_cap = int(min(hit_cap, free_bytes // 4 // 16))
     # candidates are re-scored model by model: room for ONE model's worth (its sites plus the few
     # windows within the fixed-point error of the threshold)
     cand_cap = int(min(max(exp.max() * 1.25, 1 << 16), (1 << 30) - 1)) if want_hits else 0

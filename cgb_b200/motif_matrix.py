@@ -64,12 +64,15 @@ class PositionWeightMatrix(PositionMatrix):
 
     def __init__(self, alphabet, counts):
         super().__init__(alphabet, counts)
+        cols = [dict.__getitem__(self, letter) for letter in alphabet]     # the lists, in alphabet order
         for i in range(self.length):
-            total = psum(float(self[letter][i]) for letter in alphabet)
-            for letter in alphabet:
-                self[letter][i] /= total
-        for letter in alphabet:
-            dict.__setitem__(self, letter, tuple(self[letter]))
+            total = 0                                   # psum: left to right from int 0
+            for col in cols:
+                total = total + float(col[i])
+            for col in cols:
+                col[i] /= total
+        for letter, col in zip(alphabet, cols):
+            dict.__setitem__(self, letter, tuple(col))
 
     def log_odds(self, background=None):
         """log2(p / b) per cell as ``math.log(p / b, 2)`` (pssm_model.py:50)."""
@@ -83,10 +86,11 @@ class PositionWeightMatrix(PositionMatrix):
         for letter in alphabet:
             background[letter] /= total
             values[letter] = []
+        cols = {letter: dict.__getitem__(self, letter) for letter in alphabet}
         for i in range(self.length):
             for letter in alphabet:
                 b = background[letter]
-                p = self[letter][i]
+                p = cols[letter][i]
                 if b > 0:
                     logodds = math.log(p / b, 2) if p > 0 else -math.inf
                 else:
@@ -125,16 +129,19 @@ class PositionSpecificScoringMatrix(PositionMatrix):
         total = psum(background.values())
         for letter in self.alphabet:
             background[letter] /= total
+        # same terms in the same order as Biopython's double loop (position outer, letter inner),
+        # over plain lists instead of keyed look-ups
+        cols = [(background[letter], dict.__getitem__(self, letter)) for letter in self.alphabet]
+        isnan, isinf, pow2 = math.isnan, math.isinf, math.pow
         sx = 0.0
         for i in range(self.length):
-            for letter in self.alphabet:
-                logodds = self[letter, i]
-                if math.isnan(logodds):
+            for b, col in cols:
+                logodds = col[i]
+                if isnan(logodds):
                     continue
-                if math.isinf(logodds) and logodds < 0:
+                if isinf(logodds) and logodds < 0:
                     continue
-                b = background[letter]
-                p = b * math.pow(2, logodds)
+                p = b * pow2(2, logodds)
                 sx += p * logodds
         return sx
 

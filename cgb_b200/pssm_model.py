@@ -117,9 +117,10 @@ class PSSMModel(TFBindingModel):
         """pssm_model.py:159-169."""
         length = pwms[0].length
         assert all(length == pwm.length for pwm in pwms)
-        pwm_vals = {let: [psum(pwm[let][i]*w for pwm, w in zip(pwms, weights))
-                          for i in range(length)]
-                    for let in alphabet}
+        pwm_vals = {}
+        for let in alphabet:
+            cols = [(dict.__getitem__(pwm, let), w) for pwm, w in zip(pwms, weights)]
+            pwm_vals[let] = [psum(col[i]*w for col, w in cols) for i in range(length)]
         return PositionWeightMatrix(alphabet, pwm_vals)
 
     def _calculate(self, pssm, sequence):
@@ -228,18 +229,24 @@ class PSSMModel(TFBindingModel):
         """pssm_model.py:84-86.  The sites are as long as the motif, one window each: scored by
         the library on the host in the reference's arithmetic (``cgbk_score_sites_host``; a few
         thousand table look-ups are not worth a launch).  Ragged site lists take the device path."""
-        sites = self.sites
         m = self.length
-        if len(sites) == 0:
+        colls = self._collection_set
+        n_sites = len(self.__dict__["sites"]) if "sites" in self.__dict__ else sum(c.site_count for c in colls)
+        if n_sites == 0:
             return []
-        if any(len(s) != m for s in sites):
-            return self.score_seqs(sites, True)
-        rows = self.pssm.rows()
-        flat = (C.c_double * (4 * m))(*[x for row in rows for x in row])
-        raw = b"".join(s if isinstance(s, (bytes, bytearray)) else str(s).encode("ascii") for s in sites)
-        out = np.empty(len(sites), dtype=np.float64)
-        _cabi.check(_cabi.lib().cgbk_score_sites_host(flat, m, raw, len(sites), None, None, out.ctypes.data))
-        return [[float(v)] for v in out]
+        if "sites" in self.__dict__ or not all(getattr(c, "_uniform", False) and c.length == m for c in colls):
+            # (a materialised -- possibly replaced -- site list wins over the collections' bytes)
+            sites = self.sites
+            if any(len(s) != m for s in sites):
+                return self.score_seqs(sites, True)
+            raw = b"".join(s if isinstance(s, (bytes, bytearray)) else str(s).encode("ascii") for s in sites)
+        else:
+            raw = b"".join(c._raw for c in colls)           # the collections keep their sites as bytes
+        flat = np.array(self.pssm.rows(), dtype=np.float64).ravel()
+        out = np.empty(n_sites, dtype=np.float64)
+        _cabi.check(_cabi.lib().cgbk_score_sites_host(flat.ctypes.data_as(C.POINTER(C.c_double)), m, raw, n_sites, None, None,
+                                                      out.ctypes.data))
+        return [[v] for v in out.tolist()]
 
     # ------------------------------------------------------------ tiled scans
     def scan_hits(self, genome, threshold=None, revseq_order=True, hit_cap=None):

@@ -18,6 +18,10 @@ class SiteCollection:
         self._counts = counts_from_instances(self._instances)
         self._pseudocounts = pseudocounts
         self._length = len(self._instances[0])
+        # the sites back to back as bytes (what the host scorer takes), built once: collections are
+        # shared by the many models of a run (one per genome in the reference's go() loop)
+        self._uniform = all(len(s) == self._length for s in self._instances)
+        self._raw = "".join(self._instances).encode("ascii", "replace") if self._uniform else None
 
     @property
     def TF(self):
@@ -29,8 +33,12 @@ class SiteCollection:
 
     @property
     def pwm(self):
-        """site_collection.py:33-36."""
-        return normalize_counts(self._counts, self._pseudocounts)
+        """site_collection.py:33-36.  (Computed once: the matrix is immutable -- tuples per letter --
+        and every model built on the collection asks for it again.)"""
+        pwm = self.__dict__.get("_pwm_cache")
+        if pwm is None:
+            pwm = self.__dict__["_pwm_cache"] = normalize_counts(self._counts, self._pseudocounts)
+        return pwm
 
     @property
     def IC(self):
