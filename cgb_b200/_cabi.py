@@ -111,6 +111,8 @@ SYMBOLS = {
     "cgbk_regulation_pipeline_args": (C.c_int, [C.c_void_p]),
     "cgbk_genbank_index": (C.c_int, [C.c_char_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "cgbk_genbank_origin": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "cgbk_packed_capacity": (C.c_int64, [C.c_int64]),
     "cgbk_pack_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

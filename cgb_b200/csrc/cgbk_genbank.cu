@@ -176,6 +176,12 @@ extern "C" int cgbk_genbank_index(const char* block, int64_t n, int32_t* feat, i
         const int64_t line_end = nl ? (int64_t)(nl - block) : n;        // exclusive, without the newline
         const char* p = block + pos;
         const int64_t len = line_end - pos;
+        // anything after the table that starts in column 1 (CONTIG, BASE COUNT, WGS, COMMENT) is not a
+        // feature: the table ends there (the same four words genbank.parse cuts at)
+        if (len > 0 && p[0] != ' ' &&
+            (starts_with(p, len, "CONTIG") || starts_with(p, len, "BASE COUNT") || starts_with(p, len, "WGS") ||
+             starts_with(p, len, "COMMENT")))
+            break;
         if (feature_start(p, len)) {
             close_item();
             ++nf;
@@ -224,5 +230,66 @@ extern "C" int cgbk_genbank_index(const char* block, int64_t n, int32_t* feat, i
     close_item();
     free(tmp);
     *n_feat = nf; *n_qual = nq;
+    return CGBK_OK;
+}
+
+// ORIGIN block -> sequence bytes (host only).  `text + from` is the first line AFTER the "ORIGIN"
+// line; lines of position number + blocks of bases run until a line starting with "//" or the end
+// of the text.  Every byte that is not one of " 0123456789\t\r\n" is kept, ASCII lower case folded
+// to upper -- what genbank.parse did with bytes.translate, in one pass that also finds the end of
+// the record.  Standard lines ("%9d" + 6 x (" " + 10 letters) + newline, 76 bytes) take a fixed-layout
+// path.  Returns the number of bases written to `out` (capacity `cap`; CGBK_ERR_INVALID when it does
+// not fit) and, in *end_pos, the offset of the "//" line (or n).
+extern "C" int cgbk_genbank_origin(const char* text, int64_t n, int64_t from, uint8_t* out, int64_t cap,
+                                   int64_t* n_bases, int64_t* end_pos) {
+    if (!text || !out || !n_bases || !end_pos || from < 0 || from > n)
+        return cgbk_set_error(CGBK_ERR_INVALID, "NULL or out-of-range argument");
+    static unsigned char lut[256];
+    static bool ready = false;
+    if (!ready) {
+        unsigned char t[256];
+        for (int c = 0; c < 256; ++c) t[c] = (unsigned char)((c >= 'a' && c <= 'z') ? c - 32 : c);
+        const char* drop = " 0123456789\t\r\n";
+        for (const char* d = drop; *d; ++d) t[(unsigned char)*d] = 0;
+        t[0] = 0;                       // (a NUL byte cannot be told from "dropped"; GenBank text has none)
+        memcpy(lut, t, 256);
+        ready = true;                   // benign race: every thread writes the same table
+    }
+    const unsigned char* p = (const unsigned char*)text;
+    int64_t pos = from, k = 0;
+    while (pos < n) {
+        if (p[pos] == '/' && pos + 1 < n && p[pos + 1] == '/') break;
+        // fixed-layout line?
+        if (pos + 76 <= n && p[pos + 75] == '\n' && p[pos + 9] == ' ' && p[pos + 20] == ' ' && p[pos + 31] == ' ' &&
+            p[pos + 42] == ' ' && p[pos + 53] == ' ' && p[pos + 64] == ' ' && k + 60 <= cap) {
+            unsigned char all = 0xff;
+            unsigned char* o = out + k;
+            bool lead_ok = true;
+            for (int i = 0; i < 9; ++i) lead_ok &= lut[p[pos + i]] == 0;
+            if (lead_ok) {
+                for (int b = 0; b < 6; ++b) {
+                    const unsigned char* q = p + pos + 10 + 11 * b;
+                    for (int i = 0; i < 10; ++i) {
+                        const unsigned char c = lut[q[i]];
+                        o[10 * b + i] = c;
+                        all &= (unsigned char)(c != 0 ? 0xff : 0);
+                    }
+                }
+                if (all) { k += 60; pos += 76; continue; }
+            }
+        }
+        // general line: byte by byte up to the newline
+        while (pos < n && p[pos] != '\n') {
+            const unsigned char c = lut[p[pos]];
+            if (c) {
+                if (k >= cap) return cgbk_set_error(CGBK_ERR_INVALID, "sequence buffer of %lld bytes is too small", (long long)cap);
+                out[k++] = c;
+            }
+            ++pos;
+        }
+        if (pos < n) ++pos;             // the newline
+    }
+    *n_bases = k;
+    *end_pos = pos;
     return CGBK_OK;
 }

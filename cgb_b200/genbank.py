@@ -391,14 +391,44 @@ def _index_or_parse(feat_block):
     except Exception as exc:                                  # library missing / too old
         from . import _cabi
         if isinstance(exc, _cabi.CgbkError) or isinstance(exc, (OSError, AttributeError)):
-            return _parse_features(feat_block.decode("ascii", "replace"))
+            # anything after the table that starts in column 1 (CONTIG, BASE COUNT, ...) is not a
+            # feature: feature lines are indented, so the table ends at the first such line (the C
+            # index stops there by itself)
+            cut = len(feat_block)
+            for word in (b"\nCONTIG", b"\nBASE COUNT", b"\nWGS", b"\nCOMMENT"):
+                k = feat_block.find(word)
+                if 0 <= k < cut:
+                    cut = k + 1
+            return _parse_features(feat_block[:cut].decode("ascii", "replace"))
         raise
 
 
+def _origin_sequence(text, first_line):
+    """Sequence bytes of the ORIGIN block whose first data line starts at ``first_line`` and the
+    offset of the record's closing ``//`` line: one C pass (``cgbk_genbank_origin``); without the
+    library a ``find`` and one ``bytes.translate``."""
+    try:
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _cabi
+        lib = _cabi.lib()
+        out = np.empty(max(len(text) - first_line, 1), dtype=np.uint8)
+        nb, end = C.c_int64(), C.c_int64()
+        _cabi.check(lib.cgbk_genbank_origin(text, len(text), first_line, out.ctypes.data, out.size,
+                                            C.byref(nb), C.byref(end)))
+        return out[:nb.value].tobytes(), end.value
+    except (OSError, AttributeError):                          # library missing / too old
+        end = first_line if text.startswith(b"//", first_line) else text.find(b"\n//", first_line)
+        end = len(text) if end < 0 else end + (0 if text.startswith(b"//", first_line) else 1)
+        return text[first_line:end].translate(_UPPER, b" 0123456789\t\r\n"), end
+
+
 def parse(text):
-    """All records of a GenBank flat file (``str`` or ``bytes``).  The three big blocks of a
-    record (header, feature table, ORIGIN) are cut out with ``find`` and the sequence is
-    cleaned with one ``bytes.translate``: only the feature table is walked line by line."""
+    """All records of a GenBank flat file (``str`` or ``bytes``).  The blocks of a record (header,
+    feature table, ORIGIN) are located with ``find``; the feature table is indexed and the ORIGIN
+    block decoded by the library's host code, one C pass each."""
     if isinstance(text, str):
         text = text.encode("ascii", "replace")
     records = []
@@ -409,14 +439,23 @@ def parse(text):
             break
         if text[start:start + 1] == b"\n":
             start += 1
-        end = text.find(b"\n//", start)
-        if end < 0:
-            end = n
-        rec = text[start:end]
-        pos = end + 3
-        f0 = rec.find(b"\nFEATURES")
-        o0 = rec.find(b"\nORIGIN")
-        header = rec[:f0 if f0 >= 0 else (o0 if o0 >= 0 else len(rec))].decode("ascii", "replace")
+        # the record's blocks, in file order: header | FEATURES | ORIGIN | //  (a record without
+        # ORIGIN ends at its "//" line)
+        f0 = text.find(b"\nFEATURES", start)
+        o0 = text.find(b"\nORIGIN", f0 if f0 >= 0 else start)
+        if o0 < 0 or text.find(b"\n//", f0 if f0 >= 0 else start, o0) >= 0 or \
+                (f0 >= 0 and text.find(b"\nLOCUS", start + 1, f0) >= 0):
+            # no ORIGIN (or FEATURES) in THIS record: bound it by its own terminator first
+            end = text.find(b"\n//", start)
+            end = n if end < 0 else end
+            f0 = text.find(b"\nFEATURES", start, end)
+            o0 = text.find(b"\nORIGIN", start, end)
+        else:
+            end = None
+        if f0 >= 0 and o0 >= 0 and o0 < f0:
+            o0 = -1
+        head_end = f0 if f0 >= 0 else (o0 if o0 >= 0 else (end if end is not None else n))
+        header = text[start:head_end].decode("ascii", "replace")
         locus_name, accession, version, definition = "", "", "", []
         section = None
         for line in header.splitlines():
@@ -434,24 +473,22 @@ def parse(text):
                     version = rest.split()[0]
             elif section == "DEFINITION":
                 definition.append(line.strip())
-        feat_block = b""
-        if f0 >= 0:
-            block = rec[f0 + 1:o0 if o0 > f0 else len(rec)]
-            nl = block.find(b"\n")
-            feat_block = block[nl + 1:] if nl >= 0 else b""      # drop the FEATURES header line
-            # anything after the table that starts in column 1 (CONTIG, BASE COUNT, ...) is not a
-            # feature: feature lines are indented, so the table ends at the first such line
-            cut = len(feat_block)
-            for word in (b"\nCONTIG", b"\nBASE COUNT", b"\nWGS", b"\nCOMMENT"):
-                k = feat_block.find(word)
-                if 0 <= k < cut:
-                    cut = k + 1
-            feat_block = feat_block[:cut]
         sequence = b""
         if o0 >= 0:
-            nl = rec.find(b"\n", o0 + 1)
+            nl = text.find(b"\n", o0 + 1)
             if nl >= 0:
-                sequence = rec[nl + 1:].translate(_UPPER, b" 0123456789\t\r\n")
+                sequence, end_seq = _origin_sequence(text, nl + 1)
+                if end is None:
+                    end = end_seq
+        if end is None:
+            end = text.find(b"\n//", start)
+            end = n if end < 0 else end
+        feat_block = b""
+        if f0 >= 0:
+            block_end = o0 if o0 > f0 else end
+            nl = text.find(b"\n", f0 + 1, block_end)
+            feat_block = text[nl + 1:block_end] if nl >= 0 else b""      # drop the FEATURES header line
+        pos = end + 2
         description = " ".join(definition)
         if description.endswith("."):
             description = description[:-1]

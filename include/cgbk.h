@@ -150,6 +150,16 @@ int cgbk_pack_host(const uint8_t* ascii, int64_t n_bases, uint32_t* bases2, uint
  * Nothing is written beyond the capacities; n_feat / n_qual always return the full counts. */
 int cgbk_genbank_index(const char* block, int64_t n, int32_t* feat, int32_t feat_cap, int32_t* qual,
                        int32_t qual_cap, int32_t* n_feat, int32_t* n_qual);
+/* (the index stops at the first line that starts with CONTIG, BASE COUNT, WGS or COMMENT in column 1:
+ * the sections that may follow the table) */
+
+/* ORIGIN block of a GenBank record -> sequence bytes (host only; replaces str(record.seq) of
+ * SeqIO.read, cgb/chromid.py:32-35,57-60).  `from` = offset of the first line after the "ORIGIN"
+ * line.  Every byte that is not one of " 0123456789\t\r\n" is kept, ASCII lower case folded to upper,
+ * up to a line starting with "//" or the end of the text.  n_bases = bytes written to `out` (capacity
+ * `cap`: CGBK_ERR_INVALID when it does not fit), end_pos = offset of the "//" line (or n). */
+int cgbk_genbank_origin(const char* text, int64_t n, int64_t from, uint8_t* out, int64_t cap,
+                        int64_t* n_bases, int64_t* end_pos);
 
 /* ---- handles ---------------------------------------------------------------- */
 

@@ -166,3 +166,74 @@ def test_empty_and_headerless_tables():
     assert _features_from_index("") == [] and _parse_features("") == []
     junk = "no feature here\n   nor here\n"
     assert _features_from_index(junk) == _parse_features(junk) == []
+
+
+def _plain_records(text):
+    """An independent reading of a multi-record flat file: records cut at the '//' lines, the ORIGIN
+    block cleaned with str methods, the feature table bounded by FEATURES / ORIGIN / section words."""
+    out = []
+    for chunk in text.replace("\r\n", "\n").split("\n//"):
+        if "LOCUS" not in chunk:
+            continue
+        chunk = chunk[chunk.index("LOCUS"):]
+        seq = ""
+        if "\nORIGIN" in chunk:
+            head, origin = chunk.split("\nORIGIN", 1)
+            origin = origin.split("\n", 1)[1] if "\n" in origin else ""
+            seq = "".join(ch for ch in origin if ch not in " 0123456789\t\r\n").upper()
+        else:
+            head = chunk
+        n_gene = 0
+        if "\nFEATURES" in head:
+            table = head.split("\nFEATURES", 1)[1]
+            for word in ("\nCONTIG", "\nBASE COUNT", "\nWGS", "\nCOMMENT"):
+                table = table.split(word)[0]
+            n_gene = sum(1 for line in table.split("\n") if line.startswith("     gene "))
+        out.append((seq, n_gene))
+    return out
+
+
+def test_origin_decoder_and_record_bounds():
+    """cgbk_genbank_origin + the record cutting of genbank.parse against an independent reading:
+    several records in one file, one without ORIGIN (CONTIG only), one without FEATURES, ragged and
+    non-standard ORIGIN lines, lower / upper case, IUPAC codes, CRLF line ends."""
+    import random
+
+    from genbank_writer import genbank_text
+    rng = random.Random(11)
+
+    def rep(n, k):
+        seq = "".join(rng.choice("ACGTNRYacgtn") for _ in range(n))
+        feats = [{"type": "source", "start": 0, "end": n, "strand": 1, "compound": False, "qualifiers": {}}]
+        for j in range(k):
+            a = 10 + 90 * j
+            feats.append({"type": "gene", "start": a, "end": a + 60, "strand": 1 if j % 2 else -1, "compound": False,
+                          "qualifiers": {"locus_tag": ["T%d_%03d" % (n, j)]}})
+            feats.append({"type": "CDS", "start": a, "end": a + 60, "strand": 1 if j % 2 else -1, "compound": False,
+                          "qualifiers": {"locus_tag": ["T%d_%03d" % (n, j)], "product": ["protein // not a terminator"]}})
+        return {"accession": "R%d.1" % n, "description": "record of %d" % n, "sequence": seq, "features": feats}
+
+    a, b, c, d = (genbank_text(rep(n, k)) for n, k in ((1234, 6), (600, 3), (61, 0), (7, 0)))
+    # b: ORIGIN replaced by a CONTIG section (no sequence); c: no feature table at all;
+    # d: a hand-written ORIGIN with blocks of 5 and trailing blanks
+    b = b[:b.index("ORIGIN")] + "CONTIG      join(XX000001.1:1..600)\n//\n"
+    c = c[:c.index("FEATURES")] + c[c.index("ORIGIN"):]
+    d = d[:d.index("ORIGIN")] + "BASE COUNT      2 a 2 c 2 g 1 t\nORIGIN      \n        1 acgtn ry  \n\n//\n"
+    for text in (a + b + c + d, c + a, d + b + a, (a + b + c + d).replace("\n", "\r\n"), a[:-3], a.upper()):
+        exp = _plain_records(text)
+        for src in (text, text.encode("ascii")):
+            got = genbank.parse(src)
+            assert [(r.sequence.decode("ascii"), sum(1 for f in r.features if f.type == "gene")) for r in got] == exp
+    recs = genbank.parse(a + b + c + d)
+    assert [r.id for r in recs] == ["R1234.1", "R600.1", "R61.1", "R7.1"] and recs[3].sequence == b"ACGTNRY"
+    assert len(recs[1].sequence) == 0 and len(recs[2].features) == 0
+    # the decoder alone: capacity errors and the end offset
+    import ctypes as C
+    from cgb_b200 import _cabi
+    lib = _cabi.lib()
+    blob = b"        1 acgtacgtac gtacgtacgt acgtacgtac gtacgtacgt acgtacgtac gtacgtacgt\n       61 ac\n//\nLOCUS"
+    out = np.zeros(80, dtype=np.uint8)
+    nb, end = C.c_int64(), C.c_int64()
+    assert lib.cgbk_genbank_origin(blob, len(blob), 0, out.ctypes.data, 80, C.byref(nb), C.byref(end)) == 0
+    assert nb.value == 62 and out[:62].tobytes() == b"ACGT" * 15 + b"AC" and blob[end.value:end.value + 2] == b"//"
+    assert lib.cgbk_genbank_origin(blob, len(blob), 0, out.ctypes.data, 61, C.byref(nb), C.byref(end)) != 0
