@@ -135,7 +135,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.cgbk_version() != 210:
+        if L.cgbk_version() != 211:
             raise CgbkError("libcgbk.so version %d does not match the Python layer" % L.cgbk_version())
         _lib = L
     return _lib

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CGBK_VERSION 210
+#define CGBK_VERSION 211
 
 /* status codes; the Python layer maps them to the reference's exception types */
 #define CGBK_OK 0

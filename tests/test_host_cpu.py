@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(_cabi.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _cabi.lib().cgbk_version() == 210
+    assert _cabi.lib().cgbk_version() == 211
 
 
 def test_site_collection_pwm(golden, lexa):
