@@ -530,6 +530,22 @@ def run_ours(args):
                "d2h": "every site record (8 B, sorted per motif) and every background record lands in pinned host "
                       "memory; the sites of one sub-batch cross PCIe while the next sub-batch is scanned",
                "host_binding": numa}
+        e2e["d2h_gb_per_s_achieved"] = round(d2h_all / (e2e_ms * 1e-3) / 1e9, 1)
+        # what the box can move device -> host with every rank copying at once (the end-to-end leg is
+        # bounded by it: every site record crosses PCIe into ONE host's memory): 2 x 1 GiB per rank
+        probe_d = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        probe_h = pinned[:1 << 30] if pinned.numel() >= (1 << 30) else torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+        probe_h.copy_(probe_d, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            probe_h.copy_(probe_d, non_blocking=True)
+        torch.cuda.synchronize()
+        rate = 2 * float(1 << 30) / (time.perf_counter() - t0) / 1e9
+        e2e["d2h_gb_per_s_platform"] = {"aggregate_all_ranks_copying": round(float(sum_over_ranks([rate])[0]), 1),
+                                        "slowest_rank": round(float(-max_over_ranks([-rate])[0]), 1),
+                                        "how": "2 x 1 GiB device -> pinned host per rank, all ranks at once"}
+        del probe_d, probe_h
         del pinned
     clocks = sampler.stop() if rank == 0 else None
 
