@@ -498,7 +498,8 @@ def run_ours(args):
 
         def e2e_step():
             gg = PackedGenome.from_sequences(None, dev, pinned=[pinned])        # H2D + pack
-            r = mb.scan_batch(models, gg, thr, n_bins=args.bins, win_cap=cap, to_host=True, sink=sink)
+            r = mb.scan_batch(models, gg, thr, n_bins=args.bins, win_cap=cap, to_host=True, sink=sink,
+                              split=not args.e2e_records8)
             if world > 1:
                 own = np.concatenate([r["stats"][:, :3], r["hist"].astype(np.float64)], axis=1) \
                     if r["hist"] is not None else r["stats"][:, :3].copy()
@@ -520,15 +521,24 @@ def run_ours(args):
         barrier()
         e2e_s = time.perf_counter() - t0
         e2e_ms = float(max_over_ranks([e2e_s * 1e3 / e2e_steps])[0])
-        d2h = sink_count[0] / e2e_steps * 8 + len(models) * (8 * _cabi.BG_COUNT + 8 * args.bins + 8 * _cabi.CTR_COUNT)
+        site_bytes = 8 if args.e2e_records8 else 6
+        block_bytes = 0 if args.e2e_records8 else 4 * len(models) * (int(_cabi.lib().cgbk_split_sites_blocks(g.cap_bases)) + 1)
+        d2h = sink_count[0] / e2e_steps * site_bytes + block_bytes + \
+            len(models) * (8 * _cabi.BG_COUNT + 8 * args.bins + 8 * _cabi.CTR_COUNT)
         d2h_all = float(sum_over_ranks([d2h])[0])
         h2d_all = float(sum_over_ranks([float(hi - lo)])[0])
         e2e = {"value": units_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),
                "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_ms, "steps": e2e_steps,
-               "call": "PackedGenome.from_sequences(pinned ASCII) + motif_batch.scan_batch(to_host=True) "
-                       "-> cgbk_pack_ascii / cgbk_scan_batch / cgbk_sort_hits",
-               "d2h": "every site record (8 B, sorted per motif) and every background record lands in pinned host "
-                      "memory; the sites of one sub-batch cross PCIe while the next sub-batch is scanned",
+               "call": "PackedGenome.from_sequences(pinned ASCII) + motif_batch.scan_batch(to_host=True%s) "
+                       "-> cgbk_pack_ascii / cgbk_scan_batch%s" % (("", "") if args.e2e_records8 else
+                                                                   (", split=True", " / cgbk_split_sites")),
+               "d2h": ("every site record (8 B, sorted per motif)" if args.e2e_records8 else
+                       "every site (6 B: uint16 offset in its 4 096-base block + strand, float32 score; plus one int32 "
+                       "per block and motif -- the 8-byte records are rebuilt exactly on the host, "
+                       "motif_batch.SplitSites)") +
+                      " and every background record lands in pinned host memory; the sites of one sub-batch cross "
+                      "PCIe while the next sub-batch is scanned",
+               "sites_per_step": int(sink_count[0] / e2e_steps),
                "host_binding": numa}
         e2e["d2h_gb_per_s_achieved"] = round(d2h_all / (e2e_ms * 1e-3) / 1e9, 1)
         # what the box can move device -> host with every rank copying at once (the end-to-end leg is
@@ -806,6 +816,8 @@ def main():
                     help="smallest sequence shard; ranks beyond bp / this split the motif set instead")
     ap.add_argument("--cpu-sample-bp", type=int, default=20_000)
     ap.add_argument("--ref-sample-bp", type=int, default=100_000)
+    ap.add_argument("--e2e-records8", action="store_true",
+                    help="end-to-end leg with 8-byte site records instead of the 6-byte split form")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
     ap.add_argument("--no-posteriors", action="store_true", help="skip the config-2 leg")

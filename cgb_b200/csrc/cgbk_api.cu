@@ -1291,3 +1291,20 @@ extern "C" int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cg
     g_launch_info[0] = launches; g_launch_info[1] = tiles_total; g_launch_info[2] = 0;
     return CGBK_OK;
 }
+
+// ---------------------------------------------------------------------------
+// split site records (see split_sites_kernel, cgbk_exact.cu)
+// ---------------------------------------------------------------------------
+extern "C" int64_t cgbk_split_sites_blocks(int64_t cap_bases) { return (cap_bases + 4095) / 4096; }
+
+extern "C" int cgbk_split_sites(const uint64_t* d_hits8, int64_t n, int64_t cap_bases, uint16_t* d_local,
+                                float* d_score, int32_t* d_block_start, void* stream) {
+    if (n < 0 || cap_bases < 0 || !d_block_start || (n > 0 && (!d_hits8 || !d_local || !d_score)))
+        return cgbk_set_error(CGBK_ERR_INVALID, "NULL or negative argument");
+    if (n >= (1ll << 31)) return cgbk_set_error(CGBK_ERR_UNSUPPORTED, "more than 2^31 - 1 sites in one list");
+    const int dev = cgbk_device_of(d_block_start);
+    ON_DEVICE(dev);
+    CUDA_TRY(launch_split_sites((const unsigned long long*)d_hits8, n, d_local, d_score, d_block_start,
+                                cgbk_split_sites_blocks(cap_bases), cgbk_device_sms(dev), (cudaStream_t)stream));
+    return CGBK_OK;
+}

@@ -39,6 +39,38 @@ def unpack_hits(rec):
     return gpos, strand, score
 
 
+class SplitSites(object):
+    """One model's ordered site list in the 6-byte split form (``cgbk_split_sites``): ``local``
+    uint16 = (offset inside the 4 096-base block) << 1 | minus strand, ``score`` float32,
+    ``block_start`` int32 [blocks + 1].  Views of pinned staging memory when handed to a ``sink``
+    (valid until it returns); :meth:`copy` detaches."""
+    BLOCK_SHIFT = 12
+
+    def __init__(self, local, score, block_start):
+        self.local, self.score, self.block_start = local, score, block_start
+
+    def __len__(self):
+        return len(self.local)
+
+    def copy(self):
+        return SplitSites(self.local.copy(), self.score.copy(), self.block_start.copy())
+
+    def positions(self):
+        """Offsets into the packed buffer (int64), ascending."""
+        counts = np.diff(self.block_start.astype(np.int64))
+        base = np.repeat(np.arange(len(counts), dtype=np.int64) << self.BLOCK_SHIFT, counts)
+        return base + (self.local >> np.uint16(1)).astype(np.int64)
+
+    def strands(self):
+        return (1 - 2 * (self.local & np.uint16(1)).astype(np.int32)).astype(np.int32)
+
+    def records(self):
+        """The same sites as ``cgbk_hit8`` records (uint64), bit for bit what the 8-byte path delivers."""
+        return (self.positions().astype(np.uint64) << np.uint64(33)) | \
+            ((self.local & np.uint16(1)).astype(np.uint64) << np.uint64(32)) | \
+            self.score.view(np.uint32).astype(np.uint64)
+
+
 class ModelBatch:
     """Device tables of many :class:`PSSMModel` in one block.  The models' handles are borrowed
     from the batch, which they keep alive; models that already have tables are left alone."""
@@ -81,16 +113,29 @@ class _ScanBuffers:
     """Device and pinned host buffers of :func:`scan_batch`, kept on the genome and reused between
     calls.  Two hit buffers: while the host receives the sites of one sub-batch, the next is scanned."""
 
-    def __init__(self, dev, n_models, n_bins, hit_cap, work_bytes, host_hits):
+    def __init__(self, dev, n_models, n_bins, hit_cap, work_bytes, host_hits, split_blocks=0):
         self.n_models, self.n_bins, self.hit_cap, self.work_bytes = n_models, n_bins, hit_cap, work_bytes
+        self.split_blocks = split_blocks
         # stats | histograms | counters back to back: the library clears them with one memset
         n_rec = n_models * _cabi.BG_COUNT + n_models * n_bins + (n_models + 1) * _cabi.CTR_COUNT
         self.record = torch.empty(n_rec, dtype=torch.int64, device=dev)
         self.host_record = torch.empty(n_rec, dtype=torch.int64).pin_memory()
         n_buf = 2 if host_hits else 1
         self.hits = [torch.empty(max(hit_cap, 1), dtype=torch.int64, device=dev) for _ in range(n_buf)]
-        self.host_hits = [torch.empty(max(hit_cap, 1), dtype=torch.int64).pin_memory() for _ in range(n_buf)] \
-            if host_hits else []
+        if host_hits and split_blocks:
+            # split transfer: the 8-byte records never leave the device; 2 + 4 bytes per site and one
+            # int32 per 4 096-base block and model go to the host instead
+            nb1 = split_blocks + 1
+            self.host_hits = [True] * n_buf
+            self.d_local = [torch.empty(max(hit_cap, 1), dtype=torch.int16, device=dev) for _ in range(n_buf)]
+            self.d_score = [torch.empty(max(hit_cap, 1), dtype=torch.float32, device=dev) for _ in range(n_buf)]
+            self.d_blocks = [torch.empty(n_models * nb1, dtype=torch.int32, device=dev) for _ in range(n_buf)]
+            self.h_local = [torch.empty(max(hit_cap, 1), dtype=torch.int16).pin_memory() for _ in range(n_buf)]
+            self.h_score = [torch.empty(max(hit_cap, 1), dtype=torch.float32).pin_memory() for _ in range(n_buf)]
+            self.h_blocks = [torch.empty(n_models * nb1, dtype=torch.int32).pin_memory() for _ in range(n_buf)]
+        else:
+            self.host_hits = [torch.empty(max(hit_cap, 1), dtype=torch.int64).pin_memory() for _ in range(n_buf)] \
+                if host_hits else []
         self.copied = [None] * n_buf                  # event: the D2H out of hits[p] has finished
         self.copy_stream = torch.cuda.Stream(device=dev) if host_hits else None
         self.work = torch.empty(work_bytes, dtype=torch.uint8, device=dev)
@@ -102,14 +147,14 @@ class _ScanBuffers:
 _BUFFER_CACHE = {}
 
 
-def _buffers(genome, n_models, n_bins, hit_cap, work_bytes, host_hits):
+def _buffers(genome, n_models, n_bins, hit_cap, work_bytes, host_hits, split_blocks=0):
     key = genome.device.index or 0
     b = _BUFFER_CACHE.get(key)
     if (b is None or b.n_models < n_models or b.n_bins != n_bins or b.hit_cap < hit_cap or b.work_bytes < work_bytes
-            or (host_hits and not b.host_hits)):
+            or (host_hits and not b.host_hits) or (host_hits and b.split_blocks != split_blocks)):
         _BUFFER_CACHE.pop(key, None)
         b = None                                          # free the old buffers first
-        b = _ScanBuffers(genome.device, n_models, n_bins, hit_cap, work_bytes, host_hits)
+        b = _ScanBuffers(genome.device, n_models, n_bins, hit_cap, work_bytes, host_hits, split_blocks)
         _BUFFER_CACHE[key] = b
     return b
 
@@ -143,7 +188,7 @@ def estimated_cost_ms(model, n_windows):
 
 
 def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, revseq_order=True,
-               hit_cap=None, to_host=True, sink=None, recycle=False, kernel_ms=None, site_ms=None):
+               hit_cap=None, to_host=True, sink=None, recycle=False, kernel_ms=None, site_ms=None, split=False):
     """Background record and thresholded sites of every model over ``genome`` (a PackedGenome).
 
     ``thresholds``: ``"patser"`` (each model's own, pssm_model.py:72-77), a sequence of floats, or
@@ -160,6 +205,11 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
     to the hit buffer; each sub-batch's sites cross PCIe on a copy stream (pinned staging) while
     the next sub-batch is scanned.  ``sink(k, records)``: called with model k's records as a
     view of the pinned staging buffer instead of a fresh array (valid until it returns).
+    ``split`` (with ``to_host``): the sites travel in the 6-byte split form (:class:`SplitSites`:
+    uint16 block-local offset + strand, float32 score, one int32 per 4 096-base block) instead of
+    8-byte records -- a quarter fewer bytes over PCIe, which is what bounds a large scan end to end;
+    ``hits`` / the ``sink`` then get :class:`SplitSites` objects (``.records()`` rebuilds the 8-byte
+    records exactly).
     ``to_host=False``: device tensors; the sites stay in the device hit buffer, so the whole
     batch must fit ``hit_cap`` (ValueError otherwise) -- unless ``recycle``: then the buffer is
     reused from sub-batch to sub-batch and ``hits`` holds the per-model COUNTS only (a consumer
@@ -222,8 +272,22 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
     host_hits = want_hits and to_host
     pending = None        # (first model, cum offsets, buffer index) of the sub-batch whose sites are in flight
 
+    split_blocks = int(lib.cgbk_split_sites_blocks(genome.cap_bases)) if (split and want_hits and to_host) else 0
+
     def deliver(first, cum, p, buf):
         buf.copied[p].synchronize()
+        if split_blocks:
+            nb1 = split_blocks + 1
+            loc, sc = buf.h_local[p].numpy().view(np.uint16), buf.h_score[p].numpy()
+            blk = buf.h_blocks[p].numpy()
+            for k in range(len(cum) - 1):
+                seg = SplitSites(loc[cum[k]:cum[k + 1]], sc[cum[k]:cum[k + 1]], blk[k * nb1:(k + 1) * nb1])
+                if sink is not None:
+                    sink(first + k, seg)
+                    hits_out[first + k] = len(seg)
+                else:
+                    hits_out[first + k] = seg.copy()
+            return
         host = buf.host_hits[p].numpy().view(np.uint64)
         for k in range(len(cum) - 1):
             seg = host[cum[k]:cum[k + 1]]
@@ -243,7 +307,7 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
             acc += exp[j]
             j += 1
         n = j - i
-        buf = _buffers(genome, K, n_bins, hit_cap, work_bytes, host_hits)
+        buf = _buffers(genome, K, n_bins, hit_cap, work_bytes, host_hits, split_blocks)
         p = n_sub & 1 if host_hits else 0
         if host_hits and buf.copied[p] is not None and pending is not None and pending[2] == p:
             deliver(*pending, buf)                         # cannot happen with two buffers, kept for safety
@@ -332,7 +396,21 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
                 ready.record(stream)
                 with torch.cuda.stream(buf.copy_stream):
                     buf.copy_stream.wait_event(ready)
-                    if used:
+                    if split_blocks:
+                        # per model: records -> (uint16, float32) + block index, on the copy stream
+                        nb1 = split_blocks + 1
+                        cs = buf.copy_stream.cuda_stream
+                        base8, base2, base4 = buf.hits[p].data_ptr(), buf.d_local[p].data_ptr(), buf.d_score[p].data_ptr()
+                        baseb = buf.d_blocks[p].data_ptr()
+                        for k in range(n_done):
+                            o = int(cum[k])
+                            _cabi.check(lib.cgbk_split_sites(base8 + 8 * o, int(cum[k + 1]) - o, int(genome.cap_bases),
+                                                             base2 + 2 * o, base4 + 4 * o, baseb + 4 * nb1 * k, cs))
+                        if used:
+                            buf.h_local[p][:used].copy_(buf.d_local[p][:used], non_blocking=True)
+                            buf.h_score[p][:used].copy_(buf.d_score[p][:used], non_blocking=True)
+                        buf.h_blocks[p][:n_done * nb1].copy_(buf.d_blocks[p][:n_done * nb1], non_blocking=True)
+                    elif used:
                         buf.host_hits[p][:used].copy_(buf.hits[p][:used], non_blocking=True)
                     buf.copied[p] = torch.cuda.Event()
                     buf.copied[p].record(buf.copy_stream)
@@ -353,7 +431,7 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
             n_sub += 1
         i += n_done
     if pending is not None:
-        deliver(*pending, _buffers(genome, K, n_bins, hit_cap, work_bytes, host_hits))
+        deliver(*pending, _buffers(genome, K, n_bins, hit_cap, work_bytes, host_hits, split_blocks))
     return {"stats": stats_out, "hist": hist_out, "hits": hits_out, "counters": ctr_out, "launches": launches}
 
 

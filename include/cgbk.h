@@ -316,6 +316,17 @@ int cgbk_scan_batch(cgbk_model* const* models, int n_models, const cgbk_genome* 
 int64_t cgbk_sort_hits_workspace_bytes(int64_t n);
 int cgbk_sort_hits(cgbk_hit8* d_hits8, int64_t n, void* d_tmp, int64_t tmp_bytes, void* stream);
 
+/* Split form of an ORDERED site list of one model for the trip to the host: 6 bytes per site
+ * instead of 8 (every site of a large scan crosses PCIe; the reference keeps its sites as Python
+ * objects, genome.py:433-445).
+ *   local[k]       uint16: (offset of site k inside its 4 096-base block of the packed buffer) << 1 | minus
+ *   score[k]       float32: the score, bit for bit
+ *   block_start[b] b = 0 .. cgbk_split_sites_blocks(cap_bases): first site at or after base b * 4096
+ * position of site k = (block << 12) + (local[k] >> 1): the 8-byte records can be rebuilt exactly. */
+int64_t cgbk_split_sites_blocks(int64_t cap_bases);
+int cgbk_split_sites(const cgbk_hit8* d_hits8, int64_t n, int64_t cap_bases, uint16_t* d_local, float* d_score,
+                     int32_t* d_block_start, void* stream);
+
 /* Recompute CGBK_BG_MEAN / CGBK_BG_STD from n/sum/sumsq in d_stats (after an
  * all-reduce of the raw sums across ranks). */
 int cgbk_background_finalize(double* d_stats, void* stream);

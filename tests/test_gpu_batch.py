@@ -352,3 +352,35 @@ def test_histogram_modes_agree_and_narrow_range_clamps(lexa, lexa_weights):
     assert np.abs(np.cumsum(h) - np.cumsum(eh)).max() <= max(2, near)
     assert h[0] > 0.1 * len(b) and h[-1] > 0.001 * len(b)          # the clamped tails are really there
     assert abs(narrow["stats"][_cabi.BG_MEAN].item() - mu) < 1e-6  # moments do not depend on the range
+
+
+def test_split_site_transfer_equals_the_8_byte_records(lexa, lexa_weights):
+    """scan_batch(split=True): the sites cross PCIe as uint16 block-local offset + strand, float32
+    score and one int32 per 4 096-base block; rebuilt on the host they are bit for bit the 8-byte
+    records of the standard path -- two replicons (the second starts at a 512-aligned offset of the
+    packed buffer), a dense, a sparse and a hit-less model, sub-batches forced by a small hit buffer,
+    and the sink form."""
+    rng = np.random.default_rng(21)
+    site_lists = [["".join("ACGT"[i] for i in rng.integers(0, 4, m)) for _ in range(10)] for m in (8, 13, 22, 30)]
+    Ms = [PSSMModel([SiteCollection(s)], [1.0]) for s in site_lists]
+    Ms.append(PSSMModel([SiteCollection(s) for s in [mo["sites"] for mo in lexa["motifs"]]], lexa_weights["site_count"]))
+    seqs = [O.synthetic_genome(700_001, 71, n_frac=0.0004), O.synthetic_genome(123_457, 72)]
+    g = PackedGenome.from_sequences(seqs)
+    thr = [M.threshold() for M in Ms]
+    thr[2] = 1e9                                                   # no site at all
+    ref = mb.scan_batch(Ms, g, thr, n_bins=64)
+    got = mb.scan_batch(Ms, g, thr, n_bins=64, split=True)
+    assert np.array_equal(ref["stats"], got["stats"]) and np.array_equal(ref["hist"], got["hist"])
+    assert len(ref["hits"][2]) == 0 and len(got["hits"][2]) == 0
+    for a, b in zip(ref["hits"], got["hits"]):
+        assert isinstance(b, mb.SplitSites) and len(a) == len(b)
+        assert np.array_equal(b.records(), a)
+        gp, st, sc = mb.unpack_hits(a)
+        assert np.array_equal(b.positions(), gp) and np.array_equal(b.strands(), st) and np.array_equal(b.score, sc)
+        assert b.block_start[0] == 0 and b.block_start[-1] == len(a) and np.all(np.diff(b.block_start) >= 0)
+    # small hit buffer -> several sub-batches; sink receives views of the staging memory
+    seen = {}
+    small = mb.scan_batch(Ms, g, thr, n_bins=64, split=True, hit_cap=max(len(h) for h in ref["hits"]) + 8,
+                          sink=lambda k, s: seen.__setitem__(k, s.records().copy()))
+    assert [small["hits"][k] for k in range(len(Ms))] == [len(h) for h in ref["hits"]]
+    assert all(np.array_equal(seen[k], ref["hits"][k]) for k in range(len(Ms)))

@@ -192,3 +192,27 @@ def test_score_self_on_the_host_matches_verbatim_reference(golden, lexa, lexa_we
         M2.__dict__["sites"] = [edited]
         assert abs(M2.score_self()[0][0] - O.score_seq(om, edited, True)[0][0]) < 1e-13
     assert m == 22
+
+
+def test_split_sites_rebuild_records_on_the_host():
+    """SplitSites (the 6-byte transfer form of a site list) against a numpy statement of the split:
+    positions, strands and the 8-byte records come back exactly, empty blocks and an empty list too."""
+    from cgb_b200 import motif_batch as mb
+    rng = np.random.default_rng(5)
+    cap = 5 * 4096 + 512
+    for n in (0, 1, 37, 4000):
+        pos = np.sort(rng.integers(0, cap, size=n)).astype(np.int64)
+        if n > 30:
+            pos[10:20] = pos[10]                       # both strands at one position, a block with many sites
+            pos = np.sort(pos)
+        minus = rng.integers(0, 2, size=n).astype(np.uint64)
+        score = rng.normal(0, 5, size=n).astype(np.float32)
+        rec = (pos.astype(np.uint64) << np.uint64(33)) | (minus << np.uint64(32)) | score.view(np.uint32).astype(np.uint64)
+        nb = (cap + 4095) // 4096
+        local = (((pos & 4095) << 1) | minus.astype(np.int64)).astype(np.uint16)
+        block_start = np.searchsorted(pos, np.arange(nb + 1, dtype=np.int64) << 12, side="left").astype(np.int32)
+        s = mb.SplitSites(local, score, block_start)
+        assert len(s) == n and np.array_equal(s.records(), rec) and np.array_equal(s.positions(), pos)
+        assert np.array_equal(s.strands(), 1 - 2 * minus.astype(np.int32))
+        gp, st, sc = mb.unpack_hits(s.records())
+        assert np.array_equal(gp, pos) and np.array_equal(sc, score)
