@@ -97,6 +97,8 @@ SYMBOLS = {
     "cgbk_sort_hits": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "cgbk_split_sites_blocks": (C.c_int64, [C.c_int64]),
     "cgbk_split_sites": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cgbk_split_sites_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
     "cgbk_pipeline_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int, C.c_int]),
     "cgbk_pipeline_staging_bytes": (C.c_int64, [C.c_int]),
     "cgbk_regulation_pipeline": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int,

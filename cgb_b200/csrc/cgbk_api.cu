@@ -1304,7 +1304,23 @@ extern "C" int cgbk_split_sites(const uint64_t* d_hits8, int64_t n, int64_t cap_
     if (n >= (1ll << 31)) return cgbk_set_error(CGBK_ERR_UNSUPPORTED, "more than 2^31 - 1 sites in one list");
     const int dev = cgbk_device_of(d_block_start);
     ON_DEVICE(dev);
-    CUDA_TRY(launch_split_sites((const unsigned long long*)d_hits8, n, d_local, d_score, d_block_start,
+    CUDA_TRY(launch_split_sites((const unsigned long long*)d_hits8, nullptr, 1, n, d_local, d_score, d_block_start,
                                 cgbk_split_sites_blocks(cap_bases), cgbk_device_sms(dev), (cudaStream_t)stream));
+    return CGBK_OK;
+}
+
+// the lists of n_models models back to back in ONE launch: d_cum (device, int64 [n_models + 1]) holds
+// where each list starts; block_start is [n_models][blocks + 1], relative to the start of each list
+extern "C" int cgbk_split_sites_batch(const uint64_t* d_hits8, const int64_t* d_cum, int n_models, int64_t n_total,
+                                      int64_t cap_bases, uint16_t* d_local, float* d_score, int32_t* d_block_start,
+                                      void* stream) {
+    if (n_models < 1 || n_total < 0 || cap_bases < 0 || !d_cum || !d_block_start ||
+        (n_total > 0 && (!d_hits8 || !d_local || !d_score)))
+        return cgbk_set_error(CGBK_ERR_INVALID, "NULL or negative argument");
+    const int dev = cgbk_device_of(d_block_start);
+    ON_DEVICE(dev);
+    CUDA_TRY(launch_split_sites((const unsigned long long*)d_hits8, (const long long*)d_cum, n_models, n_total, d_local,
+                                d_score, d_block_start, cgbk_split_sites_blocks(cap_bases), cgbk_device_sms(dev),
+                                (cudaStream_t)stream));
     return CGBK_OK;
 }

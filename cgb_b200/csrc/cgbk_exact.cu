@@ -807,36 +807,46 @@ cudaError_t launch_bg_finalize(const double* partials, int n_partials, double* d
 // ---------------------------------------------------------------------------
 #define CGBK_SITE_BLOCK_SHIFT 12
 
-__global__ void __launch_bounds__(256) split_sites_kernel(const unsigned long long* __restrict__ hits8, long long n,
-                                                          unsigned short* __restrict__ local16,
+__global__ void __launch_bounds__(256) split_sites_kernel(const unsigned long long* __restrict__ hits8,
+                                                          const long long* __restrict__ cum, int n_models,
+                                                          long long n_single, unsigned short* __restrict__ local16,
                                                           float* __restrict__ score32, int* __restrict__ block_start,
                                                           long long n_blocks) {
+    // lists of n_models models back to back: model i holds records [cum[i], cum[i + 1]) (cum == NULL:
+    // one list of n_single records)
     const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long nt = (long long)gridDim.x * blockDim.x;
+    const long long n = cum ? __ldg(cum + n_models) : n_single;
     for (long long k = t0; k < n; k += nt) {
         const unsigned long long rec = __ldcs(hits8 + k);
         const unsigned long long gpos = rec >> 33;
         local16[k] = (unsigned short)(((gpos & ((1u << CGBK_SITE_BLOCK_SHIFT) - 1u)) << 1) | ((rec >> 32) & 1ull));
         score32[k] = __uint_as_float((unsigned int)rec);
     }
-    // block_start[b] = lower bound of base b << 12 in the (ascending) positions
-    for (long long b = t0; b <= n_blocks; b += nt) {
+    // block_start[i][b] = lower bound of base b << 12 in model i's (ascending) positions, relative
+    // to the start of its list
+    const long long nb1 = n_blocks + 1;
+    for (long long j = t0; j < nb1 * n_models; j += nt) {
+        const int i = (int)(j / nb1);
+        const long long b = j - (long long)i * nb1;
+        const long long first = cum ? __ldg(cum + i) : 0, last = cum ? __ldg(cum + i + 1) : n_single;
         const unsigned long long want = (unsigned long long)b << CGBK_SITE_BLOCK_SHIFT;
-        long long lo = 0, hi = n;
+        long long lo = first, hi = last;
         while (lo < hi) {
             const long long mid = (lo + hi) >> 1;
             if ((__ldg(hits8 + mid) >> 33) < want) lo = mid + 1; else hi = mid;
         }
-        block_start[b] = (int)lo;
+        block_start[j] = (int)(lo - first);
     }
 }
 
-cudaError_t launch_split_sites(const unsigned long long* hits8, long long n, unsigned short* local16, float* score32,
-                               int* block_start, long long n_blocks, int sms, cudaStream_t st) {
-    long long work = n > n_blocks + 1 ? n : n_blocks + 1;
+cudaError_t launch_split_sites(const unsigned long long* hits8, const long long* d_cum, int n_models, long long n,
+                               unsigned short* local16, float* score32, int* block_start, long long n_blocks,
+                               int sms, cudaStream_t st) {
+    long long work = n > (n_blocks + 1) * n_models ? n : (n_blocks + 1) * n_models;
     long long blocks = (work + 255) / 256;
     if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
     if (blocks < 1) blocks = 1;
-    split_sites_kernel<<<(int)blocks, 256, 0, st>>>(hits8, n, local16, score32, block_start, n_blocks);
+    split_sites_kernel<<<(int)blocks, 256, 0, st>>>(hits8, d_cum, n_models, n, local16, score32, block_start, n_blocks);
     return cudaGetLastError();
 }

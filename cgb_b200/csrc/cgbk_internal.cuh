@@ -197,8 +197,9 @@ cudaError_t launch_bg_finalize_int(const unsigned long long* partials, int n_par
 
 cudaError_t launch_bg_finalize_batch(double* d_stats, int n_records, cudaStream_t st);
 
-cudaError_t launch_split_sites(const unsigned long long* hits8, long long n, unsigned short* local16, float* score32,
-                               int* block_start, long long n_blocks, int sms, cudaStream_t st);
+cudaError_t launch_split_sites(const unsigned long long* hits8, const long long* d_cum, int n_models, long long n,
+                               unsigned short* local16, float* score32, int* block_start, long long n_blocks,
+                               int sms, cudaStream_t st);
 
 cudaError_t launch_region_stats(const cgbk_model* mdl, GenomeView g, const long long* d_start, const int* d_nwin,
                                 int n_regions, double hist_lo, double hist_hi, int n_bins,

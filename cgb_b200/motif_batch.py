@@ -133,11 +133,13 @@ class _ScanBuffers:
             self.h_local = [torch.empty(max(hit_cap, 1), dtype=torch.int16).pin_memory() for _ in range(n_buf)]
             self.h_score = [torch.empty(max(hit_cap, 1), dtype=torch.float32).pin_memory() for _ in range(n_buf)]
             self.h_blocks = [torch.empty(n_models * nb1, dtype=torch.int32).pin_memory() for _ in range(n_buf)]
+            self.d_cum = [torch.empty(n_models + 1, dtype=torch.int64, device=dev) for _ in range(n_buf)]
+            self.h_cum = [torch.empty(n_models + 1, dtype=torch.int64).pin_memory() for _ in range(n_buf)]
         else:
             self.host_hits = [torch.empty(max(hit_cap, 1), dtype=torch.int64).pin_memory() for _ in range(n_buf)] \
                 if host_hits else []
         self.copied = [None] * n_buf                  # event: the D2H out of hits[p] has finished
-        self.copy_stream = torch.cuda.Stream(device=dev) if host_hits else None
+        self.copy_stream = torch.cuda.Stream(device=dev, priority=-1) if host_hits else None
         self.work = torch.empty(work_bytes, dtype=torch.uint8, device=dev)
 
 
@@ -187,8 +189,84 @@ def estimated_cost_ms(model, n_windows):
         _SITE_MS_PER_SITE * expected_hits(model, n_windows)
 
 
+def interleave_order(cost_ms, sites):
+    """Processing order for a batch whose sites go to the host while the next models are scanned:
+    models whose site lists are long for their scan time (PCIe-heavy) and models that are mostly scan
+    time are interleaved so that, all along the batch, sites sent and device time spent keep the
+    batch's overall ratio -- the copies of one sub-batch then take about as long as the scan of the
+    next, instead of a run of dense motifs waiting on PCIe and a run of sparse ones leaving it idle.
+    Deterministic; returns a permutation (list of indices)."""
+    n = len(cost_ms)
+    tot_c, tot_s = float(sum(cost_ms)), float(sum(sites))
+    if n < 3 or tot_c <= 0 or tot_s <= 0:
+        return list(range(n))
+    ratio = tot_s / tot_c
+    heavy = sorted((i for i in range(n) if sites[i] > ratio * cost_ms[i]), key=lambda i: (-float(sites[i]), i))
+    light = sorted((i for i in range(n) if not sites[i] > ratio * cost_ms[i]), key=lambda i: (float(sites[i]), i))
+    order, cs, cc = [], 0.0, 0.0
+    while heavy or light:
+        if heavy and (not light or cs <= ratio * cc):
+            i = heavy.pop(0)
+        else:
+            i = light.pop(0)
+        order.append(i)
+        cs += float(sites[i])
+        cc += float(cost_ms[i])
+    return order
+
+
 def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, revseq_order=True,
-               hit_cap=None, to_host=True, sink=None, recycle=False, kernel_ms=None, site_ms=None, split=False):
+               hit_cap=None, to_host=True, sink=None, recycle=False, kernel_ms=None, site_ms=None, split=False,
+               interleave=None):
+    """Background record and thresholded sites of every model over ``genome`` (a PackedGenome);
+    see :func:`_scan_batch_in_order` for the arguments.  ``interleave`` (default: on for batches of 8
+    or more models whose sites go to the host): the models are PROCESSED in :func:`interleave_order`
+    so that the site copies overlap the scans all along the batch; everything is returned (and
+    handed to the ``sink``) under the caller's indices."""
+    models = list(models)
+    K = len(models)
+    want_hits = thresholds is not None
+    if interleave is None:
+        interleave = want_hits and to_host and K >= 8
+    if not (interleave and want_hits and K > 2):
+        return _scan_batch_in_order(models, genome, thresholds, n_bins, win_cap, revseq_order, hit_cap, to_host, sink,
+                                    recycle, kernel_ms, site_ms, split)
+    from .pssm_model import prepare_thresholds
+    if isinstance(thresholds, str):
+        if thresholds != "patser":
+            raise ValueError
+        prepare_thresholds(models)
+        thresholds = [M.threshold() for M in models]
+    if len(thresholds) != K:
+        raise ValueError("one threshold per model")
+    nwin = genome.total_windows(min(M.length for M in models))
+    if win_cap is not None:
+        nwin = min(nwin, int(win_cap) * genome.n_seq)
+    order = interleave_order([estimated_cost_ms(M, nwin) for M in models], [expected_hits(M, nwin) for M in models])
+    km = np.zeros(K) if kernel_ms is not None else None
+    sm = np.zeros(K) if site_ms is not None else None
+    res = _scan_batch_in_order([models[i] for i in order], genome, [thresholds[i] for i in order], n_bins, win_cap,
+                               revseq_order, hit_cap, to_host, (lambda k, rec: sink(order[k], rec)) if sink else None,
+                               recycle, km, sm, split)
+    inv = np.empty(K, dtype=np.int64)
+    inv[order] = np.arange(K)
+    if kernel_ms is not None:
+        kernel_ms += km[inv]
+    if site_ms is not None:
+        site_ms += sm[inv]
+    out = dict(res)
+    for key in ("stats", "hist", "counters"):
+        if res[key] is not None:
+            out[key] = res[key][inv] if isinstance(res[key], np.ndarray) else res[key][torch.from_numpy(inv).to(res[key].device)]
+    if res["hits"] is not None:
+        out["hits"] = [res["hits"][int(j)] for j in inv]
+    out["order"] = order
+    return out
+
+
+def _scan_batch_in_order(models, genome, thresholds="patser", n_bins=256, win_cap=None, revseq_order=True,
+                         hit_cap=None, to_host=True, sink=None, recycle=False, kernel_ms=None, site_ms=None,
+                         split=False):
     """Background record and thresholded sites of every model over ``genome`` (a PackedGenome).
 
     ``thresholds``: ``"patser"`` (each model's own, pssm_model.py:72-77), a sequence of floats, or
@@ -398,14 +476,15 @@ def scan_batch(models, genome, thresholds="patser", n_bins=256, win_cap=None, re
                     buf.copy_stream.wait_event(ready)
                     if split_blocks:
                         # per model: records -> (uint16, float32) + block index, on the copy stream
+                        # (ONE launch for the sub-batch: it has to find its way between the scan kernels
+                        # of the next sub-batch, which keep every SM busy)
                         nb1 = split_blocks + 1
-                        cs = buf.copy_stream.cuda_stream
-                        base8, base2, base4 = buf.hits[p].data_ptr(), buf.d_local[p].data_ptr(), buf.d_score[p].data_ptr()
-                        baseb = buf.d_blocks[p].data_ptr()
-                        for k in range(n_done):
-                            o = int(cum[k])
-                            _cabi.check(lib.cgbk_split_sites(base8 + 8 * o, int(cum[k + 1]) - o, int(genome.cap_bases),
-                                                             base2 + 2 * o, base4 + 4 * o, baseb + 4 * nb1 * k, cs))
+                        buf.h_cum[p][:n_done + 1].copy_(torch.from_numpy(cum))
+                        buf.d_cum[p][:n_done + 1].copy_(buf.h_cum[p][:n_done + 1], non_blocking=True)
+                        _cabi.check(lib.cgbk_split_sites_batch(
+                            buf.hits[p].data_ptr(), buf.d_cum[p].data_ptr(), n_done, used, int(genome.cap_bases),
+                            buf.d_local[p].data_ptr(), buf.d_score[p].data_ptr(), buf.d_blocks[p].data_ptr(),
+                            buf.copy_stream.cuda_stream))
                         if used:
                             buf.h_local[p][:used].copy_(buf.d_local[p][:used], non_blocking=True)
                             buf.h_score[p][:used].copy_(buf.d_score[p][:used], non_blocking=True)

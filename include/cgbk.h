@@ -326,6 +326,12 @@ int cgbk_sort_hits(cgbk_hit8* d_hits8, int64_t n, void* d_tmp, int64_t tmp_bytes
 int64_t cgbk_split_sites_blocks(int64_t cap_bases);
 int cgbk_split_sites(const cgbk_hit8* d_hits8, int64_t n, int64_t cap_bases, uint16_t* d_local, float* d_score,
                      int32_t* d_block_start, void* stream);
+/* The lists of n_models models, back to back, in one launch: d_cum (DEVICE, int64 [n_models + 1]) = where
+ * each list starts (d_cum[n_models] = n_total, each list below 2^31 sites); d_block_start is
+ * [n_models][blocks + 1], relative to the start of each list. */
+int cgbk_split_sites_batch(const cgbk_hit8* d_hits8, const int64_t* d_cum, int n_models, int64_t n_total,
+                           int64_t cap_bases, uint16_t* d_local, float* d_score, int32_t* d_block_start,
+                           void* stream);
 
 /* Recompute CGBK_BG_MEAN / CGBK_BG_STD from n/sum/sumsq in d_stats (after an
  * all-reduce of the raw sums across ranks). */

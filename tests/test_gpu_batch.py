@@ -384,3 +384,26 @@ def test_split_site_transfer_equals_the_8_byte_records(lexa, lexa_weights):
                           sink=lambda k, s: seen.__setitem__(k, s.records().copy()))
     assert [small["hits"][k] for k in range(len(Ms))] == [len(h) for h in ref["hits"]]
     assert all(np.array_equal(seen[k], ref["hits"][k]) for k in range(len(Ms)))
+
+
+def test_interleaved_processing_order_returns_the_callers_indices():
+    """scan_batch processes a large batch in interleave_order (dense and sparse motifs alternate so
+    that the site copies overlap the scans); records, histograms, site lists and the sink's indices
+    must be those of the caller's order, identical to the in-order run."""
+    rng = np.random.default_rng(33)
+    lens = [8, 30, 12, 9, 22, 16, 8, 27, 10, 19]
+    site_lists = [["".join("ACGT"[i] for i in rng.integers(0, 4, m)) for _ in range(int(rng.integers(4, 30)))] for m in lens]
+    Ms = [PSSMModel([SiteCollection(s)], [1.0]) for s in site_lists]
+    g = PackedGenome.from_sequences([O.synthetic_genome(900_000, 81, n_frac=0.0003)])
+    a = mb.scan_batch(Ms, g, "patser", n_bins=32, interleave=False)
+    seen = {}
+    cap = int(max(len(h) for h in a["hits"]) * 1.2) + 64
+    b = mb.scan_batch(Ms, g, "patser", n_bins=32, interleave=True, hit_cap=cap,
+                      sink=lambda k, rec: seen.__setitem__(k, rec.copy()))
+    assert sorted(b["order"]) == list(range(len(Ms))) and b["order"] != list(range(len(Ms)))
+    assert np.array_equal(a["stats"], b["stats"]) and np.array_equal(a["hist"], b["hist"])
+    assert np.array_equal(a["counters"][:, _cabi.CTR_HITS], b["counters"][:, _cabi.CTR_HITS])
+    for k in range(len(Ms)):
+        assert b["hits"][k] == len(a["hits"][k]) and np.array_equal(seen[k], a["hits"][k])
+    c = mb.scan_batch(Ms, g, "patser", n_bins=32)                # default for >= 8 models to the host: interleaved
+    assert all(np.array_equal(x, y) for x, y in zip(a["hits"], c["hits"]))

@@ -216,3 +216,22 @@ def test_split_sites_rebuild_records_on_the_host():
         assert np.array_equal(s.strands(), 1 - 2 * minus.astype(np.int32))
         gp, st, sc = mb.unpack_hits(s.records())
         assert np.array_equal(gp, pos) and np.array_equal(sc, score)
+
+
+def test_interleave_order_tracks_the_batch_ratio():
+    """motif_batch.interleave_order: a permutation, deterministic, and along the processing order the
+    sites sent stay within one heavy model of (overall ratio x device time spent)."""
+    from cgb_b200 import motif_batch as mb
+    rng = np.random.default_rng(2)
+    for n in (0, 1, 2, 3, 17, 200):
+        cost = rng.uniform(1.0, 2.5, size=n)
+        sites = np.where(rng.random(n) < 0.2, rng.uniform(5e7, 3e8, size=n), rng.uniform(1e3, 2e6, size=n))
+        order = mb.interleave_order(cost.tolist(), sites.tolist())
+        assert sorted(order) == list(range(n)) and order == mb.interleave_order(list(cost), list(sites))
+        if n >= 17:
+            ratio = sites.sum() / cost.sum()
+            gap = np.abs(np.cumsum(sites[order]) - ratio * np.cumsum(cost[order]))
+            heavy_left = np.array([sites[order[k:]].max() if k < n else 0 for k in range(n)])
+            assert np.all(gap[:-1] <= sites.max() + ratio * cost.max())
+            assert sites[order[0]] == sites.max()          # a PCIe-heavy model first: the copies start early
+    assert mb.interleave_order([1.0, 1.0, 1.0], [0, 0, 0]) == [0, 1, 2]
