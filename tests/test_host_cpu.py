@@ -231,7 +231,6 @@ def test_interleave_order_tracks_the_batch_ratio():
         if n >= 17:
             ratio = sites.sum() / cost.sum()
             gap = np.abs(np.cumsum(sites[order]) - ratio * np.cumsum(cost[order]))
-            heavy_left = np.array([sites[order[k:]].max() if k < n else 0 for k in range(n)])
             assert np.all(gap[:-1] <= sites.max() + ratio * cost.max())
             assert sites[order[0]] == sites.max()          # a PCIe-heavy model first: the copies start early
     assert mb.interleave_order([1.0, 1.0, 1.0], [0, 0, 0]) == [0, 1, 2]
