@@ -348,7 +348,7 @@ def _scan_batch_in_order(models, genome, thresholds="patser", n_bins=256, win_ca
     hits_out = [None] * K if want_hits else None
     launches = 0
     host_hits = want_hits and to_host
-    pending = None        # (first model, cum offsets, buffer index) of the sub-batch whose sites are in flight
+    pending = None        # (first model, cum offsets, buffer index, buffers) of the sub-batch whose sites are in flight
 
     split_blocks = int(lib.cgbk_split_sites_blocks(genome.cap_bases)) if (split and want_hits and to_host) else 0
 
@@ -388,7 +388,7 @@ def _scan_batch_in_order(models, genome, thresholds="patser", n_bins=256, win_ca
         buf = _buffers(genome, K, n_bins, hit_cap, work_bytes, host_hits, split_blocks)
         p = n_sub & 1 if host_hits else 0
         if host_hits and buf.copied[p] is not None and pending is not None and pending[2] == p:
-            deliver(*pending, buf)                         # cannot happen with two buffers, kept for safety
+            deliver(*pending)                         # cannot happen with two buffers, kept for safety
             pending = None
         hp = (C.c_void_p * n)(*[h.value for h in handles_all[i:j]])
         # stats | hist | counters of n models, adjacent, at the head of the record buffer
@@ -429,7 +429,7 @@ def _scan_batch_in_order(models, genome, thresholds="patser", n_bins=256, win_ca
                 exp[i + bad] = max(exp[i + bad], need)
                 if need > cand_cap:
                     if pending is not None:            # the buffers are about to be re-allocated
-                        deliver(*pending, buf)
+                        deliver(*pending)
                         pending = None
                     cand_cap = int(need)
                     work_bytes = int(lib.cgbk_scan_batch_workspace_bytes(
@@ -443,7 +443,7 @@ def _scan_batch_in_order(models, genome, thresholds="patser", n_bins=256, win_ca
                         raise MemoryError("model %d needs %d hit records, more than the device can hold"
                                           % (i, int(need)))
                     if pending is not None:
-                        deliver(*pending, buf)
+                        deliver(*pending)
                         pending = None
                     hit_cap = max(hit_cap, int(need))
                     cand_cap = max(cand_cap, int(need))
@@ -494,8 +494,8 @@ def _scan_batch_in_order(models, genome, thresholds="patser", n_bins=256, win_ca
                     buf.copied[p] = torch.cuda.Event()
                     buf.copied[p].record(buf.copy_stream)
                 if pending is not None:
-                    deliver(*pending, buf)
-                pending = (i, cum, p)
+                    deliver(*pending)
+                pending = (i, cum, p, buf)     # (the tuple keeps ITS buffers alive should the cache re-allocate)
                 # the next scan must not overwrite hits[p ^ 1] before ITS copy is done: deliver()
                 # above has just waited for it
             elif recycle:
@@ -510,7 +510,7 @@ def _scan_batch_in_order(models, genome, thresholds="patser", n_bins=256, win_ca
             n_sub += 1
         i += n_done
     if pending is not None:
-        deliver(*pending, _buffers(genome, K, n_bins, hit_cap, work_bytes, host_hits, split_blocks))
+        deliver(*pending)
     return {"stats": stats_out, "hist": hist_out, "hits": hits_out, "counters": ctr_out, "launches": launches}
 
 

@@ -407,3 +407,30 @@ def test_interleaved_processing_order_returns_the_callers_indices():
         assert b["hits"][k] == len(a["hits"][k]) and np.array_equal(seen[k], a["hits"][k])
     c = mb.scan_batch(Ms, g, "patser", n_bins=32)                # default for >= 8 models to the host: interleaved
     assert all(np.array_equal(x, y) for x, y in zip(a["hits"], c["hits"]))
+
+
+def test_underestimated_site_counts_rerun_with_larger_buffers(lexa, lexa_weights):
+    """Explicit thresholds far below the Patser point: the expected site counts (guessed from the
+    information content) are too small, the candidate buffer overflows in the MIDDLE of a sub-batch
+    while the sites of the previous models are still on their way to the host, and the scan grows
+    its buffers and runs the rest again.  Found by tools/fuzz_parity.py --mode batch (the in-flight
+    copy used to be looked up in the re-allocated buffers)."""
+    rng = np.random.default_rng(44)
+    site_lists = [["".join("ACGT"[i] for i in rng.integers(0, 4, m)) for _ in range(12)] for m in (14, 10, 21, 9)]
+    Ms = [PSSMModel([SiteCollection(s)], [1.0]) for s in site_lists]
+    oms = [O.OracleModel([s], [1.0]) for s in site_lists]
+    seq = O.synthetic_genome(400_000, 91, n_frac=0.0005)
+    g = PackedGenome.from_sequences([seq])
+    thr = [M.threshold() for M in Ms]
+    thr[1] = float(Ms[1].pssm.min) - 1.0            # every window, both strands
+    thr[3] = float(np.quantile(c_oracle.score_seq(oms[3], seq)[2], 0.5))
+    mb.release_buffers()
+    for split in (False, True):
+        res = mb.scan_batch(Ms, g, thr, n_bins=32, split=split)
+        for k, om in enumerate(oms):
+            ep, es, ev = c_oracle.scan_hits(om, seq, thr[k])
+            rec = res["hits"][k].records() if split else res["hits"][k]
+            gp, st, sc = mb.unpack_hits(rec)
+            assert np.array_equal(gp, ep) and np.array_equal(st, es) and np.array_equal(sc, ev), (split, k)
+        assert len(res["hits"][1]) >= 2 * (len(seq) - 10 + 1) - 2000     # (windows with N are repaired, not skipped)
+        mb.release_buffers()

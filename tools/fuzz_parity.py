@@ -217,17 +217,70 @@ def chunks_case(seed):
     return info
 
 
+def batch_case(seed):
+    """cgbk_scan_batch (fused scan in its lean modes + site pass) on a random motif set over a ragged
+    sequence set: per motif the background record against the oracle's scores of every window, the
+    ordered site list bit for bit against the oracle's hit loop, the split transfer form against the
+    8-byte records, and the record of a second run against the first (repeatability)."""
+    from cgb_b200 import PackedGenome, PSSMModel, SiteCollection, _cabi
+    from cgb_b200 import motif_batch as mb
+    from oracle import c_oracle, np_oracle as O
+    rng = np.random.default_rng(seed)
+    K = int(rng.integers(1, 6))
+    lens = [int(rng.integers(1, 33)) for _ in range(K)]
+    site_sets = []
+    for m in lens:
+        cols = rng.dirichlet([rng.choice([0.3, 0.5, 1.0, 3.0])] * 4, size=m)
+        site_sets.append(["".join("ACGT"[rng.choice(4, p=cols[j])] for j in range(m))
+                          for _ in range(int(rng.integers(5, 40)))])
+    Ms = [PSSMModel([SiteCollection(s)], [1.0]) for s in site_sets]
+    oms = [O.OracleModel([s], [1.0]) for s in site_sets]
+    m_max = max(lens)
+    sizes = [int(rng.choice([m_max, m_max + 1, m_max + 2, 100, 1000, 1023, 1024, 1025, 4063, 4064, 4065, 4066, 4067,
+                             33000])) for _ in range(int(rng.integers(0, 4)))]
+    sizes.append(int(rng.choice([20000, 150000, 600000, 1500000, 2600000])))
+    sizes = [max(n, m_max) for n in sizes]
+    rng.shuffle(sizes)
+    seqs = [random_sequence(rng, n) for n in sizes]
+    g = PackedGenome.from_sequences(seqs)
+    info = {"seed": seed, "lens": lens, "sizes": sizes}
+    scores = [np.concatenate([c_oracle.score_seq(om, s)[2] for s in seqs]) for om in oms]
+    thr = [float(np.quantile(b, rng.choice([0.5, 0.9, 0.99, 0.999]))) if rng.random() < 0.7 else M.threshold()
+           for b, M in zip(scores, Ms)]
+    bins = int(rng.choice([0, 1, 64, 256]))
+    res = mb.scan_batch(Ms, g, thr, n_bins=bins)
+    again = mb.scan_batch(Ms, g, thr, n_bins=bins, split=True)
+    assert np.array_equal(res["stats"][:, :5], again["stats"][:, :5]), (info, "repeat")
+    off = np.asarray(g.seq_off, dtype=np.int64)
+    for k, (M, om, b) in enumerate(zip(Ms, oms, scores)):
+        st = res["stats"][k]
+        assert st[_cabi.BG_N] == len(b), (info, "count", k)
+        if bins:
+            assert int(res["hist"][k].sum()) == len(b), (info, "hist sum", k)
+        assert abs(st[_cabi.BG_MEAN] - b.mean()) < 1e-6 and abs(st[_cabi.BG_STD] - b.std()) < 1e-6, \
+            (info, "moments", k, st[_cabi.BG_MEAN] - b.mean(), st[_cabi.BG_STD] - b.std())
+        gp, strand, score = mb.unpack_hits(res["hits"][k])
+        assert np.array_equal(again["hits"][k].records(), res["hits"][k]), (info, "split", k)
+        ep, es, ev = [], [], []
+        for j, s in enumerate(seqs):
+            p, sd, v = c_oracle.scan_hits(om, s, thr[k])
+            ep.append(p + off[j]); es.append(sd); ev.append(v)
+        ep, es, ev = np.concatenate(ep), np.concatenate(es), np.concatenate(ev)
+        assert np.array_equal(gp, ep) and np.array_equal(strand, es) and np.array_equal(score, ev), (info, "hits", k)
+    return info
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=120.0)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--mode", choices=["kernels", "sites", "chunks"], default="kernels")
+    ap.add_argument("--mode", choices=["kernels", "sites", "chunks", "batch"], default="kernels")
     args = ap.parse_args()
     t0 = time.time()
     n, seed = 0, args.seed
     worst = {"plane": 0.0, "rescore": 0.0}
     while time.time() - t0 < args.seconds:
-        info = {"kernels": one_case, "sites": sites_case, "chunks": chunks_case}[args.mode](seed)
+        info = {"kernels": one_case, "sites": sites_case, "chunks": chunks_case, "batch": batch_case}[args.mode](seed)
         worst["plane"] = max(worst["plane"], info.get("posterior_err_plane", (0.0, 0.0))[0])
         worst["rescore"] = max(worst["rescore"], info.get("posterior_err_rescore", (0.0, 0.0))[0])
         seed += 1
