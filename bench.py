@@ -624,6 +624,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "step_ms": spread(step_ms_max),
             "own_work_ms_by_rank": [round(float(x), 2) for x in own_by_rank.mean(axis=1)],
+            "step_ms_each": [round(float(x), 2) for x in step_ms_max],
+            "own_work_ms_each": [[round(float(x), 1) for x in row] for row in own_by_rank],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32 fixed point (2^-21..2^-28 per motif) scan, f64 exact re-score of site candidates, f64 moments",
             "data": "synthetic",
