@@ -222,3 +222,77 @@ def test_plan_grid_and_motif_groups():
         for k in groups[r // S]:
             seen[k] += max(0, min(cap, bp - lo - int(m_len[k]) + 1))
     assert np.array_equal(seen, bp - m_len + 1)
+
+
+def _grid_models(K=5):
+    rng = np.random.default_rng(77)
+    lens = [8, 30, 13, 22, 17][:K]
+    return [O.OracleModel([["".join("ACGT"[i] for i in rng.integers(0, 4, m)) for _ in range(10)]], [1.0]) for m in lens]
+
+
+def _grid_worker(rank, world, port, n, q):
+    """One rank of bench.py's step on the CPU: its sequence shard (window starts capped, halo kept) for
+    its motif group, rows of the other motifs zero, ONE all-reduce of the whole record table."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import bench
+        oms = _grid_models()
+        K, nb, m_max = len(oms), 24, max(om.length for om in oms)
+        seq = O.synthetic_genome(n, 12)
+        S, M = cdist.plan_grid(world, n, min_shard_bases=n // 2)
+        groups = cdist.plan_motif_shards([float(om.length) for om in oms], M)
+        lo, cap, hi = bench.shard_bounds(n, m_max, S, rank % S)
+        shard = seq[lo:hi]
+        stats = torch.zeros(K, _cabi.BG_COUNT, dtype=torch.float64)
+        hist = torch.zeros(K, nb, dtype=torch.int64)
+        hits = {}
+        for k in groups[rank // S]:
+            om = oms[k]
+            _, _, b = c_oracle.score_seq(om, shard)
+            b = b[:max(0, min(cap, n - lo - om.length + 1))]          # the windows that START in this shard
+            stats[k, 0], stats[k, 1], stats[k, 2] = len(b), b.sum(), (b * b).sum()
+            hist[k] = torch.from_numpy(np.histogram(b, bins=np.linspace(-60, 40, nb + 1))[0])
+            p, s, v = c_oracle.scan_hits(om, shard, 2.0)
+            keep = p < cap
+            hits[k] = (p[keep] + lo, s[keep], v[keep])
+        cdist.allreduce_batch(stats, hist)
+        q.put((rank, (S, M), groups, stats.numpy().copy(), hist.numpy().copy(), hits))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_motif_group_by_sequence_shard_grid_gloo():
+    """World size 4 = 2 sequence shards x 2 motif groups (the N = 4 / N = 8 layout of bench.py) on the
+    CPU: after the ONE all-reduce EVERY rank holds the complete record of EVERY motif, equal to the
+    one-process scan; the ranks' site lists, put together, are the one-process site lists."""
+    n, world = 30011, 4
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_grid_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get() for _ in range(world)]
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    oms = _grid_models()
+    seq = O.synthetic_genome(n, 12)
+    assert all(g[1] == (2, 2) for g in got)
+    groups = got[0][2]
+    assert sorted(k for grp in groups for k in grp) == list(range(len(oms)))
+    for k, om in enumerate(oms):
+        _, _, b = c_oracle.score_seq(om, seq)
+        eh = np.histogram(b, bins=np.linspace(-60, 40, 25))[0]
+        for rank, _, _, stats, hist, _ in got:                       # every rank, every motif
+            assert stats[k, _cabi.BG_N] == len(b) == n - om.length + 1
+            assert abs(stats[k, _cabi.BG_MEAN] - b.mean()) < 1e-10 and abs(stats[k, _cabi.BG_STD] - b.std()) < 1e-9
+            assert np.array_equal(hist[k], eh)
+        parts = sorted((g[5][k] for g in got if k in g[5]), key=lambda t: (t[0][0] if len(t[0]) else 0))
+        assert len(parts) == 2                                       # one per sequence shard
+        p, s, v = c_oracle.scan_hits(om, seq, 2.0)
+        assert np.array_equal(np.concatenate([x[0] for x in parts]), p)
+        assert np.array_equal(np.concatenate([x[1] for x in parts]), s)
+        assert np.array_equal(np.concatenate([x[2] for x in parts]), v)
