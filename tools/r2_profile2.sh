@@ -26,3 +26,8 @@ for b in keep:
     for r in b: w.writerow(r[:12])
 PY
 du -sh $OUT
+# the split kernel of the end-to-end leg (site records -> 6-byte form on the copy stream)
+BENCH_E2E="python bench.py --motifs 12 --bp 1000000000 --steps 1 --warmup 1 --no-cpu --no-posteriors --e2e-steps 1"
+ncu --set full --clock-control none -k regex:split_sites -c 4 -o $TMP/r2b_split -f $BENCH_E2E > $OUT/r2b_ncu_split.log 2>&1
+echo "full split rc=$?"
+ncu -i $TMP/r2b_split.ncu-rep --page raw --csv > $OUT/r2b_ncu_split_sites_raw.csv 2>/dev/null
