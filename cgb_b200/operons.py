@@ -117,9 +117,18 @@ def predict_operons_genome(gene_tables, probability_th, sigma, regulation_probab
 
 
 def _tags_products(opr, gt):
-    tags = [gt.locus_tag[g] for g in opr.genes]
-    prods = [gt.locus_tag[g] + ' (%s)' % gt.product[g] for g in opr.genes]
-    return ', '.join(tags), ', '.join(prods)
+    """'locus_tags' and 'products' cells of an operon row.  Both reports (operons, regulons) ask for
+    every operon of the genome: the per-gene strings are built once per gene table and kept on it."""
+    cells = gt.__dict__.get("_report_cells")
+    if cells is None:
+        lt, pr = gt.locus_tag, gt.product
+        cells = gt.__dict__["_report_cells"] = (lt, [t + ' (%s)' % p for t, p in zip(lt, pr)])
+    lt, lp = cells
+    genes = opr.genes
+    if len(genes) == 1:
+        g = genes[0]
+        return lt[g], lp[g]
+    return ', '.join([lt[g] for g in genes]), ', '.join([lp[g] for g in genes])
 
 
 def operons_rows(operons, gene_tables):
@@ -152,6 +161,4 @@ def regulon_rows(results, gene_tables):
 
 def write_rows(filename, rows):
     with open(filename, 'w', newline='') as f:
-        w = csv.writer(f)
-        for row in rows:
-            w.writerow(row)
+        csv.writer(f).writerows(rows)
