@@ -49,19 +49,106 @@ def directons(gt):
 
 def intergenic_distance_threshold(gene_tables, sigma=1.0):
     """Genome.intergenic_distance_threshold: sigma * mean distance between the first two genes
-    of every directon with more than one gene, over all replicons."""
-    dists = []
+    of every directon with more than one gene, over all replicons.  (The distances are integers:
+    their sum is exact in any order, misc.mean's left-to-right sum / float(len) included.)"""
+    total, count = 0, 0
     for gt in gene_tables:
-        st, en = np.asarray(gt.start).tolist(), np.asarray(gt.end).tolist()
-        dists.extend(max(st[d[0]], st[d[1]]) - min(en[d[0]], en[d[1]]) for d in directons(gt) if len(d) > 1)
-    total = 0
-    for x in dists:                      # misc.mean: left-to-right sum / float(len)
-        total = total + x
-    return sigma * (total / float(len(dists)))
+        n = len(gt)
+        if n < 2:
+            continue
+        st = np.asarray(gt.start, dtype=np.int64)
+        en = np.asarray(gt.end, dtype=np.int64)
+        sd = np.asarray(gt.strand)
+        order = np.argsort(st, kind="stable")
+        so = sd[order]
+        run_start = np.concatenate([[0], np.nonzero(so[1:] != so[:-1])[0] + 1])
+        run_end = np.append(run_start[1:], n)
+        multi = run_end - run_start > 1
+        fwd = so[run_start] == 1
+        # first two genes of the walk: the run's first two, or (walked backwards) its last two
+        a = np.where(fwd, run_start, run_end - 1)[multi]
+        b = np.where(fwd, run_start + 1, run_end - 2)[multi]
+        ga, gb = order[a], order[b]
+        d = np.maximum(st[ga], st[gb]) - np.minimum(en[ga], en[gb])
+        total += int(d.sum())
+        count += int(len(d))
+    return sigma * (total / float(count))
 
 
 def predict_operons(gt, distance_th, probability_th, regulation_probability, start_id=1, accession=None):
     """Chromid.operon_prediction for one replicon.  ``regulation_probability``: per-gene posterior
+    (array in GeneTable order); genes above ``probability_th`` start a new operon unless
+    ``probability_th == 1.0`` (splitting off).  Returns ``(operons, n_splits)``.
+
+    Array form of the reference's ``while directons_rest`` loop (chromid.py:216-232).  The loop walks
+    every directon once per pass and peels one operon off its front; a pair of neighbouring genes is
+    therefore examined exactly once, an operon is a maximal run of a directon without a break (the
+    distance to the previous gene at or above the threshold, or -- the distance being below it -- a
+    posterior above the threshold), and the operons come out ordered by (pass = index of the run in
+    its directon, directon).  All of that is computed with array operations; ids, gene order, splits
+    counted and every field are those of the loop (``predict_operons_loop``, compared in the tests)."""
+    n = len(gt)
+    if n == 0:
+        return [], 0
+    st = np.asarray(gt.start, dtype=np.int64)
+    en = np.asarray(gt.end, dtype=np.int64)
+    sd = np.asarray(gt.strand)
+    if probability_th != 1.0:
+        split = np.asarray(regulation_probability) > probability_th
+    else:
+        split = np.zeros(n, dtype=bool)
+    # directons: runs of one strand along the (stable) start order; a run whose strand is not +1 is
+    # walked from its last gene backwards
+    order = np.argsort(st, kind="stable")
+    so = sd[order]
+    new_run = np.empty(n, dtype=bool)
+    new_run[0] = True
+    new_run[1:] = so[1:] != so[:-1]
+    run_of = np.cumsum(new_run) - 1
+    run_start = np.nonzero(new_run)[0]
+    run_len = np.diff(np.append(run_start, n))
+    pos = np.arange(n)
+    k = pos - run_start[run_of]
+    backwards = so[run_start][run_of] != 1
+    walk = order[np.where(backwards, run_start[run_of] + run_len[run_of] - 1 - k, pos)]   # genes in loop order
+    # breaks between neighbours of a walk (Gene.distance, gene.py:283-288)
+    a, b = walk[:-1], walk[1:]
+    far = (np.maximum(st[a], st[b]) - np.minimum(en[a], en[b])) >= distance_th
+    brk = np.ones(n, dtype=bool)
+    brk[1:] = new_run[1:] | far | split[b]
+    splits = int(np.count_nonzero(~new_run[1:] & ~far & split[b]))
+    seg_of = np.cumsum(brk) - 1                         # operon (segment) of every walked gene
+    seg_start = np.nonzero(brk)[0]
+    n_seg = len(seg_start)
+    seg_run = run_of[seg_start]
+    first_seg_of_run = np.searchsorted(seg_run, np.arange(len(run_start)))
+    seg_pass = np.arange(n_seg) - first_seg_of_run[seg_run]
+    seg_order = np.lexsort((seg_run, seg_pass))         # the loop's order: pass, then directon
+    rank_of_seg = np.empty(n_seg, dtype=np.int64)
+    rank_of_seg[seg_order] = np.arange(n_seg)
+    # genes of every operon sorted by start, ties in walk order (sorted() is stable, operon.py:26)
+    g_order = np.lexsort((pos, st[walk], rank_of_seg[seg_of]))
+    genes_sorted = walk[g_order]
+    counts = np.diff(np.append(seg_start, n))[seg_order]
+    bounds = np.concatenate([[0], np.cumsum(counts)])
+    o_start = np.minimum.reduceat(st[genes_sorted], bounds[:-1])
+    o_end = np.maximum.reduceat(en[genes_sorted], bounds[:-1])
+    o_strand = sd[genes_sorted[bounds[:-1]]]
+    o_first = np.where(o_strand == 1, genes_sorted[bounds[:-1]], genes_sorted[bounds[1:] - 1])   # operon.py:68-73
+    prob = np.asarray(regulation_probability, dtype=np.float64)[o_first].tolist() \
+        if regulation_probability is not None else [float("nan")] * n_seg
+    chrom = accession if accession is not None else gt.seq_index
+    gl, bl = genes_sorted.tolist(), bounds.tolist()
+    seq_index = gt.seq_index
+    out = [Operon(start_id + i, seq_index, chrom, gl[bl[i]:bl[i + 1]], s0, e0, sd0, f0, p0)
+           for i, (s0, e0, sd0, f0, p0) in enumerate(zip(o_start.tolist(), o_end.tolist(), o_strand.tolist(),
+                                                         o_first.tolist(), prob))]
+    return out, splits
+
+
+def predict_operons_loop(gt, distance_th, probability_th, regulation_probability, start_id=1, accession=None):
+    """The reference's loop shape over plain lists (kept as the differential check of
+    :func:`predict_operons`).  Chromid.operon_prediction for one replicon.  ``regulation_probability``: per-gene posterior
     (array in GeneTable order); genes above ``probability_th`` start a new operon unless
     ``probability_th == 1.0`` (splitting off).  Returns ``(operons, n_splits)``."""
     if probability_th != 1.0:

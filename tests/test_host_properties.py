@@ -49,3 +49,39 @@ def test_operons_partition_the_genes(genes, th, sigma, seed):
         assert o.first_gene == (o.genes[0] if o.strand == 1 else o.genes[-1])
         assert o.start == min(start[g] for g in o.genes) and o.end == max(end[g] for g in o.genes)
     assert [o.operon_id for o in oprs] == list(range(1, len(oprs) + 1))
+
+
+def test_array_operon_prediction_equals_the_reference_loop_shape():
+    """operons.predict_operons (array operations) against predict_operons_loop (the reference's
+    ``while directons_rest`` loop over lists, chromid.py:216-232) on random gene tables: equal starts,
+    strand 0, overlapping genes, every threshold regime.  Operon ids, gene order inside an operon,
+    start / end / strand / first gene / probability and the number of splits must be identical."""
+    import numpy as np
+
+    from cgb_b200 import GeneTable
+    from cgb_b200 import operons as op
+    rng = np.random.default_rng(123)
+    for trial in range(150):
+        n = int(rng.integers(1, 70))
+        L = 30000
+        start = np.sort(rng.integers(0, L - 1000, size=n))
+        if n > 4 and rng.random() < 0.4:
+            start[1] = start[0]
+            start[4] = start[3]
+        rng.shuffle(start)
+        end = start + rng.integers(30, 900, size=n)
+        strand = rng.choice([1, -1], size=n)
+        if rng.random() < 0.15:
+            strand[int(rng.integers(0, n))] = 0
+        gt = GeneTable(start.tolist(), end.tolist(), strand.tolist(), L, seq_index=int(rng.integers(0, 3)))
+        prob = rng.random(n)
+        for pth in (1.0, 0.5, 0.05):
+            for dth in (50.0, 180.25, -20.0, 1e9):
+                a, sa = op.predict_operons(gt, dth, pth, prob, start_id=5, accession="ACC")
+                b, sb = op.predict_operons_loop(gt, dth, pth, prob, start_id=5, accession="ACC")
+                assert a == b and sa == sb
+                assert sorted(g for o in a for g in o.genes) == list(range(n))
+        a, _ = op.predict_operons(gt, 100.0, 1.0, None)
+        b, _ = op.predict_operons_loop(gt, 100.0, 1.0, None)
+        assert [x[:8] for x in a] == [y[:8] for y in b] and all(np.isnan(x[8]) for x in a)
+    assert op.predict_operons(GeneTable([], [], [], 10), 1.0, 1.0, None) == ([], 0)
