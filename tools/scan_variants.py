@@ -4,6 +4,11 @@ step: scan + site pass) for one representative motif per group count G = 2..8 ov
 sequence, for every library given (CGBK_LIB selects the build; one subprocess per library).
 
     python tools/scan_variants.py [--bp 250000000] [--libs libcgbk.so,libcgbk_t512.so]
+
+Variant libraries come from cgb_b200.build.build_library(out="libcgbk_x.so", defines=[...]); the
+epilogue keeps three switches that rebuild earlier forms for such comparisons: -DCGBK_MINMAX_DIFF
+(|f - r| as max - min), -DCGBK_F2I_CORR (soft-max correction through F2I), -DCGBK_BIN_MULHI (histogram
+bin as subtract + high multiply); thread counts per group count: -DCGBK_STATS_THREADS_G3=640 etc.
 """
 import argparse
 import json
