@@ -231,11 +231,15 @@ class PSSMModel(TFBindingModel):
         thousand table look-ups are not worth a launch).  Ragged site lists take the device path."""
         m = self.length
         colls = self._collection_set
-        n_sites = len(self.__dict__["sites"]) if "sites" in self.__dict__ else sum(c.site_count for c in colls)
+        # the collections' own byte strings serve when every collection is one of ours with sites of
+        # the motif's length; a materialised -- possibly replaced -- site list wins over them, and
+        # any other collection type (PSSMModel.from_pwm, a caller's class) goes through its .sites
+        fast = "sites" not in self.__dict__ and all(
+            getattr(c, "_uniform", False) and getattr(c, "_raw", None) is not None and c.length == m for c in colls)
+        n_sites = sum(c.site_count for c in colls) if fast else len(self.sites)
         if n_sites == 0:
             return []
-        if "sites" in self.__dict__ or not all(getattr(c, "_uniform", False) and c.length == m for c in colls):
-            # (a materialised -- possibly replaced -- site list wins over the collections' bytes)
+        if not fast:
             sites = self.sites
             if any(len(s) != m for s in sites):
                 return self.score_seqs(sites, True)

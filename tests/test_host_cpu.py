@@ -234,3 +234,22 @@ def test_interleave_order_tracks_the_batch_ratio():
             assert np.all(gap[:-1] <= sites.max() + ratio * cost.max())
             assert sites[order[0]] == sites.max()          # a PCIe-heavy model first: the copies start early
     assert mb.interleave_order([1.0, 1.0, 1.0], [0, 0, 0]) == [0, 1, 2]
+
+
+def test_score_self_with_foreign_collection_types():
+    """score_self takes the collections' cached site bytes only when every collection is a
+    cgb_b200 SiteCollection; PSSMModel.from_pwm (a bare PWM with optional sites) and duck-typed
+    collections go through ``.sites`` and give the same numbers."""
+    vals = {"A": [0.7, 0.1, 0.1, 0.25], "C": [0.1, 0.7, 0.1, 0.25], "G": [0.1, 0.1, 0.7, 0.25], "T": [0.1, 0.1, 0.1, 0.25]}
+    sites = ["ACGT", "ACGA", "TCGT", "ACGT"]
+    a = PSSMModel.from_pwm(vals, sites=sites).score_self()
+    assert len(a) == 4 and a[0] == a[3] and a[0][0] > a[2][0]
+    assert PSSMModel.from_pwm(vals).score_self() == []
+
+    class Duck(object):                                    # what a caller's own collection class offers
+        def __init__(self, sites):
+            self._c = SiteCollection(sites)
+            self.pwm, self.sites, self.site_count, self.length = self._c.pwm, self._c.sites, len(sites), 4
+    mine = PSSMModel([SiteCollection(sites)], [1.0]).score_self()
+    duck = PSSMModel([Duck(sites)], [1.0]).score_self()
+    assert mine == duck and len(mine) == 4
