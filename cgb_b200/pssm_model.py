@@ -119,7 +119,7 @@ class PSSMModel(TFBindingModel):
         assert all(length == pwm.length for pwm in pwms)
         pwm_vals = {}
         for let in alphabet:
-            cols = [(dict.__getitem__(pwm, let), w) for pwm, w in zip(pwms, weights)]
+            cols = [(dict.__getitem__(pwm, let) if isinstance(pwm, dict) else pwm[let], w) for pwm, w in zip(pwms, weights)]
             pwm_vals[let] = [psum(col[i]*w for col, w in cols) for i in range(length)]
         return PositionWeightMatrix(alphabet, pwm_vals)
 
