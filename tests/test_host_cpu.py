@@ -253,3 +253,26 @@ def test_score_self_with_foreign_collection_types():
     mine = PSSMModel([SiteCollection(sites)], [1.0]).score_self()
     duck = PSSMModel([Duck(sites)], [1.0]).score_self()
     assert mine == duck and len(mine) == 4
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) on a tiny sample: one
+    JSON line with the contract's keys, our metric / unit, impl = reference, a cpu_baseline object
+    describing the run and an e2e object repeating the value with zero transfer bytes."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2",
+                        "--warmup", "1", "--ref-sample-bp", "2000", "--motifs", "5"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-800:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "bp*motif/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 2 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and d["metric"].startswith("PSWM scan")
