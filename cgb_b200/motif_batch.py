@@ -479,6 +479,9 @@ def _scan_batch_in_order(models, genome, thresholds="patser", n_bins=256, win_ca
                         # (ONE launch for the sub-batch: it has to find its way between the scan kernels
                         # of the next sub-batch, which keep every SM busy)
                         nb1 = split_blocks + 1
+                        if n_done and int(np.diff(cum).max()) >= (1 << 31):
+                            raise ValueError("a site list of 2^31 or more records cannot take the split form "
+                                             "(int32 block index): use split=False")
                         buf.h_cum[p][:n_done + 1].copy_(torch.from_numpy(cum))
                         buf.d_cum[p][:n_done + 1].copy_(buf.h_cum[p][:n_done + 1], non_blocking=True)
                         _cabi.check(lib.cgbk_split_sites_batch(
